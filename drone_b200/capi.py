@@ -1,0 +1,103 @@
+"""ctypes view of the C ABI in include/b200drone.h (libb200drone.so).
+
+This is the only way Python reaches the CUDA kernels; there is no CPU path.
+Loading fails loudly when the library has not been built
+(`python -c "import __graft_entry__ as g; g.build()"` or `make -C drone_b200/csrc`).
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libb200drone.so")
+
+B2D_OK, B2D_EINVAL, B2D_ENOMEM, B2D_ECUDA, B2D_ESTATE = 0, -1, -2, -3, -4
+MATH_FAST, MATH_STRICT = 0, 1
+RESET_PHILOX, RESET_INJECT = 0, 1
+MEM_DEVICE, MEM_HOST = 0, 1
+LOG_FIELDS = ("episode_return", "episode_length", "rings_passed", "collision_rate", "oob",
+              "timeout", "score", "perf", "n")  # DR/dronelib.h:52-63
+
+
+class Buffers(C.Structure):
+    _fields_ = [("observations", C.c_void_p), ("actions", C.c_void_p), ("rewards", C.c_void_p),
+                ("terminals", C.c_void_p), ("truncations", C.c_void_p), ("location", C.c_int)]
+
+
+class RaceCfg(C.Structure):
+    _fields_ = [("num_envs", C.c_int), ("max_rings", C.c_int), ("max_moves", C.c_int),
+                ("device", C.c_int), ("seed", C.c_uint64), ("env_id_base", C.c_uint32),
+                ("math", C.c_int), ("write_clamped_actions", C.c_int)]
+
+
+class SwarmCfg(C.Structure):
+    _fields_ = [("num_envs", C.c_int), ("num_agents", C.c_int), ("max_rings", C.c_int),
+                ("device", C.c_int), ("seed", C.c_uint64), ("env_id_base", C.c_uint32),
+                ("math", C.c_int), ("write_clamped_actions", C.c_int)]
+
+
+# every symbol include/b200drone.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "b2d_race_create": (C.c_int, [C.POINTER(_P), C.POINTER(RaceCfg), C.POINTER(Buffers)]),
+    "b2d_swarm_create": (C.c_int, [C.POINTER(_P), C.POINTER(SwarmCfg), C.POINTER(Buffers)]),
+    "b2d_vec_close": (C.c_int, [_P]),
+    "b2d_vec_reset": (C.c_int, [_P, C.c_uint64, _P]),
+    "b2d_vec_step": (C.c_int, [_P, _P]),
+    "b2d_vec_step_from": (C.c_int, [_P, _P, _P]),
+    "b2d_vec_step_host": (C.c_int, [_P, _P]),
+    "b2d_vec_reset_host": (C.c_int, [_P, C.c_uint64, _P]),
+    "b2d_vec_log": (C.c_int, [_P, C.POINTER(C.c_float), _P]),
+    "b2d_vec_log_begin": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(C.c_int)]),
+    "b2d_vec_log_end": (C.c_int, [_P, C.POINTER(C.c_float), _P]),
+    "b2d_get_buffers": (C.c_int, [_P, C.POINTER(Buffers)]),
+    "b2d_num_agents": (C.c_int, [_P]),
+    "b2d_obs_dim": (C.c_int, [_P]),
+    "b2d_state_blob_floats": (C.c_int, [_P]),
+    "b2d_kernel_launches": (C.c_longlong, [_P]),
+    "b2d_step_count": (C.c_int, [_P, C.POINTER(C.c_uint32), _P]),
+    "b2d_get_state": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_float)]),
+    "b2d_put_state": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_float)]),
+    "b2d_observe": (C.c_int, [_P, _P]),
+    "b2d_set_math": (C.c_int, [_P, C.c_int]),
+    "b2d_set_reset_mode": (C.c_int, [_P, C.c_int]),
+    "b2d_set_reset_payload": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "b2d_set_step_count": (C.c_int, [_P, C.c_uint32]),
+    "b2d_last_error": (C.c_char_p, []),
+    "b2d_version": (C.c_int, []),
+}
+
+_LIB = None
+
+
+class B2DError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200drone error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load libb200drone.so (once).  No fallback: a missing library is an error."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: the CUDA library has not been built and there is no "
+                "CPU fallback. Run `python -c 'import __graft_entry__ as g; g.build()'`.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc < 0:
+        msg = lib().b2d_last_error().decode("utf-8", "replace")
+        if rc == B2D_EINVAL:
+            raise ValueError(msg)
+        if rc == B2D_ENOMEM:
+            raise MemoryError(msg)
+        raise B2DError(rc, msg)
+    return rc

@@ -1,0 +1,443 @@
+// api.cu -- host side of libb200drone.so: the C ABI declared in include/b200drone.h.
+//
+// Thin by design: owns device memory, fills the kernel argument structs and
+// launches on the caller's stream.  There is NO CPU implementation behind this
+// file -- without a CUDA device every entry point that would compute returns
+// B2D_ECUDA.
+#include "../../include/b200drone.h"
+#include "race_kernels.cuh"
+#include "swarm_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace b2d;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) return fail(B2D_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+enum { KIND_RACE = 0, KIND_SWARM = 1 };
+
+struct b2d_vec {
+    int kind;
+    int device;
+    int num_envs, num_agents /* rows */, obs_dim, blob_floats;
+    int math, write_clamped;
+    RaceDev race;
+    SwarmDev swarm;
+    // device contract buffers (owned unless external)
+    b2d_buffers dev;
+    bool own_obs, own_act, own_rew, own_term, own_trunc;
+    // host mirrors for the *_host entry points
+    b2d_buffers host;
+    bool has_host;
+    std::vector<void *> allocs; // state arrays etc.
+    float *d_payload;
+    float *d_blob_tmp;
+    int *d_ids_tmp;
+    size_t blob_tmp_cap;
+    long long *d_log_out;
+    long long h_log_out[16];
+    double h_flog_out[8];
+    long long launches;
+    cudaStream_t copy_streams[2];
+    cudaEvent_t ev_step, ev_copy[2];
+};
+
+template <class T> static int dev_alloc(b2d_vec *v, T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess) return fail(B2D_ENOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+    e = cudaMemset(q, 0, count * sizeof(T));
+    if (e != cudaSuccess) return fail(B2D_ECUDA, "cudaMemset: %s", cudaGetErrorString(e));
+    v->allocs.push_back(q);
+    *p = (T *)q;
+    return B2D_OK;
+}
+
+static int check_ext(const b2d_buffers *ext) {
+    if (!ext) return B2D_OK;
+    if (ext->location != B2D_MEM_DEVICE && ext->location != B2D_MEM_HOST)
+        return fail(B2D_EINVAL, "buffers.location must be B2D_MEM_DEVICE or B2D_MEM_HOST");
+    if (ext->location == B2D_MEM_DEVICE) {
+        if (((uintptr_t)ext->observations & 15u) || ((uintptr_t)ext->actions & 15u))
+            return fail(B2D_EINVAL, "observations and actions must be 16-byte aligned");
+        if (((uintptr_t)ext->rewards & 3u)) return fail(B2D_EINVAL, "rewards must be 4-byte aligned");
+    }
+    return B2D_OK;
+}
+
+// allocate / adopt the contract buffers; rows = num_agents
+static int setup_buffers(b2d_vec *v, const b2d_buffers *ext) {
+    const size_t rows = (size_t)v->num_agents;
+    const bool ext_dev = ext && ext->location == B2D_MEM_DEVICE;
+    memset(&v->dev, 0, sizeof(v->dev));
+    v->dev.location = B2D_MEM_DEVICE;
+    int rc;
+    if (ext_dev && ext->observations) v->dev.observations = ext->observations;
+    else if ((rc = dev_alloc(v, &v->dev.observations, rows * v->obs_dim))) return rc;
+    if (ext_dev && ext->actions) v->dev.actions = ext->actions;
+    else if ((rc = dev_alloc(v, &v->dev.actions, rows * 4))) return rc;
+    if (ext_dev && ext->rewards) v->dev.rewards = ext->rewards;
+    else if ((rc = dev_alloc(v, &v->dev.rewards, rows))) return rc;
+    if (ext_dev && ext->terminals) v->dev.terminals = ext->terminals;
+    else if ((rc = dev_alloc(v, &v->dev.terminals, rows))) return rc;
+    if (ext_dev && ext->truncations) v->dev.truncations = ext->truncations;
+    else if ((rc = dev_alloc(v, &v->dev.truncations, rows))) return rc;
+    v->has_host = ext && ext->location == B2D_MEM_HOST;
+    if (v->has_host) v->host = *ext;
+    return B2D_OK;
+}
+
+static int finish_create(b2d_vec *v) {
+    int rc;
+    if ((rc = dev_alloc(v, &v->d_log_out, 16))) return rc;
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&v->copy_streams[k], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&v->ev_copy[k], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&v->ev_step, cudaEventDisableTiming));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return B2D_OK;
+}
+
+extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d_buffers *ext) {
+    if (!out || !cfg) return fail(B2D_EINVAL, "b2d_race_create: null argument");
+    *out = nullptr;
+    if (cfg->num_envs <= 0) return fail(B2D_EINVAL, "num_envs must be greater than 0");
+    if (cfg->max_rings <= 0 || cfg->max_rings > 4096) return fail(B2D_EINVAL, "max_rings must be in [1, 4096]");
+    if (cfg->max_moves <= 0) return fail(B2D_EINVAL, "max_moves must be positive");
+    if (cfg->math != B2D_MATH_FAST && cfg->math != B2D_MATH_STRICT) return fail(B2D_EINVAL, "unknown math mode");
+    int rc = check_ext(ext);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    b2d_vec *v = new (std::nothrow) b2d_vec();
+    if (!v) return fail(B2D_ENOMEM, "out of host memory");
+    v->kind = KIND_RACE;
+    v->device = cfg->device;
+    v->num_envs = v->num_agents = cfg->num_envs;
+    v->obs_dim = B2D_RACE_OBS;
+    v->blob_floats = B2D_RACE_BLOB + 6 * cfg->max_rings;
+    v->math = cfg->math;
+    v->write_clamped = cfg->write_clamped_actions;
+    RaceDev &d = v->race;
+    memset(&d, 0, sizeof(d));
+    d.n = cfg->num_envs;
+    d.ld = (cfg->num_envs + RACE_BLOCK - 1) / RACE_BLOCK * RACE_BLOCK;
+    d.max_rings = cfg->max_rings;
+    d.max_moves = cfg->max_moves;
+    d.key0 = (uint32_t)cfg->seed;
+    d.key1 = (uint32_t)(cfg->seed >> 32);
+    d.env_id_base = cfg->env_id_base;
+    d.reset_mode = B2D_RESET_PHILOX;
+    const size_t ld = d.ld;
+    if ((rc = setup_buffers(v, ext)) || (rc = dev_alloc(v, &d.S, 5 * ld)) || (rc = dev_alloc(v, &d.P, 3 * ld)) ||
+        (rc = dev_alloc(v, &d.PJ, ld)) || (rc = dev_alloc(v, &d.C0, ld)) || (rc = dev_alloc(v, &d.C1, ld)) ||
+        (rc = dev_alloc(v, &d.G0, (size_t)d.max_rings * ld)) || (rc = dev_alloc(v, &d.G1, (size_t)d.max_rings * ld)) ||
+        (rc = dev_alloc(v, &d.ctl, 1)) || (rc = finish_create(v))) {
+        b2d_vec_close(v);
+        return rc;
+    }
+    d.obs = v->dev.observations;
+    d.act_in = v->dev.actions;
+    d.act_out = v->write_clamped ? v->dev.actions : nullptr;
+    d.rew = v->dev.rewards;
+    d.term = v->dev.terminals;
+    cudaFuncSetAttribute(race_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RACE_BLOCK * RACE_OBS * 4);
+    cudaFuncSetAttribute(race_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RACE_BLOCK * RACE_OBS * 4);
+    *out = v;
+    return B2D_OK;
+}
+
+extern "C" int b2d_swarm_create(b2d_vec **out, const b2d_swarm_cfg *cfg, const b2d_buffers *ext) {
+    (void)cfg; (void)ext;
+    if (out) *out = nullptr;
+    return fail(B2D_ESTATE, "swarm env not built in this library version");
+}
+
+extern "C" int b2d_vec_close(b2d_vec *v) {
+    if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    cudaSetDevice(v->device);
+    cudaDeviceSynchronize();
+    for (void *p : v->allocs) cudaFree(p);
+    if (v->d_payload) cudaFree(v->d_payload);
+    if (v->d_blob_tmp) cudaFree(v->d_blob_tmp);
+    if (v->d_ids_tmp) cudaFree(v->d_ids_tmp);
+    for (int k = 0; k < 2; k++) {
+        if (v->copy_streams[k]) cudaStreamDestroy(v->copy_streams[k]);
+        if (v->ev_copy[k]) cudaEventDestroy(v->ev_copy[k]);
+    }
+    if (v->ev_step) cudaEventDestroy(v->ev_step);
+    delete v;
+    return B2D_OK;
+}
+
+static int launch_check(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B2D_ECUDA, "%s launch: %s", what, cudaGetErrorString(e));
+    return B2D_OK;
+}
+
+extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
+    if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (v->kind == KIND_RACE) {
+        RaceDev &d = v->race;
+        d.key0 = (uint32_t)seed;
+        d.key1 = (uint32_t)(seed >> 32);
+        if (d.reset_mode == B2D_RESET_INJECT && !d.payload) return fail(B2D_ESTATE, "inject mode without a payload");
+        race_ctl_reset_kernel<<<1, 32, 0, st>>>(d.ctl, 0u, 0);
+        race_reset_kernel<<<(d.n + 127) / 128, 128, 0, st>>>(d);
+        v->launches += 2;
+        return launch_check("race_reset_kernel");
+    }
+    swarm_vec_reset(v->swarm, seed, st, &v->launches);
+    return launch_check("swarm_reset_kernel");
+}
+
+static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st) {
+    if (v->kind == KIND_RACE) {
+        RaceDev d = v->race;
+        if (actions) d.act_in = actions;
+        const int grid = d.ld / RACE_BLOCK;
+        const size_t smem = RACE_BLOCK * RACE_OBS * sizeof(float);
+        if (v->math == B2D_MATH_STRICT) race_step_kernel<true><<<grid, RACE_BLOCK, smem, st>>>(d);
+        else race_step_kernel<false><<<grid, RACE_BLOCK, smem, st>>>(d);
+        v->launches += 1;
+        return launch_check("race_step_kernel");
+    }
+    swarm_vec_step(v->swarm, actions, v->math, st, &v->launches);
+    return launch_check("swarm_step_kernel");
+}
+
+extern "C" int b2d_vec_step(b2d_vec *v, void *stream) {
+    if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    return step_impl(v, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int b2d_vec_step_from(b2d_vec *v, const float *device_actions, void *stream) {
+    if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    if (!device_actions || ((uintptr_t)device_actions & 15u)) return fail(B2D_EINVAL, "actions must be a 16-byte aligned device pointer");
+    return step_impl(v, device_actions, (cudaStream_t)stream);
+}
+
+// Host-buffer step: one kernel (it is far shorter than the PCIe transfers); the D2H of
+// observations is split across two copy streams so both DMA engines stay busy.
+extern "C" int b2d_vec_step_host(b2d_vec *v, void *stream) {
+    if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    if (!v->has_host) return fail(B2D_ESTATE, "handle was not created with host buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t rows = (size_t)v->num_agents;
+    CUDA_TRY(cudaMemcpyAsync(v->dev.actions, v->host.actions, rows * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = step_impl(v, nullptr, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(v->ev_step, st));
+    // rewards/terminals (+clamped actions) on copy stream 0, observations split over both
+    const size_t half = (rows / 2) * v->obs_dim;
+    const size_t total = rows * v->obs_dim;
+    for (int k = 0; k < 2; k++) CUDA_TRY(cudaStreamWaitEvent(v->copy_streams[k], v->ev_step, 0));
+    CUDA_TRY(cudaMemcpyAsync(v->host.observations, v->dev.observations, half * sizeof(float), cudaMemcpyDeviceToHost, v->copy_streams[0]));
+    CUDA_TRY(cudaMemcpyAsync(v->host.observations + half, v->dev.observations + half, (total - half) * sizeof(float), cudaMemcpyDeviceToHost, v->copy_streams[1]));
+    CUDA_TRY(cudaMemcpyAsync(v->host.rewards, v->dev.rewards, rows * sizeof(float), cudaMemcpyDeviceToHost, v->copy_streams[0]));
+    CUDA_TRY(cudaMemcpyAsync(v->host.terminals, v->dev.terminals, rows, cudaMemcpyDeviceToHost, v->copy_streams[1]));
+    if (v->write_clamped)
+        CUDA_TRY(cudaMemcpyAsync(v->host.actions, v->dev.actions, rows * 4 * sizeof(float), cudaMemcpyDeviceToHost, v->copy_streams[0]));
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(cudaEventRecord(v->ev_copy[k], v->copy_streams[k]));
+        CUDA_TRY(cudaStreamWaitEvent(st, v->ev_copy[k], 0));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B2D_OK;
+}
+
+extern "C" int b2d_vec_reset_host(b2d_vec *v, uint64_t seed, void *stream) {
+    if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    if (!v->has_host) return fail(B2D_ESTATE, "handle was not created with host buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = b2d_vec_reset(v, seed, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(v->host.observations, v->dev.observations, (size_t)v->num_agents * v->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B2D_OK;
+}
+
+// ---------------------------------------------------------------- vec_log
+extern "C" int b2d_vec_log_begin(b2d_vec *v, void *stream, long long **device_sums, int *count) {
+    if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    Ctl *ctl = v->kind == KIND_RACE ? v->race.ctl : v->swarm.ctl;
+    if (v->kind == KIND_RACE) race_log_snapshot_kernel<<<1, 32, 0, st>>>(ctl, v->d_log_out);
+    else swarm_log_snapshot_kernel<<<1, 32, 0, st>>>(ctl, v->d_log_out);
+    v->launches += 1;
+    if (device_sums) *device_sums = v->d_log_out;
+    if (count) *count = 16;
+    return launch_check("log_snapshot_kernel");
+}
+
+extern "C" int b2d_vec_log_end(b2d_vec *v, float out[B2D_LOG_FIELDS], void *stream) {
+    if (!v || !out) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(v->h_log_out, v->d_log_out, 16 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int k = 0; k < B2D_LOG_FIELDS; k++) out[k] = 0.0f;
+    const long long *a = v->h_log_out;
+    const double n = (double)a[ACC_N];
+    if (a[ACC_N] == 0) return B2D_OK;
+    if (v->kind == KIND_RACE) {
+        // Log field order: DR/dronelib.h:52-63; averaging: EB:588-591
+        out[0] = (float)((double)a[ACC_RETURN] / n);
+        out[1] = (float)((double)a[ACC_LENGTH] / n);
+        out[2] = 0.0f;
+        out[3] = (float)((double)a[ACC_COLLISION] / n);
+        out[4] = (float)((double)a[ACC_OOB] / n);
+        out[5] = (float)((double)a[ACC_TIMEOUT] / n);
+        out[6] = (float)((double)a[ACC_COUNT] / n); // score: only episodes that ended in the last step
+        out[7] = (float)((double)a[ACC_RINGS] / (double)v->race.max_rings / n);
+        out[8] = (float)n;
+    } else {
+        swarm_log_finish(a, out);
+    }
+    return B2D_OK;
+}
+
+extern "C" int b2d_vec_log(b2d_vec *v, float out[B2D_LOG_FIELDS], void *stream) {
+    int rc = b2d_vec_log_begin(v, stream, nullptr, nullptr);
+    if (rc) return rc;
+    return b2d_vec_log_end(v, out, stream);
+}
+
+// ---------------------------------------------------------------- introspection
+extern "C" int b2d_get_buffers(const b2d_vec *v, b2d_buffers *out) {
+    if (!v || !out) return fail(B2D_EINVAL, "null argument");
+    *out = v->dev;
+    return B2D_OK;
+}
+extern "C" int b2d_num_agents(const b2d_vec *v) { return v ? v->num_agents : fail(B2D_EINVAL, "null handle"); }
+extern "C" int b2d_obs_dim(const b2d_vec *v) { return v ? v->obs_dim : fail(B2D_EINVAL, "null handle"); }
+extern "C" int b2d_state_blob_floats(const b2d_vec *v) { return v ? v->blob_floats : fail(B2D_EINVAL, "null handle"); }
+extern "C" long long b2d_kernel_launches(const b2d_vec *v) { return v ? v->launches : -1; }
+
+extern "C" int b2d_step_count(b2d_vec *v, uint32_t *steps, void *stream) {
+    if (!v || !steps) return fail(B2D_EINVAL, "null argument");
+    Ctl *ctl = v->kind == KIND_RACE ? v->race.ctl : v->swarm.ctl;
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    CUDA_TRY(cudaMemcpy(steps, &ctl->epoch, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return B2D_OK;
+}
+
+extern "C" int b2d_set_step_count(b2d_vec *v, uint32_t steps) {
+    if (!v) return fail(B2D_EINVAL, "null handle");
+    Ctl *ctl = v->kind == KIND_RACE ? v->race.ctl : v->swarm.ctl;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(&ctl->epoch, &steps, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return B2D_OK;
+}
+
+// ---------------------------------------------------------------- state hooks
+static int ensure_tmp(b2d_vec *v, int n) {
+    const size_t need = (size_t)n * v->blob_floats;
+    if (need > v->blob_tmp_cap) {
+        if (v->d_blob_tmp) cudaFree(v->d_blob_tmp);
+        if (v->d_ids_tmp) cudaFree(v->d_ids_tmp);
+        v->d_blob_tmp = nullptr;
+        v->d_ids_tmp = nullptr;
+        v->blob_tmp_cap = 0;
+        if (cudaMalloc(&v->d_blob_tmp, need * sizeof(float)) != cudaSuccess) return fail(B2D_ENOMEM, "cudaMalloc blob staging");
+        if (cudaMalloc(&v->d_ids_tmp, (size_t)n * sizeof(int)) != cudaSuccess) return fail(B2D_ENOMEM, "cudaMalloc id staging");
+        v->blob_tmp_cap = need;
+    }
+    return B2D_OK;
+}
+
+extern "C" int b2d_get_state(b2d_vec *v, const int *env_ids, int n, float *host_blobs) {
+    if (!v || !host_blobs || n <= 0 || n > v->num_envs) return fail(B2D_EINVAL, "b2d_get_state: bad argument");
+    int rc = ensure_tmp(v, n);
+    if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (env_ids) {
+        for (int k = 0; k < n; k++)
+            if (env_ids[k] < 0 || env_ids[k] >= v->num_envs) return fail(B2D_EINVAL, "env id out of range");
+        CUDA_TRY(cudaMemcpy(v->d_ids_tmp, env_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (v->kind == KIND_RACE) race_pack_kernel<<<(n + 127) / 128, 128>>>(v->race, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
+    else swarm_pack_kernel<<<(n + 127) / 128, 128>>>(v->swarm, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
+    v->launches += 1;
+    if ((rc = launch_check("pack_kernel"))) return rc;
+    CUDA_TRY(cudaMemcpy(host_blobs, v->d_blob_tmp, (size_t)n * v->blob_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2D_OK;
+}
+
+extern "C" int b2d_put_state(b2d_vec *v, const int *env_ids, int n, const float *host_blobs) {
+    if (!v || !host_blobs || n <= 0 || n > v->num_envs) return fail(B2D_EINVAL, "b2d_put_state: bad argument");
+    int rc = ensure_tmp(v, n);
+    if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (env_ids) {
+        for (int k = 0; k < n; k++)
+            if (env_ids[k] < 0 || env_ids[k] >= v->num_envs) return fail(B2D_EINVAL, "env id out of range");
+        CUDA_TRY(cudaMemcpy(v->d_ids_tmp, env_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMemcpy(v->d_blob_tmp, host_blobs, (size_t)n * v->blob_floats * sizeof(float), cudaMemcpyHostToDevice));
+    if (v->kind == KIND_RACE) race_unpack_kernel<<<(n + 127) / 128, 128>>>(v->race, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
+    else swarm_unpack_kernel<<<(n + 127) / 128, 128>>>(v->swarm, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
+    v->launches += 1;
+    if ((rc = launch_check("unpack_kernel"))) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    return B2D_OK;
+}
+
+extern "C" int b2d_observe(b2d_vec *v, void *stream) {
+    if (!v) return fail(B2D_EINVAL, "null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (v->kind == KIND_RACE) race_observe_kernel<<<(v->race.n + 127) / 128, 128, 0, st>>>(v->race);
+    else swarm_observe_launch(v->swarm, st);
+    v->launches += 1;
+    return launch_check("observe_kernel");
+}
+
+// ---------------------------------------------------------------- configuration hooks
+extern "C" int b2d_set_math(b2d_vec *v, int math) {
+    if (!v || (math != B2D_MATH_FAST && math != B2D_MATH_STRICT)) return fail(B2D_EINVAL, "unknown math mode");
+    v->math = math;
+    return B2D_OK;
+}
+
+extern "C" int b2d_set_reset_mode(b2d_vec *v, int mode) {
+    if (!v || (mode != B2D_RESET_PHILOX && mode != B2D_RESET_INJECT)) return fail(B2D_EINVAL, "unknown reset mode");
+    if (v->kind == KIND_RACE) v->race.reset_mode = mode;
+    else v->swarm.reset_mode = mode;
+    return B2D_OK;
+}
+
+extern "C" int b2d_set_reset_payload(b2d_vec *v, const float *host_payload) {
+    if (!v || !host_payload) return fail(B2D_EINVAL, "null argument");
+    const size_t bytes = (size_t)v->num_envs * v->blob_floats * sizeof(float);
+    if (!v->d_payload) {
+        if (cudaMalloc(&v->d_payload, bytes) != cudaSuccess) return fail(B2D_ENOMEM, "cudaMalloc payload");
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(v->d_payload, host_payload, bytes, cudaMemcpyHostToDevice));
+    if (v->kind == KIND_RACE) v->race.payload = v->d_payload;
+    else v->swarm.payload = v->d_payload;
+    return B2D_OK;
+}
+
+extern "C" const char *b2d_last_error(void) { return g_err; }
+extern "C" int b2d_version(void) { return B2D_VERSION; }

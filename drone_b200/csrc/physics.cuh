@@ -1,0 +1,322 @@
+// physics.cuh -- quadrotor rigid-body step shared by the race and swarm kernels.
+//
+// What it computes follows the reference's dronelib (R = pufferlib/ocean/drone_race):
+//   rates()        R/dronelib.h:302-381  compute_derivatives
+//   probe()        R/dronelib.h:383-392  step (Euler probe + quaternion renormalise)
+//   advance_body() R/dronelib.h:394-449  rk4_step + move_drone's clamps
+// STRICT=true transcribes one IEEE op per reference op (bit-exact with the CPU
+// build); STRICT=false is the production path: FMA contraction, reciprocals
+// hoisted out of the four derivative evaluations, the thrust rotation reduced
+// to the third column of the rotation matrix, rsqrt renormalisation.
+#pragma once
+#include "b2d_math.cuh"
+
+namespace b2d {
+
+struct DroneParams {
+    float mass, ixx, iyy, izz, arm, kt, kad, kd, bd, g, mrpm, kmot, jmot;
+};
+
+template <class T> struct Body {
+    V3<T> pos, vel;
+    Q4<T> q;
+    V3<T> w;
+    T rpm[4];
+};
+template <class T> struct Rate { // d(pos)/dt is the probed body's own velocity
+    V3<T> dvel;
+    Q4<T> dq;
+    V3<T> dw;
+    T drpm[4];
+};
+
+#define B2D_DT 0.05f
+#define B2D_MAX_VEL 50.0f
+#define B2D_MAX_OMEGA 50.0f
+
+// ------------------------------------------------------------------ strict path
+__device__ __forceinline__ void rates_strict(const Body<xf> &b, const DroneParams &p, const xf want[4],
+                                             xf inv_kmot, Rate<xf> &k) {
+    xf thrust[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) k.drpm[m] = inv_kmot * (want[m] - b.rpm[m]);
+#pragma unroll
+    for (int m = 0; m < 4; m++) thrust[m] = xf(p.kt) * (b.rpm[m] * b.rpm[m]);
+    V3<xf> lift_body;
+    lift_body.x = xf(0.0f); lift_body.y = xf(0.0f);
+    lift_body.z = thrust[0] + thrust[1] + thrust[2] + thrust[3];
+    V3<xf> lift = qrot(b.q, lift_body);
+    xf nbd = xf(-p.bd);
+    k.dvel.x = (lift.x + nbd * b.vel.x) / xf(p.mass);
+    k.dvel.y = (lift.y + nbd * b.vel.y) / xf(p.mass);
+    k.dvel.z = ((lift.z + nbd * b.vel.z) / xf(p.mass)) - xf(p.g);
+    Q4<xf> wq;
+    wq.w = xf(0.0f); wq.x = b.w.x; wq.y = b.w.y; wq.z = b.w.z;
+    Q4<xf> dq = qmul(b.q, wq);
+    k.dq.w = dq.w * xf(0.5f); k.dq.x = dq.x * xf(0.5f); k.dq.y = dq.y * xf(0.5f); k.dq.z = dq.z * xf(0.5f);
+    xf tpx = xf(p.arm) * (thrust[1] - thrust[3]);
+    xf tpy = xf(p.arm) * (thrust[2] - thrust[0]);
+    xf tpz = xf(p.kd) * (thrust[0] - thrust[1] + thrust[2] - thrust[3]);
+    xf tmz = xf(p.jmot) * (k.drpm[0] - k.drpm[1] + k.drpm[2] - k.drpm[3]);
+    xf nkad = xf(-p.kad);
+    xf tix = (xf(p.iyy) - xf(p.izz)) * b.w.y * b.w.z;
+    xf tiy = (xf(p.izz) - xf(p.ixx)) * b.w.z * b.w.x;
+    xf tiz = (xf(p.ixx) - xf(p.iyy)) * b.w.x * b.w.y;
+    k.dw.x = (tpx + nkad * b.w.x + tix) / xf(p.ixx);
+    k.dw.y = (tpy + nkad * b.w.y + tiy) / xf(p.iyy);
+    k.dw.z = (tpz + nkad * b.w.z + tiz + tmz) / xf(p.izz);
+}
+
+__device__ __forceinline__ void probe_strict(const Body<xf> &b, const V3<xf> &dpos, const Rate<xf> &k, xf h,
+                                             Body<xf> &o) {
+    o.pos.x = b.pos.x + dpos.x * h; o.pos.y = b.pos.y + dpos.y * h; o.pos.z = b.pos.z + dpos.z * h;
+    o.vel.x = b.vel.x + k.dvel.x * h; o.vel.y = b.vel.y + k.dvel.y * h; o.vel.z = b.vel.z + k.dvel.z * h;
+    o.q.w = b.q.w + k.dq.w * h; o.q.x = b.q.x + k.dq.x * h;
+    o.q.y = b.q.y + k.dq.y * h; o.q.z = b.q.z + k.dq.z * h;
+    o.w.x = b.w.x + k.dw.x * h; o.w.y = b.w.y + k.dw.y * h; o.w.z = b.w.z + k.dw.z * h;
+#pragma unroll
+    for (int m = 0; m < 4; m++) o.rpm[m] = b.rpm[m] + k.drpm[m] * h;
+    xf n = xsqrt(o.q.w * o.q.w + o.q.x * o.q.x + o.q.y * o.q.y + o.q.z * o.q.z);
+    if (n.v > 0.0f) {
+        o.q.w = o.q.w / n; o.q.x = o.q.x / n; o.q.y = o.q.y / n; o.q.z = o.q.z / n;
+    }
+}
+
+// state layout: s[0:3] pos, [3:6] vel, [6:10] quat wxyz, [10:13] omega, [13:17] rpm
+__device__ __forceinline__ void advance_body_strict(float s[17], const DroneParams &p, const float act[4]) {
+    Body<xf> b, tmp;
+    b.pos.x = s[0]; b.pos.y = s[1]; b.pos.z = s[2];
+    b.vel.x = s[3]; b.vel.y = s[4]; b.vel.z = s[5];
+    b.q.w = s[6]; b.q.x = s[7]; b.q.y = s[8]; b.q.z = s[9];
+    b.w.x = s[10]; b.w.y = s[11]; b.w.z = s[12];
+#pragma unroll
+    for (int m = 0; m < 4; m++) b.rpm[m] = s[13 + m];
+    xf want[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) want[m] = (xf(act[m]) + xf(1.0f)) * xf(0.5f) * xf(p.mrpm);
+    const xf inv_kmot = xf(1.0f) / xf(p.kmot);
+    const xf h = xf(B2D_DT) * xf(1.0f);
+    const xf hh = h * xf(0.5f);
+    const xf two = xf(2.0f);
+
+    Rate<xf> k, acc;
+    V3<xf> accp;
+    // k1
+    rates_strict(b, p, want, inv_kmot, k);
+    acc = k;
+    accp = b.vel;
+    probe_strict(b, b.vel, k, hh, tmp);
+    // k2
+    rates_strict(tmp, p, want, inv_kmot, k);
+    {
+        V3<xf> v2 = tmp.vel;
+#define B2D_ACC2(f) acc.f = acc.f + two * k.f
+        accp.x = accp.x + two * v2.x; accp.y = accp.y + two * v2.y; accp.z = accp.z + two * v2.z;
+        B2D_ACC2(dvel.x); B2D_ACC2(dvel.y); B2D_ACC2(dvel.z);
+        B2D_ACC2(dq.w); B2D_ACC2(dq.x); B2D_ACC2(dq.y); B2D_ACC2(dq.z);
+        B2D_ACC2(dw.x); B2D_ACC2(dw.y); B2D_ACC2(dw.z);
+        B2D_ACC2(drpm[0]); B2D_ACC2(drpm[1]); B2D_ACC2(drpm[2]); B2D_ACC2(drpm[3]);
+        probe_strict(b, v2, k, hh, tmp);
+    }
+    // k3
+    rates_strict(tmp, p, want, inv_kmot, k);
+    {
+        V3<xf> v3 = tmp.vel;
+        accp.x = accp.x + two * v3.x; accp.y = accp.y + two * v3.y; accp.z = accp.z + two * v3.z;
+        B2D_ACC2(dvel.x); B2D_ACC2(dvel.y); B2D_ACC2(dvel.z);
+        B2D_ACC2(dq.w); B2D_ACC2(dq.x); B2D_ACC2(dq.y); B2D_ACC2(dq.z);
+        B2D_ACC2(dw.x); B2D_ACC2(dw.y); B2D_ACC2(dw.z);
+        B2D_ACC2(drpm[0]); B2D_ACC2(drpm[1]); B2D_ACC2(drpm[2]); B2D_ACC2(drpm[3]);
+#undef B2D_ACC2
+        probe_strict(b, v3, k, h, tmp);
+    }
+    // k4
+    rates_strict(tmp, p, want, inv_kmot, k);
+    const xf h6 = h / xf(6.0f);
+#define B2D_FIN(dst, a, kk) dst = dst + ((a) + (kk)) * h6
+    B2D_FIN(b.pos.x, accp.x, tmp.vel.x); B2D_FIN(b.pos.y, accp.y, tmp.vel.y); B2D_FIN(b.pos.z, accp.z, tmp.vel.z);
+    B2D_FIN(b.vel.x, acc.dvel.x, k.dvel.x); B2D_FIN(b.vel.y, acc.dvel.y, k.dvel.y); B2D_FIN(b.vel.z, acc.dvel.z, k.dvel.z);
+    B2D_FIN(b.q.w, acc.dq.w, k.dq.w); B2D_FIN(b.q.x, acc.dq.x, k.dq.x);
+    B2D_FIN(b.q.y, acc.dq.y, k.dq.y); B2D_FIN(b.q.z, acc.dq.z, k.dq.z);
+    B2D_FIN(b.w.x, acc.dw.x, k.dw.x); B2D_FIN(b.w.y, acc.dw.y, k.dw.y); B2D_FIN(b.w.z, acc.dw.z, k.dw.z);
+#pragma unroll
+    for (int m = 0; m < 4; m++) B2D_FIN(b.rpm[m], acc.drpm[m], k.drpm[m]);
+#undef B2D_FIN
+    xf n = xsqrt(b.q.w * b.q.w + b.q.x * b.q.x + b.q.y * b.q.y + b.q.z * b.q.z);
+    if (n.v > 0.0f) {
+        b.q.w = b.q.w / n; b.q.x = b.q.x / n; b.q.y = b.q.y / n; b.q.z = b.q.z / n;
+    }
+    s[0] = b.pos.x.v; s[1] = b.pos.y.v; s[2] = b.pos.z.v;
+    s[3] = xclamp(b.vel.x, -B2D_MAX_VEL, B2D_MAX_VEL).v;
+    s[4] = xclamp(b.vel.y, -B2D_MAX_VEL, B2D_MAX_VEL).v;
+    s[5] = xclamp(b.vel.z, -B2D_MAX_VEL, B2D_MAX_VEL).v;
+    s[6] = b.q.w.v; s[7] = b.q.x.v; s[8] = b.q.y.v; s[9] = b.q.z.v;
+    s[10] = xclamp(b.w.x, -B2D_MAX_OMEGA, B2D_MAX_OMEGA).v;
+    s[11] = xclamp(b.w.y, -B2D_MAX_OMEGA, B2D_MAX_OMEGA).v;
+    s[12] = xclamp(b.w.z, -B2D_MAX_OMEGA, B2D_MAX_OMEGA).v;
+#pragma unroll
+    for (int m = 0; m < 4; m++) s[13 + m] = b.rpm[m].v;
+}
+
+// ------------------------------------------------------------------ fast path
+struct FastConsts {
+    float inv_mass, inv_ixx, inv_iyy, inv_izz, inv_kmot;
+    float d_yz, d_zx, d_xy; // inertia differences of the gyroscopic term
+    float want[4];
+};
+
+__device__ __forceinline__ void rates_fast(const Body<float> &b, const DroneParams &p, const FastConsts &c,
+                                           Rate<float> &k) {
+    float t0 = p.kt * (b.rpm[0] * b.rpm[0]);
+    float t1 = p.kt * (b.rpm[1] * b.rpm[1]);
+    float t2 = p.kt * (b.rpm[2] * b.rpm[2]);
+    float t3 = p.kt * (b.rpm[3] * b.rpm[3]);
+#pragma unroll
+    for (int m = 0; m < 4; m++) k.drpm[m] = c.inv_kmot * (c.want[m] - b.rpm[m]);
+    const float lift = (t0 + t1) + (t2 + t3);
+    const Q4<float> &q = b.q;
+    // q (0,0,0,L) q* = L * third column of the (unnormalised) rotation matrix
+    float ax = 2.0f * (q.x * q.z + q.w * q.y);
+    float ay = 2.0f * (q.y * q.z - q.w * q.x);
+    float az = (q.w * q.w - q.x * q.x) + (q.z * q.z - q.y * q.y);
+    k.dvel.x = (lift * ax - p.bd * b.vel.x) * c.inv_mass;
+    k.dvel.y = (lift * ay - p.bd * b.vel.y) * c.inv_mass;
+    k.dvel.z = (lift * az - p.bd * b.vel.z) * c.inv_mass - p.g;
+    k.dq.w = 0.5f * (-q.x * b.w.x - q.y * b.w.y - q.z * b.w.z);
+    k.dq.x = 0.5f * (q.w * b.w.x + q.y * b.w.z - q.z * b.w.y);
+    k.dq.y = 0.5f * (q.w * b.w.y - q.x * b.w.z + q.z * b.w.x);
+    k.dq.z = 0.5f * (q.w * b.w.z + q.x * b.w.y - q.y * b.w.x);
+    float tpx = p.arm * (t1 - t3);
+    float tpy = p.arm * (t2 - t0);
+    float tpz = p.kd * ((t0 - t1) + (t2 - t3));
+    float tmz = p.jmot * ((k.drpm[0] - k.drpm[1]) + (k.drpm[2] - k.drpm[3]));
+    k.dw.x = (tpx - p.kad * b.w.x + c.d_yz * b.w.y * b.w.z) * c.inv_ixx;
+    k.dw.y = (tpy - p.kad * b.w.y + c.d_zx * b.w.z * b.w.x) * c.inv_iyy;
+    k.dw.z = (tpz - p.kad * b.w.z + c.d_xy * b.w.x * b.w.y + tmz) * c.inv_izz;
+}
+
+__device__ __forceinline__ void qnormalize_fast(Q4<float> &q) {
+    float n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
+    float inv = n2 > 0.0f ? rsqrtf(n2) : 1.0f;
+    q.w *= inv; q.x *= inv; q.y *= inv; q.z *= inv;
+}
+
+__device__ __forceinline__ void probe_fast(const Body<float> &b, const V3<float> &dpos, const Rate<float> &k,
+                                           float h, Body<float> &o) {
+    o.pos.x = b.pos.x + dpos.x * h; o.pos.y = b.pos.y + dpos.y * h; o.pos.z = b.pos.z + dpos.z * h;
+    o.vel.x = b.vel.x + k.dvel.x * h; o.vel.y = b.vel.y + k.dvel.y * h; o.vel.z = b.vel.z + k.dvel.z * h;
+    o.q.w = b.q.w + k.dq.w * h; o.q.x = b.q.x + k.dq.x * h;
+    o.q.y = b.q.y + k.dq.y * h; o.q.z = b.q.z + k.dq.z * h;
+    o.w.x = b.w.x + k.dw.x * h; o.w.y = b.w.y + k.dw.y * h; o.w.z = b.w.z + k.dw.z * h;
+#pragma unroll
+    for (int m = 0; m < 4; m++) o.rpm[m] = b.rpm[m] + k.drpm[m] * h;
+    qnormalize_fast(o.q);
+}
+
+__device__ __forceinline__ void advance_body_fast(float s[17], const DroneParams &p, const float act[4]) {
+    Body<float> b, tmp;
+    b.pos.x = s[0]; b.pos.y = s[1]; b.pos.z = s[2];
+    b.vel.x = s[3]; b.vel.y = s[4]; b.vel.z = s[5];
+    b.q.w = s[6]; b.q.x = s[7]; b.q.y = s[8]; b.q.z = s[9];
+    b.w.x = s[10]; b.w.y = s[11]; b.w.z = s[12];
+#pragma unroll
+    for (int m = 0; m < 4; m++) b.rpm[m] = s[13 + m];
+    FastConsts c;
+    c.inv_mass = __frcp_rn(p.mass);
+    c.inv_ixx = __frcp_rn(p.ixx);
+    c.inv_iyy = __frcp_rn(p.iyy);
+    c.inv_izz = __frcp_rn(p.izz);
+    c.inv_kmot = __frcp_rn(p.kmot);
+    c.d_yz = p.iyy - p.izz; c.d_zx = p.izz - p.ixx; c.d_xy = p.ixx - p.iyy;
+    const float half_mrpm = 0.5f * p.mrpm;
+#pragma unroll
+    for (int m = 0; m < 4; m++) c.want[m] = (act[m] + 1.0f) * half_mrpm;
+    const float h = B2D_DT, hh = 0.5f * B2D_DT, h6 = B2D_DT / 6.0f;
+
+    Rate<float> k, acc;
+    V3<float> accp;
+    rates_fast(b, p, c, k);
+    acc = k;
+    accp = b.vel;
+    probe_fast(b, b.vel, k, hh, tmp);
+#define B2D_ACC2(f) acc.f = fmaf(2.0f, k.f, acc.f)
+#define B2D_ACCALL()                                                                     \
+    B2D_ACC2(dvel.x); B2D_ACC2(dvel.y); B2D_ACC2(dvel.z);                                \
+    B2D_ACC2(dq.w); B2D_ACC2(dq.x); B2D_ACC2(dq.y); B2D_ACC2(dq.z);                      \
+    B2D_ACC2(dw.x); B2D_ACC2(dw.y); B2D_ACC2(dw.z);                                      \
+    B2D_ACC2(drpm[0]); B2D_ACC2(drpm[1]); B2D_ACC2(drpm[2]); B2D_ACC2(drpm[3])
+    rates_fast(tmp, p, c, k);
+    {
+        V3<float> v = tmp.vel;
+        accp.x = fmaf(2.0f, v.x, accp.x); accp.y = fmaf(2.0f, v.y, accp.y); accp.z = fmaf(2.0f, v.z, accp.z);
+        B2D_ACCALL();
+        probe_fast(b, v, k, hh, tmp);
+    }
+    rates_fast(tmp, p, c, k);
+    {
+        V3<float> v = tmp.vel;
+        accp.x = fmaf(2.0f, v.x, accp.x); accp.y = fmaf(2.0f, v.y, accp.y); accp.z = fmaf(2.0f, v.z, accp.z);
+        B2D_ACCALL();
+        probe_fast(b, v, k, h, tmp);
+    }
+#undef B2D_ACCALL
+#undef B2D_ACC2
+    rates_fast(tmp, p, c, k);
+#define B2D_FIN(dst, a, kk) dst = fmaf((a) + (kk), h6, dst)
+    B2D_FIN(b.pos.x, accp.x, tmp.vel.x); B2D_FIN(b.pos.y, accp.y, tmp.vel.y); B2D_FIN(b.pos.z, accp.z, tmp.vel.z);
+    B2D_FIN(b.vel.x, acc.dvel.x, k.dvel.x); B2D_FIN(b.vel.y, acc.dvel.y, k.dvel.y); B2D_FIN(b.vel.z, acc.dvel.z, k.dvel.z);
+    B2D_FIN(b.q.w, acc.dq.w, k.dq.w); B2D_FIN(b.q.x, acc.dq.x, k.dq.x);
+    B2D_FIN(b.q.y, acc.dq.y, k.dq.y); B2D_FIN(b.q.z, acc.dq.z, k.dq.z);
+    B2D_FIN(b.w.x, acc.dw.x, k.dw.x); B2D_FIN(b.w.y, acc.dw.y, k.dw.y); B2D_FIN(b.w.z, acc.dw.z, k.dw.z);
+#pragma unroll
+    for (int m = 0; m < 4; m++) B2D_FIN(b.rpm[m], acc.drpm[m], k.drpm[m]);
+#undef B2D_FIN
+    qnormalize_fast(b.q);
+    s[0] = b.pos.x; s[1] = b.pos.y; s[2] = b.pos.z;
+    s[3] = fminf(fmaxf(b.vel.x, -B2D_MAX_VEL), B2D_MAX_VEL);
+    s[4] = fminf(fmaxf(b.vel.y, -B2D_MAX_VEL), B2D_MAX_VEL);
+    s[5] = fminf(fmaxf(b.vel.z, -B2D_MAX_VEL), B2D_MAX_VEL);
+    s[6] = b.q.w; s[7] = b.q.x; s[8] = b.q.y; s[9] = b.q.z;
+    s[10] = fminf(fmaxf(b.w.x, -B2D_MAX_OMEGA), B2D_MAX_OMEGA);
+    s[11] = fminf(fmaxf(b.w.y, -B2D_MAX_OMEGA), B2D_MAX_OMEGA);
+    s[12] = fminf(fmaxf(b.w.z, -B2D_MAX_OMEGA), B2D_MAX_OMEGA);
+#pragma unroll
+    for (int m = 0; m < 4; m++) s[13 + m] = b.rpm[m];
+}
+
+template <bool STRICT>
+__device__ __forceinline__ void advance_body(float s[17], const DroneParams &p, const float act[4]) {
+    if constexpr (STRICT) advance_body_strict(s, p, act);
+    else advance_body_fast(s, p, act);
+}
+
+// ------------------------------------------------------------------ gate crossing
+// DR/dronelib.h:462-489.  Returns +1 (clean pass in the normal's direction), edge_value
+// (rim hit: -1.0f in the race copy, -0.0f in the swarm copy) or 0.  T=xf keeps the
+// reference's rounding; the decision thresholds 1.5 / 2.5 are exact in binary32.
+template <class T>
+__device__ __forceinline__ float gate_event(const float before[3], const float after[3], const float ring[6],
+                                            float edge_value) {
+    T ax = T(before[0]) - T(ring[0]), ay = T(before[1]) - T(ring[1]), az = T(before[2]) - T(ring[2]);
+    T bx = T(after[0]) - T(ring[0]), by = T(after[1]) - T(ring[1]), bz = T(after[2]) - T(ring[2]);
+    T nx = T(ring[3]), ny = T(ring[4]), nz = T(ring[5]);
+    T d0 = ax * nx + ay * ny + az * nz;
+    T d1 = bx * nx + by * ny + bz * nz;
+    float f0 = fval(d0), f1 = fval(d1);
+    bool forward = f0 < 0.0f && f1 > 0.0f;
+    bool backward = f0 > 0.0f && f1 < 0.0f;
+    if (forward || backward) {
+        T dx = T(after[0]) - T(before[0]), dy = T(after[1]) - T(before[1]), dz = T(after[2]) - T(before[2]);
+        T t = (-d0) / (nx * dx + ny * dy + nz * dz);
+        T hx = T(before[0]) + dx * t - T(ring[0]);
+        T hy = T(before[1]) + dy * t - T(ring[1]);
+        T hz = T(before[2]) + dz * t - T(ring[2]);
+        T r2 = hx * hx + hy * hy + hz * hz;
+        float r = fval(tsqrt(r2));
+        if (r < 1.5f && forward) return 1.0f;
+        if (r < 2.5f) return edge_value;
+    }
+    return 0.0f;
+}
+
+} // namespace b2d

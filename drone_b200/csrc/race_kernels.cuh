@@ -1,0 +1,499 @@
+// race_kernels.cuh -- device side of the single-drone ring-race env (sm_100a).
+//
+// Reference behaviour restated (R = pufferlib/ocean/drone_race):
+//   race_step_kernel    R/drone_race.h:156-208 c_step  (+ EB:520-522 vec_step loop)
+//   race_observe()      R/drone_race.h:72-125  compute_observations
+//   race_fresh_episode  R/drone_race.h:127-154 c_reset, R/dronelib.h:141-183,250-300,451-460
+//   log accumulation    R/drone_race.h:61-70   add_log, EB:572-591 vec_log
+//
+// Layout in HBM (ld = num_envs rounded up to 256; lane i touches element i of
+// every array, so each warp access is one contiguous 512-byte float4 run):
+//   S  float4[5][ld]  (px,py,pz,vx) (vy,vz,qw,qx) (qy,qz,wx,wy) (wz,r0,r1,r2) (r3,tick,ring_idx,ep_return)
+//   P  float4[3][ld]  (mass,ixx,iyy,izz) (arm,k_thrust,k_ang_damp,k_drag) (b_drag,gravity,max_rpm,k_mot)
+//   PJ float [ld]     j_mot
+//   C0 float4[ld], C1 float2[ld]   the CURRENT ring (pos.xyz,n.x) (n.y,n.z): no dependent gather per step
+//   G0 float4[R][ld], G1 float2[R][ld]  all rings of the episode (read on a ring pass, written on reset)
+// Per env-step the kernel reads 172 B (act 16, S 80, P 52, C 24) and writes
+// 201 B (S 80, obs 116, reward 4, terminal 1) = 373 algorithmic bytes.
+#pragma once
+#include "physics.cuh"
+
+namespace b2d {
+
+constexpr int RACE_BLOCK = 256;
+constexpr int RACE_OBS = 29;
+constexpr int RESET_MAX_ATTEMPTS = 16;
+
+// integer episode-statistics accumulators (all race Log fields are integer valued)
+enum { ACC_N = 0, ACC_RETURN, ACC_LENGTH, ACC_RINGS, ACC_OOB, ACC_COLLISION, ACC_TIMEOUT, ACC_SPARE, ACC_COUNT };
+
+struct Ctl {
+    unsigned int epoch;  // vec steps completed since the last vec_reset (Philox counter word)
+    unsigned int ticket; // blocks finished in the running step
+    unsigned int pad[2];
+    long long acc[ACC_COUNT];
+    long long score_step[2]; // sum of score over episodes that ended in step (epoch & 1): R/drone_race.h:160
+    double facc[8];          // float-valued sums (swarm)
+};
+
+struct RaceDev {
+    int n, ld, max_rings, max_moves;
+    float4 *S;
+    float4 *P;
+    float *PJ;
+    float4 *C0;
+    float2 *C1;
+    float4 *G0;
+    float2 *G1;
+    const float *act_in; // [n][4] actions read this step
+    float *act_out;      // [n][4] clamped actions written back, or nullptr
+    float *obs;          // [n][29]
+    float *rew;          // [n]
+    unsigned char *term; // [n]
+    Ctl *ctl;
+    const float *payload; // [n][33+6R] next-episode blobs (inject mode)
+    uint32_t key0, key1, env_id_base;
+    int reset_mode; // b2d_reset_mode
+};
+
+// ---------------------------------------------------------------- observations
+// s: 17-float body state; ring: pos(3) normal(3); row: 29 floats (stride 1)
+template <bool STRICT>
+__device__ __forceinline__ void race_observe(const float s[17], float mrpm, const float ring[6], float *row) {
+    if constexpr (STRICT) {
+        Q4<xf> q, qi;
+        q.w = s[6]; q.x = s[7]; q.y = s[8]; q.z = s[9];
+        qi.w = q.w; qi.x = -q.x; qi.y = -q.y; qi.z = -q.z;
+        V3<xf> d, nrm, vel, zax;
+        d.x = xf(ring[0]) - xf(s[0]); d.y = xf(ring[1]) - xf(s[1]); d.z = xf(ring[2]) - xf(s[2]);
+        nrm.x = ring[3]; nrm.y = ring[4]; nrm.z = ring[5];
+        vel.x = s[3]; vel.y = s[4]; vel.z = s[5];
+        zax.x = 0.0f; zax.y = 0.0f; zax.z = 1.0f;
+        V3<xf> to = qrot(qi, d), bn = qrot(qi, nrm), vb = qrot(qi, vel), up = qrot(q, zax);
+        float o0 = (to.x / xf(10.0f)).v, o1 = (to.y / xf(10.0f)).v, o2 = (to.z / xf(10.0f)).v;
+        row[0] = o0; row[1] = o1; row[2] = o2;
+        row[3] = bn.x.v; row[4] = bn.y.v; row[5] = bn.z.v;
+        // "next ring" = ring_buffer[ring_idx % max_rings] is the current ring again (R/drone_race.h:77)
+        row[6] = o0; row[7] = o1; row[8] = o2;
+        row[9] = bn.x.v; row[10] = bn.y.v; row[11] = bn.z.v;
+        row[12] = (vb.x / xf(B2D_MAX_VEL)).v; row[13] = (vb.y / xf(B2D_MAX_VEL)).v; row[14] = (vb.z / xf(B2D_MAX_VEL)).v;
+        row[15] = (xf(s[10]) / xf(B2D_MAX_OMEGA)).v; row[16] = (xf(s[11]) / xf(B2D_MAX_OMEGA)).v;
+        row[17] = (xf(s[12]) / xf(B2D_MAX_OMEGA)).v;
+        row[18] = up.x.v; row[19] = up.y.v; row[20] = up.z.v;
+        row[21] = s[6]; row[22] = s[7]; row[23] = s[8]; row[24] = s[9];
+#pragma unroll
+        for (int m = 0; m < 4; m++) row[25 + m] = (xf(s[13 + m]) / xf(mrpm)).v;
+    } else {
+        const float w = s[6], x = s[7], y = s[8], z = s[9];
+        // (unnormalised) rotation matrix of q; world->body is its transpose
+        const float ww = w * w, xx = x * x, yy = y * y, zz = z * z;
+        const float xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+        const float r00 = (ww + xx) - (yy + zz), r11 = (ww - xx) + (yy - zz), r22 = (ww - xx) - (yy - zz);
+        const float r01 = 2.0f * (xy - wz), r10 = 2.0f * (xy + wz);
+        const float r02 = 2.0f * (xz + wy), r20 = 2.0f * (xz - wy);
+        const float r12 = 2.0f * (yz - wx), r21 = 2.0f * (yz + wx);
+        const float dx = ring[0] - s[0], dy = ring[1] - s[1], dz = ring[2] - s[2];
+        const float o0 = 0.1f * (r00 * dx + r10 * dy + r20 * dz);
+        const float o1 = 0.1f * (r01 * dx + r11 * dy + r21 * dz);
+        const float o2 = 0.1f * (r02 * dx + r12 * dy + r22 * dz);
+        const float n0 = r00 * ring[3] + r10 * ring[4] + r20 * ring[5];
+        const float n1 = r01 * ring[3] + r11 * ring[4] + r21 * ring[5];
+        const float n2 = r02 * ring[3] + r12 * ring[4] + r22 * ring[5];
+        row[0] = o0; row[1] = o1; row[2] = o2; row[3] = n0; row[4] = n1; row[5] = n2;
+        row[6] = o0; row[7] = o1; row[8] = o2; row[9] = n0; row[10] = n1; row[11] = n2;
+        row[12] = 0.02f * (r00 * s[3] + r10 * s[4] + r20 * s[5]);
+        row[13] = 0.02f * (r01 * s[3] + r11 * s[4] + r21 * s[5]);
+        row[14] = 0.02f * (r02 * s[3] + r12 * s[4] + r22 * s[5]);
+        row[15] = 0.02f * s[10]; row[16] = 0.02f * s[11]; row[17] = 0.02f * s[12];
+        row[18] = r02; row[19] = r12; row[20] = r22;
+        row[21] = w; row[22] = x; row[23] = y; row[24] = z;
+        const float inv = __frcp_rn(mrpm);
+#pragma unroll
+        for (int m = 0; m < 4; m++) row[25 + m] = s[13 + m] * inv;
+    }
+}
+
+// ---------------------------------------------------------------- state <-> SoA
+__device__ __forceinline__ void race_store_state(const RaceDev &d, int i, const float s[17], int tick, int ring_idx,
+                                                 float ep_ret) {
+    d.S[0 * (size_t)d.ld + i] = make_float4(s[0], s[1], s[2], s[3]);
+    d.S[1 * (size_t)d.ld + i] = make_float4(s[4], s[5], s[6], s[7]);
+    d.S[2 * (size_t)d.ld + i] = make_float4(s[8], s[9], s[10], s[11]);
+    d.S[3 * (size_t)d.ld + i] = make_float4(s[12], s[13], s[14], s[15]);
+    d.S[4 * (size_t)d.ld + i] = make_float4(s[16], __int_as_float(tick), __int_as_float(ring_idx), ep_ret);
+}
+
+__device__ __forceinline__ void race_load_ring(const RaceDev &d, int i, int r, float ring[6]) {
+    float4 a = d.G0[(size_t)r * d.ld + i];
+    float2 b = d.G1[(size_t)r * d.ld + i];
+    ring[0] = a.x; ring[1] = a.y; ring[2] = a.z; ring[3] = a.w; ring[4] = b.x; ring[5] = b.y;
+}
+
+__device__ __forceinline__ void race_store_current_ring(const RaceDev &d, int i, const float ring[6]) {
+    d.C0[i] = make_float4(ring[0], ring[1], ring[2], ring[3]);
+    d.C1[i] = make_float2(ring[4], ring[5]);
+}
+
+// ---------------------------------------------------------------- fresh episode
+// Counter-based reset stream (DESIGN.md "reset stream"): Philox4x32-10 with
+// key=(seed lo, seed hi) and counter=(global env id, epoch, item, attempt);
+// item 2r / 2r+1 = ring r (x,y,z,u1 / u2,u3), 0x1000+k = size and the 12
+// jitter factors, 0x2000 = spawn position.  Same distributions and formulas as
+// the reference's c_reset; arithmetic is one IEEE op at a time so the CPU
+// oracle (oracle/drone_oracle.c:race_fresh_episode) reproduces it bit for bit.
+__device__ __noinline__ void race_fresh_episode(const RaceDev &d, int i, uint32_t epoch, float *obs_row) {
+    float s[17];
+#pragma unroll
+    for (int k = 0; k < 17; k++) s[k] = 0.0f;
+    s[6] = 1.0f;
+    float ring0[6];
+    int tick = 0, ring_idx = 0;
+    float ep_ret = 0.0f;
+    float mrpm;
+
+    if (d.reset_mode == 1 /* B2D_RESET_INJECT */) {
+        const float *b = d.payload + (size_t)i * (33 + 6 * d.max_rings);
+#pragma unroll
+        for (int k = 0; k < 17; k++) s[k] = b[k];
+        d.P[0 * (size_t)d.ld + i] = make_float4(b[17], b[18], b[19], b[20]);
+        d.P[1 * (size_t)d.ld + i] = make_float4(b[21], b[22], b[23], b[24]);
+        d.P[2 * (size_t)d.ld + i] = make_float4(b[25], b[26], b[27], b[28]);
+        d.PJ[i] = b[29];
+        mrpm = b[27];
+        tick = (int)b[30]; ring_idx = (int)b[31]; ep_ret = b[32];
+        for (int r = 0; r < d.max_rings; r++) {
+            const float *g = b + 33 + 6 * r;
+            d.G0[(size_t)r * d.ld + i] = make_float4(g[0], g[1], g[2], g[3]);
+            d.G1[(size_t)r * d.ld + i] = make_float2(g[4], g[5]);
+        }
+        const float *g = b + 33 + 6 * (ring_idx < d.max_rings ? ring_idx : 0);
+#pragma unroll
+        for (int k = 0; k < 6; k++) ring0[k] = g[k];
+    } else {
+        const uint32_t env = d.env_id_base + (uint32_t)i;
+        // rings: R/dronelib.h:451-460 (each at least 2*radius from its predecessor)
+        float px = 0.0f, py = 0.0f, pz = 0.0f;
+        for (int r = 0; r < d.max_rings; r++) {
+            float g[6];
+            for (uint32_t t = 0; t < RESET_MAX_ATTEMPTS; t++) {
+                uint4 a = philox4x32_10(make_uint4(env, epoch, 2u * r, t), d.key0, d.key1);
+                uint4 b = philox4x32_10(make_uint4(env, epoch, 2u * r + 1u, t), d.key0, d.key1);
+                xf cx = lerp_u(-6.0f, 6.0f, unit_from_word(a.x));
+                xf cy = lerp_u(-6.0f, 6.0f, unit_from_word(a.y));
+                xf cz = lerp_u(-6.0f, 6.0f, unit_from_word(a.z));
+                xf u1 = unit_from_word(a.w), u2 = unit_from_word(b.x), u3 = unit_from_word(b.y);
+                // R/dronelib.h:141-159 rndquat, :177-178 normal = q . z-axis
+                xf ra = xsqrt(xf(1.0f) - u1), rb = xsqrt(u1);
+                float th2 = __double2float_rn(__dmul_rn(6.283185307179586, (double)u2.v));
+                float th3 = __double2float_rn(__dmul_rn(6.283185307179586, (double)u3.v));
+                float s2, c2, s3, c3;
+                sincos_det(th2, s2, c2);
+                sincos_det(th3, s3, c3);
+                Q4<xf> q;
+                q.w = ra * xf(s2); q.x = ra * xf(c2); q.y = rb * xf(s3); q.z = rb * xf(c3);
+                V3<xf> zax;
+                zax.x = 0.0f; zax.y = 0.0f; zax.z = 1.0f;
+                V3<xf> nrm = qrot(q, zax);
+                g[0] = cx.v; g[1] = cy.v; g[2] = cz.v; g[3] = nrm.x.v; g[4] = nrm.y.v; g[5] = nrm.z.v;
+                if (r == 0) break;
+                xf ex = cx - xf(px), ey = cy - xf(py), ez = cz - xf(pz);
+                xf dist = xsqrt(ex * ex + ey * ey + ez * ez);
+                if (!(dist.v < 4.0f)) break;
+            }
+            px = g[0]; py = g[1]; pz = g[2];
+            d.G0[(size_t)r * d.ld + i] = make_float4(g[0], g[1], g[2], g[3]);
+            d.G1[(size_t)r * d.ld + i] = make_float2(g[4], g[5]);
+            if (r == 0) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) ring0[k] = g[k];
+            }
+        }
+        // R/dronelib.h:250-290 init_drone(size ~ U(0.05, 0.8), dr = 0.1)
+        float u[16];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            uint4 w = philox4x32_10(make_uint4(env, epoch, 0x1000u + k, 0u), d.key0, d.key1);
+            u[4 * k + 0] = unit_from_word(w.x).v; u[4 * k + 1] = unit_from_word(w.y).v;
+            u[4 * k + 2] = unit_from_word(w.z).v; u[4 * k + 3] = unit_from_word(w.w).v;
+        }
+        const float jlo = __fsub_rn(1.0f, 0.1f), jhi = __fadd_rn(1.0f, 0.1f);
+        xf size = lerp_u(0.05f, 0.8f, xf(u[0]));
+        xf uj[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) uj[k] = (k == 8) ? lerp_u(0.99f, 1.01f, xf(u[1 + k])) : lerp_u(jlo, jhi, xf(u[1 + k]));
+        xf arm = size / xf(2.0f);
+        xf mass_scale = xf(cube_det(arm.v)) / xf(cube_det(0.1f));
+        xf mass = xf(1.0f) * mass_scale * uj[0];
+        xf base_iscale = xf(1.0f) * xf(0.1f) * xf(0.1f);
+        xf iscale = mass * (arm * arm) / base_iscale;
+        xf ixx = xf(0.01f) * iscale * uj[1];
+        xf iyy = xf(0.01f) * iscale * uj[2];
+        xf izz = xf(0.02f) * iscale * uj[3];
+        xf kt_scale = (mass * arm) / (xf(1.0f) * xf(0.1f));
+        xf kt = xf(3e-5f) * kt_scale * uj[4];
+        xf base_avg = (xf(0.01f) + xf(0.01f) + xf(0.02f)) / xf(3.0f);
+        xf avg = (ixx + iyy + izz) / xf(3.0f);
+        xf kad = xf(0.2f) * (avg / base_avg) * uj[5];
+        xf drag_scale = (arm * arm) / (xf(0.1f) * xf(0.1f));
+        xf kd = xf(1e-6f) * drag_scale * uj[6];
+        xf bd = xf(0.1f) * drag_scale * uj[7];
+        xf grav = xf(9.81f) * uj[8];
+        xf mr = xf(750.0f) * (xf(0.1f) / arm) * uj[9];
+        xf kmot = xf(0.1f) * uj[10];
+        xf jmot = xf(1e-5f) * iscale * uj[11];
+        d.P[0 * (size_t)d.ld + i] = make_float4(mass.v, ixx.v, iyy.v, izz.v);
+        d.P[1 * (size_t)d.ld + i] = make_float4(arm.v, kt.v, kad.v, kd.v);
+        d.P[2 * (size_t)d.ld + i] = make_float4(bd.v, grav.v, mr.v, kmot.v);
+        d.PJ[i] = jmot.v;
+        mrpm = mr.v;
+        // spawn at least 2*radius from ring 0: R/drone_race.h:143-149
+        for (uint32_t t = 0; t < RESET_MAX_ATTEMPTS; t++) {
+            uint4 w = philox4x32_10(make_uint4(env, epoch, 0x2000u, t), d.key0, d.key1);
+            xf cx = lerp_u(-9.0f, 9.0f, unit_from_word(w.x));
+            xf cy = lerp_u(-9.0f, 9.0f, unit_from_word(w.y));
+            xf cz = lerp_u(-9.0f, 9.0f, unit_from_word(w.z));
+            s[0] = cx.v; s[1] = cy.v; s[2] = cz.v;
+            xf ex = cx - xf(ring0[0]), ey = cy - xf(ring0[1]), ez = cz - xf(ring0[2]);
+            xf dist = xsqrt(ex * ex + ey * ey + ez * ez);
+            if (!(dist.v < 4.0f)) break;
+        }
+    }
+    race_store_state(d, i, s, tick, ring_idx, ep_ret);
+    race_store_current_ring(d, i, ring0);
+    race_observe<true>(s, mrpm, ring0, obs_row);
+}
+
+// ---------------------------------------------------------------- TMA bulk store helpers
+__device__ __forceinline__ void tma_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *ssrc, uint32_t bytes) {
+    uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---------------------------------------------------------------- the step kernel
+// One thread per env, 256 envs per CTA.  Finished envs are compacted into a
+// per-CTA list and re-initialised by the first lanes of the CTA so the (long,
+// rare) reset path does not run divergently inside every warp.  Observations
+// are staged in shared memory and leave the SM as one 29,696-byte TMA bulk
+// store per CTA (row-major [N,29] rows are 116 B, not a multiple of 16).
+template <bool STRICT>
+__global__ void __launch_bounds__(RACE_BLOCK, 2) race_step_kernel(const __grid_constant__ RaceDev d) {
+    extern __shared__ __align__(128) float s_obs[]; // [RACE_BLOCK][29]
+    __shared__ int s_nreset;
+    __shared__ int s_acc[8];
+    __shared__ unsigned short s_list[RACE_BLOCK];
+
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * RACE_BLOCK + tid;
+    const bool valid = i < d.n;
+    if (tid < 8) s_acc[tid] = 0;
+    if (tid == 8) s_nreset = 0;
+    const uint32_t epoch = d.ctl->epoch + 1u;
+    __syncthreads();
+
+    if (valid) {
+        const size_t ld = d.ld;
+        float4 a4 = reinterpret_cast<const float4 *>(d.act_in)[i];
+        float4 q0 = d.S[0 * ld + i], q1 = d.S[1 * ld + i], q2 = d.S[2 * ld + i], q3 = d.S[3 * ld + i],
+               q4 = d.S[4 * ld + i];
+        float4 p0 = d.P[0 * ld + i], p1 = d.P[1 * ld + i], p2 = d.P[2 * ld + i];
+        float pj = d.PJ[i];
+        float4 c0 = d.C0[i];
+        float2 c1 = d.C1[i];
+
+        float s[17] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x};
+        int tick = __float_as_int(q4.y) + 1;
+        int ring_idx = __float_as_int(q4.z);
+        float ep_ret = q4.w;
+        DroneParams p = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, pj};
+        float ring[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
+
+        // clamp the action (written back only on request): R/dronelib.h:437
+        float act[4];
+        if constexpr (STRICT) {
+            act[0] = xclamp(xf(a4.x), -1.0f, 1.0f).v; act[1] = xclamp(xf(a4.y), -1.0f, 1.0f).v;
+            act[2] = xclamp(xf(a4.z), -1.0f, 1.0f).v; act[3] = xclamp(xf(a4.w), -1.0f, 1.0f).v;
+        } else {
+            act[0] = fminf(fmaxf(a4.x, -1.0f), 1.0f); act[1] = fminf(fmaxf(a4.y, -1.0f), 1.0f);
+            act[2] = fminf(fmaxf(a4.z, -1.0f), 1.0f); act[3] = fminf(fmaxf(a4.w, -1.0f), 1.0f);
+        }
+        if (d.act_out) reinterpret_cast<float4 *>(d.act_out)[i] = make_float4(act[0], act[1], act[2], act[3]);
+
+        const float before[3] = {s[0], s[1], s[2]};
+        advance_body<STRICT>(s, p, act);
+
+        // ---- episode logic: R/drone_race.h:165-203
+        float reward = 0.0f;
+        int cause = -1; // ACC_OOB / ACC_COLLISION / ACC_TIMEOUT / ACC_SPARE(course complete)
+        const bool oob = s[0] < -10.0f || s[0] > 10.0f || s[1] < -10.0f || s[1] > 10.0f || s[2] < -10.0f || s[2] > 10.0f;
+        if (oob) {
+            reward = -1.0f;
+            ep_ret -= 1.0f;
+            cause = ACC_OOB;
+        } else {
+            float gate;
+            if constexpr (STRICT) gate = gate_event<xf>(before, s, ring, -1.0f);
+            else gate = gate_event<float>(before, s, ring, -1.0f);
+            reward = gate;
+            ep_ret += gate;
+            if (gate > 0.0f) {
+                ring_idx += 1;
+            }
+            if (gate < 0.0f) {
+                cause = ACC_COLLISION;
+            } else if (tick == d.max_moves) {
+                cause = ACC_TIMEOUT;
+            } else if (ring_idx == d.max_rings) {
+                cause = ACC_SPARE;
+            } else if (gate > 0.0f) {
+                race_load_ring(d, i, ring_idx, ring);
+                race_store_current_ring(d, i, ring);
+            }
+        }
+        d.rew[i] = reward;
+        d.term[i] = cause >= 0 ? 1 : 0;
+
+        if (cause < 0) {
+            race_store_state(d, i, s, tick, ring_idx, ep_ret);
+            race_observe<STRICT>(s, p.mrpm, ring, s_obs + tid * RACE_OBS);
+        } else {
+            // add_log: R/drone_race.h:61-70 (score == ring_idx at every call site)
+            atomicAdd(&s_acc[ACC_N], 1);
+            atomicAdd(&s_acc[ACC_RETURN], __float2int_rn(ep_ret));
+            atomicAdd(&s_acc[ACC_LENGTH], tick);
+            atomicAdd(&s_acc[ACC_RINGS], ring_idx);
+            if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
+            s_list[atomicAdd(&s_nreset, 1)] = (unsigned short)tid;
+        }
+    }
+    __syncthreads();
+
+    // ---- compacted auto-reset: lane r of the CTA re-initialises the r-th finished env
+    const int nreset = s_nreset;
+    if (tid < nreset) {
+        const int li = s_list[tid];
+        race_fresh_episode(d, blockIdx.x * RACE_BLOCK + li, epoch, s_obs + li * RACE_OBS);
+    }
+    __syncthreads();
+
+    // ---- observations out: one TMA bulk store per full CTA tile
+    const int row0 = blockIdx.x * RACE_BLOCK;
+    const int rows = min(RACE_BLOCK, d.n - row0);
+    float *gobs = d.obs + (size_t)row0 * RACE_OBS;
+    if (rows == RACE_BLOCK) {
+        if (tid == 0) {
+            tma_store_fence();
+            tma_store_1d(gobs, s_obs, RACE_BLOCK * RACE_OBS * sizeof(float));
+        }
+    } else {
+        for (int k = tid; k < rows * RACE_OBS; k += RACE_BLOCK) gobs[k] = s_obs[k];
+    }
+
+    // ---- episode statistics: CTA partial sums -> device accumulators
+    if (tid < 7) {
+        int v = s_acc[tid];
+        if (v != 0) atomicAdd((unsigned long long *)&d.ctl->acc[tid], (unsigned long long)(long long)v);
+        if (tid == ACC_RINGS && nreset > 0)
+            atomicAdd((unsigned long long *)&d.ctl->score_step[epoch & 1u], (unsigned long long)(long long)v);
+    }
+    if (tid == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(&d.ctl->ticket, 1u);
+        if (t == gridDim.x - 1) { // last CTA of this step closes the epoch
+            d.ctl->score_step[(epoch + 1u) & 1u] = 0;
+            d.ctl->ticket = 0;
+            d.ctl->epoch = epoch;
+        }
+        if (rows == RACE_BLOCK) tma_store_wait_read();
+    }
+}
+
+// ---------------------------------------------------------------- vec_reset / observe / blobs
+__global__ void __launch_bounds__(128) race_reset_kernel(const __grid_constant__ RaceDev d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    race_fresh_episode(d, i, 0u, d.obs + (size_t)i * RACE_OBS);
+}
+
+__global__ void race_ctl_reset_kernel(Ctl *ctl, unsigned int epoch, int clear_acc) {
+    if (threadIdx.x == 0) {
+        ctl->epoch = epoch;
+        ctl->ticket = 0;
+        if (clear_acc) {
+            for (int k = 0; k < ACC_COUNT; k++) ctl->acc[k] = 0;
+            ctl->score_step[0] = ctl->score_step[1] = 0;
+            for (int k = 0; k < 8; k++) ctl->facc[k] = 0.0;
+        }
+    }
+}
+
+// snapshot + clear for vec_log: out[0..7] = acc, out[8] = score of the last step
+__global__ void race_log_snapshot_kernel(Ctl *ctl, long long *out) {
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < ACC_COUNT; k++) { out[k] = ctl->acc[k]; ctl->acc[k] = 0; }
+        out[ACC_COUNT] = ctl->score_step[ctl->epoch & 1u];
+        ctl->score_step[0] = ctl->score_step[1] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(128) race_observe_kernel(const RaceDev d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    const size_t ld = d.ld;
+    float4 q0 = d.S[0 * ld + i], q1 = d.S[1 * ld + i], q2 = d.S[2 * ld + i], q3 = d.S[3 * ld + i], q4 = d.S[4 * ld + i];
+    float s[17] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x};
+    float4 c0 = d.C0[i];
+    float2 c1 = d.C1[i];
+    float ring[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
+    race_observe<true>(s, d.P[2 * ld + i].z, ring, d.obs + (size_t)i * RACE_OBS);
+}
+
+// blob layout: include/b200drone.h b2d_get_state
+__global__ void race_pack_kernel(const RaceDev d, const int *ids, int n, float *blobs) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int i = ids ? ids[k] : k;
+    const size_t ld = d.ld;
+    float *b = blobs + (size_t)k * (33 + 6 * d.max_rings);
+    float4 q0 = d.S[0 * ld + i], q1 = d.S[1 * ld + i], q2 = d.S[2 * ld + i], q3 = d.S[3 * ld + i], q4 = d.S[4 * ld + i];
+    float4 p0 = d.P[0 * ld + i], p1 = d.P[1 * ld + i], p2 = d.P[2 * ld + i];
+    b[0] = q0.x; b[1] = q0.y; b[2] = q0.z; b[3] = q0.w; b[4] = q1.x; b[5] = q1.y; b[6] = q1.z; b[7] = q1.w;
+    b[8] = q2.x; b[9] = q2.y; b[10] = q2.z; b[11] = q2.w; b[12] = q3.x; b[13] = q3.y; b[14] = q3.z; b[15] = q3.w;
+    b[16] = q4.x;
+    b[17] = p0.x; b[18] = p0.y; b[19] = p0.z; b[20] = p0.w; b[21] = p1.x; b[22] = p1.y; b[23] = p1.z; b[24] = p1.w;
+    b[25] = p2.x; b[26] = p2.y; b[27] = p2.z; b[28] = p2.w; b[29] = d.PJ[i];
+    b[30] = (float)__float_as_int(q4.y); b[31] = (float)__float_as_int(q4.z); b[32] = q4.w;
+    for (int r = 0; r < d.max_rings; r++) {
+        float ring[6];
+        race_load_ring(d, i, r, ring);
+        for (int c = 0; c < 6; c++) b[33 + 6 * r + c] = ring[c];
+    }
+}
+
+__global__ void race_unpack_kernel(const RaceDev d, const int *ids, int n, const float *blobs) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int i = ids ? ids[k] : k;
+    const size_t ld = d.ld;
+    const float *b = blobs + (size_t)k * (33 + 6 * d.max_rings);
+    float s[17];
+    for (int c = 0; c < 17; c++) s[c] = b[c];
+    const int ring_idx = (int)b[31];
+    race_store_state(d, i, s, (int)b[30], ring_idx, b[32]);
+    d.P[0 * ld + i] = make_float4(b[17], b[18], b[19], b[20]);
+    d.P[1 * ld + i] = make_float4(b[21], b[22], b[23], b[24]);
+    d.P[2 * ld + i] = make_float4(b[25], b[26], b[27], b[28]);
+    d.PJ[i] = b[29];
+    for (int r = 0; r < d.max_rings; r++) {
+        const float *g = b + 33 + 6 * r;
+        d.G0[(size_t)r * ld + i] = make_float4(g[0], g[1], g[2], g[3]);
+        d.G1[(size_t)r * ld + i] = make_float2(g[4], g[5]);
+    }
+    const float *g = b + 33 + 6 * (ring_idx < d.max_rings ? ring_idx : 0);
+    race_store_current_ring(d, i, g);
+}
+
+} // namespace b2d

@@ -1,0 +1,171 @@
+/* b200drone.h -- C ABI of the B200-native drone env step (libb200drone.so).
+ *
+ * Drop-in boundary for the batched environment step of PufferLib's Ocean drone
+ * envs.  Each entry point names the reference interface it replaces
+ * (EB = pufferlib/ocean/env_binding.h, DR = pufferlib/ocean/drone_race,
+ * DS = pufferlib/ocean/drone_swarm).  Plain pointers and sizes only: no torch,
+ * no Python, no C++ types.  All functions return B2D_OK (0) or a negative
+ * b2d_status and never throw; b2d_last_error() describes the last failure of
+ * the calling thread.  One host thread per handle; everything that takes a
+ * stream is stream-ordered, asynchronous and CUDA-graph capturable unless
+ * stated otherwise (no allocation, no sync, no host-side state mutation that
+ * a graph replay would miss).
+ *
+ * Env state lives on the device in SoA float4 arrays owned by the handle; the
+ * contract buffers (observations/actions/rewards/terminals/truncations) keep
+ * the reference's flat row-major layout (PL/pufferlib.py:22-43) and may be
+ * caller-owned device memory (zero-copy: torch tensors, DLPack) or host
+ * memory mirrored by b2d_vec_step_host().
+ */
+#ifndef B200DRONE_H
+#define B200DRONE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2D_VERSION 1
+#define B2D_RACE_OBS 29      /* DR/drone_race.py:17-22 */
+#define B2D_SWARM_OBS 41     /* DS/drone_swarm.py:19-24 */
+#define B2D_ACT 4
+#define B2D_LOG_FIELDS 9     /* DR/dronelib.h:52-63 */
+#define B2D_RACE_BLOB 33     /* + 6*max_rings floats, see b2d_get_state */
+#define B2D_SWARM_AGENT_BLOB 47
+
+typedef struct b2d_vec b2d_vec; /* replaces VecEnv, EB:262-265 */
+
+typedef enum b2d_status {
+    B2D_OK = 0,
+    B2D_EINVAL = -1, /* bad argument / layout   (reference: TypeError / ValueError) */
+    B2D_ENOMEM = -2, /* allocation failed       (reference: MemoryError, EB:57-60) */
+    B2D_ECUDA = -3,  /* CUDA runtime error */
+    B2D_ESTATE = -4  /* call not valid in the handle's current state */
+} b2d_status;
+
+typedef enum b2d_math {
+    B2D_MATH_FAST = 0,  /* FMA contraction, hoisted reciprocals; within 1e-5 rel of the reference per step */
+    B2D_MATH_STRICT = 1 /* one IEEE-754 binary32 op per reference op, no FMA: bit-exact with the reference C */
+} b2d_math;
+
+typedef enum b2d_reset_mode {
+    B2D_RESET_PHILOX = 0, /* counter-based Philox4x32-10 stream keyed by (seed, env id, step, item, attempt) */
+    B2D_RESET_INJECT = 1  /* parity hook: an env that terminates takes its next episode from the payload buffer */
+} b2d_reset_mode;
+
+typedef enum b2d_mem { B2D_MEM_DEVICE = 0, B2D_MEM_HOST = 1 } b2d_mem;
+
+/* The flat buffer contract of PufferEnv.set_buffers (PL/pufferlib.py:22-43).
+ * Row counts are num_agents = num_envs (race) or num_envs*num_agents (swarm).
+ * A NULL member is allocated by the library (device memory). */
+typedef struct b2d_buffers {
+    float *observations;        /* [num_agents, obs_dim] f32 row-major, 16-byte aligned */
+    float *actions;             /* [num_agents, 4] f32, 16-byte aligned */
+    float *rewards;             /* [num_agents] f32 */
+    unsigned char *terminals;   /* [num_agents] u8 */
+    unsigned char *truncations; /* [num_agents] u8, never written (EB:136, EB:421) */
+    int location;               /* b2d_mem: where the non-NULL pointers live */
+} b2d_buffers;
+
+/* kwargs of DR/binding.c:6-11 (my_init) + placement */
+typedef struct b2d_race_cfg {
+    int num_envs;
+    int max_rings;           /* DR/drone_race.py:15, default 10 */
+    int max_moves;           /* DR/drone_race.py:16, default 1000 */
+    int device;              /* CUDA device ordinal */
+    uint64_t seed;           /* Philox key until the first b2d_vec_reset */
+    uint32_t env_id_base;    /* global id of env 0 (multi-GPU shards keep results invariant to the split) */
+    int math;                /* b2d_math */
+    int write_clamped_actions; /* 1: store clamp(action,-1,1) back like DR/dronelib.h:437 */
+} b2d_race_cfg;
+
+/* kwargs of DS/binding.c:6-11 + placement */
+typedef struct b2d_swarm_cfg {
+    int num_envs;
+    int num_agents;          /* drones per env, DS/drone_swarm.py:11 */
+    int max_rings;
+    int device;
+    uint64_t seed;
+    uint32_t env_id_base;
+    int math;
+    int write_clamped_actions;
+} b2d_swarm_cfg;
+
+/* ---- construction / destruction ------------------------------------------
+ * b2d_race_create replaces env_init x num_envs + vectorize (EB:50-174,450-480;
+ * the path DR/drone_race.py:37-51 takes) and vec_init (EB:288-446).  `ext` may
+ * be NULL (library allocates device buffers) or name caller-owned buffers; the
+ * library never frees caller memory (ownership as in the reference: buffers
+ * belong to the caller, env structs to the binding). Synchronous. */
+int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d_buffers *ext);
+int b2d_swarm_create(b2d_vec **out, const b2d_swarm_cfg *cfg, const b2d_buffers *ext);
+/* replaces vec_close (EB:600-613). Synchronous. */
+int b2d_vec_close(b2d_vec *vec);
+
+/* ---- the hot path ----------------------------------------------------------
+ * replaces vec_reset (EB:482-506): every env starts a fresh episode and its
+ * observation row is written.  seed re-keys the reset stream. */
+int b2d_vec_reset(b2d_vec *vec, uint64_t seed, void *cuda_stream);
+/* replaces vec_step (EB:508-524): reads actions, writes observations, rewards,
+ * terminals in place (device buffers), auto-resets finished envs. */
+int b2d_vec_step(b2d_vec *vec, void *cuda_stream);
+/* same, reading this step's actions from another device buffer of the same
+ * shape (a policy's output tensor, or one slice of an action tape) */
+int b2d_vec_step_from(b2d_vec *vec, const float *device_actions, void *cuda_stream);
+/* host-buffer form of vec_step for callers that keep the reference's NumPy
+ * buffers: copies actions H2D, steps, copies observations/rewards/terminals
+ * D2H (chunked and overlapped), then synchronises.  Host pointers default to
+ * the b2d_buffers given at create time (location == B2D_MEM_HOST); pinned
+ * memory is fastest.  Not capturable. */
+int b2d_vec_step_host(b2d_vec *vec, void *cuda_stream);
+/* host-buffer form of vec_reset: reset + observations D2H + sync */
+int b2d_vec_reset_host(b2d_vec *vec, uint64_t seed, void *cuda_stream);
+
+/* ---- episode statistics ----------------------------------------------------
+ * replaces vec_log (EB:564-598).  out[0..8] follow the Log field order
+ * (episode_return, episode_length, rings_passed, collision_rate, oob, timeout,
+ * score, perf, n); fields are divided by n like EB:588-591 and out[8] is the
+ * raw episode count; all zeros when no episode finished (reference returns
+ * {}).  Accumulators are cleared.  Synchronises the stream. */
+int b2d_vec_log(b2d_vec *vec, float out[B2D_LOG_FIELDS], void *cuda_stream);
+/* split form for multi-GPU: begin snapshots+clears the accumulators into a
+ * device array of `*count` int64 sums (stream-ordered, no sync) that the
+ * caller may all-reduce (NCCL sum) in place; end synchronises and averages. */
+int b2d_vec_log_begin(b2d_vec *vec, void *cuda_stream, long long **device_sums, int *count);
+int b2d_vec_log_end(b2d_vec *vec, float out[B2D_LOG_FIELDS], void *cuda_stream);
+
+/* ---- introspection ------------------------------------------------------------ */
+int b2d_get_buffers(const b2d_vec *vec, b2d_buffers *device_buffers); /* raw device pointers (DLPack / torch views) */
+int b2d_num_agents(const b2d_vec *vec); /* rows of the contract buffers */
+int b2d_obs_dim(const b2d_vec *vec);
+int b2d_state_blob_floats(const b2d_vec *vec); /* floats per env in get/put_state blobs */
+long long b2d_kernel_launches(const b2d_vec *vec); /* kernels launched by this handle so far */
+int b2d_step_count(b2d_vec *vec, uint32_t *steps, void *cuda_stream); /* steps since the last reset (sync) */
+
+/* ---- state hooks (env_get / env_put, EB:228-260; also the env checkpoint) ---
+ * Race blob per env, float32[33 + 6*max_rings], ints stored as exact floats:
+ *   [0:3] pos [3:6] vel [6:10] quat(w,x,y,z) [10:13] omega [13:17] rpms
+ *   [17:30] mass,ixx,iyy,izz,arm_len,k_thrust,k_ang_damp,k_drag,b_drag,gravity,max_rpm,k_mot,j_mot
+ *   [30] tick [31] ring_idx [32] episodic_return, then per ring pos(3), normal(3).
+ * env_ids == NULL means envs 0..n-1.  Host blobs; synchronous. */
+int b2d_get_state(b2d_vec *vec, const int *env_ids, int n, float *host_blobs);
+int b2d_put_state(b2d_vec *vec, const int *env_ids, int n, const float *host_blobs);
+/* recompute observation rows from the current state (after put_state) */
+int b2d_observe(b2d_vec *vec, void *cuda_stream);
+
+/* ---- parity / configuration hooks --------------------------------------------- */
+int b2d_set_math(b2d_vec *vec, int math);
+int b2d_set_reset_mode(b2d_vec *vec, int reset_mode);
+/* host_payload: [num_envs][state blob] next-episode states for B2D_RESET_INJECT (copied; synchronous) */
+int b2d_set_reset_payload(b2d_vec *vec, const float *host_payload);
+int b2d_set_step_count(b2d_vec *vec, uint32_t steps);
+
+const char *b2d_last_error(void);
+int b2d_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DRONE_H */

@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """The oracle front-end (test infrastructure); builds liboracle.so on first use."""
+    from oracle import pyoracle
+    if not os.path.exists(pyoracle.ORACLE_SO):
+        pyoracle.build()
+    return pyoracle

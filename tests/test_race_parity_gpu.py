@@ -1,0 +1,236 @@
+"""GPU parity tests for the race env: CUDA path (through the C ABI) vs the oracle.
+
+Oracle = the unmodified reference C (oracle/_ref, when its prebuilt .so is
+present) and our CPU restatement (oracle/liboracle.so).  Protocol:
+identical initial states + identical action tape; whenever the oracle resets an
+env, its post-reset state is injected into the device through the reset payload.
+
+Bars:  strict math  -> every output word bit-exact.
+       fast math    -> integer/boolean outputs bit-exact, continuous outputs within
+                       REL_TOL=1e-5 relative (ABS_TOL=1e-6 floor) per step.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5
+ABS_TOL = 1e-6
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _tape(n, steps=16, seed=1234, scale=1.3):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-scale, scale, size=(steps, n, 4)).astype(np.float32)
+
+
+def _make_cpu(oracle, n, use_ref=True, **kw):
+    if use_ref and oracle.have_ref():
+        return oracle.RefRace(n, **kw), "reference"
+    return oracle.OrcRace(n, **kw), "port"
+
+
+def _record(cpu, tape, T, seed):
+    """Run the CPU side for T steps; record outputs and the reset payload of every step."""
+    n = cpu.n
+    cpu.reset(seed)
+    init_state = cpu.get_state()
+    init_obs = cpu.observations.copy()
+    obs = np.zeros((T, n, 29), np.float32)
+    rew = np.zeros((T, n), np.float32)
+    term = np.zeros((T, n), np.uint8)
+    payload = np.zeros((T, n, cpu.blob), np.float32)
+    acts = np.zeros((T, n, 4), np.float32)
+    for t in range(T):
+        cpu.step(tape[t % len(tape)])
+        acts[t] = cpu.actions  # clamped in place by the reference
+        obs[t], rew[t], term[t] = cpu.observations, cpu.rewards, cpu.terminals
+        idx = np.flatnonzero(term[t])
+        if len(idx):
+            payload[t, idx] = cpu.get_state(idx)
+    return dict(init_state=init_state, init_obs=init_obs, obs=obs, rew=rew, term=term, payload=payload,
+                clamped=acts, final_state=cpu.get_state())
+
+
+@pytest.mark.parametrize("n,T,seed", [(2048, 400, 42), (300, 1100, 7)])
+def test_strict_bit_exact_vs_reference_with_injected_resets(oracle, n, T, seed):
+    from drone_b200 import capi
+    from drone_b200.vec import RaceVec
+    cpu, kind = _make_cpu(oracle, n)
+    tape = _tape(n)
+    rec = _record(cpu, tape, T, seed)
+    ref_log = cpu.log()
+
+    vec = RaceVec(n, math="strict", write_clamped_actions=True)
+    vec.set_reset_mode(capi.RESET_INJECT)
+    vec.put_state(rec["init_state"])
+    vec.observe()
+    torch.cuda.synchronize()
+    assert np.array_equal(_bits(vec.observations.cpu().numpy()), _bits(rec["init_obs"]))
+    dtape = torch.from_numpy(tape).cuda()
+    for t in range(T):
+        vec.set_reset_payload(rec["payload"][t])
+        vec.actions.copy_(dtape[t % len(tape)])
+        vec.step()
+        o = vec.observations.cpu().numpy()
+        assert np.array_equal(vec.terminals.cpu().numpy(), rec["term"][t]), f"terminals differ at step {t} ({kind})"
+        assert np.array_equal(_bits(vec.rewards.cpu().numpy()), _bits(rec["rew"][t])), f"rewards differ at step {t}"
+        assert np.array_equal(_bits(o), _bits(rec["obs"][t])), f"observations differ at step {t}"
+        assert np.array_equal(_bits(vec.actions.cpu().numpy()), _bits(rec["clamped"][t])), "clamped actions differ"
+    assert np.array_equal(_bits(vec.get_state()), _bits(rec["final_state"]))
+    # vec_log: sums over the whole run (reference sums floats, we sum integers)
+    got = vec.log()
+    n_ep = float(ref_log[8])
+    assert got["n"] == n_ep and n_ep > 0
+    assert got["episode_length"] == pytest.approx(ref_log[1] / n_ep, rel=1e-6)
+    assert got["episode_return"] == pytest.approx(ref_log[0] / n_ep, rel=1e-6)
+    assert got["oob"] == pytest.approx(ref_log[4] / n_ep, rel=1e-6)
+    assert got["collision_rate"] == pytest.approx(ref_log[3] / n_ep, rel=1e-6)
+    assert got["timeout"] == pytest.approx(ref_log[5] / n_ep, rel=1e-6)
+    assert got["perf"] == pytest.approx(ref_log[7] / n_ep, rel=1e-5, abs=1e-7)
+    assert got["score"] == pytest.approx(ref_log[6] / n_ep, rel=1e-6, abs=1e-9)
+    vec.close()
+    cpu.close()
+
+
+def test_strict_philox_free_running_bit_exact_vs_port(oracle):
+    """Device-native resets (Philox) against the same stream in the CPU restatement:
+    nothing injected, 1000 steps, every word identical including reset states."""
+    from drone_b200.vec import RaceVec
+    n, T, seed = 4096 + 37, 1000, 2025  # ragged tail CTA
+    cpu = oracle.OrcRace(n, seed=seed)
+    cpu.reset(seed, mode=oracle.RESET_PHILOX)
+    vec = RaceVec(n, math="strict", seed=seed)
+    vec.reset(seed)
+    torch.cuda.synchronize()
+    assert np.array_equal(_bits(vec.get_state()), _bits(cpu.get_state()))
+    assert np.array_equal(_bits(vec.observations.cpu().numpy()), _bits(cpu.observations))
+    tape = _tape(n, scale=1.0)
+    dtape = torch.from_numpy(tape).cuda()
+    nterm = 0
+    for t in range(T):
+        cpu.step(tape[t % 16], mode=oracle.RESET_PHILOX)
+        vec.step(dtape[t % 16])
+        assert np.array_equal(vec.terminals.cpu().numpy(), cpu.terminals), f"terminals differ at step {t}"
+        assert np.array_equal(_bits(vec.rewards.cpu().numpy()), _bits(cpu.rewards)), f"rewards differ at step {t}"
+        assert np.array_equal(_bits(vec.observations.cpu().numpy()), _bits(cpu.observations)), f"obs differ at step {t}"
+        nterm += int(cpu.terminals.sum())
+    assert nterm > 1000
+    assert vec.step_count == T == cpu.epoch
+    assert np.array_equal(_bits(vec.get_state()), _bits(cpu.get_state()))
+    ref_log, got = cpu.log(), vec.log()
+    assert got["n"] == float(ref_log[8]) == float(nterm)
+    assert got["episode_length"] == pytest.approx(ref_log[1] / ref_log[8], rel=1e-6)
+    vec.close()
+    cpu.close()
+
+
+def _close(a, b):
+    return np.abs(a - b) <= ABS_TOL + REL_TOL * np.abs(b)
+
+
+_STATE_GROUPS = [(0, 3), (3, 6), (6, 10), (10, 13), (13, 17)]  # pos, vel, quat, omega, rpm
+
+
+def _close_state(a, b):
+    """State vectors: each component within ABS_TOL + REL_TOL * max-norm of the physical
+    vector it belongs to (a small omega.y next to omega.x = 17 rad/s carries the rounding of
+    the large component through the gyroscopic cross terms)."""
+    ok = np.ones(a.shape, bool)
+    for lo, hi in _STATE_GROUPS:
+        scale = np.abs(b[:, lo:hi]).max(axis=1, keepdims=True)
+        ok[:, lo:hi] = np.abs(a[:, lo:hi] - b[:, lo:hi]) <= ABS_TOL + REL_TOL * scale
+    return ok
+
+
+def test_fast_math_per_step_tolerance_with_resync(oracle):
+    """Fast (FMA) kernel: every step starts from the oracle's exact state; integer outputs
+    must be identical, continuous outputs within REL_TOL / ABS_TOL."""
+    from drone_b200 import capi
+    from drone_b200.vec import RaceVec
+    n, T, seed = 1024, 300, 11
+    cpu, kind = _make_cpu(oracle, n)
+    tape = _tape(n)
+    cpu.reset(seed)
+    vec = RaceVec(n, math="fast")
+    vec.set_reset_mode(capi.RESET_INJECT)
+    dtape = torch.from_numpy(tape).cuda()
+    worst = 0.0
+    flips = 0
+    for t in range(T):
+        before = cpu.get_state()
+        vec.put_state(before)
+        cpu.step(tape[t % 16])
+        idx = np.flatnonzero(cpu.terminals)
+        payload = np.zeros((n, cpu.blob), np.float32)
+        if len(idx):
+            payload[idx] = cpu.get_state(idx)
+        vec.set_reset_payload(payload)
+        vec.step(dtape[t % 16])
+        term = vec.terminals.cpu().numpy()
+        rew = vec.rewards.cpu().numpy()
+        obs = vec.observations.cpu().numpy()
+        flips += int((term != cpu.terminals).sum())
+        assert np.array_equal(term, cpu.terminals), f"terminal flipped at step {t} ({kind})"
+        assert np.array_equal(rew, cpu.rewards), f"reward differs at step {t}"
+        ok = _close(obs, cpu.observations)
+        assert ok.all(), f"obs outside tolerance at step {t}: max abs err {np.abs(obs - cpu.observations).max()}"
+        st = vec.get_state()
+        ref_st = cpu.get_state()
+        keep = cpu.terminals == 0  # finished envs were re-initialised from the payload (exact)
+        ok = _close_state(st[keep, :17], ref_st[keep, :17])
+        assert ok.all(), f"state outside tolerance at step {t}"
+        assert np.array_equal(st[:, 30:33], ref_st[:, 30:33])  # tick, ring_idx, episodic_return
+        worst = max(worst, float(np.abs(obs - cpu.observations).max()))
+    print(f"fast-math per-step max abs obs error over {T} steps x {n} envs: {worst:.3e}; terminal flips: {flips}")
+    vec.close()
+    cpu.close()
+
+
+def test_fast_math_free_running_drift(oracle):
+    """Drift without resync: both sides free-run from one initial state on the same actions
+    (resets injected); envs are compared while their episode history still agrees."""
+    from drone_b200 import capi
+    from drone_b200.vec import RaceVec
+    n, T, seed = 1024, 1000, 5
+    cpu, kind = _make_cpu(oracle, n)
+    rng = np.random.default_rng(3)
+    tape = (-0.24 + 0.05 * rng.standard_normal((16, n, 4))).astype(np.float32)  # near-hover: long episodes
+    cpu.reset(seed)
+    vec = RaceVec(n, math="fast")
+    vec.set_reset_mode(capi.RESET_INJECT)
+    vec.put_state(cpu.get_state())
+    dtape = torch.from_numpy(tape).cuda()
+    agree = np.ones(n, bool)
+    max_pos = max_quat = 0.0
+    mean_pos = []
+    for t in range(T):
+        cpu.step(tape[t % 16])
+        idx = np.flatnonzero(cpu.terminals)
+        payload = np.zeros((n, cpu.blob), np.float32)
+        if len(idx):
+            payload[idx] = cpu.get_state(idx)
+        vec.set_reset_payload(payload)
+        vec.step(dtape[t % 16])
+        term = vec.terminals.cpu().numpy()
+        agree &= term == cpu.terminals
+        if t % 50 == 49 or t == T - 1:
+            st, ref_st = vec.get_state(), cpu.get_state()
+            a = agree
+            dp = np.abs(st[a, 0:3] - ref_st[a, 0:3]).max(axis=1)
+            dq = np.abs(st[a, 6:10] - ref_st[a, 6:10]).max(axis=1)
+            max_pos, max_quat = max(max_pos, float(dp.max())), max(max_quat, float(dq.max()))
+            mean_pos.append(float(dp.mean()))
+    frac = agree.mean()
+    print(f"fast-math free-running drift over {T} steps ({kind}): max |dpos| {max_pos:.3e} m, "
+          f"max |dquat| {max_quat:.3e}, mean |dpos| {np.mean(mean_pos):.3e}; "
+          f"{frac * 100:.2f}% of envs kept an identical event history")
+    assert frac > 0.98
+    assert max_pos < 5e-2 and max_quat < 5e-2
+    vec.close()
+    cpu.close()
