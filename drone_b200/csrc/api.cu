@@ -147,10 +147,17 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
     d.key1 = (uint32_t)(cfg->seed >> 32);
     d.env_id_base = cfg->env_id_base;
     d.reset_mode = B2D_RESET_PHILOX;
+    {   // refill CTAs: sized for ~6% of the envs finishing per step, at most one per SM
+        int step_ctas = d.ld / RACE_BLOCK;
+        d.refill_ctas = step_ctas / 16 + 1;
+        if (d.refill_ctas > 148) d.refill_ctas = 148;
+    }
     const size_t ld = d.ld;
     if ((rc = setup_buffers(v, ext)) || (rc = dev_alloc(v, &d.S, 5 * ld)) || (rc = dev_alloc(v, &d.P, 3 * ld)) ||
         (rc = dev_alloc(v, &d.PJ, ld)) || (rc = dev_alloc(v, &d.C0, ld)) || (rc = dev_alloc(v, &d.C1, ld)) ||
-        (rc = dev_alloc(v, &d.G0, (size_t)d.max_rings * ld)) || (rc = dev_alloc(v, &d.G1, (size_t)d.max_rings * ld)) ||
+        (rc = dev_alloc(v, &d.G0, 2 * (size_t)d.max_rings * ld)) || (rc = dev_alloc(v, &d.G1, 2 * (size_t)d.max_rings * ld)) ||
+        (rc = dev_alloc(v, &d.N, 3 * ld)) || (rc = dev_alloc(v, &d.NJ, ld)) || (rc = dev_alloc(v, &d.NS, ld)) ||
+        (rc = dev_alloc(v, &d.EP, ld)) || (rc = dev_alloc(v, &d.SLOT_EP, ld)) || (rc = dev_alloc(v, &d.refill, 2 * ld)) ||
         (rc = dev_alloc(v, &d.ctl, 1)) || (rc = finish_create(v))) {
         b2d_vec_close(v);
         return rc;
@@ -216,7 +223,7 @@ static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st) {
     if (v->kind == KIND_RACE) {
         RaceDev d = v->race;
         if (actions) d.act_in = actions;
-        const int grid = d.ld / RACE_BLOCK;
+        const int grid = d.ld / RACE_BLOCK + d.refill_ctas;
         const size_t smem = RACE_BLOCK * RACE_OBS * sizeof(float);
         if (v->math == B2D_MATH_STRICT) race_step_kernel<true><<<grid, RACE_BLOCK, smem, st>>>(d);
         else race_step_kernel<false><<<grid, RACE_BLOCK, smem, st>>>(d);

@@ -1,20 +1,30 @@
 // race_kernels.cuh -- device side of the single-drone ring-race env (sm_100a).
 //
 // Reference behaviour restated (R = pufferlib/ocean/drone_race):
-//   race_step_kernel    R/drone_race.h:156-208 c_step  (+ EB:520-522 vec_step loop)
-//   race_observe()      R/drone_race.h:72-125  compute_observations
-//   race_fresh_episode  R/drone_race.h:127-154 c_reset, R/dronelib.h:141-183,250-300,451-460
-//   log accumulation    R/drone_race.h:61-70   add_log, EB:572-591 vec_log
+//   race_step_kernel       R/drone_race.h:156-208 c_step  (+ EB:520-522 vec_step loop)
+//   race_observe()         R/drone_race.h:72-125  compute_observations
+//   race_generate_episode  R/drone_race.h:127-154 c_reset, R/dronelib.h:141-183,250-300,451-460
+//   log accumulation       R/drone_race.h:61-70   add_log, EB:572-591 vec_log
 //
 // Layout in HBM (ld = num_envs rounded up to 256; lane i touches element i of
 // every array, so each warp access is one contiguous 512-byte float4 run):
-//   S  float4[5][ld]  (px,py,pz,vx) (vy,vz,qw,qx) (qy,qz,wx,wy) (wz,r0,r1,r2) (r3,tick,ring_idx,ep_return)
+//   S  float4[5][ld]  (px,py,pz,vx) (vy,vz,qw,qx) (qy,qz,wx,wy) (wz,r0,r1,r2) (r3,tick,ring word,ep_return)
+//                     ring word = ring_idx | ring-buffer parity << 30
 //   P  float4[3][ld]  (mass,ixx,iyy,izz) (arm,k_thrust,k_ang_damp,k_drag) (b_drag,gravity,max_rpm,k_mot)
 //   PJ float [ld]     j_mot
 //   C0 float4[ld], C1 float2[ld]   the CURRENT ring (pos.xyz,n.x) (n.y,n.z): no dependent gather per step
-//   G0 float4[R][ld], G1 float2[R][ld]  all rings of the episode (read on a ring pass, written on reset)
+//   G0 float4[2][R][ld], G1 float2[2][R][ld]  rings of the live episode (buffer `parity`) and of the
+//                     prepared next episode (the other buffer); read on a ring pass / episode start
+//   N float4[3][ld], NJ float[ld], NS float4[ld]  prepared next episode: params, j_mot, spawn position
+//   EP u32[ld] live episode number, SLOT_EP u32[ld] episode number held by the prepared slot
 // Per env-step the kernel reads 172 B (act 16, S 80, P 52, C 24) and writes
 // 201 B (S 80, obs 116, reward 4, terminal 1) = 373 algorithmic bytes.
+//
+// Auto-reset without a reset on the critical path: an env that finishes ADOPTS its
+// prepared episode (13 params + spawn + ring 0: a handful of loads/stores) and queues
+// itself on a refill list; the next launch carries a few extra CTAs that regenerate the
+// consumed slots (Philox + trig, ~3000 dependent instructions each) with every lane
+// busy, overlapped with the step CTAs of that launch.
 #pragma once
 #include "physics.cuh"
 
@@ -28,9 +38,9 @@ constexpr int RESET_MAX_ATTEMPTS = 16;
 enum { ACC_N = 0, ACC_RETURN, ACC_LENGTH, ACC_RINGS, ACC_OOB, ACC_COLLISION, ACC_TIMEOUT, ACC_SPARE, ACC_COUNT };
 
 struct Ctl {
-    unsigned int epoch;  // vec steps completed since the last vec_reset (Philox counter word)
-    unsigned int ticket; // blocks finished in the running step
-    unsigned int pad[2];
+    unsigned int epoch;  // vec steps completed since the last vec_reset
+    unsigned int ticket; // CTAs finished in the running step
+    unsigned int refill_count[2]; // entries in refill list (epoch & 1)
     long long acc[ACC_COUNT];
     long long score_step[2]; // sum of score over episodes that ended in step (epoch & 1): R/drone_race.h:160
     double facc[8];          // float-valued sums (swarm)
@@ -45,6 +55,12 @@ struct RaceDev {
     float2 *C1;
     float4 *G0;
     float2 *G1;
+    float4 *N;
+    float *NJ;
+    float4 *NS;
+    uint32_t *EP;
+    uint32_t *SLOT_EP;
+    uint2 *refill; // [2][ld] (env | target ring buffer << 31, episode number to generate)
     const float *act_in; // [n][4] actions read this step
     float *act_out;      // [n][4] clamped actions written back, or nullptr
     float *obs;          // [n][29]
@@ -54,6 +70,7 @@ struct RaceDev {
     const float *payload; // [n][33+6R] next-episode blobs (inject mode)
     uint32_t key0, key1, env_id_base;
     int reset_mode; // b2d_reset_mode
+    int refill_ctas; // CTAs at the front of the step grid that refill consumed slots
 };
 
 // ---------------------------------------------------------------- observations
@@ -123,9 +140,9 @@ __device__ __forceinline__ void race_store_state(const RaceDev &d, int i, const 
     d.S[4 * (size_t)d.ld + i] = make_float4(s[16], __int_as_float(tick), __int_as_float(ring_idx), ep_ret);
 }
 
-__device__ __forceinline__ void race_load_ring(const RaceDev &d, int i, int r, float ring[6]) {
-    float4 a = d.G0[(size_t)r * d.ld + i];
-    float2 b = d.G1[(size_t)r * d.ld + i];
+__device__ __forceinline__ void race_load_ring(const RaceDev &d, int i, int par, int r, float ring[6]) {
+    float4 a = d.G0[((size_t)par * d.max_rings + r) * d.ld + i];
+    float2 b = d.G1[((size_t)par * d.max_rings + r) * d.ld + i];
     ring[0] = a.x; ring[1] = a.y; ring[2] = a.z; ring[3] = a.w; ring[4] = b.x; ring[5] = b.y;
 }
 
@@ -134,133 +151,189 @@ __device__ __forceinline__ void race_store_current_ring(const RaceDev &d, int i,
     d.C1[i] = make_float2(ring[4], ring[5]);
 }
 
-// ---------------------------------------------------------------- fresh episode
+// ---------------------------------------------------------------- episode generator
 // Counter-based reset stream (DESIGN.md "reset stream"): Philox4x32-10 with
-// key=(seed lo, seed hi) and counter=(global env id, epoch, item, attempt);
-// item 2r / 2r+1 = ring r (x,y,z,u1 / u2,u3), 0x1000+k = size and the 12
-// jitter factors, 0x2000 = spawn position.  Same distributions and formulas as
-// the reference's c_reset; arithmetic is one IEEE op at a time so the CPU
-// oracle (oracle/drone_oracle.c:race_fresh_episode) reproduces it bit for bit.
-__device__ __noinline__ void race_fresh_episode(const RaceDev &d, int i, uint32_t epoch, float *obs_row) {
+// key=(seed lo, seed hi) and counter=(global env id, episode number, item, attempt);
+// item 2r / 2r+1 = ring r (x,y,z,u1 / u2,u3), 0x1000+k = size and the 12 jitter
+// factors, 0x2000 = spawn position.  The k-th episode of an env is therefore a pure
+// function of (seed, env id, k), whenever it gets generated.  Same distributions and
+// formulas as the reference's c_reset (R/drone_race.h:127-151, R/dronelib.h:141-183,
+// 250-300, 451-460); arithmetic is one IEEE op at a time so the CPU oracle
+// (oracle/drone_oracle.c:race_fresh_episode) reproduces it bit for bit.
+// Rings go straight to ring buffer `tb` of env i; params/spawn/ring 0 come back in registers.
+__device__ __noinline__ void race_generate_episode(const RaceDev &d, int i, uint32_t episode, int tb,
+                                                   float params[13], float spawn[3], float ring0[6]) {
+    const uint32_t env = d.env_id_base + (uint32_t)i;
+    const size_t gbase = (size_t)tb * d.max_rings * d.ld + i;
+    // rings: R/dronelib.h:451-460 (each at least 2*radius from its predecessor)
+    float px = 0.0f, py = 0.0f, pz = 0.0f;
+    for (int r = 0; r < d.max_rings; r++) {
+        float g[6];
+        for (uint32_t t = 0; t < RESET_MAX_ATTEMPTS; t++) {
+            uint4 a = philox4x32_10(make_uint4(env, episode, 2u * r, t), d.key0, d.key1);
+            uint4 b = philox4x32_10(make_uint4(env, episode, 2u * r + 1u, t), d.key0, d.key1);
+            xf cx = lerp_u(-6.0f, 6.0f, unit_from_word(a.x));
+            xf cy = lerp_u(-6.0f, 6.0f, unit_from_word(a.y));
+            xf cz = lerp_u(-6.0f, 6.0f, unit_from_word(a.z));
+            xf u1 = unit_from_word(a.w), u2 = unit_from_word(b.x), u3 = unit_from_word(b.y);
+            // R/dronelib.h:141-159 rndquat, :177-178 normal = q . z-axis
+            xf ra = xsqrt(xf(1.0f) - u1), rb = xsqrt(u1);
+            float th2 = __double2float_rn(__dmul_rn(6.283185307179586, (double)u2.v));
+            float th3 = __double2float_rn(__dmul_rn(6.283185307179586, (double)u3.v));
+            float s2, c2, s3, c3;
+            sincos_det(th2, s2, c2);
+            sincos_det(th3, s3, c3);
+            Q4<xf> q;
+            q.w = ra * xf(s2); q.x = ra * xf(c2); q.y = rb * xf(s3); q.z = rb * xf(c3);
+            V3<xf> zax;
+            zax.x = 0.0f; zax.y = 0.0f; zax.z = 1.0f;
+            V3<xf> nrm = qrot(q, zax);
+            g[0] = cx.v; g[1] = cy.v; g[2] = cz.v; g[3] = nrm.x.v; g[4] = nrm.y.v; g[5] = nrm.z.v;
+            if (r == 0) break;
+            xf ex = cx - xf(px), ey = cy - xf(py), ez = cz - xf(pz);
+            xf dist = xsqrt(ex * ex + ey * ey + ez * ez);
+            if (!(dist.v < 4.0f)) break;
+        }
+        px = g[0]; py = g[1]; pz = g[2];
+        d.G0[gbase + (size_t)r * d.ld] = make_float4(g[0], g[1], g[2], g[3]);
+        d.G1[gbase + (size_t)r * d.ld] = make_float2(g[4], g[5]);
+        if (r == 0) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) ring0[k] = g[k];
+        }
+    }
+    // R/dronelib.h:250-290 init_drone(size ~ U(0.05, 0.8), dr = 0.1)
+    float u[16];
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+        uint4 w = philox4x32_10(make_uint4(env, episode, 0x1000u + k, 0u), d.key0, d.key1);
+        u[4 * k + 0] = unit_from_word(w.x).v; u[4 * k + 1] = unit_from_word(w.y).v;
+        u[4 * k + 2] = unit_from_word(w.z).v; u[4 * k + 3] = unit_from_word(w.w).v;
+    }
+    const float jlo = __fsub_rn(1.0f, 0.1f), jhi = __fadd_rn(1.0f, 0.1f);
+    xf size = lerp_u(0.05f, 0.8f, xf(u[0]));
+    xf uj[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) uj[k] = (k == 8) ? lerp_u(0.99f, 1.01f, xf(u[1 + k])) : lerp_u(jlo, jhi, xf(u[1 + k]));
+    xf arm = size / xf(2.0f);
+    xf mass_scale = xf(cube_det(arm.v)) / xf(cube_det(0.1f));
+    xf mass = xf(1.0f) * mass_scale * uj[0];
+    xf base_iscale = xf(1.0f) * xf(0.1f) * xf(0.1f);
+    xf iscale = mass * (arm * arm) / base_iscale;
+    xf ixx = xf(0.01f) * iscale * uj[1];
+    xf iyy = xf(0.01f) * iscale * uj[2];
+    xf izz = xf(0.02f) * iscale * uj[3];
+    xf kt_scale = (mass * arm) / (xf(1.0f) * xf(0.1f));
+    xf kt = xf(3e-5f) * kt_scale * uj[4];
+    xf base_avg = (xf(0.01f) + xf(0.01f) + xf(0.02f)) / xf(3.0f);
+    xf avg = (ixx + iyy + izz) / xf(3.0f);
+    xf kad = xf(0.2f) * (avg / base_avg) * uj[5];
+    xf drag_scale = (arm * arm) / (xf(0.1f) * xf(0.1f));
+    xf kd = xf(1e-6f) * drag_scale * uj[6];
+    xf bd = xf(0.1f) * drag_scale * uj[7];
+    xf grav = xf(9.81f) * uj[8];
+    xf mr = xf(750.0f) * (xf(0.1f) / arm) * uj[9];
+    xf kmot = xf(0.1f) * uj[10];
+    xf jmot = xf(1e-5f) * iscale * uj[11];
+    params[0] = mass.v; params[1] = ixx.v; params[2] = iyy.v; params[3] = izz.v;
+    params[4] = arm.v; params[5] = kt.v; params[6] = kad.v; params[7] = kd.v;
+    params[8] = bd.v; params[9] = grav.v; params[10] = mr.v; params[11] = kmot.v; params[12] = jmot.v;
+    // spawn at least 2*radius from ring 0: R/drone_race.h:143-149
+    for (uint32_t t = 0; t < RESET_MAX_ATTEMPTS; t++) {
+        uint4 w = philox4x32_10(make_uint4(env, episode, 0x2000u, t), d.key0, d.key1);
+        xf cx = lerp_u(-9.0f, 9.0f, unit_from_word(w.x));
+        xf cy = lerp_u(-9.0f, 9.0f, unit_from_word(w.y));
+        xf cz = lerp_u(-9.0f, 9.0f, unit_from_word(w.z));
+        spawn[0] = cx.v; spawn[1] = cy.v; spawn[2] = cz.v;
+        xf ex = cx - xf(ring0[0]), ey = cy - xf(ring0[1]), ez = cz - xf(ring0[2]);
+        xf dist = xsqrt(ex * ex + ey * ey + ez * ez);
+        if (!(dist.v < 4.0f)) break;
+    }
+}
+
+__device__ __forceinline__ void race_store_params(const RaceDev &d, int i, const float p[13]) {
+    d.P[0 * (size_t)d.ld + i] = make_float4(p[0], p[1], p[2], p[3]);
+    d.P[1 * (size_t)d.ld + i] = make_float4(p[4], p[5], p[6], p[7]);
+    d.P[2 * (size_t)d.ld + i] = make_float4(p[8], p[9], p[10], p[11]);
+    d.PJ[i] = p[12];
+}
+
+// Generate episode `episode` of env i into the env's PREPARED slot (next params, next spawn,
+// ring buffer tb) and publish it by tagging the slot with the episode number.
+__device__ __forceinline__ void race_fill_slot(const RaceDev &d, int i, uint32_t episode, int tb) {
+    float p[13], spawn[3], ring0[6];
+    race_generate_episode(d, i, episode, tb, p, spawn, ring0);
+    d.N[0 * (size_t)d.ld + i] = make_float4(p[0], p[1], p[2], p[3]);
+    d.N[1 * (size_t)d.ld + i] = make_float4(p[4], p[5], p[6], p[7]);
+    d.N[2 * (size_t)d.ld + i] = make_float4(p[8], p[9], p[10], p[11]);
+    d.NJ[i] = p[12];
+    d.NS[i] = make_float4(spawn[0], spawn[1], spawn[2], 0.0f);
+    __threadfence();
+    d.SLOT_EP[i] = episode;
+}
+
+// A finished env starts its next episode.  Normal case: adopt the prepared slot (a few
+// loads/stores, the ring buffers just swap roles).  If the slot is not ready (the env
+// finished twice before a refill ran) generate the episode in place.  Parity hook
+// (B2D_RESET_INJECT): take the oracle's post-reset state from the payload instead.
+template <bool STRICT>
+__device__ __forceinline__ void race_begin_episode(const RaceDev &d, int i, int par, float *obs_row, uint2 *refill_entry,
+                                                   bool *want_refill) {
     float s[17];
 #pragma unroll
     for (int k = 0; k < 17; k++) s[k] = 0.0f;
     s[6] = 1.0f;
     float ring0[6];
     int tick = 0, ring_idx = 0;
-    float ep_ret = 0.0f;
-    float mrpm;
-
+    float ep_ret = 0.0f, mrpm;
+    *want_refill = false;
     if (d.reset_mode == 1 /* B2D_RESET_INJECT */) {
         const float *b = d.payload + (size_t)i * (33 + 6 * d.max_rings);
 #pragma unroll
         for (int k = 0; k < 17; k++) s[k] = b[k];
-        d.P[0 * (size_t)d.ld + i] = make_float4(b[17], b[18], b[19], b[20]);
-        d.P[1 * (size_t)d.ld + i] = make_float4(b[21], b[22], b[23], b[24]);
-        d.P[2 * (size_t)d.ld + i] = make_float4(b[25], b[26], b[27], b[28]);
-        d.PJ[i] = b[29];
+        race_store_params(d, i, b + 17);
         mrpm = b[27];
         tick = (int)b[30]; ring_idx = (int)b[31]; ep_ret = b[32];
+        const size_t gbase = (size_t)par * d.max_rings * d.ld + i;
         for (int r = 0; r < d.max_rings; r++) {
             const float *g = b + 33 + 6 * r;
-            d.G0[(size_t)r * d.ld + i] = make_float4(g[0], g[1], g[2], g[3]);
-            d.G1[(size_t)r * d.ld + i] = make_float2(g[4], g[5]);
+            d.G0[gbase + (size_t)r * d.ld] = make_float4(g[0], g[1], g[2], g[3]);
+            d.G1[gbase + (size_t)r * d.ld] = make_float2(g[4], g[5]);
         }
         const float *g = b + 33 + 6 * (ring_idx < d.max_rings ? ring_idx : 0);
 #pragma unroll
         for (int k = 0; k < 6; k++) ring0[k] = g[k];
     } else {
-        const uint32_t env = d.env_id_base + (uint32_t)i;
-        // rings: R/dronelib.h:451-460 (each at least 2*radius from its predecessor)
-        float px = 0.0f, py = 0.0f, pz = 0.0f;
-        for (int r = 0; r < d.max_rings; r++) {
-            float g[6];
-            for (uint32_t t = 0; t < RESET_MAX_ATTEMPTS; t++) {
-                uint4 a = philox4x32_10(make_uint4(env, epoch, 2u * r, t), d.key0, d.key1);
-                uint4 b = philox4x32_10(make_uint4(env, epoch, 2u * r + 1u, t), d.key0, d.key1);
-                xf cx = lerp_u(-6.0f, 6.0f, unit_from_word(a.x));
-                xf cy = lerp_u(-6.0f, 6.0f, unit_from_word(a.y));
-                xf cz = lerp_u(-6.0f, 6.0f, unit_from_word(a.z));
-                xf u1 = unit_from_word(a.w), u2 = unit_from_word(b.x), u3 = unit_from_word(b.y);
-                // R/dronelib.h:141-159 rndquat, :177-178 normal = q . z-axis
-                xf ra = xsqrt(xf(1.0f) - u1), rb = xsqrt(u1);
-                float th2 = __double2float_rn(__dmul_rn(6.283185307179586, (double)u2.v));
-                float th3 = __double2float_rn(__dmul_rn(6.283185307179586, (double)u3.v));
-                float s2, c2, s3, c3;
-                sincos_det(th2, s2, c2);
-                sincos_det(th3, s3, c3);
-                Q4<xf> q;
-                q.w = ra * xf(s2); q.x = ra * xf(c2); q.y = rb * xf(s3); q.z = rb * xf(c3);
-                V3<xf> zax;
-                zax.x = 0.0f; zax.y = 0.0f; zax.z = 1.0f;
-                V3<xf> nrm = qrot(q, zax);
-                g[0] = cx.v; g[1] = cy.v; g[2] = cz.v; g[3] = nrm.x.v; g[4] = nrm.y.v; g[5] = nrm.z.v;
-                if (r == 0) break;
-                xf ex = cx - xf(px), ey = cy - xf(py), ez = cz - xf(pz);
-                xf dist = xsqrt(ex * ex + ey * ey + ez * ez);
-                if (!(dist.v < 4.0f)) break;
-            }
-            px = g[0]; py = g[1]; pz = g[2];
-            d.G0[(size_t)r * d.ld + i] = make_float4(g[0], g[1], g[2], g[3]);
-            d.G1[(size_t)r * d.ld + i] = make_float2(g[4], g[5]);
-            if (r == 0) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) ring0[k] = g[k];
-            }
+        const uint32_t want = d.EP[i] + 1u;
+        const int npar = par ^ 1;
+        float p[13];
+        if (__ldcg(&d.SLOT_EP[i]) == want) {
+            __threadfence();
+            const size_t ld = d.ld;
+            float4 a = __ldcg(&d.N[0 * ld + i]), b = __ldcg(&d.N[1 * ld + i]), c = __ldcg(&d.N[2 * ld + i]);
+            float4 sp = __ldcg(&d.NS[i]);
+            p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
+            p[8] = c.x; p[9] = c.y; p[10] = c.z; p[11] = c.w; p[12] = __ldcg(&d.NJ[i]);
+            s[0] = sp.x; s[1] = sp.y; s[2] = sp.z;
+            const size_t g = (size_t)npar * d.max_rings * d.ld + i;
+            float4 r0 = __ldcg(&d.G0[g]);
+            float2 r1 = __ldcg(&d.G1[g]);
+            ring0[0] = r0.x; ring0[1] = r0.y; ring0[2] = r0.z; ring0[3] = r0.w; ring0[4] = r1.x; ring0[5] = r1.y;
+        } else {
+            float spawn[3];
+            race_generate_episode(d, i, want, npar, p, spawn, ring0);
+            s[0] = spawn[0]; s[1] = spawn[1]; s[2] = spawn[2];
         }
-        // R/dronelib.h:250-290 init_drone(size ~ U(0.05, 0.8), dr = 0.1)
-        float u[16];
-#pragma unroll
-        for (uint32_t k = 0; k < 4; k++) {
-            uint4 w = philox4x32_10(make_uint4(env, epoch, 0x1000u + k, 0u), d.key0, d.key1);
-            u[4 * k + 0] = unit_from_word(w.x).v; u[4 * k + 1] = unit_from_word(w.y).v;
-            u[4 * k + 2] = unit_from_word(w.z).v; u[4 * k + 3] = unit_from_word(w.w).v;
-        }
-        const float jlo = __fsub_rn(1.0f, 0.1f), jhi = __fadd_rn(1.0f, 0.1f);
-        xf size = lerp_u(0.05f, 0.8f, xf(u[0]));
-        xf uj[12];
-#pragma unroll
-        for (int k = 0; k < 12; k++) uj[k] = (k == 8) ? lerp_u(0.99f, 1.01f, xf(u[1 + k])) : lerp_u(jlo, jhi, xf(u[1 + k]));
-        xf arm = size / xf(2.0f);
-        xf mass_scale = xf(cube_det(arm.v)) / xf(cube_det(0.1f));
-        xf mass = xf(1.0f) * mass_scale * uj[0];
-        xf base_iscale = xf(1.0f) * xf(0.1f) * xf(0.1f);
-        xf iscale = mass * (arm * arm) / base_iscale;
-        xf ixx = xf(0.01f) * iscale * uj[1];
-        xf iyy = xf(0.01f) * iscale * uj[2];
-        xf izz = xf(0.02f) * iscale * uj[3];
-        xf kt_scale = (mass * arm) / (xf(1.0f) * xf(0.1f));
-        xf kt = xf(3e-5f) * kt_scale * uj[4];
-        xf base_avg = (xf(0.01f) + xf(0.01f) + xf(0.02f)) / xf(3.0f);
-        xf avg = (ixx + iyy + izz) / xf(3.0f);
-        xf kad = xf(0.2f) * (avg / base_avg) * uj[5];
-        xf drag_scale = (arm * arm) / (xf(0.1f) * xf(0.1f));
-        xf kd = xf(1e-6f) * drag_scale * uj[6];
-        xf bd = xf(0.1f) * drag_scale * uj[7];
-        xf grav = xf(9.81f) * uj[8];
-        xf mr = xf(750.0f) * (xf(0.1f) / arm) * uj[9];
-        xf kmot = xf(0.1f) * uj[10];
-        xf jmot = xf(1e-5f) * iscale * uj[11];
-        d.P[0 * (size_t)d.ld + i] = make_float4(mass.v, ixx.v, iyy.v, izz.v);
-        d.P[1 * (size_t)d.ld + i] = make_float4(arm.v, kt.v, kad.v, kd.v);
-        d.P[2 * (size_t)d.ld + i] = make_float4(bd.v, grav.v, mr.v, kmot.v);
-        d.PJ[i] = jmot.v;
-        mrpm = mr.v;
-        // spawn at least 2*radius from ring 0: R/drone_race.h:143-149
-        for (uint32_t t = 0; t < RESET_MAX_ATTEMPTS; t++) {
-            uint4 w = philox4x32_10(make_uint4(env, epoch, 0x2000u, t), d.key0, d.key1);
-            xf cx = lerp_u(-9.0f, 9.0f, unit_from_word(w.x));
-            xf cy = lerp_u(-9.0f, 9.0f, unit_from_word(w.y));
-            xf cz = lerp_u(-9.0f, 9.0f, unit_from_word(w.z));
-            s[0] = cx.v; s[1] = cy.v; s[2] = cz.v;
-            xf ex = cx - xf(ring0[0]), ey = cy - xf(ring0[1]), ez = cz - xf(ring0[2]);
-            xf dist = xsqrt(ex * ex + ey * ey + ez * ez);
-            if (!(dist.v < 4.0f)) break;
-        }
+        race_store_params(d, i, p);
+        mrpm = p[10];
+        d.EP[i] = want;
+        par = npar;
+        *want_refill = true;
+        *refill_entry = make_uint2((uint32_t)i | ((uint32_t)(par ^ 1) << 31), want + 1u);
     }
-    race_store_state(d, i, s, tick, ring_idx, ep_ret);
+    race_store_state(d, i, s, tick, ring_idx | (par << 30), ep_ret);
     race_store_current_ring(d, i, ring0);
-    race_observe<true>(s, mrpm, ring0, obs_row);
+    race_observe<STRICT>(s, mrpm, ring0, obs_row);
 }
 
 // ---------------------------------------------------------------- TMA bulk store helpers
@@ -274,157 +347,208 @@ __device__ __forceinline__ void tma_store_1d(void *gdst, const void *ssrc, uint3
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------- the step kernel
-// One thread per env, 256 envs per CTA.  Finished envs are compacted into a
-// per-CTA list and re-initialised by the first lanes of the CTA so the (long,
-// rare) reset path does not run divergently inside every warp.  Observations
-// are staged in shared memory and leave the SM as one 29,696-byte TMA bulk
+// Grid = refill_ctas + ld/256 CTAs of 256 threads.
+//   CTAs [0, refill_ctas): regenerate the prepared slots consumed in the previous step.
+//   the rest: one thread per env, 256 envs per CTA.  Finished envs are compacted into a
+//   per-CTA list and started on their next episode by the first lanes of the CTA.
+// Observations are staged in shared memory and leave the SM as one 29,696-byte TMA bulk
 // store per CTA (row-major [N,29] rows are 116 B, not a multiple of 16).
 template <bool STRICT>
 __global__ void __launch_bounds__(RACE_BLOCK, 2) race_step_kernel(const __grid_constant__ RaceDev d) {
     extern __shared__ __align__(128) float s_obs[]; // [RACE_BLOCK][29]
     __shared__ int s_nreset;
+    __shared__ int s_nrefill;
+    __shared__ unsigned int s_refill_base;
     __shared__ int s_acc[8];
     __shared__ unsigned short s_list[RACE_BLOCK];
 
     const int tid = threadIdx.x;
-    const int i = blockIdx.x * RACE_BLOCK + tid;
-    const bool valid = i < d.n;
-    if (tid < 8) s_acc[tid] = 0;
-    if (tid == 8) s_nreset = 0;
     const uint32_t epoch = d.ctl->epoch + 1u;
-    __syncthreads();
 
-    if (valid) {
-        const size_t ld = d.ld;
-        float4 a4 = reinterpret_cast<const float4 *>(d.act_in)[i];
-        float4 q0 = d.S[0 * ld + i], q1 = d.S[1 * ld + i], q2 = d.S[2 * ld + i], q3 = d.S[3 * ld + i],
-               q4 = d.S[4 * ld + i];
-        float4 p0 = d.P[0 * ld + i], p1 = d.P[1 * ld + i], p2 = d.P[2 * ld + i];
-        float pj = d.PJ[i];
-        float4 c0 = d.C0[i];
-        float2 c1 = d.C1[i];
-
-        float s[17] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x};
-        int tick = __float_as_int(q4.y) + 1;
-        int ring_idx = __float_as_int(q4.z);
-        float ep_ret = q4.w;
-        DroneParams p = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, pj};
-        float ring[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
-
-        // clamp the action (written back only on request): R/dronelib.h:437
-        float act[4];
-        if constexpr (STRICT) {
-            act[0] = xclamp(xf(a4.x), -1.0f, 1.0f).v; act[1] = xclamp(xf(a4.y), -1.0f, 1.0f).v;
-            act[2] = xclamp(xf(a4.z), -1.0f, 1.0f).v; act[3] = xclamp(xf(a4.w), -1.0f, 1.0f).v;
-        } else {
-            act[0] = fminf(fmaxf(a4.x, -1.0f), 1.0f); act[1] = fminf(fmaxf(a4.y, -1.0f), 1.0f);
-            act[2] = fminf(fmaxf(a4.z, -1.0f), 1.0f); act[3] = fminf(fmaxf(a4.w, -1.0f), 1.0f);
-        }
-        if (d.act_out) reinterpret_cast<float4 *>(d.act_out)[i] = make_float4(act[0], act[1], act[2], act[3]);
-
-        const float before[3] = {s[0], s[1], s[2]};
-        advance_body<STRICT>(s, p, act);
-
-        // ---- episode logic: R/drone_race.h:165-203
-        float reward = 0.0f;
-        int cause = -1; // ACC_OOB / ACC_COLLISION / ACC_TIMEOUT / ACC_SPARE(course complete)
-        const bool oob = s[0] < -10.0f || s[0] > 10.0f || s[1] < -10.0f || s[1] > 10.0f || s[2] < -10.0f || s[2] > 10.0f;
-        if (oob) {
-            reward = -1.0f;
-            ep_ret -= 1.0f;
-            cause = ACC_OOB;
-        } else {
-            float gate;
-            if constexpr (STRICT) gate = gate_event<xf>(before, s, ring, -1.0f);
-            else gate = gate_event<float>(before, s, ring, -1.0f);
-            reward = gate;
-            ep_ret += gate;
-            if (gate > 0.0f) {
-                ring_idx += 1;
-            }
-            if (gate < 0.0f) {
-                cause = ACC_COLLISION;
-            } else if (tick == d.max_moves) {
-                cause = ACC_TIMEOUT;
-            } else if (ring_idx == d.max_rings) {
-                cause = ACC_SPARE;
-            } else if (gate > 0.0f) {
-                race_load_ring(d, i, ring_idx, ring);
-                race_store_current_ring(d, i, ring);
-            }
-        }
-        d.rew[i] = reward;
-        d.term[i] = cause >= 0 ? 1 : 0;
-
-        if (cause < 0) {
-            race_store_state(d, i, s, tick, ring_idx, ep_ret);
-            race_observe<STRICT>(s, p.mrpm, ring, s_obs + tid * RACE_OBS);
-        } else {
-            // add_log: R/drone_race.h:61-70 (score == ring_idx at every call site)
-            atomicAdd(&s_acc[ACC_N], 1);
-            atomicAdd(&s_acc[ACC_RETURN], __float2int_rn(ep_ret));
-            atomicAdd(&s_acc[ACC_LENGTH], tick);
-            atomicAdd(&s_acc[ACC_RINGS], ring_idx);
-            if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
-            s_list[atomicAdd(&s_nreset, 1)] = (unsigned short)tid;
-        }
-    }
-    __syncthreads();
-
-    // ---- compacted auto-reset: lane r of the CTA re-initialises the r-th finished env
-    const int nreset = s_nreset;
-    if (tid < nreset) {
-        const int li = s_list[tid];
-        race_fresh_episode(d, blockIdx.x * RACE_BLOCK + li, epoch, s_obs + li * RACE_OBS);
-    }
-    __syncthreads();
-
-    // ---- observations out: one TMA bulk store per full CTA tile
-    const int row0 = blockIdx.x * RACE_BLOCK;
-    const int rows = min(RACE_BLOCK, d.n - row0);
-    float *gobs = d.obs + (size_t)row0 * RACE_OBS;
-    if (rows == RACE_BLOCK) {
-        if (tid == 0) {
-            tma_store_fence();
-            tma_store_1d(gobs, s_obs, RACE_BLOCK * RACE_OBS * sizeof(float));
+    if ((int)blockIdx.x < d.refill_ctas) {
+        // ---- refill role: slots consumed during step epoch-1
+        const unsigned int src = (epoch - 1u) & 1u;
+        const unsigned int cnt = d.ctl->refill_count[src];
+        const uint2 *list = d.refill + (size_t)src * d.ld;
+        for (unsigned int k = blockIdx.x * RACE_BLOCK + tid; k < cnt; k += d.refill_ctas * RACE_BLOCK) {
+            uint2 e = list[k];
+            race_fill_slot(d, (int)(e.x & 0x7fffffffu), e.y, (int)(e.x >> 31));
         }
     } else {
-        for (int k = tid; k < rows * RACE_OBS; k += RACE_BLOCK) gobs[k] = s_obs[k];
+        const int bidx = blockIdx.x - d.refill_ctas;
+        const int i = bidx * RACE_BLOCK + tid;
+        const bool valid = i < d.n;
+        if (tid < 8) s_acc[tid] = 0;
+        if (tid == 8) s_nreset = 0;
+        if (tid == 9) s_nrefill = 0;
+        __syncthreads();
+
+        if (valid) {
+            const size_t ld = d.ld;
+            float4 a4 = reinterpret_cast<const float4 *>(d.act_in)[i];
+            float4 q0 = d.S[0 * ld + i], q1 = d.S[1 * ld + i], q2 = d.S[2 * ld + i], q3 = d.S[3 * ld + i],
+                   q4 = d.S[4 * ld + i];
+            float4 p0 = d.P[0 * ld + i], p1 = d.P[1 * ld + i], p2 = d.P[2 * ld + i];
+            float pj = d.PJ[i];
+            float4 c0 = d.C0[i];
+            float2 c1 = d.C1[i];
+
+            float s[17] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x};
+            int tick = __float_as_int(q4.y) + 1;
+            const int ring_word = __float_as_int(q4.z);
+            int ring_idx = ring_word & 0x3fffffff;
+            const int par = (ring_word >> 30) & 1;
+            float ep_ret = q4.w;
+            DroneParams p = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, pj};
+            float ring[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
+
+            // clamp the action (written back only on request): R/dronelib.h:437
+            float act[4];
+            if constexpr (STRICT) {
+                act[0] = xclamp(xf(a4.x), -1.0f, 1.0f).v; act[1] = xclamp(xf(a4.y), -1.0f, 1.0f).v;
+                act[2] = xclamp(xf(a4.z), -1.0f, 1.0f).v; act[3] = xclamp(xf(a4.w), -1.0f, 1.0f).v;
+            } else {
+                act[0] = fminf(fmaxf(a4.x, -1.0f), 1.0f); act[1] = fminf(fmaxf(a4.y, -1.0f), 1.0f);
+                act[2] = fminf(fmaxf(a4.z, -1.0f), 1.0f); act[3] = fminf(fmaxf(a4.w, -1.0f), 1.0f);
+            }
+            if (d.act_out) reinterpret_cast<float4 *>(d.act_out)[i] = make_float4(act[0], act[1], act[2], act[3]);
+
+            const float before[3] = {s[0], s[1], s[2]};
+            advance_body<STRICT>(s, p, act);
+
+            // ---- episode logic: R/drone_race.h:165-203
+            float reward = 0.0f;
+            int cause = -1; // ACC_OOB / ACC_COLLISION / ACC_TIMEOUT / ACC_SPARE(course complete)
+            const bool oob = s[0] < -10.0f || s[0] > 10.0f || s[1] < -10.0f || s[1] > 10.0f || s[2] < -10.0f || s[2] > 10.0f;
+            if (oob) {
+                reward = -1.0f;
+                ep_ret -= 1.0f;
+                cause = ACC_OOB;
+            } else {
+                float gate;
+                if constexpr (STRICT) gate = gate_event<xf>(before, s, ring, -1.0f);
+                else gate = gate_event<float>(before, s, ring, -1.0f);
+                reward = gate;
+                ep_ret += gate;
+                if (gate > 0.0f) ring_idx += 1;
+                if (gate < 0.0f) {
+                    cause = ACC_COLLISION;
+                } else if (tick == d.max_moves) {
+                    cause = ACC_TIMEOUT;
+                } else if (ring_idx == d.max_rings) {
+                    cause = ACC_SPARE;
+                } else if (gate > 0.0f) {
+                    race_load_ring(d, i, par, ring_idx, ring);
+                    race_store_current_ring(d, i, ring);
+                }
+            }
+            d.rew[i] = reward;
+            d.term[i] = cause >= 0 ? 1 : 0;
+
+            if (cause < 0) {
+                race_store_state(d, i, s, tick, ring_idx | (par << 30), ep_ret);
+                race_observe<STRICT>(s, p.mrpm, ring, s_obs + tid * RACE_OBS);
+            } else {
+                // add_log: R/drone_race.h:61-70 (score == ring_idx at every call site)
+                atomicAdd(&s_acc[ACC_N], 1);
+                atomicAdd(&s_acc[ACC_RETURN], __float2int_rn(ep_ret));
+                atomicAdd(&s_acc[ACC_LENGTH], tick);
+                atomicAdd(&s_acc[ACC_RINGS], ring_idx);
+                if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
+                s_list[atomicAdd(&s_nreset, 1)] = (unsigned short)(tid | (par << 15));
+            }
+        }
+        __syncthreads();
+
+        // ---- compacted auto-reset: lane r of the CTA starts the r-th finished env on its next episode
+        const int nreset = s_nreset;
+        uint2 entry = make_uint2(0u, 0u);
+        bool want_refill = false;
+        int slot = 0;
+        if (tid < nreset) {
+            const int li = s_list[tid] & 0x7fff;
+            race_begin_episode<STRICT>(d, bidx * RACE_BLOCK + li, s_list[tid] >> 15, s_obs + li * RACE_OBS, &entry,
+                                       &want_refill);
+            if (want_refill) slot = atomicAdd(&s_nrefill, 1);
+        }
+        __syncthreads();
+        if (nreset > 0) {
+            if (tid == 0 && s_nrefill > 0) s_refill_base = atomicAdd(&d.ctl->refill_count[epoch & 1u], (unsigned int)s_nrefill);
+            __syncthreads();
+            if (want_refill) d.refill[(size_t)(epoch & 1u) * d.ld + s_refill_base + slot] = entry;
+        }
+
+        // ---- observations out: one TMA bulk store per full CTA tile
+        const int row0 = bidx * RACE_BLOCK;
+        const int rows = min(RACE_BLOCK, d.n - row0);
+        float *gobs = d.obs + (size_t)row0 * RACE_OBS;
+        if (rows == RACE_BLOCK) {
+            if (tid == 0) {
+                tma_store_fence();
+                tma_store_1d(gobs, s_obs, RACE_BLOCK * RACE_OBS * sizeof(float));
+            }
+        } else {
+            for (int k = tid; k < rows * RACE_OBS; k += RACE_BLOCK) gobs[k] = s_obs[k];
+        }
+
+        // ---- episode statistics: CTA partial sums -> device accumulators
+        if (tid < 7 && nreset > 0) {
+            int v = s_acc[tid];
+            if (v != 0) atomicAdd((unsigned long long *)&d.ctl->acc[tid], (unsigned long long)(long long)v);
+            if (tid == ACC_RINGS)
+                atomicAdd((unsigned long long *)&d.ctl->score_step[epoch & 1u], (unsigned long long)(long long)v);
+        }
+        if (tid == 0 && rows == RACE_BLOCK) tma_store_wait_read();
     }
 
-    // ---- episode statistics: CTA partial sums -> device accumulators
-    if (tid < 7) {
-        int v = s_acc[tid];
-        if (v != 0) atomicAdd((unsigned long long *)&d.ctl->acc[tid], (unsigned long long)(long long)v);
-        if (tid == ACC_RINGS && nreset > 0)
-            atomicAdd((unsigned long long *)&d.ctl->score_step[epoch & 1u], (unsigned long long)(long long)v);
-    }
+    // ---- every CTA takes a ticket; the last one closes the step
+    __syncthreads();
     if (tid == 0) {
         __threadfence();
         unsigned int t = atomicAdd(&d.ctl->ticket, 1u);
-        if (t == gridDim.x - 1) { // last CTA of this step closes the epoch
+        if (t == gridDim.x - 1) {
             d.ctl->score_step[(epoch + 1u) & 1u] = 0;
+            d.ctl->refill_count[(epoch + 1u) & 1u] = 0; // the list this launch consumed; step epoch+1 appends to it
             d.ctl->ticket = 0;
+            __threadfence();
             d.ctl->epoch = epoch;
         }
-        if (rows == RACE_BLOCK) tma_store_wait_read();
     }
 }
 
 // ---------------------------------------------------------------- vec_reset / observe / blobs
+// vec_reset (EB:500-504): episode 0 becomes the live episode, episode 1 the prepared one.
 __global__ void __launch_bounds__(128) race_reset_kernel(const __grid_constant__ RaceDev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
-    race_fresh_episode(d, i, 0u, d.obs + (size_t)i * RACE_OBS);
+    if (d.reset_mode == 1 /* B2D_RESET_INJECT */) {
+        uint2 e;
+        bool w;
+        race_begin_episode<true>(d, i, 0, d.obs + (size_t)i * RACE_OBS, &e, &w);
+        return;
+    }
+    float p[13], spawn[3], ring0[6], s[17];
+    race_generate_episode(d, i, 0u, 0, p, spawn, ring0);
+#pragma unroll
+    for (int k = 0; k < 17; k++) s[k] = 0.0f;
+    s[6] = 1.0f;
+    s[0] = spawn[0]; s[1] = spawn[1]; s[2] = spawn[2];
+    race_store_params(d, i, p);
+    race_store_state(d, i, s, 0, 0, 0.0f);
+    race_store_current_ring(d, i, ring0);
+    race_observe<true>(s, p[10], ring0, d.obs + (size_t)i * RACE_OBS);
+    d.EP[i] = 0u;
+    race_fill_slot(d, i, 1u, 1);
 }
 
 __global__ void race_ctl_reset_kernel(Ctl *ctl, unsigned int epoch, int clear_acc) {
     if (threadIdx.x == 0) {
         ctl->epoch = epoch;
         ctl->ticket = 0;
+        ctl->refill_count[0] = ctl->refill_count[1] = 0;
+        ctl->score_step[0] = ctl->score_step[1] = 0;
         if (clear_acc) {
             for (int k = 0; k < ACC_COUNT; k++) ctl->acc[k] = 0;
-            ctl->score_step[0] = ctl->score_step[1] = 0;
             for (int k = 0; k < 8; k++) ctl->facc[k] = 0.0;
         }
     }
@@ -465,10 +589,11 @@ __global__ void race_pack_kernel(const RaceDev d, const int *ids, int n, float *
     b[16] = q4.x;
     b[17] = p0.x; b[18] = p0.y; b[19] = p0.z; b[20] = p0.w; b[21] = p1.x; b[22] = p1.y; b[23] = p1.z; b[24] = p1.w;
     b[25] = p2.x; b[26] = p2.y; b[27] = p2.z; b[28] = p2.w; b[29] = d.PJ[i];
-    b[30] = (float)__float_as_int(q4.y); b[31] = (float)__float_as_int(q4.z); b[32] = q4.w;
+    const int ring_word = __float_as_int(q4.z);
+    b[30] = (float)__float_as_int(q4.y); b[31] = (float)(ring_word & 0x3fffffff); b[32] = q4.w;
     for (int r = 0; r < d.max_rings; r++) {
         float ring[6];
-        race_load_ring(d, i, r, ring);
+        race_load_ring(d, i, (ring_word >> 30) & 1, r, ring);
         for (int c = 0; c < 6; c++) b[33 + 6 * r + c] = ring[c];
     }
 }
@@ -482,15 +607,13 @@ __global__ void race_unpack_kernel(const RaceDev d, const int *ids, int n, const
     float s[17];
     for (int c = 0; c < 17; c++) s[c] = b[c];
     const int ring_idx = (int)b[31];
-    race_store_state(d, i, s, (int)b[30], ring_idx, b[32]);
-    d.P[0 * ld + i] = make_float4(b[17], b[18], b[19], b[20]);
-    d.P[1 * ld + i] = make_float4(b[21], b[22], b[23], b[24]);
-    d.P[2 * ld + i] = make_float4(b[25], b[26], b[27], b[28]);
-    d.PJ[i] = b[29];
+    const int par = (__float_as_int(d.S[4 * ld + i].z) >> 30) & 1; // keep the env's ring-buffer parity
+    race_store_state(d, i, s, (int)b[30], ring_idx | (par << 30), b[32]);
+    race_store_params(d, i, b + 17);
     for (int r = 0; r < d.max_rings; r++) {
         const float *g = b + 33 + 6 * r;
-        d.G0[(size_t)r * ld + i] = make_float4(g[0], g[1], g[2], g[3]);
-        d.G1[(size_t)r * ld + i] = make_float2(g[4], g[5]);
+        d.G0[((size_t)par * d.max_rings + r) * ld + i] = make_float4(g[0], g[1], g[2], g[3]);
+        d.G1[((size_t)par * d.max_rings + r) * ld + i] = make_float2(g[4], g[5]);
     }
     const float *g = b + 33 + 6 * (ring_idx < d.max_rings ? ring_idx : 0);
     race_store_current_ring(d, i, g);

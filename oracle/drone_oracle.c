@@ -147,7 +147,7 @@ void orc_sincos_det(float theta, float *s, float *c) {
 typedef struct {
     int mode;          /* ORC_RESET_LIBC or ORC_RESET_PHILOX */
     uint32_t key[2];
-    uint32_t env, epoch;
+    uint32_t env, episode;
 } RandSrc;
 
 /* R/drone_race/dronelib.h:81-83; (float)RAND_MAX == 2^31 */
@@ -156,7 +156,7 @@ static inline float lerp_u(float a, float b, float u) { return a + u * (b - a); 
 static inline float libc_rndf(float a, float b) { return lerp_u(a, b, u_from_i31(rand())); }
 
 static void philox_words(const RandSrc *rs, uint32_t item, uint32_t attempt, uint32_t w[4]) {
-    uint32_t ctr[4] = {rs->env, rs->epoch, item, attempt};
+    uint32_t ctr[4] = {rs->env, rs->episode, item, attempt};
     orc_philox4x32_10(ctr, rs->key, w);
 }
 static inline float u_from_word(uint32_t w) { return u_from_i31((int32_t)(w >> 1)); }
@@ -173,7 +173,8 @@ struct OrcRace {
     float *logs;    /* [n][9]  R/drone_race/dronelib.h:52-63 field order */
     uint32_t key[2];
     uint32_t env_id_base;
-    uint32_t epoch; /* number of vec steps taken since the last vec_reset (Philox counter word) */
+    uint32_t epoch; /* number of vec steps taken since the last vec_reset */
+    uint32_t *episode; /* [n] number of the live episode of each env (Philox counter word) */
 };
 
 OrcRace *orc_race_create(int n, int max_rings, int max_moves) {
@@ -188,6 +189,7 @@ OrcRace *orc_race_create(int n, int max_rings, int max_moves) {
     o->ep_ret = (float *)calloc((size_t)n, sizeof(float));
     o->rings = (float *)calloc((size_t)n * max_rings * 6, sizeof(float));
     o->logs = (float *)calloc((size_t)n * 9, sizeof(float));
+    o->episode = (uint32_t *)calloc((size_t)n, sizeof(uint32_t));
     for (int i = 0; i < n; i++) o->state[(size_t)i * 17 + 6] = 1.0f;
     return o;
 }
@@ -195,7 +197,7 @@ OrcRace *orc_race_create(int n, int max_rings, int max_moves) {
 void orc_race_close(OrcRace *o) {
     if (!o) return;
     free(o->state); free(o->params); free(o->tick); free(o->ring_idx);
-    free(o->ep_ret); free(o->rings); free(o->logs); free(o);
+    free(o->ep_ret); free(o->rings); free(o->logs); free(o->episode); free(o);
 }
 
 void orc_race_set_philox(OrcRace *o, uint64_t seed, uint32_t env_id_base) {
@@ -327,7 +329,7 @@ static void race_fresh_episode(OrcRace *o, int i, const RandSrc *rs) {
             if (!(dist3(c, r0) < min_gap)) break;
         }
     } else {
-        /* device stream: counter = (env, epoch, item, attempt); see DESIGN.md "reset stream" */
+        /* device stream: counter = (env, episode number, item, attempt); see DESIGN.md "reset stream" */
         uint32_t w[4], w2[4];
         for (int r = 0; r < o->max_rings; r++) {
             float *g = rings + 6 * r;
@@ -571,11 +573,13 @@ static void race_log_episode(OrcRace *o, int i, float oob, float hit, float time
     l[8] += 1.0f;
 }
 
-static void race_new_episode(OrcRace *o, int i, int mode, const float *payload) {
+/* first = 1 for vec_reset (episode 0), 0 for an auto-reset (next episode number) */
+static void race_new_episode(OrcRace *o, int i, int mode, const float *payload, int first) {
     if (mode == ORC_RESET_INJECT) {
         orc_race_put_state(o, i, payload + (size_t)i * (ORC_RACE_BLOB + 6 * o->max_rings));
     } else {
-        RandSrc rs = {mode, {o->key[0], o->key[1]}, o->env_id_base + (uint32_t)i, o->epoch};
+        o->episode[i] = first ? 0u : o->episode[i] + 1u;
+        RandSrc rs = {mode, {o->key[0], o->key[1]}, o->env_id_base + (uint32_t)i, o->episode[i]};
         race_fresh_episode(o, i, &rs);
     }
 }
@@ -584,7 +588,7 @@ void orc_race_reset(OrcRace *o, int mode, int seed, const float *payload, float 
     o->epoch = 0;
     for (int i = 0; i < o->n; i++) {
         if (mode == ORC_RESET_LIBC) srand(i + seed * o->n); /* EB:500-504 */
-        race_new_episode(o, i, mode, payload);
+        race_new_episode(o, i, mode, payload, 1);
         if (obs) orc_race_observe(o, i, obs + (size_t)i * ORC_RACE_OBS);
     }
 }
@@ -639,7 +643,7 @@ static void race_step_one(OrcRace *o, int i, int mode, float *actions, const flo
             }
         }
     }
-    if (ended) race_new_episode(o, i, mode, payload);
+    if (ended) race_new_episode(o, i, mode, payload, 0);
     orc_race_observe(o, i, obs + (size_t)i * ORC_RACE_OBS);
     if (events) events[i] = ev;
 }

@@ -28,7 +28,7 @@ extern "C" {
 /* how an env that terminates gets its next episode */
 enum {
     ORC_RESET_LIBC = 0,   /* reference draw order from libc rand() (+1 discarded rand() per drone-step) */
-    ORC_RESET_PHILOX = 1, /* the device's counter-based stream (drone_b200/csrc/reset_stream.md in DESIGN.md) */
+    ORC_RESET_PHILOX = 1, /* the device's counter-based stream (DESIGN.md "reset stream") */
     ORC_RESET_INJECT = 2, /* post-reset state supplied by the caller (payload blob per env) */
 };
 

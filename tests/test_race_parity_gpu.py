@@ -234,3 +234,30 @@ def test_fast_math_free_running_drift(oracle):
     assert max_pos < 5e-2 and max_quat < 5e-2
     vec.close()
     cpu.close()
+
+
+@pytest.mark.parametrize("max_moves", [1, 2, 7])
+def test_philox_back_to_back_episodes_bit_exact(oracle, max_moves):
+    """Envs that finish every step (max_moves=1) or every few steps: the prepared-episode
+    slot is consumed faster than the refill CTAs can restock it, so the in-place generation
+    path runs too.  Every episode must still be the pure function of (seed, env, episode
+    number) the CPU restatement computes."""
+    from drone_b200.vec import RaceVec
+    n, T, seed = 5000, 40, 99
+    cpu = oracle.OrcRace(n, max_moves=max_moves, seed=seed)
+    cpu.reset(seed, mode=oracle.RESET_PHILOX)
+    vec = RaceVec(n, max_moves=max_moves, math="strict", seed=seed)
+    vec.reset(seed)
+    tape = _tape(n, scale=1.0)
+    dtape = torch.from_numpy(tape).cuda()
+    for t in range(T):
+        cpu.step(tape[t % 16], mode=oracle.RESET_PHILOX)
+        vec.step(dtape[t % 16])
+        assert np.array_equal(vec.terminals.cpu().numpy(), cpu.terminals), f"terminals differ at step {t}"
+        assert np.array_equal(_bits(vec.observations.cpu().numpy()), _bits(cpu.observations)), f"obs differ at step {t}"
+    assert np.array_equal(_bits(vec.get_state()), _bits(cpu.get_state()))
+    got, ref = vec.log(), cpu.log()
+    assert got["n"] == float(ref[8])
+    assert got["timeout"] == pytest.approx(ref[5] / ref[8], rel=1e-6)
+    vec.close()
+    cpu.close()
