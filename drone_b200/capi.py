@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libb200drone.so")
+LIB_PATH = os.environ.get("B2D_LIBRARY") or os.path.join(HERE, "lib", "libb200drone.so")
 
 B2D_OK, B2D_EINVAL, B2D_ENOMEM, B2D_ECUDA, B2D_ESTATE = 0, -1, -2, -3, -4
 MATH_FAST, MATH_STRICT = 0, 1

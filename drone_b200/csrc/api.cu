@@ -140,7 +140,7 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
     RaceDev &d = v->race;
     memset(&d, 0, sizeof(d));
     d.n = cfg->num_envs;
-    d.ld = (cfg->num_envs + RACE_BLOCK - 1) / RACE_BLOCK * RACE_BLOCK;
+    d.ld = (cfg->num_envs + RACE_LD_ALIGN - 1) / RACE_LD_ALIGN * RACE_LD_ALIGN;
     d.max_rings = cfg->max_rings;
     d.max_moves = cfg->max_moves;
     d.key0 = (uint32_t)cfg->seed;
@@ -150,7 +150,7 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
     {   // refill CTAs: sized for ~6% of the envs finishing per step, at most one per SM
         int step_ctas = d.ld / RACE_BLOCK;
         d.refill_ctas = step_ctas / 16 + 1;
-        if (d.refill_ctas > 148) d.refill_ctas = 148;
+        if (d.refill_ctas > 2 * 148) d.refill_ctas = 2 * 148;
     }
     const size_t ld = d.ld;
     if ((rc = setup_buffers(v, ext)) || (rc = dev_alloc(v, &d.S, 5 * ld)) || (rc = dev_alloc(v, &d.P, 3 * ld)) ||
@@ -402,6 +402,11 @@ extern "C" int b2d_put_state(b2d_vec *v, const int *env_ids, int n, const float 
         CUDA_TRY(cudaMemcpy(v->d_ids_tmp, env_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMemcpy(v->d_blob_tmp, host_blobs, (size_t)n * v->blob_floats * sizeof(float), cudaMemcpyHostToDevice));
+    if (v->kind == KIND_RACE) { // no prepared-slot refill may be in flight once states are edited
+        race_drain_kernel<<<148, 128>>>(v->race);
+        race_drain_done_kernel<<<1, 32>>>(v->race.ctl);
+        v->launches += 2;
+    }
     if (v->kind == KIND_RACE) race_unpack_kernel<<<(n + 127) / 128, 128>>>(v->race, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
     else swarm_unpack_kernel<<<(n + 127) / 128, 128>>>(v->swarm, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
     v->launches += 1;

@@ -30,7 +30,15 @@
 
 namespace b2d {
 
-constexpr int RACE_BLOCK = 256;
+#ifndef B2D_RACE_BLOCK
+#define B2D_RACE_BLOCK 128
+#endif
+#ifndef B2D_RACE_MIN_CTAS
+#define B2D_RACE_MIN_CTAS 5
+#endif
+constexpr int RACE_BLOCK = B2D_RACE_BLOCK;
+constexpr int RACE_MIN_CTAS = B2D_RACE_MIN_CTAS;
+constexpr int RACE_LD_ALIGN = 256; // row padding of the SoA arrays
 constexpr int RACE_OBS = 29;
 constexpr int RESET_MAX_ATTEMPTS = 16;
 
@@ -272,68 +280,92 @@ __device__ __forceinline__ void race_fill_slot(const RaceDev &d, int i, uint32_t
     d.SLOT_EP[i] = episode;
 }
 
-// A finished env starts its next episode.  Normal case: adopt the prepared slot (a few
-// loads/stores, the ring buffers just swap roles).  If the slot is not ready (the env
-// finished twice before a refill ran) generate the episode in place.  Parity hook
-// (B2D_RESET_INJECT): take the oracle's post-reset state from the payload instead.
+// Generate episode `episode` in place as the LIVE episode of env i (rings into buffer tb, params
+// into P, fresh state, current ring, observation row).  Only used when the prepared slot cannot
+// be trusted (see race_begin_episode) and by vec_reset.
 template <bool STRICT>
-__device__ __forceinline__ void race_begin_episode(const RaceDev &d, int i, int par, float *obs_row, uint2 *refill_entry,
-                                                   bool *want_refill) {
-    float s[17];
+__device__ __noinline__ void race_begin_generated(const RaceDev &d, int i, uint32_t episode, int tb, float *obs_row) {
+    float p[13], spawn[3], ring0[6], s[17];
+    race_generate_episode(d, i, episode, tb, p, spawn, ring0);
 #pragma unroll
     for (int k = 0; k < 17; k++) s[k] = 0.0f;
     s[6] = 1.0f;
-    float ring0[6];
-    int tick = 0, ring_idx = 0;
-    float ep_ret = 0.0f, mrpm;
+    s[0] = spawn[0]; s[1] = spawn[1]; s[2] = spawn[2];
+    race_store_params(d, i, p);
+    race_store_state(d, i, s, 0, tb << 30, 0.0f);
+    race_store_current_ring(d, i, ring0);
+    race_observe<STRICT>(s, p[10], ring0, obs_row);
+}
+
+// Parity hook (B2D_RESET_INJECT): the next episode is the oracle's post-reset state from the payload.
+template <bool STRICT>
+__device__ __noinline__ void race_inject_episode(const RaceDev &d, int i, int par, float *obs_row) {
+    const float *b = d.payload + (size_t)i * (33 + 6 * d.max_rings);
+    float s[17];
+#pragma unroll
+    for (int k = 0; k < 17; k++) s[k] = b[k];
+    race_store_params(d, i, b + 17);
+    const int tick = (int)b[30], ring_idx = (int)b[31];
+    const size_t gbase = (size_t)par * d.max_rings * d.ld + i;
+    for (int r = 0; r < d.max_rings; r++) {
+        const float *g = b + 33 + 6 * r;
+        d.G0[gbase + (size_t)r * d.ld] = make_float4(g[0], g[1], g[2], g[3]);
+        d.G1[gbase + (size_t)r * d.ld] = make_float2(g[4], g[5]);
+    }
+    const float *g = b + 33 + 6 * (ring_idx < d.max_rings ? ring_idx : 0);
+    race_store_state(d, i, s, tick, ring_idx | (par << 30), b[32]);
+    race_store_current_ring(d, i, g);
+    race_observe<STRICT>(s, b[27], g, obs_row);
+}
+
+// A finished env starts its next episode.  Normal case: ADOPT the prepared slot -- every load
+// it needs is independent (one memory latency), the two ring buffers just swap roles, and the
+// consumed slot is queued for a refill CTA of the next launch.  `tick` is the length of the
+// episode that just ended: an episode of length 1 ended in the launch right after the one
+// that consumed the slot, i.e. the refill may be running concurrently in THIS launch, so the
+// episode is generated in place instead (same pure function of (seed, env, episode number)).
+// The slot's episode tag is still verified, which also covers states edited by put_state.
+template <bool STRICT>
+__device__ __forceinline__ void race_begin_episode(const RaceDev &d, int i, int par, int tick, float *obs_row,
+                                                   uint2 *refill_entry, bool *want_refill) {
     *want_refill = false;
     if (d.reset_mode == 1 /* B2D_RESET_INJECT */) {
-        const float *b = d.payload + (size_t)i * (33 + 6 * d.max_rings);
-#pragma unroll
-        for (int k = 0; k < 17; k++) s[k] = b[k];
-        race_store_params(d, i, b + 17);
-        mrpm = b[27];
-        tick = (int)b[30]; ring_idx = (int)b[31]; ep_ret = b[32];
-        const size_t gbase = (size_t)par * d.max_rings * d.ld + i;
-        for (int r = 0; r < d.max_rings; r++) {
-            const float *g = b + 33 + 6 * r;
-            d.G0[gbase + (size_t)r * d.ld] = make_float4(g[0], g[1], g[2], g[3]);
-            d.G1[gbase + (size_t)r * d.ld] = make_float2(g[4], g[5]);
-        }
-        const float *g = b + 33 + 6 * (ring_idx < d.max_rings ? ring_idx : 0);
-#pragma unroll
-        for (int k = 0; k < 6; k++) ring0[k] = g[k];
-    } else {
-        const uint32_t want = d.EP[i] + 1u;
-        const int npar = par ^ 1;
-        float p[13];
-        if (__ldcg(&d.SLOT_EP[i]) == want) {
-            __threadfence();
-            const size_t ld = d.ld;
-            float4 a = __ldcg(&d.N[0 * ld + i]), b = __ldcg(&d.N[1 * ld + i]), c = __ldcg(&d.N[2 * ld + i]);
-            float4 sp = __ldcg(&d.NS[i]);
-            p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
-            p[8] = c.x; p[9] = c.y; p[10] = c.z; p[11] = c.w; p[12] = __ldcg(&d.NJ[i]);
-            s[0] = sp.x; s[1] = sp.y; s[2] = sp.z;
-            const size_t g = (size_t)npar * d.max_rings * d.ld + i;
-            float4 r0 = __ldcg(&d.G0[g]);
-            float2 r1 = __ldcg(&d.G1[g]);
-            ring0[0] = r0.x; ring0[1] = r0.y; ring0[2] = r0.z; ring0[3] = r0.w; ring0[4] = r1.x; ring0[5] = r1.y;
-        } else {
-            float spawn[3];
-            race_generate_episode(d, i, want, npar, p, spawn, ring0);
-            s[0] = spawn[0]; s[1] = spawn[1]; s[2] = spawn[2];
-        }
-        race_store_params(d, i, p);
-        mrpm = p[10];
-        d.EP[i] = want;
-        par = npar;
-        *want_refill = true;
-        *refill_entry = make_uint2((uint32_t)i | ((uint32_t)(par ^ 1) << 31), want + 1u);
+        race_inject_episode<STRICT>(d, i, par, obs_row);
+        return;
     }
-    race_store_state(d, i, s, tick, ring_idx | (par << 30), ep_ret);
-    race_store_current_ring(d, i, ring0);
-    race_observe<STRICT>(s, mrpm, ring0, obs_row);
+    const size_t ld = d.ld;
+    const int npar = par ^ 1;
+    const size_t g = (size_t)npar * d.max_rings * ld + i;
+    // all loads of the adoption are independent: issue them together (L2-coherent, they may
+    // have been written by another SM in an earlier launch)
+    const uint32_t ep = __ldcg(&d.EP[i]);
+    const uint32_t slot_ep = __ldcg(&d.SLOT_EP[i]);
+    float4 a = __ldcg(&d.N[0 * ld + i]), b = __ldcg(&d.N[1 * ld + i]), c = __ldcg(&d.N[2 * ld + i]);
+    float nj = __ldcg(&d.NJ[i]);
+    float4 sp = __ldcg(&d.NS[i]);
+    float4 r0 = __ldcg(&d.G0[g]);
+    float2 r1 = __ldcg(&d.G1[g]);
+    const uint32_t want = ep + 1u;
+    if (tick >= 2 && slot_ep == want) {
+        float s[17];
+#pragma unroll
+        for (int k = 0; k < 17; k++) s[k] = 0.0f;
+        s[6] = 1.0f;
+        s[0] = sp.x; s[1] = sp.y; s[2] = sp.z;
+        const float ring0[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+        d.P[0 * ld + i] = a;
+        d.P[1 * ld + i] = b;
+        d.P[2 * ld + i] = c;
+        d.PJ[i] = nj;
+        race_store_state(d, i, s, 0, npar << 30, 0.0f);
+        race_store_current_ring(d, i, ring0);
+        race_observe<STRICT>(s, c.z, ring0, obs_row);
+    } else {
+        race_begin_generated<STRICT>(d, i, want, npar, obs_row);
+    }
+    d.EP[i] = want;
+    *want_refill = true;
+    *refill_entry = make_uint2((uint32_t)i | ((uint32_t)par << 31), want + 1u);
 }
 
 // ---------------------------------------------------------------- TMA bulk store helpers
@@ -347,26 +379,30 @@ __device__ __forceinline__ void tma_store_1d(void *gdst, const void *ssrc, uint3
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------- the step kernel
-// Grid = refill_ctas + ld/256 CTAs of 256 threads.
+// Grid = refill_ctas + ld/RACE_BLOCK CTAs of RACE_BLOCK threads.
 //   CTAs [0, refill_ctas): regenerate the prepared slots consumed in the previous step.
-//   the rest: one thread per env, 256 envs per CTA.  Finished envs are compacted into a
-//   per-CTA list and started on their next episode by the first lanes of the CTA.
-// Observations are staged in shared memory and leave the SM as one 29,696-byte TMA bulk
-// store per CTA (row-major [N,29] rows are 116 B, not a multiple of 16).
+//   the rest: one thread per env.  Warps run independently (no CTA barrier after the
+//   prologue): each warp stages its 32 observation rows in its own shared-memory tile and
+//   ships them as one 3,712-byte TMA bulk store (row-major [N,29] rows are 116 B, not a
+//   multiple of 16, so per-lane vector stores cannot be coalesced).  Lanes whose env
+//   finished adopt the prepared next episode in place.  The last warp of a CTA to finish
+//   flushes the CTA's episode statistics and refill entries (one global atomic each).
 template <bool STRICT>
-__global__ void __launch_bounds__(RACE_BLOCK, 2) race_step_kernel(const __grid_constant__ RaceDev d) {
+__global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(const __grid_constant__ RaceDev d) {
     extern __shared__ __align__(128) float s_obs[]; // [RACE_BLOCK][29]
-    __shared__ int s_nreset;
     __shared__ int s_nrefill;
-    __shared__ unsigned int s_refill_base;
+    __shared__ int s_done;
     __shared__ int s_acc[8];
-    __shared__ unsigned short s_list[RACE_BLOCK];
+    __shared__ uint2 s_entries[RACE_BLOCK];
 
     const int tid = threadIdx.x;
-    const uint32_t epoch = d.ctl->epoch + 1u;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    bool closer = false; // this thread takes the CTA's ticket
 
     if ((int)blockIdx.x < d.refill_ctas) {
         // ---- refill role: slots consumed during step epoch-1
+        const uint32_t epoch = d.ctl->epoch + 1u;
         const unsigned int src = (epoch - 1u) & 1u;
         const unsigned int cnt = d.ctl->refill_count[src];
         const uint2 *list = d.refill + (size_t)src * d.ld;
@@ -374,14 +410,17 @@ __global__ void __launch_bounds__(RACE_BLOCK, 2) race_step_kernel(const __grid_c
             uint2 e = list[k];
             race_fill_slot(d, (int)(e.x & 0x7fffffffu), e.y, (int)(e.x >> 31));
         }
+        __syncthreads();
+        closer = tid == 0;
     } else {
         const int bidx = blockIdx.x - d.refill_ctas;
         const int i = bidx * RACE_BLOCK + tid;
         const bool valid = i < d.n;
         if (tid < 8) s_acc[tid] = 0;
-        if (tid == 8) s_nreset = 0;
-        if (tid == 9) s_nrefill = 0;
+        if (tid == 8) s_nrefill = 0;
+        if (tid == 9) s_done = 0;
         __syncthreads();
+        float *my_row = s_obs + tid * RACE_OBS;
 
         if (valid) {
             const size_t ld = d.ld;
@@ -447,7 +486,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, 2) race_step_kernel(const __grid_c
 
             if (cause < 0) {
                 race_store_state(d, i, s, tick, ring_idx | (par << 30), ep_ret);
-                race_observe<STRICT>(s, p.mrpm, ring, s_obs + tid * RACE_OBS);
+                race_observe<STRICT>(s, p.mrpm, ring, my_row);
             } else {
                 // add_log: R/drone_race.h:61-70 (score == ring_idx at every call site)
                 atomicAdd(&s_acc[ACC_N], 1);
@@ -455,56 +494,66 @@ __global__ void __launch_bounds__(RACE_BLOCK, 2) race_step_kernel(const __grid_c
                 atomicAdd(&s_acc[ACC_LENGTH], tick);
                 atomicAdd(&s_acc[ACC_RINGS], ring_idx);
                 if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
-                s_list[atomicAdd(&s_nreset, 1)] = (unsigned short)(tid | (par << 15));
+                uint2 entry;
+                bool want_refill;
+                race_begin_episode<STRICT>(d, i, par, tick, my_row, &entry, &want_refill);
+                if (want_refill) s_entries[atomicAdd(&s_nrefill, 1)] = entry;
             }
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- compacted auto-reset: lane r of the CTA starts the r-th finished env on its next episode
-        const int nreset = s_nreset;
-        uint2 entry = make_uint2(0u, 0u);
-        bool want_refill = false;
-        int slot = 0;
-        if (tid < nreset) {
-            const int li = s_list[tid] & 0x7fff;
-            race_begin_episode<STRICT>(d, bidx * RACE_BLOCK + li, s_list[tid] >> 15, s_obs + li * RACE_OBS, &entry,
-                                       &want_refill);
-            if (want_refill) slot = atomicAdd(&s_nrefill, 1);
-        }
-        __syncthreads();
-        if (nreset > 0) {
-            if (tid == 0 && s_nrefill > 0) s_refill_base = atomicAdd(&d.ctl->refill_count[epoch & 1u], (unsigned int)s_nrefill);
-            __syncthreads();
-            if (want_refill) d.refill[(size_t)(epoch & 1u) * d.ld + s_refill_base + slot] = entry;
-        }
-
-        // ---- observations out: one TMA bulk store per full CTA tile
-        const int row0 = bidx * RACE_BLOCK;
-        const int rows = min(RACE_BLOCK, d.n - row0);
-        float *gobs = d.obs + (size_t)row0 * RACE_OBS;
-        if (rows == RACE_BLOCK) {
-            if (tid == 0) {
+        // ---- observations out: one TMA bulk store per full warp tile
+        const int row0 = bidx * RACE_BLOCK + warp * 32;
+        const int rows = min(32, d.n - row0);
+        const float *tile = s_obs + warp * 32 * RACE_OBS;
+        const bool bulk = rows == 32;
+        if (bulk) {
+            if (lane == 0) {
                 tma_store_fence();
-                tma_store_1d(gobs, s_obs, RACE_BLOCK * RACE_OBS * sizeof(float));
+                tma_store_1d(d.obs + (size_t)row0 * RACE_OBS, tile, 32 * RACE_OBS * sizeof(float));
             }
-        } else {
-            for (int k = tid; k < rows * RACE_OBS; k += RACE_BLOCK) gobs[k] = s_obs[k];
+        } else if (rows > 0) {
+            float *gobs = d.obs + (size_t)row0 * RACE_OBS;
+            for (int k = lane; k < rows * RACE_OBS; k += 32) gobs[k] = tile[k];
         }
 
-        // ---- episode statistics: CTA partial sums -> device accumulators
-        if (tid < 7 && nreset > 0) {
-            int v = s_acc[tid];
-            if (v != 0) atomicAdd((unsigned long long *)&d.ctl->acc[tid], (unsigned long long)(long long)v);
-            if (tid == ACC_RINGS)
-                atomicAdd((unsigned long long *)&d.ctl->score_step[epoch & 1u], (unsigned long long)(long long)v);
+        // ---- CTA epilogue by whichever warp finishes last
+        int last = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            last = atomicAdd(&s_done, 1) == RACE_BLOCK / 32 - 1;
         }
-        if (tid == 0 && rows == RACE_BLOCK) tma_store_wait_read();
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence_block();
+            const uint32_t epoch = d.ctl->epoch + 1u; // only the CTA's last warp needs the step number
+            if (lane < 7) {
+                int v = s_acc[lane];
+                if (v != 0) {
+                    atomicAdd((unsigned long long *)&d.ctl->acc[lane], (unsigned long long)(long long)v);
+                    if (lane == ACC_RINGS)
+                        atomicAdd((unsigned long long *)&d.ctl->score_step[epoch & 1u], (unsigned long long)(long long)v);
+                }
+            }
+            const int nref = s_nrefill;
+            if (nref > 0) {
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(&d.ctl->refill_count[epoch & 1u], (unsigned int)nref);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                uint2 *list = d.refill + (size_t)(epoch & 1u) * d.ld + base;
+                for (int k = lane; k < nref; k += 32) list[k] = s_entries[k];
+            }
+            __syncwarp();
+            closer = lane == 0;
+        }
+        if (bulk && lane == 0) tma_store_wait_read();
     }
 
-    // ---- every CTA takes a ticket; the last one closes the step
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
+    // ---- every CTA takes a ticket; the last one closes the step.  No device-scope fence is
+    // needed: everything a CTA publishes is consumed by the NEXT launch, and the closing
+    // writes touch only words no CTA of this launch reads after taking its ticket.
+    if (closer) {
+        const uint32_t epoch = d.ctl->epoch + 1u;
         unsigned int t = atomicAdd(&d.ctl->ticket, 1u);
         if (t == gridDim.x - 1) {
             d.ctl->score_step[(epoch + 1u) & 1u] = 0;
@@ -522,23 +571,28 @@ __global__ void __launch_bounds__(128) race_reset_kernel(const __grid_constant__
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
     if (d.reset_mode == 1 /* B2D_RESET_INJECT */) {
-        uint2 e;
-        bool w;
-        race_begin_episode<true>(d, i, 0, d.obs + (size_t)i * RACE_OBS, &e, &w);
+        race_inject_episode<true>(d, i, 0, d.obs + (size_t)i * RACE_OBS);
         return;
     }
-    float p[13], spawn[3], ring0[6], s[17];
-    race_generate_episode(d, i, 0u, 0, p, spawn, ring0);
-#pragma unroll
-    for (int k = 0; k < 17; k++) s[k] = 0.0f;
-    s[6] = 1.0f;
-    s[0] = spawn[0]; s[1] = spawn[1]; s[2] = spawn[2];
-    race_store_params(d, i, p);
-    race_store_state(d, i, s, 0, 0, 0.0f);
-    race_store_current_ring(d, i, ring0);
-    race_observe<true>(s, p[10], ring0, d.obs + (size_t)i * RACE_OBS);
+    race_begin_generated<true>(d, i, 0u, 0, d.obs + (size_t)i * RACE_OBS);
     d.EP[i] = 0u;
     race_fill_slot(d, i, 1u, 1);
+}
+
+// Refill every slot still queued from the last step now (instead of overlapped with the next
+// step) -- used before state is edited from outside (put_state), so that no refill is in flight
+// while the edited env may finish again.
+__global__ void __launch_bounds__(128) race_drain_kernel(const __grid_constant__ RaceDev d) {
+    const unsigned int src = d.ctl->epoch & 1u;
+    const unsigned int cnt = d.ctl->refill_count[src];
+    const uint2 *list = d.refill + (size_t)src * d.ld;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
+        uint2 e = list[k];
+        race_fill_slot(d, (int)(e.x & 0x7fffffffu), e.y, (int)(e.x >> 31));
+    }
+}
+__global__ void race_drain_done_kernel(Ctl *ctl) {
+    if (threadIdx.x == 0) ctl->refill_count[ctl->epoch & 1u] = 0;
 }
 
 __global__ void race_ctl_reset_kernel(Ctl *ctl, unsigned int epoch, int clear_acc) {
