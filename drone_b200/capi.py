@@ -62,6 +62,7 @@ SYMBOLS = {
     "b2d_set_reset_mode": (C.c_int, [_P, C.c_int]),
     "b2d_set_reset_payload": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "b2d_set_step_count": (C.c_int, [_P, C.c_uint32]),
+    "b2d_profile_kernels": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
     "b2d_last_error": (C.c_char_p, []),
     "b2d_version": (C.c_int, []),
 }

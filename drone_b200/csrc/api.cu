@@ -40,6 +40,7 @@ struct b2d_vec {
     int device;
     int num_envs, num_agents /* rows */, obs_dim, blob_floats;
     int math, write_clamped;
+    int step_ctas;
     RaceDev race;
     SwarmDev swarm;
     // device contract buffers (owned unless external)
@@ -59,6 +60,9 @@ struct b2d_vec {
     long long launches;
     cudaStream_t copy_streams[2];
     cudaEvent_t ev_step, ev_copy[2];
+    // optional per-kernel timing (b2d_profile_kernels): event triples of the profiled steps
+    bool profile;
+    std::vector<cudaEvent_t> prof_events;
 };
 
 template <class T> static int dev_alloc(b2d_vec *v, T **p, size_t count) {
@@ -147,28 +151,37 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
     d.key1 = (uint32_t)(cfg->seed >> 32);
     d.env_id_base = cfg->env_id_base;
     d.reset_mode = B2D_RESET_PHILOX;
-    {   // refill CTAs: sized for ~6% of the envs finishing per step, at most one per SM
-        int step_ctas = d.ld / RACE_BLOCK;
-        d.refill_ctas = step_ctas / 16 + 1;
-        if (d.refill_ctas > 2 * 148) d.refill_ctas = 2 * 148;
+    {   // persistent grid: one resident set of step CTAs per SM (or fewer for small N)
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        const int warps_per_cta = RACE_BLOCK / 32;
+        const int ntiles = (cfg->num_envs + 31) / 32;
+        int step_ctas = (ntiles + warps_per_cta - 1) / warps_per_cta;
+        if (step_ctas > sms * RACE_MIN_CTAS) step_ctas = sms * RACE_MIN_CTAS;
+        v->step_ctas = step_ctas;
     }
     const size_t ld = d.ld;
+    d.queue_cap = (((cfg->num_envs + 31) / 32 + QUEUE_ENV_SHARDS - 1) / QUEUE_ENV_SHARDS) * 32;
     if ((rc = setup_buffers(v, ext)) || (rc = dev_alloc(v, &d.S, 5 * ld)) || (rc = dev_alloc(v, &d.P, 3 * ld)) ||
         (rc = dev_alloc(v, &d.PJ, ld)) || (rc = dev_alloc(v, &d.C0, ld)) || (rc = dev_alloc(v, &d.C1, ld)) ||
         (rc = dev_alloc(v, &d.G0, 2 * (size_t)d.max_rings * ld)) || (rc = dev_alloc(v, &d.G1, 2 * (size_t)d.max_rings * ld)) ||
         (rc = dev_alloc(v, &d.N, 3 * ld)) || (rc = dev_alloc(v, &d.NJ, ld)) || (rc = dev_alloc(v, &d.NS, ld)) ||
-        (rc = dev_alloc(v, &d.EP, ld)) || (rc = dev_alloc(v, &d.SLOT_EP, ld)) || (rc = dev_alloc(v, &d.refill, 2 * ld)) ||
+        (rc = dev_alloc(v, &d.EP, ld)) || (rc = dev_alloc(v, &d.SLOT_EP, ld)) || (rc = dev_alloc(v, &d.refill, 2 * (size_t)QUEUE_ENV_SHARDS * d.queue_cap)) ||
         (rc = dev_alloc(v, &d.ctl, 1)) || (rc = finish_create(v))) {
         b2d_vec_close(v);
         return rc;
     }
+    race_ctl_reset_kernel<<<1, 32>>>(d.ctl, 0u, 1, (d.n + 31) / 32);
+    cudaDeviceSynchronize();
     d.obs = v->dev.observations;
     d.act_in = v->dev.actions;
     d.act_out = v->write_clamped ? v->dev.actions : nullptr;
     d.rew = v->dev.rewards;
     d.term = v->dev.terminals;
-    cudaFuncSetAttribute(race_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RACE_BLOCK * RACE_OBS * 4);
-    cudaFuncSetAttribute(race_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RACE_BLOCK * RACE_OBS * 4);
+    cudaFuncSetAttribute(race_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RACE_SMEM_BYTES);
+    cudaFuncSetAttribute(race_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RACE_SMEM_BYTES);
+    cudaFuncSetAttribute(race_step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(race_step_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     *out = v;
     return B2D_OK;
 }
@@ -210,7 +223,7 @@ extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
         d.key0 = (uint32_t)seed;
         d.key1 = (uint32_t)(seed >> 32);
         if (d.reset_mode == B2D_RESET_INJECT && !d.payload) return fail(B2D_ESTATE, "inject mode without a payload");
-        race_ctl_reset_kernel<<<1, 32, 0, st>>>(d.ctl, 0u, 0);
+        race_ctl_reset_kernel<<<1, 32, 0, st>>>(d.ctl, 0u, 0, (d.n + 31) / 32);
         race_reset_kernel<<<(d.n + 127) / 128, 128, 0, st>>>(d);
         v->launches += 2;
         return launch_check("race_reset_kernel");
@@ -223,11 +236,25 @@ static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st) {
     if (v->kind == KIND_RACE) {
         RaceDev d = v->race;
         if (actions) d.act_in = actions;
-        const int grid = d.ld / RACE_BLOCK + d.refill_ctas;
-        const size_t smem = RACE_BLOCK * RACE_OBS * sizeof(float);
-        if (v->math == B2D_MATH_STRICT) race_step_kernel<true><<<grid, RACE_BLOCK, smem, st>>>(d);
-        else race_step_kernel<false><<<grid, RACE_BLOCK, smem, st>>>(d);
-        v->launches += 1;
+        const int grid = v->step_ctas;
+        const size_t smem = RACE_SMEM_BYTES;
+        // sized for ~3% of the envs finishing per step; grid-stride covers the rest
+        cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
+        if (v->profile) {
+            for (int k = 0; k < 3; k++) { cudaEventCreate(&pe[k]); v->prof_events.push_back(pe[k]); }
+            cudaEventRecord(pe[0], st);
+        }
+        const dim3 adopt_ctas((unsigned)(d.n / (128 * 32 * QUEUE_ENV_SHARDS) + 1), QUEUE_ENV_SHARDS);
+        if (v->math == B2D_MATH_STRICT) {
+            race_step_kernel<true><<<grid, RACE_BLOCK, smem, st>>>(d);
+            race_adopt_kernel<true><<<adopt_ctas, 128, 0, st>>>(d);
+        } else {
+            race_step_kernel<false><<<grid, RACE_BLOCK, smem, st>>>(d);
+            if (v->profile) cudaEventRecord(pe[1], st);
+            race_adopt_kernel<false><<<adopt_ctas, 128, 0, st>>>(d);
+            if (v->profile) cudaEventRecord(pe[2], st);
+        }
+        v->launches += 2;
         return launch_check("race_step_kernel");
     }
     swarm_vec_step(v->swarm, actions, v->math, st, &v->launches);
@@ -403,8 +430,8 @@ extern "C" int b2d_put_state(b2d_vec *v, const int *env_ids, int n, const float 
     }
     CUDA_TRY(cudaMemcpy(v->d_blob_tmp, host_blobs, (size_t)n * v->blob_floats * sizeof(float), cudaMemcpyHostToDevice));
     if (v->kind == KIND_RACE) { // no prepared-slot refill may be in flight once states are edited
-        race_drain_kernel<<<148, 128>>>(v->race);
-        race_drain_done_kernel<<<1, 32>>>(v->race.ctl);
+        race_drain_kernel<<<dim3(4, QUEUE_ENV_SHARDS), 128>>>(v->race);
+        race_drain_done_kernel<<<1, 64>>>(v->race.ctl);
         v->launches += 2;
     }
     if (v->kind == KIND_RACE) race_unpack_kernel<<<(n + 127) / 128, 128>>>(v->race, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
@@ -448,6 +475,37 @@ extern "C" int b2d_set_reset_payload(b2d_vec *v, const float *host_payload) {
     CUDA_TRY(cudaMemcpy(v->d_payload, host_payload, bytes, cudaMemcpyHostToDevice));
     if (v->kind == KIND_RACE) v->race.payload = v->d_payload;
     else v->swarm.payload = v->d_payload;
+    return B2D_OK;
+}
+
+// Per-kernel timing of the steps issued while profiling is on.  enable=1 starts recording
+// CUDA events around the step kernel and the adopt kernel of every subsequent step (fast math);
+// enable=0 synchronises, returns the mean durations in microseconds (out_us[0] = step kernel,
+// out_us[1] = adopt kernel, out_us[2] = profiled steps) and stops.  Not capturable.
+extern "C" int b2d_profile_kernels(b2d_vec *v, int enable, float out_us[3]) {
+    if (!v) return fail(B2D_EINVAL, "null handle");
+    if (enable) {
+        v->profile = true;
+        return B2D_OK;
+    }
+    v->profile = false;
+    CUDA_TRY(cudaDeviceSynchronize());
+    double a = 0, b = 0;
+    const size_t n = v->prof_events.size() / 3;
+    for (size_t k = 0; k < n; k++) {
+        float t0 = 0, t1 = 0;
+        cudaEventElapsedTime(&t0, v->prof_events[3 * k], v->prof_events[3 * k + 1]);
+        cudaEventElapsedTime(&t1, v->prof_events[3 * k + 1], v->prof_events[3 * k + 2]);
+        a += t0;
+        b += t1;
+    }
+    for (cudaEvent_t e : v->prof_events) cudaEventDestroy(e);
+    v->prof_events.clear();
+    if (out_us) {
+        out_us[0] = n ? (float)(a / n * 1e3) : 0.0f;
+        out_us[1] = n ? (float)(b / n * 1e3) : 0.0f;
+        out_us[2] = (float)n;
+    }
     return B2D_OK;
 }
 

@@ -33,8 +33,14 @@ namespace b2d {
 #ifndef B2D_RACE_BLOCK
 #define B2D_RACE_BLOCK 128
 #endif
+#ifndef B2D_EXPERIMENT_SKIP_MATH
+#define B2D_EXPERIMENT_SKIP_MATH 0
+#endif
+#ifndef B2D_STATIC_TILES
+#define B2D_STATIC_TILES 0
+#endif
 #ifndef B2D_RACE_MIN_CTAS
-#define B2D_RACE_MIN_CTAS 5
+#define B2D_RACE_MIN_CTAS 4
 #endif
 constexpr int RACE_BLOCK = B2D_RACE_BLOCK;
 constexpr int RACE_MIN_CTAS = B2D_RACE_MIN_CTAS;
@@ -45,13 +51,24 @@ constexpr int RESET_MAX_ATTEMPTS = 16;
 // integer episode-statistics accumulators (all race Log fields are integer valued)
 enum { ACC_N = 0, ACC_RETURN, ACC_LENGTH, ACC_RINGS, ACC_OOB, ACC_COLLISION, ACC_TIMEOUT, ACC_SPARE, ACC_COUNT };
 
+constexpr int QUEUE_TILE_SHARDS = 16;
+constexpr int QUEUE_ENV_SHARDS = 64;
+struct alignas(256) PaddedCounter {
+    unsigned int v;
+    unsigned int pad[63];
+};
+
 struct Ctl {
     unsigned int epoch;  // vec steps completed since the last vec_reset
     unsigned int ticket; // CTAs finished in the running step
-    unsigned int refill_count[2]; // entries in refill list (epoch & 1)
+    unsigned int pad0[2];
     long long acc[ACC_COUNT];
     long long score_step[2]; // sum of score over episodes that ended in step (epoch & 1): R/drone_race.h:160
     double facc[8];          // float-valued sums (swarm)
+    // Hot counters, one per 256-byte line: same-address atomics serialise in L2 at a few ns each,
+    // so 32K claims per launch on ONE word would bound the kernel; sharded they vanish.
+    PaddedCounter tile_next[QUEUE_TILE_SHARDS];       // tile scheduler: next unclaimed tile of each shard
+    PaddedCounter queue_count[2][QUEUE_ENV_SHARDS];   // finished/refill queue (epoch & 1), sharded by tile % shards
 };
 
 struct RaceDev {
@@ -68,7 +85,8 @@ struct RaceDev {
     float4 *NS;
     uint32_t *EP;
     uint32_t *SLOT_EP;
-    uint2 *refill; // [2][ld] (env | target ring buffer << 31, episode number to generate)
+    uint2 *refill; // [2][QUEUE_ENV_SHARDS][queue_cap] (env | ring buffer << 31, tick or episode number)
+    int queue_cap; // entries per queue shard: every env of every tile that maps to the shard
     const float *act_in; // [n][4] actions read this step
     float *act_out;      // [n][4] clamped actions written back, or nullptr
     float *obs;          // [n][29]
@@ -78,7 +96,6 @@ struct RaceDev {
     const float *payload; // [n][33+6R] next-episode blobs (inject mode)
     uint32_t key0, key1, env_id_base;
     int reset_mode; // b2d_reset_mode
-    int refill_ctas; // CTAs at the front of the step grid that refill consumed slots
 };
 
 // ---------------------------------------------------------------- observations
@@ -318,54 +335,81 @@ __device__ __noinline__ void race_inject_episode(const RaceDev &d, int i, int pa
     race_observe<STRICT>(s, b[27], g, obs_row);
 }
 
-// A finished env starts its next episode.  Normal case: ADOPT the prepared slot -- every load
-// it needs is independent (one memory latency), the two ring buffers just swap roles, and the
-// consumed slot is queued for a refill CTA of the next launch.  `tick` is the length of the
-// episode that just ended: an episode of length 1 ended in the launch right after the one
-// that consumed the slot, i.e. the refill may be running concurrently in THIS launch, so the
-// episode is generated in place instead (same pure function of (seed, env, episode number)).
-// The slot's episode tag is still verified, which also covers states edited by put_state.
+// A finished env starts its next episode (race_adopt_kernel, right after the step launch).
+// Normal case: ADOPT the prepared slot -- every load it needs is independent and issued at once
+// (race_adopt_issue), then race_adopt_finish swaps the ring buffers' roles, installs
+// params/spawn/ring 0 and writes the first observation.  The slot was restocked by the refill
+// CTAs of an earlier step launch; its episode tag is verified anyway and a mismatch (possible
+// only if state was edited from outside mid-flight) falls back to generating the episode in
+// place: same pure function of (seed, env, episode number).
+struct AdoptLoads {
+    uint32_t ep, slot_ep;
+    float4 a, b, c, sp, r0;
+    float2 r1;
+    float nj;
+};
+
+__device__ __forceinline__ uint32_t ldcg_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldcg_f32(const float *p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ldcg_f32x2(const float2 *p) {
+    float2 v;
+    asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldcg_f32x4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// volatile asm loads: L2-coherent (.cg; the data may come from another SM's refill in an earlier
+// launch) and pinned here, so the compiler cannot sink them behind the tag comparison
+__device__ __forceinline__ void race_adopt_issue(const RaceDev &d, int i, int par, AdoptLoads &l) {
+    const size_t ld = d.ld;
+    const size_t g = (size_t)(par ^ 1) * d.max_rings * ld + i;
+    l.ep = ldcg_u32(&d.EP[i]);
+    l.slot_ep = ldcg_u32(&d.SLOT_EP[i]);
+    l.a = ldcg_f32x4(&d.N[0 * ld + i]);
+    l.b = ldcg_f32x4(&d.N[1 * ld + i]);
+    l.c = ldcg_f32x4(&d.N[2 * ld + i]);
+    l.nj = ldcg_f32(&d.NJ[i]);
+    l.sp = ldcg_f32x4(&d.NS[i]);
+    l.r0 = ldcg_f32x4(&d.G0[g]);
+    l.r1 = ldcg_f32x2(&d.G1[g]);
+}
+
 template <bool STRICT>
-__device__ __forceinline__ void race_begin_episode(const RaceDev &d, int i, int par, int tick, float *obs_row,
-                                                   uint2 *refill_entry, bool *want_refill) {
-    *want_refill = false;
-    if (d.reset_mode == 1 /* B2D_RESET_INJECT */) {
-        race_inject_episode<STRICT>(d, i, par, obs_row);
-        return;
-    }
+__device__ __forceinline__ uint2 race_adopt_finish(const RaceDev &d, int i, int par, const AdoptLoads &l, float *obs_row) {
     const size_t ld = d.ld;
     const int npar = par ^ 1;
-    const size_t g = (size_t)npar * d.max_rings * ld + i;
-    // all loads of the adoption are independent: issue them together (L2-coherent, they may
-    // have been written by another SM in an earlier launch)
-    const uint32_t ep = __ldcg(&d.EP[i]);
-    const uint32_t slot_ep = __ldcg(&d.SLOT_EP[i]);
-    float4 a = __ldcg(&d.N[0 * ld + i]), b = __ldcg(&d.N[1 * ld + i]), c = __ldcg(&d.N[2 * ld + i]);
-    float nj = __ldcg(&d.NJ[i]);
-    float4 sp = __ldcg(&d.NS[i]);
-    float4 r0 = __ldcg(&d.G0[g]);
-    float2 r1 = __ldcg(&d.G1[g]);
-    const uint32_t want = ep + 1u;
-    if (tick >= 2 && slot_ep == want) {
+    const uint32_t want = l.ep + 1u;
+    if (l.slot_ep == want) {
         float s[17];
 #pragma unroll
         for (int k = 0; k < 17; k++) s[k] = 0.0f;
         s[6] = 1.0f;
-        s[0] = sp.x; s[1] = sp.y; s[2] = sp.z;
-        const float ring0[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
-        d.P[0 * ld + i] = a;
-        d.P[1 * ld + i] = b;
-        d.P[2 * ld + i] = c;
-        d.PJ[i] = nj;
+        s[0] = l.sp.x; s[1] = l.sp.y; s[2] = l.sp.z;
+        const float ring0[6] = {l.r0.x, l.r0.y, l.r0.z, l.r0.w, l.r1.x, l.r1.y};
+        d.P[0 * ld + i] = l.a;
+        d.P[1 * ld + i] = l.b;
+        d.P[2 * ld + i] = l.c;
+        d.PJ[i] = l.nj;
         race_store_state(d, i, s, 0, npar << 30, 0.0f);
         race_store_current_ring(d, i, ring0);
-        race_observe<STRICT>(s, c.z, ring0, obs_row);
+        race_observe<STRICT>(s, l.c.z, ring0, obs_row);
     } else {
         race_begin_generated<STRICT>(d, i, want, npar, obs_row);
     }
     d.EP[i] = want;
-    *want_refill = true;
-    *refill_entry = make_uint2((uint32_t)i | ((uint32_t)par << 31), want + 1u);
+    return make_uint2((uint32_t)i | ((uint32_t)par << 31), want + 1u);
 }
 
 // ---------------------------------------------------------------- TMA bulk store helpers
@@ -378,147 +422,294 @@ __device__ __forceinline__ void tma_store_1d(void *gdst, const void *ssrc, uint3
 }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// ---------------------------------------------------------------- async copy helpers
+__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *sdst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *sdst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// per-warp shared memory: 11 staged float4 per lane (inputs of the NEXT tile, in flight while the
+// current tile computes) + the 32x29 observation tile of the current tile
+constexpr int RACE_STAGE_SLOTS = 11; // act, S0..S4, P0..P2, C0, (j_mot | - | C1.x C1.y)
+constexpr int RACE_WARP_SMEM = RACE_STAGE_SLOTS * 32 * 16 + 32 * RACE_OBS * 4;
+constexpr int RACE_SMEM_BYTES = (RACE_BLOCK / 32) * RACE_WARP_SMEM;
+
+__device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *stage, int lane, int i) {
+    const size_t ld = d.ld;
+    cp_async16(&stage[0 * 32 + lane], reinterpret_cast<const float4 *>(d.act_in) + i);
+#pragma unroll
+    for (int k = 0; k < 5; k++) cp_async16(&stage[(1 + k) * 32 + lane], &d.S[k * ld + i]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) cp_async16(&stage[(6 + k) * 32 + lane], &d.P[k * ld + i]);
+    cp_async16(&stage[9 * 32 + lane], &d.C0[i]);
+    float *tail = reinterpret_cast<float *>(&stage[10 * 32 + lane]);
+    cp_async4(tail, &d.PJ[i]);
+    cp_async8(tail + 2, &d.C1[i]);
+}
+
+// ---------------------------------------------------------------- queues
+__device__ __forceinline__ uint2 *race_queue(const RaceDev &d, unsigned int which, int shard) {
+    return d.refill + ((size_t)which * QUEUE_ENV_SHARDS + shard) * d.queue_cap;
+}
+// tile shard s owns tiles [s*per, min((s+1)*per, ntiles))
+__device__ __forceinline__ int race_tiles_per_shard(int ntiles) { return (ntiles + QUEUE_TILE_SHARDS - 1) / QUEUE_TILE_SHARDS; }
+
+// Blocking claim with stealing (lane 0 only): used once the warp's home shard ran dry.
+__device__ __noinline__ int race_claim_tile_slow(Ctl *ctl, int home, int ntiles) {
+    const int per = race_tiles_per_shard(ntiles);
+    for (int k = 1; k < QUEUE_TILE_SHARDS; k++) {
+        const int s = (home + k) % QUEUE_TILE_SHARDS;
+        const int end = min((s + 1) * per, ntiles);
+        if ((int)*((volatile unsigned int *)&ctl->tile_next[s].v) < end) {
+            const int t = (int)atomicAdd(&ctl->tile_next[s].v, 1u);
+            if (t < end) return t;
+        }
+    }
+    return ntiles;
+}
+
 // ---------------------------------------------------------------- the step kernel
-// Grid = refill_ctas + ld/RACE_BLOCK CTAs of RACE_BLOCK threads.
-//   CTAs [0, refill_ctas): regenerate the prepared slots consumed in the previous step.
-//   the rest: one thread per env.  Warps run independently (no CTA barrier after the
-//   prologue): each warp stages its 32 observation rows in its own shared-memory tile and
-//   ships them as one 3,712-byte TMA bulk store (row-major [N,29] rows are 116 B, not a
-//   multiple of 16, so per-lane vector stores cannot be coalesced).  Lanes whose env
-//   finished adopt the prepared next episode in place.  The last warp of a CTA to finish
-//   flushes the CTA's episode statistics and refill entries (one global atomic each).
+// Persistent grid (one resident set of CTAs per SM), RACE_BLOCK threads each; every warp is
+// independent and never waits on another.
+//   prologue: the first ceil(count/32) warps regenerate the prepared slots consumed in the
+//     previous step (32 slots per warp, every lane busy: Philox + trig, ~3000 dependent
+//     instructions), overlapped with the other warps' stepping.
+//   main loop: warps pull tiles of 32 envs (one env per lane) from a global atomic tile counter,
+//     so late starters simply take fewer tiles.  While a tile computes (~1000 FP32 instructions
+//     per lane) the inputs of the warp's next tile stream into shared memory with cp.async and
+//     the tile after that is being claimed, so HBM / atomic latency is paid once per warp, not
+//     once per tile.  Each warp stages its 32 observation rows in its own shared-memory tile
+//     and ships them as one 3,712-byte TMA bulk store (row-major [N,29] rows are 116 B, not a
+//     multiple of 16, so per-lane vector stores cannot be coalesced).  Lanes whose env finished
+//     book the episode statistics (summed per CTA in shared memory) and queue the env for
+//     race_adopt_kernel (one global atomic per warp-tile that had a finish).
 template <bool STRICT>
 __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(const __grid_constant__ RaceDev d) {
-    extern __shared__ __align__(128) float s_obs[]; // [RACE_BLOCK][29]
-    __shared__ int s_nrefill;
+    extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ int s_done;
     __shared__ int s_acc[8];
-    __shared__ uint2 s_entries[RACE_BLOCK];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     bool closer = false; // this thread takes the CTA's ticket
-
-    if ((int)blockIdx.x < d.refill_ctas) {
-        // ---- refill role: slots consumed during step epoch-1
-        const uint32_t epoch = d.ctl->epoch + 1u;
-        const unsigned int src = (epoch - 1u) & 1u;
-        const unsigned int cnt = d.ctl->refill_count[src];
-        const uint2 *list = d.refill + (size_t)src * d.ld;
-        for (unsigned int k = blockIdx.x * RACE_BLOCK + tid; k < cnt; k += d.refill_ctas * RACE_BLOCK) {
-            uint2 e = list[k];
-            race_fill_slot(d, (int)(e.x & 0x7fffffffu), e.y, (int)(e.x >> 31));
-        }
-        __syncthreads();
-        closer = tid == 0;
-    } else {
-        const int bidx = blockIdx.x - d.refill_ctas;
-        const int i = bidx * RACE_BLOCK + tid;
-        const bool valid = i < d.n;
+    {
         if (tid < 8) s_acc[tid] = 0;
-        if (tid == 8) s_nrefill = 0;
-        if (tid == 9) s_done = 0;
+        if (tid == 8) s_done = 0;
         __syncthreads();
-        float *my_row = s_obs + tid * RACE_OBS;
+        float4 *stage = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM);
+        float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_SLOTS * 32 * 16);
+        float *my_row = tile_obs + lane * RACE_OBS;
+        const int warps_total = gridDim.x * (RACE_BLOCK / 32);
+        const int gw = blockIdx.x * (RACE_BLOCK / 32) + warp;
+        const int ntiles = (d.n + 31) >> 5;
+        const uint32_t epoch = d.ctl->epoch + 1u;
+        bool store_pending = false;
+        unsigned int pend_m = 0u, pend_base = 0u; // finished-env queue entries awaiting their slot
+        bool pend_fin = false;
+        int pend_shard = 0;
+        uint2 pend_entry = make_uint2(0u, 0u);
 
-        if (valid) {
-            const size_t ld = d.ld;
-            float4 a4 = reinterpret_cast<const float4 *>(d.act_in)[i];
-            float4 q0 = d.S[0 * ld + i], q1 = d.S[1 * ld + i], q2 = d.S[2 * ld + i], q3 = d.S[3 * ld + i],
-                   q4 = d.S[4 * ld + i];
-            float4 p0 = d.P[0 * ld + i], p1 = d.P[1 * ld + i], p2 = d.P[2 * ld + i];
-            float pj = d.PJ[i];
-            float4 c0 = d.C0[i];
-            float2 c1 = d.C1[i];
+        // claim the first two tiles from the warp's home shard (the second claim stays in flight)
+        const int home = gw % QUEUE_TILE_SHARDS;
+        const int home_end = min((home + 1) * race_tiles_per_shard(ntiles), ntiles);
+        int tile = 0, next = 0;
+#if B2D_STATIC_TILES
+        tile = gw;
+        next = gw + warps_total;
+#else
+        if (lane == 0) {
+            tile = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
+            next = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
+            if (tile >= home_end) tile = race_claim_tile_slow(d.ctl, home, ntiles);
+        }
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+#endif
+        if (tile < ntiles && tile * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, tile * 32 + lane);
+        cp_async_commit();
 
-            float s[17] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x};
-            int tick = __float_as_int(q4.y) + 1;
-            const int ring_word = __float_as_int(q4.z);
-            int ring_idx = ring_word & 0x3fffffff;
-            const int par = (ring_word >> 30) & 1;
-            float ep_ret = q4.w;
-            DroneParams p = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, pj};
-            float ring[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
-
-            // clamp the action (written back only on request): R/dronelib.h:437
-            float act[4];
-            if constexpr (STRICT) {
-                act[0] = xclamp(xf(a4.x), -1.0f, 1.0f).v; act[1] = xclamp(xf(a4.y), -1.0f, 1.0f).v;
-                act[2] = xclamp(xf(a4.z), -1.0f, 1.0f).v; act[3] = xclamp(xf(a4.w), -1.0f, 1.0f).v;
-            } else {
-                act[0] = fminf(fmaxf(a4.x, -1.0f), 1.0f); act[1] = fminf(fmaxf(a4.y, -1.0f), 1.0f);
-                act[2] = fminf(fmaxf(a4.z, -1.0f), 1.0f); act[3] = fminf(fmaxf(a4.w, -1.0f), 1.0f);
-            }
-            if (d.act_out) reinterpret_cast<float4 *>(d.act_out)[i] = make_float4(act[0], act[1], act[2], act[3]);
-
-            const float before[3] = {s[0], s[1], s[2]};
-            advance_body<STRICT>(s, p, act);
-
-            // ---- episode logic: R/drone_race.h:165-203
-            float reward = 0.0f;
-            int cause = -1; // ACC_OOB / ACC_COLLISION / ACC_TIMEOUT / ACC_SPARE(course complete)
-            const bool oob = s[0] < -10.0f || s[0] > 10.0f || s[1] < -10.0f || s[1] > 10.0f || s[2] < -10.0f || s[2] > 10.0f;
-            if (oob) {
-                reward = -1.0f;
-                ep_ret -= 1.0f;
-                cause = ACC_OOB;
-            } else {
-                float gate;
-                if constexpr (STRICT) gate = gate_event<xf>(before, s, ring, -1.0f);
-                else gate = gate_event<float>(before, s, ring, -1.0f);
-                reward = gate;
-                ep_ret += gate;
-                if (gate > 0.0f) ring_idx += 1;
-                if (gate < 0.0f) {
-                    cause = ACC_COLLISION;
-                } else if (tick == d.max_moves) {
-                    cause = ACC_TIMEOUT;
-                } else if (ring_idx == d.max_rings) {
-                    cause = ACC_SPARE;
-                } else if (gate > 0.0f) {
-                    race_load_ring(d, i, par, ring_idx, ring);
-                    race_store_current_ring(d, i, ring);
+        // ---- prologue: restock the prepared slots consumed during step epoch-1
+        {
+            const unsigned int src = (epoch - 1u) & 1u;
+            const int shard = gw % QUEUE_ENV_SHARDS;
+            const unsigned int cnt = d.ctl->queue_count[src][shard].v;
+            const uint2 *list = race_queue(d, src, shard);
+            const unsigned int stride = (unsigned int)max(warps_total / QUEUE_ENV_SHARDS, 1) * 32u;
+            // with fewer warps than shards a warp walks several shards; the warps beyond a whole
+            // multiple of the shard count would only repeat chunks, so they skip the prologue
+            const bool spare = warps_total >= QUEUE_ENV_SHARDS && gw >= (warps_total / QUEUE_ENV_SHARDS) * QUEUE_ENV_SHARDS;
+            for (int sh = shard; sh < QUEUE_ENV_SHARDS && !spare; sh += warps_total) {
+                const unsigned int c = sh == shard ? cnt : d.ctl->queue_count[src][sh].v;
+                const uint2 *l = sh == shard ? list : race_queue(d, src, sh);
+                for (unsigned int k = (unsigned int)(gw / QUEUE_ENV_SHARDS) * 32u + lane; k < ((c + 31u) & ~31u); k += stride) {
+                    if (k < c) {
+                        uint2 e = l[k];
+                        if (e.y != 0xffffffffu) race_fill_slot(d, (int)(e.x & 0x7fffffffu), e.y, (int)(e.x >> 31));
+                    }
                 }
             }
-            d.rew[i] = reward;
-            d.term[i] = cause >= 0 ? 1 : 0;
+            __syncwarp();
+        }
 
-            if (cause < 0) {
+        while (tile < ntiles) {
+#if !B2D_STATIC_TILES
+            if (lane == 0 && next >= home_end) next = race_claim_tile_slow(d.ctl, home, ntiles);
+            next = __shfl_sync(0xffffffffu, next, 0);
+#endif
+            // entries of the previous tile's finished envs: their queue slot was reserved a whole
+            // tile ago, so the atomic's round trip is off the critical path
+            if (pend_m != 0u) {
+                pend_base = __shfl_sync(0xffffffffu, pend_base, 0);
+                if (pend_fin) race_queue(d, epoch & 1u, pend_shard)[pend_base + __popc(pend_m & ((1u << lane) - 1u))] = pend_entry;
+                pend_m = 0u;
+            }
+            const int i = tile * 32 + lane;
+            const bool valid = i < d.n;
+            cp_async_wait_all();
+            const float4 a4 = stage[0 * 32 + lane];
+            const float4 q0 = stage[1 * 32 + lane], q1 = stage[2 * 32 + lane], q2 = stage[3 * 32 + lane],
+                         q3 = stage[4 * 32 + lane], q4 = stage[5 * 32 + lane];
+            const float4 p0 = stage[6 * 32 + lane], p1 = stage[7 * 32 + lane], p2 = stage[8 * 32 + lane];
+            const float4 c0 = stage[9 * 32 + lane];
+            const float4 tl = stage[10 * 32 + lane]; // (j_mot, -, C1.x, C1.y)
+            // the previous tile's observation store must have read the tile before it is rewritten
+            if (store_pending && lane == 0) tma_store_wait_read();
+            __syncwarp();
+            if (next < ntiles && next * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, next * 32 + lane);
+            cp_async_commit();
+#if B2D_STATIC_TILES
+            const int after = next + warps_total;
+#else
+            int after = 0; // claim the tile after next now, consume the answer at the end of this tile
+            if (lane == 0) after = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
+#endif
+
+            float s[17];
+            float ring[6];
+            float mrpm = 1.0f, ep_ret = 0.0f;
+            int tick = 0, ring_idx = 0, par = 0, cause = -1;
+            if (valid) {
+                s[0] = q0.x; s[1] = q0.y; s[2] = q0.z; s[3] = q0.w; s[4] = q1.x; s[5] = q1.y; s[6] = q1.z; s[7] = q1.w;
+                s[8] = q2.x; s[9] = q2.y; s[10] = q2.z; s[11] = q2.w; s[12] = q3.x; s[13] = q3.y; s[14] = q3.z; s[15] = q3.w;
+                s[16] = q4.x;
+                tick = __float_as_int(q4.y) + 1;
+                const int ring_word = __float_as_int(q4.z);
+                ring_idx = ring_word & 0x3fffffff;
+                par = (ring_word >> 30) & 1;
+                ep_ret = q4.w;
+                DroneParams p = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, tl.x};
+                mrpm = p2.z;
+                ring[0] = c0.x; ring[1] = c0.y; ring[2] = c0.z; ring[3] = c0.w; ring[4] = tl.z; ring[5] = tl.w;
+
+                // clamp the action (written back only on request): R/dronelib.h:437
+                float act[4];
+                if constexpr (STRICT) {
+                    act[0] = xclamp(xf(a4.x), -1.0f, 1.0f).v; act[1] = xclamp(xf(a4.y), -1.0f, 1.0f).v;
+                    act[2] = xclamp(xf(a4.z), -1.0f, 1.0f).v; act[3] = xclamp(xf(a4.w), -1.0f, 1.0f).v;
+                } else {
+                    act[0] = fminf(fmaxf(a4.x, -1.0f), 1.0f); act[1] = fminf(fmaxf(a4.y, -1.0f), 1.0f);
+                    act[2] = fminf(fmaxf(a4.z, -1.0f), 1.0f); act[3] = fminf(fmaxf(a4.w, -1.0f), 1.0f);
+                }
+                if (d.act_out) reinterpret_cast<float4 *>(d.act_out)[i] = make_float4(act[0], act[1], act[2], act[3]);
+
+                const float before[3] = {s[0], s[1], s[2]};
+#if !B2D_EXPERIMENT_SKIP_MATH
+                advance_body<STRICT>(s, p, act);
+#else
+                s[3] += act[0] * p.mass + act[1] * p.ixx + act[2] * p.iyy + act[3] * p.izz + p.arm + p.kt + p.kad + p.kd + p.bd + p.g + p.kmot + p.jmot;
+#endif
+
+                // ---- episode logic: R/drone_race.h:165-203
+                float reward = 0.0f;
+                const bool oob = s[0] < -10.0f || s[0] > 10.0f || s[1] < -10.0f || s[1] > 10.0f || s[2] < -10.0f || s[2] > 10.0f;
+                if (oob) {
+                    reward = -1.0f;
+                    ep_ret -= 1.0f;
+                    cause = ACC_OOB;
+                } else {
+                    float gate;
+                    if constexpr (STRICT) gate = gate_event<xf>(before, s, ring, -1.0f);
+                    else gate = gate_event<float>(before, s, ring, -1.0f);
+                    reward = gate;
+                    ep_ret += gate;
+                    if (gate > 0.0f) ring_idx += 1;
+                    if (gate < 0.0f) {
+                        cause = ACC_COLLISION;
+                    } else if (tick == d.max_moves) {
+                        cause = ACC_TIMEOUT;
+                    } else if (ring_idx == d.max_rings) {
+                        cause = ACC_SPARE; // course complete
+                    } else if (gate > 0.0f) {
+                        race_load_ring(d, i, par, ring_idx, ring);
+                        race_store_current_ring(d, i, ring);
+                    }
+                }
+                d.rew[i] = reward;
+                d.term[i] = cause >= 0 ? 1 : 0;
+            }
+
+            // ---- lanes whose env finished only book the episode and queue the env: the next
+            // episode is installed by race_adopt_kernel right after this launch, so a rare lane
+            // event never stalls a whole warp on dependent loads here
+            const bool finished = cause >= 0;
+            const unsigned int m = __ballot_sync(0xffffffffu, finished);
+            unsigned int base = 0;
+            const int qshard = tile % QUEUE_ENV_SHARDS;
+            if (m != 0u && lane == 0) base = atomicAdd(&d.ctl->queue_count[epoch & 1u][qshard].v, (unsigned int)__popc(m));
+            if (valid && !finished) {
                 race_store_state(d, i, s, tick, ring_idx | (par << 30), ep_ret);
-                race_observe<STRICT>(s, p.mrpm, ring, my_row);
-            } else {
+                race_observe<STRICT>(s, mrpm, ring, my_row);
+            }
+            if (finished) {
                 // add_log: R/drone_race.h:61-70 (score == ring_idx at every call site)
                 atomicAdd(&s_acc[ACC_N], 1);
                 atomicAdd(&s_acc[ACC_RETURN], __float2int_rn(ep_ret));
                 atomicAdd(&s_acc[ACC_LENGTH], tick);
                 atomicAdd(&s_acc[ACC_RINGS], ring_idx);
                 if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
-                uint2 entry;
-                bool want_refill;
-                race_begin_episode<STRICT>(d, i, par, tick, my_row, &entry, &want_refill);
-                if (want_refill) s_entries[atomicAdd(&s_nrefill, 1)] = entry;
             }
-        }
-        __syncwarp();
+            __syncwarp();
 
-        // ---- observations out: one TMA bulk store per full warp tile
-        const int row0 = bidx * RACE_BLOCK + warp * 32;
-        const int rows = min(32, d.n - row0);
-        const float *tile = s_obs + warp * 32 * RACE_OBS;
-        const bool bulk = rows == 32;
-        if (bulk) {
-            if (lane == 0) {
-                tma_store_fence();
-                tma_store_1d(d.obs + (size_t)row0 * RACE_OBS, tile, 32 * RACE_OBS * sizeof(float));
+            // ---- observations out: one TMA bulk store per full warp tile
+            const int rows = min(32, d.n - tile * 32);
+            if (rows == 32) {
+                if (lane == 0) {
+                    tma_store_fence();
+                    tma_store_1d(d.obs + (size_t)tile * 32 * RACE_OBS, tile_obs, 32 * RACE_OBS * sizeof(float));
+                }
+                store_pending = true;
+            } else {
+                float *gobs = d.obs + (size_t)tile * 32 * RACE_OBS;
+                for (int k = lane; k < rows * RACE_OBS; k += 32) gobs[k] = tile_obs[k];
+                __syncwarp();
             }
-        } else if (rows > 0) {
-            float *gobs = d.obs + (size_t)row0 * RACE_OBS;
-            for (int k = lane; k < rows * RACE_OBS; k += 32) gobs[k] = tile[k];
+
+            // ---- queue the finished envs: (env | ring-buffer parity << 31, length of the ended
+            // episode); written at the top of the next iteration
+            pend_m = m;
+            pend_base = base;
+            pend_fin = finished;
+            pend_shard = qshard;
+            pend_entry = make_uint2((uint32_t)i | ((uint32_t)par << 31), (uint32_t)tick);
+            tile = next;
+            next = after;
         }
+        if (pend_m != 0u) {
+            pend_base = __shfl_sync(0xffffffffu, pend_base, 0);
+            if (pend_fin) race_queue(d, epoch & 1u, pend_shard)[pend_base + __popc(pend_m & ((1u << lane) - 1u))] = pend_entry;
+        }
+        if (store_pending && lane == 0) tma_store_wait_read();
 
         // ---- CTA epilogue by whichever warp finishes last
         int last = 0;
+        __syncwarp();
         if (lane == 0) {
             __threadfence_block();
             last = atomicAdd(&s_done, 1) == RACE_BLOCK / 32 - 1;
@@ -526,7 +717,6 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {
             __threadfence_block();
-            const uint32_t epoch = d.ctl->epoch + 1u; // only the CTA's last warp needs the step number
             if (lane < 7) {
                 int v = s_acc[lane];
                 if (v != 0) {
@@ -535,18 +725,9 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
                         atomicAdd((unsigned long long *)&d.ctl->score_step[epoch & 1u], (unsigned long long)(long long)v);
                 }
             }
-            const int nref = s_nrefill;
-            if (nref > 0) {
-                unsigned int base = 0;
-                if (lane == 0) base = atomicAdd(&d.ctl->refill_count[epoch & 1u], (unsigned int)nref);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                uint2 *list = d.refill + (size_t)(epoch & 1u) * d.ld + base;
-                for (int k = lane; k < nref; k += 32) list[k] = s_entries[k];
-            }
             __syncwarp();
             closer = lane == 0;
         }
-        if (bulk && lane == 0) tma_store_wait_read();
     }
 
     // ---- every CTA takes a ticket; the last one closes the step.  No device-scope fence is
@@ -557,10 +738,40 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         unsigned int t = atomicAdd(&d.ctl->ticket, 1u);
         if (t == gridDim.x - 1) {
             d.ctl->score_step[(epoch + 1u) & 1u] = 0;
-            d.ctl->refill_count[(epoch + 1u) & 1u] = 0; // the list this launch consumed; step epoch+1 appends to it
+            // the queue this launch consumed is the one step epoch+1 appends to
+            for (int q = 0; q < QUEUE_ENV_SHARDS; q++) d.ctl->queue_count[(epoch + 1u) & 1u][q].v = 0;
+            const int per = race_tiles_per_shard((d.n + 31) >> 5);
+            for (int q = 0; q < QUEUE_TILE_SHARDS; q++) d.ctl->tile_next[q].v = (unsigned int)(q * per);
             d.ctl->ticket = 0;
             __threadfence();
             d.ctl->epoch = epoch;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- the adopt kernel
+// Runs right after race_step_kernel: one thread per env that finished in that step (compacted,
+// every lane busy).  Installs the next episode (adopt the prepared slot / generate / inject),
+// writes the env's observation row, and rewrites the queue entry in place into the refill
+// request (env | free ring buffer << 31, episode number to prepare) that the refill CTAs of
+// the next step launch consume.
+template <bool STRICT>
+__global__ void __launch_bounds__(128) race_adopt_kernel(const __grid_constant__ RaceDev d) {
+    const unsigned int src = d.ctl->epoch & 1u; // the step kernel has already closed its epoch
+    const unsigned int cnt = d.ctl->queue_count[src][blockIdx.y].v;
+    uint2 *list = race_queue(d, src, blockIdx.y);
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
+        const uint2 e = list[k];
+        const int i = (int)(e.x & 0x7fffffffu);
+        const int par = (int)(e.x >> 31);
+        float *row = d.obs + (size_t)i * RACE_OBS;
+        if (d.reset_mode == 1 /* B2D_RESET_INJECT */) {
+            race_inject_episode<STRICT>(d, i, par, row);
+            list[k] = make_uint2(e.x, 0xffffffffu); // nothing to refill
+        } else {
+            AdoptLoads al;
+            race_adopt_issue(d, i, par, al);
+            list[k] = race_adopt_finish<STRICT>(d, i, par, al, row);
         }
     }
 }
@@ -584,22 +795,23 @@ __global__ void __launch_bounds__(128) race_reset_kernel(const __grid_constant__
 // while the edited env may finish again.
 __global__ void __launch_bounds__(128) race_drain_kernel(const __grid_constant__ RaceDev d) {
     const unsigned int src = d.ctl->epoch & 1u;
-    const unsigned int cnt = d.ctl->refill_count[src];
-    const uint2 *list = d.refill + (size_t)src * d.ld;
+    const unsigned int cnt = d.ctl->queue_count[src][blockIdx.y].v;
+    const uint2 *list = race_queue(d, src, blockIdx.y);
     for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
         uint2 e = list[k];
-        race_fill_slot(d, (int)(e.x & 0x7fffffffu), e.y, (int)(e.x >> 31));
+        if (e.y != 0xffffffffu) race_fill_slot(d, (int)(e.x & 0x7fffffffu), e.y, (int)(e.x >> 31));
     }
 }
 __global__ void race_drain_done_kernel(Ctl *ctl) {
-    if (threadIdx.x == 0) ctl->refill_count[ctl->epoch & 1u] = 0;
+    if (threadIdx.x < QUEUE_ENV_SHARDS) ctl->queue_count[ctl->epoch & 1u][threadIdx.x].v = 0;
 }
 
-__global__ void race_ctl_reset_kernel(Ctl *ctl, unsigned int epoch, int clear_acc) {
+__global__ void race_ctl_reset_kernel(Ctl *ctl, unsigned int epoch, int clear_acc, int ntiles) {
     if (threadIdx.x == 0) {
         ctl->epoch = epoch;
         ctl->ticket = 0;
-        ctl->refill_count[0] = ctl->refill_count[1] = 0;
+        for (int q = 0; q < QUEUE_ENV_SHARDS; q++) ctl->queue_count[0][q].v = ctl->queue_count[1][q].v = 0;
+        for (int q = 0; q < QUEUE_TILE_SHARDS; q++) ctl->tile_next[q].v = (unsigned int)(q * race_tiles_per_shard(ntiles));
         ctl->score_step[0] = ctl->score_step[1] = 0;
         if (clear_acc) {
             for (int k = 0; k < ACC_COUNT; k++) ctl->acc[k] = 0;

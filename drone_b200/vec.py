@@ -112,6 +112,15 @@ class _Vec:
     def step_count(self, v):
         capi.check(capi.lib().b2d_set_step_count(self.h, int(v)))
 
+    def profile_kernels(self, enable):
+        """Start (True) or stop (False) per-kernel CUDA-event timing; stopping returns
+        {'step_us', 'adopt_us', 'steps'} averaged over the steps issued in between."""
+        out = (C.c_float * 3)()
+        capi.check(capi.lib().b2d_profile_kernels(self.h, int(bool(enable)), out))
+        if not enable:
+            return {"step_us": float(out[0]), "adopt_us": float(out[1]), "steps": int(out[2])}
+        return None
+
     @property
     def kernel_launches(self):
         return int(capi.lib().b2d_kernel_launches(self.h))
