@@ -239,22 +239,15 @@ static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st) {
         const int grid = v->step_ctas;
         const size_t smem = RACE_SMEM_BYTES;
         // sized for ~3% of the envs finishing per step; grid-stride covers the rest
-        cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
+        cudaEvent_t pe[2] = {nullptr, nullptr};
         if (v->profile) {
-            for (int k = 0; k < 3; k++) { cudaEventCreate(&pe[k]); v->prof_events.push_back(pe[k]); }
+            for (int k = 0; k < 2; k++) { cudaEventCreate(&pe[k]); v->prof_events.push_back(pe[k]); }
             cudaEventRecord(pe[0], st);
         }
-        const dim3 adopt_ctas((unsigned)(d.n / (128 * 32 * QUEUE_ENV_SHARDS) + 1), QUEUE_ENV_SHARDS);
-        if (v->math == B2D_MATH_STRICT) {
-            race_step_kernel<true><<<grid, RACE_BLOCK, smem, st>>>(d);
-            race_adopt_kernel<true><<<adopt_ctas, 128, 0, st>>>(d);
-        } else {
-            race_step_kernel<false><<<grid, RACE_BLOCK, smem, st>>>(d);
-            if (v->profile) cudaEventRecord(pe[1], st);
-            race_adopt_kernel<false><<<adopt_ctas, 128, 0, st>>>(d);
-            if (v->profile) cudaEventRecord(pe[2], st);
-        }
-        v->launches += 2;
+        if (v->math == B2D_MATH_STRICT) race_step_kernel<true><<<grid, RACE_BLOCK, smem, st>>>(d);
+        else race_step_kernel<false><<<grid, RACE_BLOCK, smem, st>>>(d);
+        if (v->profile) cudaEventRecord(pe[1], st);
+        v->launches += 1;
         return launch_check("race_step_kernel");
     }
     swarm_vec_step(v->swarm, actions, v->math, st, &v->launches);
@@ -491,13 +484,11 @@ extern "C" int b2d_profile_kernels(b2d_vec *v, int enable, float out_us[3]) {
     v->profile = false;
     CUDA_TRY(cudaDeviceSynchronize());
     double a = 0, b = 0;
-    const size_t n = v->prof_events.size() / 3;
+    const size_t n = v->prof_events.size() / 2;
     for (size_t k = 0; k < n; k++) {
-        float t0 = 0, t1 = 0;
-        cudaEventElapsedTime(&t0, v->prof_events[3 * k], v->prof_events[3 * k + 1]);
-        cudaEventElapsedTime(&t1, v->prof_events[3 * k + 1], v->prof_events[3 * k + 2]);
+        float t0 = 0;
+        cudaEventElapsedTime(&t0, v->prof_events[2 * k], v->prof_events[2 * k + 1]);
         a += t0;
-        b += t1;
     }
     for (cudaEvent_t e : v->prof_events) cudaEventDestroy(e);
     v->prof_events.clear();

@@ -36,11 +36,8 @@ namespace b2d {
 #ifndef B2D_EXPERIMENT_SKIP_MATH
 #define B2D_EXPERIMENT_SKIP_MATH 0
 #endif
-#ifndef B2D_STATIC_TILES
-#define B2D_STATIC_TILES 0
-#endif
 #ifndef B2D_RACE_MIN_CTAS
-#define B2D_RACE_MIN_CTAS 4
+#define B2D_RACE_MIN_CTAS 3
 #endif
 constexpr int RACE_BLOCK = B2D_RACE_BLOCK;
 constexpr int RACE_MIN_CTAS = B2D_RACE_MIN_CTAS;
@@ -335,83 +332,6 @@ __device__ __noinline__ void race_inject_episode(const RaceDev &d, int i, int pa
     race_observe<STRICT>(s, b[27], g, obs_row);
 }
 
-// A finished env starts its next episode (race_adopt_kernel, right after the step launch).
-// Normal case: ADOPT the prepared slot -- every load it needs is independent and issued at once
-// (race_adopt_issue), then race_adopt_finish swaps the ring buffers' roles, installs
-// params/spawn/ring 0 and writes the first observation.  The slot was restocked by the refill
-// CTAs of an earlier step launch; its episode tag is verified anyway and a mismatch (possible
-// only if state was edited from outside mid-flight) falls back to generating the episode in
-// place: same pure function of (seed, env, episode number).
-struct AdoptLoads {
-    uint32_t ep, slot_ep;
-    float4 a, b, c, sp, r0;
-    float2 r1;
-    float nj;
-};
-
-__device__ __forceinline__ uint32_t ldcg_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ldcg_f32(const float *p) {
-    float v;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float2 ldcg_f32x2(const float2 *p) {
-    float2 v;
-    asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float4 ldcg_f32x4(const float4 *p) {
-    float4 v;
-    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-
-// volatile asm loads: L2-coherent (.cg; the data may come from another SM's refill in an earlier
-// launch) and pinned here, so the compiler cannot sink them behind the tag comparison
-__device__ __forceinline__ void race_adopt_issue(const RaceDev &d, int i, int par, AdoptLoads &l) {
-    const size_t ld = d.ld;
-    const size_t g = (size_t)(par ^ 1) * d.max_rings * ld + i;
-    l.ep = ldcg_u32(&d.EP[i]);
-    l.slot_ep = ldcg_u32(&d.SLOT_EP[i]);
-    l.a = ldcg_f32x4(&d.N[0 * ld + i]);
-    l.b = ldcg_f32x4(&d.N[1 * ld + i]);
-    l.c = ldcg_f32x4(&d.N[2 * ld + i]);
-    l.nj = ldcg_f32(&d.NJ[i]);
-    l.sp = ldcg_f32x4(&d.NS[i]);
-    l.r0 = ldcg_f32x4(&d.G0[g]);
-    l.r1 = ldcg_f32x2(&d.G1[g]);
-}
-
-template <bool STRICT>
-__device__ __forceinline__ uint2 race_adopt_finish(const RaceDev &d, int i, int par, const AdoptLoads &l, float *obs_row) {
-    const size_t ld = d.ld;
-    const int npar = par ^ 1;
-    const uint32_t want = l.ep + 1u;
-    if (l.slot_ep == want) {
-        float s[17];
-#pragma unroll
-        for (int k = 0; k < 17; k++) s[k] = 0.0f;
-        s[6] = 1.0f;
-        s[0] = l.sp.x; s[1] = l.sp.y; s[2] = l.sp.z;
-        const float ring0[6] = {l.r0.x, l.r0.y, l.r0.z, l.r0.w, l.r1.x, l.r1.y};
-        d.P[0 * ld + i] = l.a;
-        d.P[1 * ld + i] = l.b;
-        d.P[2 * ld + i] = l.c;
-        d.PJ[i] = l.nj;
-        race_store_state(d, i, s, 0, npar << 30, 0.0f);
-        race_store_current_ring(d, i, ring0);
-        race_observe<STRICT>(s, l.c.z, ring0, obs_row);
-    } else {
-        race_begin_generated<STRICT>(d, i, want, npar, obs_row);
-    }
-    d.EP[i] = want;
-    return make_uint2((uint32_t)i | ((uint32_t)par << 31), want + 1u);
-}
-
 // ---------------------------------------------------------------- TMA bulk store helpers
 __device__ __forceinline__ void tma_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_1d(void *gdst, const void *ssrc, uint32_t bytes) {
@@ -433,12 +353,20 @@ __device__ __forceinline__ void cp_async4(void *sdst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// all but the N most recent bulk (TMA) store groups have fully completed (writes performed)
+template <int N> __device__ __forceinline__ void tma_store_wait_done() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
-// per-warp shared memory: 11 staged float4 per lane (inputs of the NEXT tile, in flight while the
-// current tile computes) + the 32x29 observation tile of the current tile
+// per-warp shared memory:
+//   stage  11 float4 per lane: inputs of the NEXT tile, in flight while the current tile computes
+//   obs    the 32x29 observation tile of the current tile (source of the TMA bulk store)
+//   adopt  7 float4 per lane: the prepared episode of a lane whose env just finished, in
+//          flight while the NEXT tile computes
 constexpr int RACE_STAGE_SLOTS = 11; // act, S0..S4, P0..P2, C0, (j_mot | - | C1.x C1.y)
-constexpr int RACE_WARP_SMEM = RACE_STAGE_SLOTS * 32 * 16 + 32 * RACE_OBS * 4;
+constexpr int RACE_ADOPT_SLOTS = 7;  // N0..N2, spawn, ring0 (pos,n.x), (n.y n.z j_mot -), (EP SLOT_EP - -)
+constexpr int RACE_STAGE_BYTES = RACE_STAGE_SLOTS * 32 * 16;
+constexpr int RACE_TILE_BYTES = 32 * RACE_OBS * 4;
+constexpr int RACE_WARP_SMEM = RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_SLOTS * 32 * 16;
 constexpr int RACE_SMEM_BYTES = (RACE_BLOCK / 32) * RACE_WARP_SMEM;
 
 __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *stage, int lane, int i) {
@@ -452,6 +380,58 @@ __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *sta
     float *tail = reinterpret_cast<float *>(&stage[10 * 32 + lane]);
     cp_async4(tail, &d.PJ[i]);
     cp_async8(tail + 2, &d.C1[i]);
+}
+
+// the prepared episode of env i (ring buffer par^1 holds its rings) -> this lane's adopt slots
+__device__ __forceinline__ void race_prefetch_slot(const RaceDev &d, float4 *adopt, int lane, int i, int par) {
+    const size_t ld = d.ld;
+    const size_t g = (size_t)(par ^ 1) * d.max_rings * ld + i;
+#pragma unroll
+    for (int k = 0; k < 3; k++) cp_async16(&adopt[k * 32 + lane], &d.N[k * ld + i]);
+    cp_async16(&adopt[3 * 32 + lane], &d.NS[i]);
+    cp_async16(&adopt[4 * 32 + lane], &d.G0[g]);
+    float *t5 = reinterpret_cast<float *>(&adopt[5 * 32 + lane]);
+    cp_async8(t5, &d.G1[g]);
+    cp_async4(t5 + 2, &d.NJ[i]);
+    uint32_t *t6 = reinterpret_cast<uint32_t *>(&adopt[6 * 32 + lane]);
+    cp_async4(t6, &d.EP[i]);
+    cp_async4(t6 + 1, &d.SLOT_EP[i]);
+}
+
+// A finished env starts its next episode: ADOPT the prepared slot (already copied into this
+// lane's adopt slots): the two ring buffers swap roles, params / spawn / ring 0 are installed,
+// the first observation row is written, and the consumed slot is described for the refill
+// pass of the next launch.  The slot was restocked by an earlier launch; its episode tag is
+// verified anyway and a mismatch (possible only if state was edited from outside mid-flight)
+// falls back to generating the episode in place: same function of (seed, env, episode number).
+template <bool STRICT>
+__device__ __forceinline__ uint2 race_adopt_from_smem(const RaceDev &d, const float4 *adopt, int lane, int i, int par,
+                                                      float *obs_row) {
+    const size_t ld = d.ld;
+    const int npar = par ^ 1;
+    const float4 a = adopt[0 * 32 + lane], b = adopt[1 * 32 + lane], c = adopt[2 * 32 + lane];
+    const float4 sp = adopt[3 * 32 + lane], r0 = adopt[4 * 32 + lane], t5 = adopt[5 * 32 + lane];
+    const uint4 t6 = reinterpret_cast<const uint4 *>(adopt)[6 * 32 + lane];
+    const uint32_t want = t6.x + 1u;
+    if (t6.y == want) {
+        float s[17];
+#pragma unroll
+        for (int k = 0; k < 17; k++) s[k] = 0.0f;
+        s[6] = 1.0f;
+        s[0] = sp.x; s[1] = sp.y; s[2] = sp.z;
+        const float ring0[6] = {r0.x, r0.y, r0.z, r0.w, t5.x, t5.y};
+        d.P[0 * ld + i] = a;
+        d.P[1 * ld + i] = b;
+        d.P[2 * ld + i] = c;
+        d.PJ[i] = t5.z;
+        race_store_state(d, i, s, 0, npar << 30, 0.0f);
+        race_store_current_ring(d, i, ring0);
+        race_observe<STRICT>(s, c.z, ring0, obs_row);
+    } else {
+        race_begin_generated<STRICT>(d, i, want, npar, obs_row);
+    }
+    d.EP[i] = want;
+    return make_uint2((uint32_t)i | ((uint32_t)par << 31), want + 1u);
 }
 
 // ---------------------------------------------------------------- queues
@@ -476,20 +456,23 @@ __device__ __noinline__ int race_claim_tile_slow(Ctl *ctl, int home, int ntiles)
 }
 
 // ---------------------------------------------------------------- the step kernel
-// Persistent grid (one resident set of CTAs per SM), RACE_BLOCK threads each; every warp is
-// independent and never waits on another.
-//   prologue: the first ceil(count/32) warps regenerate the prepared slots consumed in the
-//     previous step (32 slots per warp, every lane busy: Philox + trig, ~3000 dependent
-//     instructions), overlapped with the other warps' stepping.
-//   main loop: warps pull tiles of 32 envs (one env per lane) from a global atomic tile counter,
-//     so late starters simply take fewer tiles.  While a tile computes (~1000 FP32 instructions
-//     per lane) the inputs of the warp's next tile stream into shared memory with cp.async and
-//     the tile after that is being claimed, so HBM / atomic latency is paid once per warp, not
-//     once per tile.  Each warp stages its 32 observation rows in its own shared-memory tile
-//     and ships them as one 3,712-byte TMA bulk store (row-major [N,29] rows are 116 B, not a
-//     multiple of 16, so per-lane vector stores cannot be coalesced).  Lanes whose env finished
-//     book the episode statistics (summed per CTA in shared memory) and queue the env for
-//     race_adopt_kernel (one global atomic per warp-tile that had a finish).
+// ONE launch per vec_step.  Persistent grid (one resident set of CTAs per SM), RACE_BLOCK
+// threads each; every warp is independent and never waits on another.
+//   prologue: the first warps regenerate the prepared slots consumed in the previous step (32
+//     slots per warp, every lane busy: Philox + trig, ~3000 dependent instructions),
+//     overlapped with the other warps' stepping.
+//   main loop: warps pull tiles of 32 envs (one env per lane) from sharded atomic tile
+//     counters, so late starters simply take fewer tiles.  Everything with memory latency is
+//     software-pipelined one tile deep and costs no registers:
+//       * the inputs of the warp's next tile stream into shared memory with cp.async while
+//         the current tile computes (~1000 FP32 instructions per lane);
+//       * the tile after that is being claimed (atomic in flight);
+//       * a lane whose env finished streams the env's prepared next episode into shared
+//         memory and installs it one tile later (no dependent-load stall, no second kernel).
+//     Each warp stages its 32 observation rows in its own shared-memory tile and ships them
+//     as one 3,712-byte TMA bulk store (row-major [N,29] rows are 116 B, not a multiple of 16,
+//     so per-lane vector stores cannot be coalesced).  Episode statistics are summed per CTA
+//     in shared memory and flushed by whichever warp of the CTA finishes last.
 template <bool STRICT>
 __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(const __grid_constant__ RaceDev d) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -499,190 +482,177 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    bool closer = false; // this thread takes the CTA's ticket
+    if (tid < 8) s_acc[tid] = 0;
+    if (tid == 8) s_done = 0;
+    __syncthreads();
+    float4 *stage = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM);
+    float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES);
+    float4 *adopt = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES + RACE_TILE_BYTES);
+    float *my_row = tile_obs + lane * RACE_OBS;
+    const int warps_total = gridDim.x * (RACE_BLOCK / 32);
+    const int gw = blockIdx.x * (RACE_BLOCK / 32) + warp;
+    const int ntiles = (d.n + 31) >> 5;
+    const uint32_t epoch = d.ctl->epoch + 1u;
+    const bool inject = d.reset_mode == 1; // B2D_RESET_INJECT (parity hook)
+
+    // claim the first tiles from the warp's home shard; two further claims stay in flight so a
+    // claim's round trip to L2 has two whole tiles to complete
+    const unsigned int src = (epoch - 1u) & 1u;
+    const int home = gw % QUEUE_TILE_SHARDS;
+    const int home_end = min((home + 1) * race_tiles_per_shard(ntiles), ntiles);
+    int tile = 0, next = 0, claim_a = 0, claim_b = 0; // raw claims (lane 0); resolved when they become `next`
+    if (lane == 0) {
+        tile = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
+        next = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
+        claim_a = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
+        if (tile >= home_end) tile = race_claim_tile_slow(d.ctl, home, ntiles);
+    }
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile < ntiles && tile * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, tile * 32 + lane);
+    cp_async_commit(); // group: inputs of the first tile
+    cp_async_commit(); // group: (empty) adoption loads "of the tile before the first"
+
+    // ---- prologue: restock the prepared slots consumed during step epoch-1
     {
-        if (tid < 8) s_acc[tid] = 0;
-        if (tid == 8) s_done = 0;
-        __syncthreads();
-        float4 *stage = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM);
-        float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_SLOTS * 32 * 16);
-        float *my_row = tile_obs + lane * RACE_OBS;
-        const int warps_total = gridDim.x * (RACE_BLOCK / 32);
-        const int gw = blockIdx.x * (RACE_BLOCK / 32) + warp;
-        const int ntiles = (d.n + 31) >> 5;
-        const uint32_t epoch = d.ctl->epoch + 1u;
-        bool store_pending = false;
-        unsigned int pend_m = 0u, pend_base = 0u; // finished-env queue entries awaiting their slot
-        bool pend_fin = false;
-        int pend_shard = 0;
-        uint2 pend_entry = make_uint2(0u, 0u);
-
-        // claim the first two tiles from the warp's home shard (the second claim stays in flight)
-        const int home = gw % QUEUE_TILE_SHARDS;
-        const int home_end = min((home + 1) * race_tiles_per_shard(ntiles), ntiles);
-        int tile = 0, next = 0;
-#if B2D_STATIC_TILES
-        tile = gw;
-        next = gw + warps_total;
-#else
-        if (lane == 0) {
-            tile = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
-            next = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
-            if (tile >= home_end) tile = race_claim_tile_slow(d.ctl, home, ntiles);
-        }
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-#endif
-        if (tile < ntiles && tile * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, tile * 32 + lane);
-        cp_async_commit();
-
-        // ---- prologue: restock the prepared slots consumed during step epoch-1
-        {
-            const unsigned int src = (epoch - 1u) & 1u;
-            const int shard = gw % QUEUE_ENV_SHARDS;
-            const unsigned int cnt = d.ctl->queue_count[src][shard].v;
-            const uint2 *list = race_queue(d, src, shard);
-            const unsigned int stride = (unsigned int)max(warps_total / QUEUE_ENV_SHARDS, 1) * 32u;
-            // with fewer warps than shards a warp walks several shards; the warps beyond a whole
-            // multiple of the shard count would only repeat chunks, so they skip the prologue
-            const bool spare = warps_total >= QUEUE_ENV_SHARDS && gw >= (warps_total / QUEUE_ENV_SHARDS) * QUEUE_ENV_SHARDS;
-            for (int sh = shard; sh < QUEUE_ENV_SHARDS && !spare; sh += warps_total) {
-                const unsigned int c = sh == shard ? cnt : d.ctl->queue_count[src][sh].v;
-                const uint2 *l = sh == shard ? list : race_queue(d, src, sh);
-                for (unsigned int k = (unsigned int)(gw / QUEUE_ENV_SHARDS) * 32u + lane; k < ((c + 31u) & ~31u); k += stride) {
-                    if (k < c) {
-                        uint2 e = l[k];
-                        if (e.y != 0xffffffffu) race_fill_slot(d, (int)(e.x & 0x7fffffffu), e.y, (int)(e.x >> 31));
-                    }
+        const unsigned int stride = (unsigned int)max(warps_total / QUEUE_ENV_SHARDS, 1) * 32u;
+        // with fewer warps than shards a warp walks several shards; the warps beyond a whole
+        // multiple of the shard count would only repeat chunks, so they skip the prologue
+        const bool spare = warps_total >= QUEUE_ENV_SHARDS && gw >= (warps_total / QUEUE_ENV_SHARDS) * QUEUE_ENV_SHARDS;
+        for (int sh = gw % QUEUE_ENV_SHARDS; sh < QUEUE_ENV_SHARDS && !spare; sh += warps_total) {
+            const unsigned int c = d.ctl->queue_count[src][sh].v;
+            const uint2 *l = race_queue(d, src, sh);
+            for (unsigned int k = (unsigned int)(gw / QUEUE_ENV_SHARDS) * 32u + lane; k < ((c + 31u) & ~31u); k += stride) {
+                if (k < c) {
+                    uint2 e = l[k];
+                    race_fill_slot(d, (int)(e.x & 0x7fffffffu), e.y, (int)(e.x >> 31));
                 }
             }
-            __syncwarp();
         }
+        __syncwarp();
+    }
 
-        while (tile < ntiles) {
-#if !B2D_STATIC_TILES
+    // state carried from one tile to the next
+    bool store_pending = false;      // a TMA store of this warp's observation tile is in flight
+    bool pend_adopt = false;         // this lane's env finished in the previous tile (Philox mode)
+    int pend_i = 0, pend_par = 0;
+    unsigned int pend_m = 0u, pend_base = 0u; // ballot of pend_adopt, refill-queue slot reserved for them
+    int pend_shard = 0;
+
+    while (true) {
+        const bool have_tile = tile < ntiles;
+        if (!have_tile && pend_m == 0u) break;
+        if (have_tile) {
             if (lane == 0 && next >= home_end) next = race_claim_tile_slow(d.ctl, home, ntiles);
             next = __shfl_sync(0xffffffffu, next, 0);
-#endif
-            // entries of the previous tile's finished envs: their queue slot was reserved a whole
-            // tile ago, so the atomic's round trip is off the critical path
-            if (pend_m != 0u) {
-                pend_base = __shfl_sync(0xffffffffu, pend_base, 0);
-                if (pend_fin) race_queue(d, epoch & 1u, pend_shard)[pend_base + __popc(pend_m & ((1u << lane) - 1u))] = pend_entry;
-                pend_m = 0u;
+        }
+        const int i = tile * 32 + lane;
+        const bool valid = have_tile && i < d.n;
+        cp_async_wait<1>(); // this tile's inputs have landed (the newest group, adoption loads, may still fly)
+        const float4 a4 = stage[0 * 32 + lane];
+        const float4 q0 = stage[1 * 32 + lane], q1 = stage[2 * 32 + lane], q2 = stage[3 * 32 + lane],
+                     q3 = stage[4 * 32 + lane], q4 = stage[5 * 32 + lane];
+        const float4 p0 = stage[6 * 32 + lane], p1 = stage[7 * 32 + lane], p2 = stage[8 * 32 + lane];
+        const float4 c0 = stage[9 * 32 + lane];
+        const float4 tl = stage[10 * 32 + lane]; // (j_mot, -, C1.x, C1.y)
+        // the previous tile's observation store must have read the tile before it is rewritten
+        if (store_pending && lane == 0) tma_store_wait_read();
+        __syncwarp();
+        if (have_tile && next < ntiles && next * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, next * 32 + lane);
+        cp_async_commit(); // group: inputs of the next tile
+        if (have_tile && lane == 0) claim_b = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
+
+        float s[17];
+        float ring[6];
+        float mrpm = 1.0f, ep_ret = 0.0f;
+        int tick = 0, ring_idx = 0, par = 0, cause = -1;
+        if (valid) {
+            s[0] = q0.x; s[1] = q0.y; s[2] = q0.z; s[3] = q0.w; s[4] = q1.x; s[5] = q1.y; s[6] = q1.z; s[7] = q1.w;
+            s[8] = q2.x; s[9] = q2.y; s[10] = q2.z; s[11] = q2.w; s[12] = q3.x; s[13] = q3.y; s[14] = q3.z; s[15] = q3.w;
+            s[16] = q4.x;
+            tick = __float_as_int(q4.y) + 1;
+            const int ring_word = __float_as_int(q4.z);
+            ring_idx = ring_word & 0x3fffffff;
+            par = (ring_word >> 30) & 1;
+            ep_ret = q4.w;
+            DroneParams p = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, tl.x};
+            mrpm = p2.z;
+            ring[0] = c0.x; ring[1] = c0.y; ring[2] = c0.z; ring[3] = c0.w; ring[4] = tl.z; ring[5] = tl.w;
+
+            // clamp the action (written back only on request): R/dronelib.h:437
+            float act[4];
+            if constexpr (STRICT) {
+                act[0] = xclamp(xf(a4.x), -1.0f, 1.0f).v; act[1] = xclamp(xf(a4.y), -1.0f, 1.0f).v;
+                act[2] = xclamp(xf(a4.z), -1.0f, 1.0f).v; act[3] = xclamp(xf(a4.w), -1.0f, 1.0f).v;
+            } else {
+                act[0] = fminf(fmaxf(a4.x, -1.0f), 1.0f); act[1] = fminf(fmaxf(a4.y, -1.0f), 1.0f);
+                act[2] = fminf(fmaxf(a4.z, -1.0f), 1.0f); act[3] = fminf(fmaxf(a4.w, -1.0f), 1.0f);
             }
-            const int i = tile * 32 + lane;
-            const bool valid = i < d.n;
-            cp_async_wait_all();
-            const float4 a4 = stage[0 * 32 + lane];
-            const float4 q0 = stage[1 * 32 + lane], q1 = stage[2 * 32 + lane], q2 = stage[3 * 32 + lane],
-                         q3 = stage[4 * 32 + lane], q4 = stage[5 * 32 + lane];
-            const float4 p0 = stage[6 * 32 + lane], p1 = stage[7 * 32 + lane], p2 = stage[8 * 32 + lane];
-            const float4 c0 = stage[9 * 32 + lane];
-            const float4 tl = stage[10 * 32 + lane]; // (j_mot, -, C1.x, C1.y)
-            // the previous tile's observation store must have read the tile before it is rewritten
-            if (store_pending && lane == 0) tma_store_wait_read();
-            __syncwarp();
-            if (next < ntiles && next * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, next * 32 + lane);
-            cp_async_commit();
-#if B2D_STATIC_TILES
-            const int after = next + warps_total;
-#else
-            int after = 0; // claim the tile after next now, consume the answer at the end of this tile
-            if (lane == 0) after = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
-#endif
+            if (d.act_out) reinterpret_cast<float4 *>(d.act_out)[i] = make_float4(act[0], act[1], act[2], act[3]);
 
-            float s[17];
-            float ring[6];
-            float mrpm = 1.0f, ep_ret = 0.0f;
-            int tick = 0, ring_idx = 0, par = 0, cause = -1;
-            if (valid) {
-                s[0] = q0.x; s[1] = q0.y; s[2] = q0.z; s[3] = q0.w; s[4] = q1.x; s[5] = q1.y; s[6] = q1.z; s[7] = q1.w;
-                s[8] = q2.x; s[9] = q2.y; s[10] = q2.z; s[11] = q2.w; s[12] = q3.x; s[13] = q3.y; s[14] = q3.z; s[15] = q3.w;
-                s[16] = q4.x;
-                tick = __float_as_int(q4.y) + 1;
-                const int ring_word = __float_as_int(q4.z);
-                ring_idx = ring_word & 0x3fffffff;
-                par = (ring_word >> 30) & 1;
-                ep_ret = q4.w;
-                DroneParams p = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, tl.x};
-                mrpm = p2.z;
-                ring[0] = c0.x; ring[1] = c0.y; ring[2] = c0.z; ring[3] = c0.w; ring[4] = tl.z; ring[5] = tl.w;
+            const float before[3] = {s[0], s[1], s[2]};
+            advance_body<STRICT>(s, p, act);
 
-                // clamp the action (written back only on request): R/dronelib.h:437
-                float act[4];
-                if constexpr (STRICT) {
-                    act[0] = xclamp(xf(a4.x), -1.0f, 1.0f).v; act[1] = xclamp(xf(a4.y), -1.0f, 1.0f).v;
-                    act[2] = xclamp(xf(a4.z), -1.0f, 1.0f).v; act[3] = xclamp(xf(a4.w), -1.0f, 1.0f).v;
-                } else {
-                    act[0] = fminf(fmaxf(a4.x, -1.0f), 1.0f); act[1] = fminf(fmaxf(a4.y, -1.0f), 1.0f);
-                    act[2] = fminf(fmaxf(a4.z, -1.0f), 1.0f); act[3] = fminf(fmaxf(a4.w, -1.0f), 1.0f);
+            // ---- episode logic: R/drone_race.h:165-203
+            float reward = 0.0f;
+            const bool oob = s[0] < -10.0f || s[0] > 10.0f || s[1] < -10.0f || s[1] > 10.0f || s[2] < -10.0f || s[2] > 10.0f;
+            if (oob) {
+                reward = -1.0f;
+                ep_ret -= 1.0f;
+                cause = ACC_OOB;
+            } else {
+                float gate;
+                if constexpr (STRICT) gate = gate_event<xf>(before, s, ring, -1.0f);
+                else gate = gate_event<float>(before, s, ring, -1.0f);
+                reward = gate;
+                ep_ret += gate;
+                if (gate > 0.0f) ring_idx += 1;
+                if (gate < 0.0f) {
+                    cause = ACC_COLLISION;
+                } else if (tick == d.max_moves) {
+                    cause = ACC_TIMEOUT;
+                } else if (ring_idx == d.max_rings) {
+                    cause = ACC_SPARE; // course complete
+                } else if (gate > 0.0f) {
+                    race_load_ring(d, i, par, ring_idx, ring);
+                    race_store_current_ring(d, i, ring);
                 }
-                if (d.act_out) reinterpret_cast<float4 *>(d.act_out)[i] = make_float4(act[0], act[1], act[2], act[3]);
-
-                const float before[3] = {s[0], s[1], s[2]};
-#if !B2D_EXPERIMENT_SKIP_MATH
-                advance_body<STRICT>(s, p, act);
-#else
-                s[3] += act[0] * p.mass + act[1] * p.ixx + act[2] * p.iyy + act[3] * p.izz + p.arm + p.kt + p.kad + p.kd + p.bd + p.g + p.kmot + p.jmot;
-#endif
-
-                // ---- episode logic: R/drone_race.h:165-203
-                float reward = 0.0f;
-                const bool oob = s[0] < -10.0f || s[0] > 10.0f || s[1] < -10.0f || s[1] > 10.0f || s[2] < -10.0f || s[2] > 10.0f;
-                if (oob) {
-                    reward = -1.0f;
-                    ep_ret -= 1.0f;
-                    cause = ACC_OOB;
-                } else {
-                    float gate;
-                    if constexpr (STRICT) gate = gate_event<xf>(before, s, ring, -1.0f);
-                    else gate = gate_event<float>(before, s, ring, -1.0f);
-                    reward = gate;
-                    ep_ret += gate;
-                    if (gate > 0.0f) ring_idx += 1;
-                    if (gate < 0.0f) {
-                        cause = ACC_COLLISION;
-                    } else if (tick == d.max_moves) {
-                        cause = ACC_TIMEOUT;
-                    } else if (ring_idx == d.max_rings) {
-                        cause = ACC_SPARE; // course complete
-                    } else if (gate > 0.0f) {
-                        race_load_ring(d, i, par, ring_idx, ring);
-                        race_store_current_ring(d, i, ring);
-                    }
-                }
-                d.rew[i] = reward;
-                d.term[i] = cause >= 0 ? 1 : 0;
             }
+            d.rew[i] = reward;
+            d.term[i] = cause >= 0 ? 1 : 0;
+        }
 
-            // ---- lanes whose env finished only book the episode and queue the env: the next
-            // episode is installed by race_adopt_kernel right after this launch, so a rare lane
-            // event never stalls a whole warp on dependent loads here
-            const bool finished = cause >= 0;
-            const unsigned int m = __ballot_sync(0xffffffffu, finished);
-            unsigned int base = 0;
-            const int qshard = tile % QUEUE_ENV_SHARDS;
-            if (m != 0u && lane == 0) base = atomicAdd(&d.ctl->queue_count[epoch & 1u][qshard].v, (unsigned int)__popc(m));
-            if (valid && !finished) {
-                race_store_state(d, i, s, tick, ring_idx | (par << 30), ep_ret);
-                race_observe<STRICT>(s, mrpm, ring, my_row);
-            }
-            if (finished) {
-                // add_log: R/drone_race.h:61-70 (score == ring_idx at every call site)
-                atomicAdd(&s_acc[ACC_N], 1);
-                atomicAdd(&s_acc[ACC_RETURN], __float2int_rn(ep_ret));
-                atomicAdd(&s_acc[ACC_LENGTH], tick);
-                atomicAdd(&s_acc[ACC_RINGS], ring_idx);
-                if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
-            }
-            __syncwarp();
+        // ---- finished lanes book the episode; their next episode is installed one tile later
+        const bool finished = cause >= 0;
+        const bool adopt_now = finished && !inject;
+        const unsigned int m = __ballot_sync(0xffffffffu, adopt_now);
+        const int qshard = tile % QUEUE_ENV_SHARDS;
+        unsigned int base = 0;
+        if (m != 0u && lane == 0) base = atomicAdd(&d.ctl->queue_count[epoch & 1u][qshard].v, (unsigned int)__popc(m));
+        if (valid && !finished) {
+            race_store_state(d, i, s, tick, ring_idx | (par << 30), ep_ret);
+            race_observe<STRICT>(s, mrpm, ring, my_row);
+        }
+        if (finished) {
+            // add_log: R/drone_race.h:61-70 (score == ring_idx at every call site)
+            atomicAdd(&s_acc[ACC_N], 1);
+            atomicAdd(&s_acc[ACC_RETURN], __float2int_rn(ep_ret));
+            atomicAdd(&s_acc[ACC_LENGTH], tick);
+            atomicAdd(&s_acc[ACC_RINGS], ring_idx);
+            if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
+            if (inject) race_inject_episode<STRICT>(d, i, par, my_row);
+        }
+        __syncwarp();
 
-            // ---- observations out: one TMA bulk store per full warp tile
+        // ---- observations out: one TMA bulk store per full warp tile (rows of lanes that
+        // finished hold stale data here; they are rewritten when the episode is installed)
+        bool stored_now = false;
+        if (have_tile) {
             const int rows = min(32, d.n - tile * 32);
             if (rows == 32) {
+                stored_now = true;
                 if (lane == 0) {
                     tma_store_fence();
-                    tma_store_1d(d.obs + (size_t)tile * 32 * RACE_OBS, tile_obs, 32 * RACE_OBS * sizeof(float));
+                    tma_store_1d(d.obs + (size_t)tile * 32 * RACE_OBS, tile_obs, RACE_TILE_BYTES);
                 }
                 store_pending = true;
             } else {
@@ -690,88 +660,76 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
                 for (int k = lane; k < rows * RACE_OBS; k += 32) gobs[k] = tile_obs[k];
                 __syncwarp();
             }
-
-            // ---- queue the finished envs: (env | ring-buffer parity << 31, length of the ended
-            // episode); written at the top of the next iteration
-            pend_m = m;
-            pend_base = base;
-            pend_fin = finished;
-            pend_shard = qshard;
-            pend_entry = make_uint2((uint32_t)i | ((uint32_t)par << 31), (uint32_t)tick);
-            tile = next;
-            next = after;
         }
+
+        // ---- install the next episode of the envs that finished in the PREVIOUS tile
+        cp_async_wait<1>(); // their prepared slots have landed (only the next tile's inputs may still fly)
         if (pend_m != 0u) {
             pend_base = __shfl_sync(0xffffffffu, pend_base, 0);
-            if (pend_fin) race_queue(d, epoch & 1u, pend_shard)[pend_base + __popc(pend_m & ((1u << lane) - 1u))] = pend_entry;
-        }
-        if (store_pending && lane == 0) tma_store_wait_read();
-
-        // ---- CTA epilogue by whichever warp finishes last
-        int last = 0;
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            last = atomicAdd(&s_done, 1) == RACE_BLOCK / 32 - 1;
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-            __threadfence_block();
-            if (lane < 7) {
-                int v = s_acc[lane];
-                if (v != 0) {
-                    atomicAdd((unsigned long long *)&d.ctl->acc[lane], (unsigned long long)(long long)v);
-                    if (lane == ACC_RINGS)
-                        atomicAdd((unsigned long long *)&d.ctl->score_step[epoch & 1u], (unsigned long long)(long long)v);
-                }
+            // their stale rows went out with the previous tile's bulk store: it must be complete
+            if (lane == 0) {
+                if (stored_now) tma_store_wait_done<1>(); // all but the store issued a moment ago
+                else tma_store_wait_done<0>();
             }
             __syncwarp();
-            closer = lane == 0;
+            if (pend_adopt) {
+                const uint2 e = race_adopt_from_smem<STRICT>(d, adopt, lane, pend_i, pend_par, d.obs + (size_t)pend_i * RACE_OBS);
+                race_queue(d, epoch & 1u, pend_shard)[pend_base + __popc(pend_m & ((1u << lane) - 1u))] = e;
+            }
+            __syncwarp();
+        }
+        // ---- and start streaming the prepared slots of the envs that finished in THIS tile
+        if (adopt_now) race_prefetch_slot(d, adopt, lane, i, par);
+        cp_async_commit(); // group: adoption loads of this tile (possibly empty)
+        pend_adopt = adopt_now;
+        pend_i = i;
+        pend_par = par;
+        pend_m = m;
+        pend_base = base;
+        pend_shard = qshard;
+
+        if (have_tile) {
+            tile = next;
+            next = claim_a; // claimed two tiles ago
+            claim_a = claim_b;
         }
     }
+    if (store_pending && lane == 0) tma_store_wait_read();
 
-    // ---- every CTA takes a ticket; the last one closes the step.  No device-scope fence is
-    // needed: everything a CTA publishes is consumed by the NEXT launch, and the closing
-    // writes touch only words no CTA of this launch reads after taking its ticket.
-    if (closer) {
-        const uint32_t epoch = d.ctl->epoch + 1u;
-        unsigned int t = atomicAdd(&d.ctl->ticket, 1u);
-        if (t == gridDim.x - 1) {
-            d.ctl->score_step[(epoch + 1u) & 1u] = 0;
-            // the queue this launch consumed is the one step epoch+1 appends to
-            for (int q = 0; q < QUEUE_ENV_SHARDS; q++) d.ctl->queue_count[(epoch + 1u) & 1u][q].v = 0;
-            const int per = race_tiles_per_shard((d.n + 31) >> 5);
-            for (int q = 0; q < QUEUE_TILE_SHARDS; q++) d.ctl->tile_next[q].v = (unsigned int)(q * per);
-            d.ctl->ticket = 0;
-            __threadfence();
-            d.ctl->epoch = epoch;
-        }
+    // ---- CTA epilogue by whichever warp finishes last
+    int last = 0;
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        last = atomicAdd(&s_done, 1) == RACE_BLOCK / 32 - 1;
     }
-}
-
-// ---------------------------------------------------------------- the adopt kernel
-// Runs right after race_step_kernel: one thread per env that finished in that step (compacted,
-// every lane busy).  Installs the next episode (adopt the prepared slot / generate / inject),
-// writes the env's observation row, and rewrites the queue entry in place into the refill
-// request (env | free ring buffer << 31, episode number to prepare) that the refill CTAs of
-// the next step launch consume.
-template <bool STRICT>
-__global__ void __launch_bounds__(128) race_adopt_kernel(const __grid_constant__ RaceDev d) {
-    const unsigned int src = d.ctl->epoch & 1u; // the step kernel has already closed its epoch
-    const unsigned int cnt = d.ctl->queue_count[src][blockIdx.y].v;
-    uint2 *list = race_queue(d, src, blockIdx.y);
-    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
-        const uint2 e = list[k];
-        const int i = (int)(e.x & 0x7fffffffu);
-        const int par = (int)(e.x >> 31);
-        float *row = d.obs + (size_t)i * RACE_OBS;
-        if (d.reset_mode == 1 /* B2D_RESET_INJECT */) {
-            race_inject_episode<STRICT>(d, i, par, row);
-            list[k] = make_uint2(e.x, 0xffffffffu); // nothing to refill
-        } else {
-            AdoptLoads al;
-            race_adopt_issue(d, i, par, al);
-            list[k] = race_adopt_finish<STRICT>(d, i, par, al, row);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+        __threadfence_block();
+        if (lane < 7) {
+            int v = s_acc[lane];
+            if (v != 0) {
+                atomicAdd((unsigned long long *)&d.ctl->acc[lane], (unsigned long long)(long long)v);
+                if (lane == ACC_RINGS)
+                    atomicAdd((unsigned long long *)&d.ctl->score_step[epoch & 1u], (unsigned long long)(long long)v);
+            }
+        }
+        __syncwarp();
+        // ---- every CTA takes a ticket; the last one closes the step.  No device-scope fence is
+        // needed: everything a CTA publishes is consumed by the NEXT launch, and the closing
+        // writes touch only words no CTA of this launch reads after taking its ticket.
+        if (lane == 0) {
+            unsigned int t = atomicAdd(&d.ctl->ticket, 1u);
+            if (t == gridDim.x - 1) {
+                d.ctl->score_step[(epoch + 1u) & 1u] = 0;
+                // the queue this launch consumed is the one step epoch+1 appends to
+                for (int q = 0; q < QUEUE_ENV_SHARDS; q++) d.ctl->queue_count[(epoch + 1u) & 1u][q].v = 0;
+                const int per = race_tiles_per_shard(ntiles);
+                for (int q = 0; q < QUEUE_TILE_SHARDS; q++) d.ctl->tile_next[q].v = (unsigned int)(q * per);
+                d.ctl->ticket = 0;
+                __threadfence();
+                d.ctl->epoch = epoch;
+            }
         }
     }
 }
