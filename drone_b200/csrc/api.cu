@@ -323,11 +323,15 @@ extern "C" int b2d_vec_log_end(b2d_vec *v, float out[B2D_LOG_FIELDS], void *stre
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpyAsync(v->h_log_out, v->d_log_out, 16 * sizeof(long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return b2d_log_average(v->kind, v->kind == KIND_RACE ? v->race.max_rings : v->swarm.max_rings, v->h_log_out, 16, out);
+}
+
+extern "C" int b2d_log_average(int kind, int max_rings, const long long *a, int count, float out[B2D_LOG_FIELDS]) {
+    if (!a || !out || count < 16 || max_rings <= 0) return fail(B2D_EINVAL, "b2d_log_average: bad argument");
     for (int k = 0; k < B2D_LOG_FIELDS; k++) out[k] = 0.0f;
-    const long long *a = v->h_log_out;
     const double n = (double)a[ACC_N];
     if (a[ACC_N] == 0) return B2D_OK;
-    if (v->kind == KIND_RACE) {
+    if (kind == KIND_RACE) {
         // Log field order: DR/dronelib.h:52-63; averaging: EB:588-591
         out[0] = (float)((double)a[ACC_RETURN] / n);
         out[1] = (float)((double)a[ACC_LENGTH] / n);
@@ -336,7 +340,7 @@ extern "C" int b2d_vec_log_end(b2d_vec *v, float out[B2D_LOG_FIELDS], void *stre
         out[4] = (float)((double)a[ACC_OOB] / n);
         out[5] = (float)((double)a[ACC_TIMEOUT] / n);
         out[6] = (float)((double)a[ACC_COUNT] / n); // score: only episodes that ended in the last step
-        out[7] = (float)((double)a[ACC_RINGS] / (double)v->race.max_rings / n);
+        out[7] = (float)((double)a[ACC_RINGS] / (double)max_rings / n);
         out[8] = (float)n;
     } else {
         swarm_log_finish(a, out);

@@ -63,11 +63,11 @@ class _Vec:
         if group is None:
             capi.check(L.b2d_vec_log(self.h, out, _stream_ptr(stream)))
         else:
-            import torch.distributed as dist
+            from .shard import reduce_log_sums
             ptr, cnt = C.c_void_p(), C.c_int()
             capi.check(L.b2d_vec_log_begin(self.h, _stream_ptr(stream), C.byref(ptr), C.byref(cnt)))
             sums = _alias(ptr.value, (cnt.value,), torch.int64, self.device, self)
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=None if group is True else group)
+            reduce_log_sums(sums, None if group is True else group)
             capi.check(L.b2d_vec_log_end(self.h, out, _stream_ptr(stream)))
         vals = [float(x) for x in out]
         if vals[8] == 0.0:

@@ -135,6 +135,9 @@ int b2d_vec_log(b2d_vec *vec, float out[B2D_LOG_FIELDS], void *cuda_stream);
  * caller may all-reduce (NCCL sum) in place; end synchronises and averages. */
 int b2d_vec_log_begin(b2d_vec *vec, void *cuda_stream, long long **device_sums, int *count);
 int b2d_vec_log_end(b2d_vec *vec, float out[B2D_LOG_FIELDS], void *cuda_stream);
+/* the averaging step of vec_log_end on host sums (kind 0 = race, 1 = swarm): pure host
+ * arithmetic, EB:588-591 + my_log; used after a cross-rank reduction of the sums */
+int b2d_log_average(int kind, int max_rings, const long long *sums, int count, float out[B2D_LOG_FIELDS]);
 
 /* ---- introspection ------------------------------------------------------------ */
 int b2d_get_buffers(const b2d_vec *vec, b2d_buffers *device_buffers); /* raw device pointers (DLPack / torch views) */

@@ -1,0 +1,77 @@
+"""Generates the golden vectors in this directory from the UNMODIFIED reference C
+(oracle/_ref, built by oracle/Makefile from /root/reference/pufferlib/pufferlib/ocean).
+
+    python tests/golden/make_golden.py          # needs /root/reference (build container only)
+
+The reference's own tests pin nothing for the drone envs, so these
+files are the pin: every run records, from the reference itself,
+  init_state / init_obs     full env state and observation rows after vec_reset(seed)
+  tape                      the action tape (cycled t % 16; |a| up to 1.3 so clamping is exercised)
+  term, rew                 every step's terminals and rewards
+  obs_hash                  FNV-1a of each env's 29 observation words at every step (bit-exactness check)
+  obs_steps / obs_full      complete observation rows at a few steps
+  ev_t / ev_env / ev_blob   every auto-reset: when, which env, and the post-reset state blob
+                            (= the payload a parity run injects in place of libc rand())
+  clamped_hash              hash of the in-place clamped action buffer at every step
+  final_state, log          state after the last step; float-wise summed Log (EB:572-580)
+Blob layout: oracle/ref_shim_race.c / include/b200drone.h b2d_get_state.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from _util import action_tape, row_hash  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+OBS_STEPS = [0, 1, 2, 3, 10, 50, 100, 250, 399]
+
+
+def race_golden(n, T, seed, max_rings=10, max_moves=1000, tape_seed=1234, scale=1.3):
+    env = po.RefRace(n, max_rings=max_rings, max_moves=max_moves)
+    tape = action_tape(n, seed=tape_seed, scale=scale)
+    env.reset(seed)
+    g = dict(meta=np.array([n, T, seed, max_rings, max_moves], np.int64), tape=tape,
+             init_state=env.get_state(), init_obs=env.observations.copy())
+    term = np.zeros((T, n), np.uint8)
+    rew = np.zeros((T, n), np.float32)
+    oh = np.zeros((T, n), np.uint32)
+    ch = np.zeros((T, n), np.uint32)
+    ev_t, ev_env, ev_blob, obs_full, obs_steps = [], [], [], [], []
+    for t in range(T):
+        env.step(tape[t % len(tape)])
+        term[t], rew[t] = env.terminals, env.rewards
+        oh[t] = row_hash(env.observations)
+        ch[t] = row_hash(env.actions)
+        idx = np.flatnonzero(env.terminals)
+        if len(idx):
+            ev_t += [t] * len(idx)
+            ev_env += idx.tolist()
+            ev_blob.append(env.get_state(idx))
+        if t in OBS_STEPS or t == T - 1:
+            obs_steps.append(t)
+            obs_full.append(env.observations.copy())
+    g.update(term=term, rew=rew, obs_hash=oh, clamped_hash=ch, ev_t=np.array(ev_t, np.int32),
+             ev_env=np.array(ev_env, np.int32),
+             ev_blob=np.concatenate(ev_blob) if ev_blob else np.zeros((0, env.blob), np.float32),
+             obs_steps=np.array(obs_steps, np.int32), obs_full=np.array(obs_full),
+             final_state=env.get_state(), log=env.log())
+    env.close()
+    return g
+
+
+if __name__ == "__main__":
+    if not po.have_ref():
+        po.build(quiet=False)
+    assert po.have_ref(), "oracle/_ref is missing and /root/reference is not here to build it"
+    for name, kw in [("race_n64_T1000_seed42.npz", dict(n=64, T=1000, seed=42)),
+                     ("race_n48_T400_seed0.npz", dict(n=48, T=400, seed=0)),
+                     # short episodes: every truncation path (max_moves) and tiny ring counts
+                     ("race_n32_T300_seed7_moves25_rings3.npz", dict(n=32, T=300, seed=7, max_rings=3, max_moves=25, scale=0.6))]:
+        g = race_golden(**kw)
+        np.savez_compressed(os.path.join(HERE, name), **g)
+        print(name, "resets:", len(g["ev_t"]), "bytes:", os.path.getsize(os.path.join(HERE, name)))
