@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--launch", default="tape", choices=["tape", "single"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -218,10 +219,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The timed loop is the reference's own cached-action perf loop (drone_race.py:83-90): one
+    # vec_step per action batch of the tape, issued through b2d_vec_step_tape (one kernel launch
+    # per step; `--launch single` issues them one b2d_vec_step_from call at a time instead).
+    def run_steps(t0, k):
+        if args.launch == "tape":
+            vec.step_tape(tape, t0 % TAPE_LEN, k)
+        else:
+            for j in range(k):
+                vec.step(tape[(t0 + j) % TAPE_LEN])
+
     t = 0
-    for _ in range(args.warmup):
-        vec.step(tape[t % TAPE_LEN])
-        t += 1
+    run_steps(t, args.warmup)
+    t += args.warmup
     barrier()
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
@@ -229,9 +239,8 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     term_count = torch.zeros((), dtype=torch.int64, device=dev)
     ev0.record(stream)
-    for _ in range(args.steps):
-        vec.step(tape[t % TAPE_LEN])
-        t += 1
+    run_steps(t, args.steps)
+    t += args.steps
     ev1.record(stream)
     barrier()
     sampler.stop()
@@ -289,7 +298,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world, f"env-sharded x{world}, no per-step collective; vec_log all-reduce over NCCL"),
-            "math": args.math, "reset_fraction_per_step": reset_frac,
+            "math": args.math, "launch": args.launch, "reset_fraction_per_step": reset_frac,
             "episode_stats": stats,
             "clocks": sampler.summary(),
             "gpu_launches": int(launches),

@@ -58,6 +58,7 @@ struct b2d_vec {
     long long h_log_out[16];
     double h_flog_out[8];
     long long launches;
+    uint32_t seq; // step-kernel launches so far (RaceDev::seq)
     cudaStream_t copy_streams[2];
     cudaEvent_t ev_step, ev_copy[2];
     // optional per-kernel timing (b2d_profile_kernels): event triples of the profiled steps
@@ -161,17 +162,16 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
         v->step_ctas = step_ctas;
     }
     const size_t ld = d.ld;
-    d.queue_cap = (((cfg->num_envs + 31) / 32 + QUEUE_ENV_SHARDS - 1) / QUEUE_ENV_SHARDS) * 32;
     if ((rc = setup_buffers(v, ext)) || (rc = dev_alloc(v, &d.S, 5 * ld)) || (rc = dev_alloc(v, &d.P, 3 * ld)) ||
-        (rc = dev_alloc(v, &d.PJ, ld)) || (rc = dev_alloc(v, &d.C0, ld)) || (rc = dev_alloc(v, &d.C1, ld)) ||
-        (rc = dev_alloc(v, &d.G0, 2 * (size_t)d.max_rings * ld)) || (rc = dev_alloc(v, &d.G1, 2 * (size_t)d.max_rings * ld)) ||
-        (rc = dev_alloc(v, &d.N, 3 * ld)) || (rc = dev_alloc(v, &d.NJ, ld)) || (rc = dev_alloc(v, &d.NS, ld)) ||
-        (rc = dev_alloc(v, &d.EP, ld)) || (rc = dev_alloc(v, &d.SLOT_EP, ld)) || (rc = dev_alloc(v, &d.refill, 2 * (size_t)QUEUE_ENV_SHARDS * d.queue_cap)) ||
+        (rc = dev_alloc(v, &d.C0, ld)) || (rc = dev_alloc(v, &d.T, ld)) ||
+        (rc = dev_alloc(v, &d.N, 3 * ld)) || (rc = dev_alloc(v, &d.NS, ld)) || (rc = dev_alloc(v, &d.NR0, ld)) ||
+        (rc = dev_alloc(v, &d.NR1, ld)) || (rc = dev_alloc(v, &d.carry, (size_t)v->step_ctas * RACE_CARRY)) ||
+        (rc = dev_alloc(v, &d.chain, (size_t)v->step_ctas)) || (rc = dev_alloc(v, &d.cta_score, (size_t)v->step_ctas)) ||
         (rc = dev_alloc(v, &d.ctl, 1)) || (rc = finish_create(v))) {
         b2d_vec_close(v);
         return rc;
     }
-    race_ctl_reset_kernel<<<1, 32>>>(d.ctl, 0u, 1, (d.n + 31) / 32);
+    race_ctl_reset_kernel<<<1, 256>>>(d.ctl, d.carry, d.cta_score, 0u, (unsigned int)v->step_ctas, 1);
     cudaDeviceSynchronize();
     d.obs = v->dev.observations;
     d.act_in = v->dev.actions;
@@ -196,6 +196,17 @@ extern "C" int b2d_vec_close(b2d_vec *v) {
     if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
     cudaSetDevice(v->device);
     cudaDeviceSynchronize();
+#if B2D_EXPERIMENT_TIMING
+    if (v->kind == KIND_RACE && v->race.ctl) {
+        unsigned long long h[12];
+        cudaMemcpy(h, v->race.ctl->dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        const double it = (double)h[4], w = (double)h[7];
+        fprintf(stderr, "[b2d timing] per tile iteration (cycles): wait_inputs %.0f  compute %.0f  store %.0f  wait_adopt %.0f  install %.0f  refill %.0f | per warp-launch: total %.0f  iterations %.2f\n",
+                h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[8] / it, h[5] / it, h[6] / w, it / w);
+        fprintf(stderr, "[b2d timing] slowest warp loop %.0f cycles; CTA busy: mean %.0f, slowest %.0f cycles (any launch)\n", (double)h[9],
+                (double)h[10] / (w / RACE_WARPS), (double)h[11]);
+    }
+#endif
     for (void *p : v->allocs) cudaFree(p);
     if (v->d_payload) cudaFree(v->d_payload);
     if (v->d_blob_tmp) cudaFree(v->d_blob_tmp);
@@ -223,7 +234,7 @@ extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
         d.key0 = (uint32_t)seed;
         d.key1 = (uint32_t)(seed >> 32);
         if (d.reset_mode == B2D_RESET_INJECT && !d.payload) return fail(B2D_ESTATE, "inject mode without a payload");
-        race_ctl_reset_kernel<<<1, 32, 0, st>>>(d.ctl, 0u, 0, (d.n + 31) / 32);
+        race_ctl_reset_kernel<<<1, 256, 0, st>>>(d.ctl, d.carry, d.cta_score, 0u, (unsigned int)v->step_ctas, 0);
         race_reset_kernel<<<(d.n + 127) / 128, 128, 0, st>>>(d);
         v->launches += 2;
         return launch_check("race_reset_kernel");
@@ -232,20 +243,34 @@ extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
     return launch_check("swarm_reset_kernel");
 }
 
-static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st) {
+// One launch of the step kernel.  `overlap`: the launch is made programmatically dependent on the
+// previous launch in the stream, which the caller guarantees is the previous step of this handle
+// (b2d_vec_step_tape); every CTA then waits for its own predecessor only (race_step_kernel).
+static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool overlap = false) {
     if (v->kind == KIND_RACE) {
         RaceDev d = v->race;
         if (actions) d.act_in = actions;
-        const int grid = v->step_ctas;
-        const size_t smem = RACE_SMEM_BYTES;
-        // sized for ~3% of the envs finishing per step; grid-stride covers the rest
+        d.seq = ++v->seq;
+        d.chain_wait = overlap ? 1 : 0;
         cudaEvent_t pe[2] = {nullptr, nullptr};
         if (v->profile) {
             for (int k = 0; k < 2; k++) { cudaEventCreate(&pe[k]); v->prof_events.push_back(pe[k]); }
             cudaEventRecord(pe[0], st);
         }
-        if (v->math == B2D_MATH_STRICT) race_step_kernel<true><<<grid, RACE_BLOCK, smem, st>>>(d);
-        else race_step_kernel<false><<<grid, RACE_BLOCK, smem, st>>>(d);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)v->step_ctas);
+        cfg.blockDim = dim3(RACE_BLOCK);
+        cfg.dynamicSmemBytes = RACE_SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = overlap ? 1 : 0;
+        cudaError_t e = v->math == B2D_MATH_STRICT ? cudaLaunchKernelEx(&cfg, race_step_kernel<true>, d)
+                                                   : cudaLaunchKernelEx(&cfg, race_step_kernel<false>, d);
+        if (e != cudaSuccess) return fail(B2D_ECUDA, "race_step_kernel launch: %s", cudaGetErrorString(e));
         if (v->profile) cudaEventRecord(pe[1], st);
         v->launches += 1;
         return launch_check("race_step_kernel");
@@ -263,6 +288,27 @@ extern "C" int b2d_vec_step_from(b2d_vec *v, const float *device_actions, void *
     if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
     if (!device_actions || ((uintptr_t)device_actions & 15u)) return fail(B2D_EINVAL, "actions must be a 16-byte aligned device pointer");
     return step_impl(v, device_actions, (cudaStream_t)stream);
+}
+
+// K steps over an action tape that is already on the device.  The launches after the first are
+// allowed to overlap the tail of their predecessor (programmatic dependent launch + per-CTA
+// completion flags): CTA c of step t+1 needs only CTA c of step t, so a straggling CTA no longer
+// idles the whole GPU between steps.  Inside a stream capture the launches are plain (the
+// sequence numbers the flags carry are host state a graph replay would not advance).
+extern "C" int b2d_vec_step_tape(b2d_vec *v, const float *device_tape, int tape_len, int first, int steps, void *stream) {
+    if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    if (!device_tape || ((uintptr_t)device_tape & 15u) || tape_len <= 0 || first < 0 || steps < 0)
+        return fail(B2D_EINVAL, "b2d_vec_step_tape: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    const size_t stride = (size_t)v->num_agents * 4;
+    for (int k = 0; k < steps; k++) {
+        const float *a = device_tape + (size_t)((first + k) % tape_len) * stride;
+        int rc = step_impl(v, a, st, k > 0 && cap == cudaStreamCaptureStatusNone && v->kind == KIND_RACE);
+        if (rc) return rc;
+    }
+    return B2D_OK;
 }
 
 // Host-buffer step: one kernel (it is far shorter than the PCIe transfers); the D2H of
@@ -310,7 +356,7 @@ extern "C" int b2d_vec_log_begin(b2d_vec *v, void *stream, long long **device_su
     if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
     cudaStream_t st = (cudaStream_t)stream;
     Ctl *ctl = v->kind == KIND_RACE ? v->race.ctl : v->swarm.ctl;
-    if (v->kind == KIND_RACE) race_log_snapshot_kernel<<<1, 32, 0, st>>>(ctl, v->d_log_out);
+    if (v->kind == KIND_RACE) race_log_snapshot_kernel<<<1, 32, 0, st>>>(ctl, v->race.cta_score, v->d_log_out);
     else swarm_log_snapshot_kernel<<<1, 32, 0, st>>>(ctl, v->d_log_out);
     v->launches += 1;
     if (device_sums) *device_sums = v->d_log_out;
@@ -369,7 +415,9 @@ extern "C" int b2d_step_count(b2d_vec *v, uint32_t *steps, void *stream) {
     if (!v || !steps) return fail(B2D_EINVAL, "null argument");
     Ctl *ctl = v->kind == KIND_RACE ? v->race.ctl : v->swarm.ctl;
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    CUDA_TRY(cudaMemcpy(steps, &ctl->epoch, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    uint32_t w[2] = {0, 1};
+    CUDA_TRY(cudaMemcpy(w, &ctl->ctas_done, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    *steps = w[1] ? w[0] / w[1] : 0;
     return B2D_OK;
 }
 
@@ -377,11 +425,26 @@ extern "C" int b2d_set_step_count(b2d_vec *v, uint32_t steps) {
     if (!v) return fail(B2D_EINVAL, "null handle");
     Ctl *ctl = v->kind == KIND_RACE ? v->race.ctl : v->swarm.ctl;
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(&ctl->epoch, &steps, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    const uint32_t done = steps * (uint32_t)(v->kind == KIND_RACE ? v->step_ctas : 1);
+    CUDA_TRY(cudaMemcpy(&ctl->ctas_done, &done, sizeof(uint32_t), cudaMemcpyHostToDevice));
     return B2D_OK;
 }
 
 // ---------------------------------------------------------------- state hooks
+// Rings that come from outside (put_state, the reset payload of the parity hook) need storage:
+// [R][ld] x 24 B, allocated the first time such a hook is used (lazily generated rings need none).
+static int ensure_external_rings(b2d_vec *v) {
+    if (v->kind != KIND_RACE || v->race.X0) return B2D_OK;
+    RaceDev &d = v->race;
+    int rc;
+    if ((rc = dev_alloc(v, &d.X0, (size_t)d.max_rings * d.ld)) || (rc = dev_alloc(v, &d.X1, (size_t)d.max_rings * d.ld))) {
+        d.X0 = nullptr;
+        d.X1 = nullptr;
+        return rc;
+    }
+    return B2D_OK;
+}
+
 static int ensure_tmp(b2d_vec *v, int n) {
     const size_t need = (size_t)n * v->blob_floats;
     if (need > v->blob_tmp_cap) {
@@ -419,6 +482,7 @@ extern "C" int b2d_put_state(b2d_vec *v, const int *env_ids, int n, const float 
     if (!v || !host_blobs || n <= 0 || n > v->num_envs) return fail(B2D_EINVAL, "b2d_put_state: bad argument");
     int rc = ensure_tmp(v, n);
     if (rc) return rc;
+    if ((rc = ensure_external_rings(v))) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
     if (env_ids) {
         for (int k = 0; k < n; k++)
@@ -427,9 +491,8 @@ extern "C" int b2d_put_state(b2d_vec *v, const int *env_ids, int n, const float 
     }
     CUDA_TRY(cudaMemcpy(v->d_blob_tmp, host_blobs, (size_t)n * v->blob_floats * sizeof(float), cudaMemcpyHostToDevice));
     if (v->kind == KIND_RACE) { // no prepared-slot refill may be in flight once states are edited
-        race_drain_kernel<<<dim3(4, QUEUE_ENV_SHARDS), 128>>>(v->race);
-        race_drain_done_kernel<<<1, 64>>>(v->race.ctl);
-        v->launches += 2;
+        race_drain_kernel<<<v->step_ctas, 32>>>(v->race);
+        v->launches += 1;
     }
     if (v->kind == KIND_RACE) race_unpack_kernel<<<(n + 127) / 128, 128>>>(v->race, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
     else swarm_unpack_kernel<<<(n + 127) / 128, 128>>>(v->swarm, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
@@ -457,6 +520,11 @@ extern "C" int b2d_set_math(b2d_vec *v, int math) {
 
 extern "C" int b2d_set_reset_mode(b2d_vec *v, int mode) {
     if (!v || (mode != B2D_RESET_PHILOX && mode != B2D_RESET_INJECT)) return fail(B2D_EINVAL, "unknown reset mode");
+    if (mode == B2D_RESET_INJECT) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        int rc = ensure_external_rings(v);
+        if (rc) return rc;
+    }
     if (v->kind == KIND_RACE) v->race.reset_mode = mode;
     else v->swarm.reset_mode = mode;
     return B2D_OK;

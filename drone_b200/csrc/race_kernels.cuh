@@ -9,22 +9,22 @@
 // Layout in HBM (ld = num_envs rounded up to 256; lane i touches element i of
 // every array, so each warp access is one contiguous 512-byte float4 run):
 //   S  float4[5][ld]  (px,py,pz,vx) (vy,vz,qw,qx) (qy,qz,wx,wy) (wz,r0,r1,r2) (r3,tick,ring word,ep_return)
-//                     ring word = ring_idx | ring-buffer parity << 30
+//                     ring word = ring_idx | (rings are external) << 30
 //   P  float4[3][ld]  (mass,ixx,iyy,izz) (arm,k_thrust,k_ang_damp,k_drag) (b_drag,gravity,max_rpm,k_mot)
-//   PJ float [ld]     j_mot
-//   C0 float4[ld], C1 float2[ld]   the CURRENT ring (pos.xyz,n.x) (n.y,n.z): no dependent gather per step
-//   G0 float4[2][R][ld], G1 float2[2][R][ld]  rings of the live episode (buffer `parity`) and of the
-//                     prepared next episode (the other buffer); read on a ring pass / episode start
-//   N float4[3][ld], NJ float[ld], NS float4[ld]  prepared next episode: params, j_mot, spawn position
-//   EP u32[ld] live episode number, SLOT_EP u32[ld] episode number held by the prepared slot
-// Per env-step the kernel reads 172 B (act 16, S 80, P 52, C 24) and writes
+//   C0 float4[ld]     the CURRENT ring (pos.xyz, n.x): no dependent gather per step
+//   T  float4[ld]     (j_mot, live episode number, current ring n.y, n.z)
+//   N float4[3][ld], NS, NR0, NR1 float4[ld]  prepared next episode: params, (spawn, j_mot), ring 0,
+//                     (.., episode tag); rings beyond the current one are generated when reached
+//   X0 float4[R][ld], X1 float2[R][ld]  rings of episodes that came from outside (reset payload of the
+//                     parity hook, put_state); allocated on first use only
+// Per env-step the kernel reads 172 B (act 16, S 80, P 52, C 24; + 4 B episode number) and writes
 // 201 B (S 80, obs 116, reward 4, terminal 1) = 373 algorithmic bytes.
 //
 // Auto-reset without a reset on the critical path: an env that finishes ADOPTS its
 // prepared episode (13 params + spawn + ring 0: a handful of loads/stores) and queues
-// itself on a refill list; the next launch carries a few extra CTAs that regenerate the
-// consumed slots (Philox + trig, ~3000 dependent instructions each) with every lane
-// busy, overlapped with the step CTAs of that launch.
+// itself on its CTA's refill ring; whenever 32 entries wait, one warp regenerates the
+// consumed slots (Philox + trig, ~7800 instructions) with every lane busy, in between
+// two of its tiles (see race_step_kernel).
 #pragma once
 #include "physics.cuh"
 
@@ -33,57 +33,63 @@ namespace b2d {
 #ifndef B2D_RACE_BLOCK
 #define B2D_RACE_BLOCK 128
 #endif
-#ifndef B2D_EXPERIMENT_SKIP_MATH
-#define B2D_EXPERIMENT_SKIP_MATH 0
-#endif
 #ifndef B2D_RACE_MIN_CTAS
 #define B2D_RACE_MIN_CTAS 3
 #endif
+#ifndef B2D_EXPERIMENT_SKIP_MATH
+#define B2D_EXPERIMENT_SKIP_MATH 0 // measurement aid: the memory pipeline without the RK4 arithmetic
+#endif
+#ifndef B2D_EXPERIMENT_TIMING
+#define B2D_EXPERIMENT_TIMING 0 // measurement aid: clock64 sums per phase, printed by b2d_vec_close
+#endif
+#if B2D_EXPERIMENT_TIMING
+#define B2D_TICK(var) const long long var = clock64()
+#else
+#define B2D_TICK(var)
+#endif
 constexpr int RACE_BLOCK = B2D_RACE_BLOCK;
+constexpr int RACE_WARPS = RACE_BLOCK / 32;
 constexpr int RACE_MIN_CTAS = B2D_RACE_MIN_CTAS;
 constexpr int RACE_LD_ALIGN = 256; // row padding of the SoA arrays
 constexpr int RACE_OBS = 29;
 constexpr int RESET_MAX_ATTEMPTS = 16;
+constexpr int RACE_QUEUE_CAP = 256;            // refill ring of one CTA (entries, power of two)
+constexpr int RACE_CARRY = 32;                 // refill entries a CTA may carry over to the next launch
+constexpr unsigned int QUEUE_EMPTY = 0xffffffffu;
 
 // integer episode-statistics accumulators (all race Log fields are integer valued)
 enum { ACC_N = 0, ACC_RETURN, ACC_LENGTH, ACC_RINGS, ACC_OOB, ACC_COLLISION, ACC_TIMEOUT, ACC_SPARE, ACC_COUNT };
 
-constexpr int QUEUE_TILE_SHARDS = 16;
-constexpr int QUEUE_ENV_SHARDS = 64;
-struct alignas(256) PaddedCounter {
-    unsigned int v;
-    unsigned int pad[63];
-};
-
+// Device-side control block.  Nothing in the step kernel reads back the result of a global
+// atomic: on B200 a returning ATOMG issued by a busy SM was measured to take 5-10 us (longer
+// than a whole tile of work), so every global update here is a fire-and-forget reduction.
 struct Ctl {
-    unsigned int epoch;  // vec steps completed since the last vec_reset
-    unsigned int ticket; // CTAs finished in the running step
+    unsigned int ctas_done; // step CTAs finished since the last vec_reset; vec steps completed = ctas_done / grid
+    unsigned int grid;      // step CTAs per launch (fixed for the life of the handle)
     unsigned int pad0[2];
     long long acc[ACC_COUNT];
-    long long score_step[2]; // sum of score over episodes that ended in step (epoch & 1): R/drone_race.h:160
     double facc[8];          // float-valued sums (swarm)
-    // Hot counters, one per 256-byte line: same-address atomics serialise in L2 at a few ns each,
-    // so 32K claims per launch on ONE word would bound the kernel; sharded they vanish.
-    PaddedCounter tile_next[QUEUE_TILE_SHARDS];       // tile scheduler: next unclaimed tile of each shard
-    PaddedCounter queue_count[2][QUEUE_ENV_SHARDS];   // finished/refill queue (epoch & 1), sharded by tile % shards
+    unsigned long long dbg[12]; // B2D_EXPERIMENT_TIMING
 };
 
 struct RaceDev {
     int n, ld, max_rings, max_moves;
     float4 *S;
     float4 *P;
-    float *PJ;
-    float4 *C0;
-    float2 *C1;
-    float4 *G0;
-    float2 *G1;
-    float4 *N;
-    float *NJ;
-    float4 *NS;
-    uint32_t *EP;
-    uint32_t *SLOT_EP;
-    uint2 *refill; // [2][QUEUE_ENV_SHARDS][queue_cap] (env | ring buffer << 31, tick or episode number)
-    int queue_cap; // entries per queue shard: every env of every tile that maps to the shard
+    float4 *C0;          // current ring (pos.xyz, n.x)
+    float4 *T;           // (j_mot, live episode number as bits, current ring n.y, n.z)
+    float4 *X0;          // external rings [R][ld] (injected episodes / put_state); allocated on first use
+    float2 *X1;
+    float4 *N;           // prepared next episode: params 0..11
+    float4 *NS;          //   (spawn.xyz, j_mot)
+    float4 *NR0;         //   ring 0 (pos.xyz, n.x)
+    float4 *NR1;         //   (n.y, n.z, episode tag as bits, -)
+    uint2 *carry;        // [grid][RACE_CARRY] refill entries a CTA did not get to (env, episode)
+    unsigned int *chain; // [grid] sequence number of the last launch CTA c completed
+    long long *cta_score; // [grid] sum of score over the episodes CTA c saw end in the LAST step (R/drone_race.h:160)
+    uint32_t seq;        // sequence number of this launch (host counter, +1 per launch)
+    int chain_wait;      // 1: launched programmatically dependent on launch seq-1 of this kernel: CTA c
+                         //    starts as soon as CTA c of that launch is done (see b2d_vec_step_tape)
     const float *act_in; // [n][4] actions read this step
     float *act_out;      // [n][4] clamped actions written back, or nullptr
     float *obs;          // [n][29]
@@ -153,24 +159,28 @@ __device__ __forceinline__ void race_observe(const float s[17], float mrpm, cons
 }
 
 // ---------------------------------------------------------------- state <-> SoA
-__device__ __forceinline__ void race_store_state(const RaceDev &d, int i, const float s[17], int tick, int ring_idx,
+// ring word = ring_idx | RING_EXTERNAL when the episode's rings live in X0/X1 (injected / put_state)
+constexpr int RING_EXTERNAL = 1 << 30;
+constexpr int RING_INDEX_MASK = RING_EXTERNAL - 1;
+
+__device__ __forceinline__ void race_store_state(const RaceDev &d, int i, const float s[17], int tick, int ring_word,
                                                  float ep_ret) {
     d.S[0 * (size_t)d.ld + i] = make_float4(s[0], s[1], s[2], s[3]);
     d.S[1 * (size_t)d.ld + i] = make_float4(s[4], s[5], s[6], s[7]);
     d.S[2 * (size_t)d.ld + i] = make_float4(s[8], s[9], s[10], s[11]);
     d.S[3 * (size_t)d.ld + i] = make_float4(s[12], s[13], s[14], s[15]);
-    d.S[4 * (size_t)d.ld + i] = make_float4(s[16], __int_as_float(tick), __int_as_float(ring_idx), ep_ret);
+    d.S[4 * (size_t)d.ld + i] = make_float4(s[16], __int_as_float(tick), __int_as_float(ring_word), ep_ret);
 }
 
-__device__ __forceinline__ void race_load_ring(const RaceDev &d, int i, int par, int r, float ring[6]) {
-    float4 a = d.G0[((size_t)par * d.max_rings + r) * d.ld + i];
-    float2 b = d.G1[((size_t)par * d.max_rings + r) * d.ld + i];
+__device__ __forceinline__ void race_load_external_ring(const RaceDev &d, int i, int r, float ring[6]) {
+    float4 a = __ldcg(&d.X0[(size_t)r * d.ld + i]);
+    float2 b = __ldcg(&d.X1[(size_t)r * d.ld + i]);
     ring[0] = a.x; ring[1] = a.y; ring[2] = a.z; ring[3] = a.w; ring[4] = b.x; ring[5] = b.y;
 }
 
 __device__ __forceinline__ void race_store_current_ring(const RaceDev &d, int i, const float ring[6]) {
     d.C0[i] = make_float4(ring[0], ring[1], ring[2], ring[3]);
-    d.C1[i] = make_float2(ring[4], ring[5]);
+    reinterpret_cast<float2 *>(&d.T[i])[1] = make_float2(ring[4], ring[5]);
 }
 
 // ---------------------------------------------------------------- episode generator
@@ -178,52 +188,51 @@ __device__ __forceinline__ void race_store_current_ring(const RaceDev &d, int i,
 // key=(seed lo, seed hi) and counter=(global env id, episode number, item, attempt);
 // item 2r / 2r+1 = ring r (x,y,z,u1 / u2,u3), 0x1000+k = size and the 12 jitter
 // factors, 0x2000 = spawn position.  The k-th episode of an env is therefore a pure
-// function of (seed, env id, k), whenever it gets generated.  Same distributions and
-// formulas as the reference's c_reset (R/drone_race.h:127-151, R/dronelib.h:141-183,
-// 250-300, 451-460); arithmetic is one IEEE op at a time so the CPU oracle
-// (oracle/drone_oracle.c:race_fresh_episode) reproduces it bit for bit.
-// Rings go straight to ring buffer `tb` of env i; params/spawn/ring 0 come back in registers.
-__device__ __noinline__ void race_generate_episode(const RaceDev &d, int i, uint32_t episode, int tb,
-                                                   float params[13], float spawn[3], float ring0[6]) {
-    const uint32_t env = d.env_id_base + (uint32_t)i;
-    const size_t gbase = (size_t)tb * d.max_rings * d.ld + i;
-    // rings: R/dronelib.h:451-460 (each at least 2*radius from its predecessor)
-    float px = 0.0f, py = 0.0f, pz = 0.0f;
-    for (int r = 0; r < d.max_rings; r++) {
-        float g[6];
-        for (uint32_t t = 0; t < RESET_MAX_ATTEMPTS; t++) {
-            uint4 a = philox4x32_10(make_uint4(env, episode, 2u * r, t), d.key0, d.key1);
-            uint4 b = philox4x32_10(make_uint4(env, episode, 2u * r + 1u, t), d.key0, d.key1);
-            xf cx = lerp_u(-6.0f, 6.0f, unit_from_word(a.x));
-            xf cy = lerp_u(-6.0f, 6.0f, unit_from_word(a.y));
-            xf cz = lerp_u(-6.0f, 6.0f, unit_from_word(a.z));
-            xf u1 = unit_from_word(a.w), u2 = unit_from_word(b.x), u3 = unit_from_word(b.y);
-            // R/dronelib.h:141-159 rndquat, :177-178 normal = q . z-axis
-            xf ra = xsqrt(xf(1.0f) - u1), rb = xsqrt(u1);
-            float th2 = __double2float_rn(__dmul_rn(6.283185307179586, (double)u2.v));
-            float th3 = __double2float_rn(__dmul_rn(6.283185307179586, (double)u3.v));
-            float s2, c2, s3, c3;
-            sincos_det(th2, s2, c2);
-            sincos_det(th3, s3, c3);
-            Q4<xf> q;
-            q.w = ra * xf(s2); q.x = ra * xf(c2); q.y = rb * xf(s3); q.z = rb * xf(c3);
-            V3<xf> zax;
-            zax.x = 0.0f; zax.y = 0.0f; zax.z = 1.0f;
-            V3<xf> nrm = qrot(q, zax);
-            g[0] = cx.v; g[1] = cy.v; g[2] = cz.v; g[3] = nrm.x.v; g[4] = nrm.y.v; g[5] = nrm.z.v;
-            if (r == 0) break;
-            xf ex = cx - xf(px), ey = cy - xf(py), ez = cz - xf(pz);
-            xf dist = xsqrt(ex * ex + ey * ey + ez * ez);
-            if (!(dist.v < 4.0f)) break;
-        }
-        px = g[0]; py = g[1]; pz = g[2];
-        d.G0[gbase + (size_t)r * d.ld] = make_float4(g[0], g[1], g[2], g[3]);
-        d.G1[gbase + (size_t)r * d.ld] = make_float2(g[4], g[5]);
-        if (r == 0) {
-#pragma unroll
-            for (int k = 0; k < 6; k++) ring0[k] = g[k];
-        }
+// function of (seed, env id, k), whenever and wherever it gets generated.  Same
+// distributions and formulas as the reference's c_reset (R/drone_race.h:127-151,
+// R/dronelib.h:141-183,250-300,451-460); arithmetic is one IEEE op at a time so the CPU
+// oracle (oracle/drone_oracle.c:race_fresh_episode) reproduces it bit for bit.
+//
+// Rings are generated LAZILY: ring r depends only on its own counters and on the final
+// position of ring r-1 (the reference redraws a ring until it is 2*radius away from its
+// predecessor, R/dronelib.h:451-460), so an episode start needs ring 0 only and a ring pass
+// generates ring r+1 from the ring just passed.  The reference's up-front loop over
+// max_rings rings would be 7/8 of the reset cost for rings that are almost never reached.
+__device__ __forceinline__ void race_generate_ring(const RaceDev &d, uint32_t env, uint32_t episode, int r,
+                                                   const float prev[3], float g[6]) {
+    for (uint32_t t = 0; t < RESET_MAX_ATTEMPTS; t++) {
+        uint4 a = philox4x32_10(make_uint4(env, episode, 2u * r, t), d.key0, d.key1);
+        uint4 b = philox4x32_10(make_uint4(env, episode, 2u * r + 1u, t), d.key0, d.key1);
+        xf cx = lerp_u(-6.0f, 6.0f, unit_from_word(a.x));
+        xf cy = lerp_u(-6.0f, 6.0f, unit_from_word(a.y));
+        xf cz = lerp_u(-6.0f, 6.0f, unit_from_word(a.z));
+        xf u1 = unit_from_word(a.w), u2 = unit_from_word(b.x), u3 = unit_from_word(b.y);
+        // R/dronelib.h:141-159 rndquat, :177-178 normal = q . z-axis
+        xf ra = xsqrt(xf(1.0f) - u1), rb = xsqrt(u1);
+        float th2 = __double2float_rn(__dmul_rn(6.283185307179586, (double)u2.v));
+        float th3 = __double2float_rn(__dmul_rn(6.283185307179586, (double)u3.v));
+        float s2, c2, s3, c3;
+        sincos_det(th2, s2, c2);
+        sincos_det(th3, s3, c3);
+        Q4<xf> q;
+        q.w = ra * xf(s2); q.x = ra * xf(c2); q.y = rb * xf(s3); q.z = rb * xf(c3);
+        V3<xf> zax;
+        zax.x = 0.0f; zax.y = 0.0f; zax.z = 1.0f;
+        V3<xf> nrm = qrot(q, zax);
+        g[0] = cx.v; g[1] = cy.v; g[2] = cz.v; g[3] = nrm.x.v; g[4] = nrm.y.v; g[5] = nrm.z.v;
+        if (r == 0) break;
+        xf ex = cx - xf(prev[0]), ey = cy - xf(prev[1]), ez = cz - xf(prev[2]);
+        xf dist = xsqrt(ex * ex + ey * ey + ez * ez);
+        if (!(dist.v < 4.0f)) break;
     }
+}
+
+// ring 0, the 13 drone parameters and the spawn position of episode `episode` of env i
+__device__ __noinline__ void race_generate_episode(const RaceDev &d, int i, uint32_t episode, float params[13],
+                                                   float spawn[3], float ring0[6]) {
+    const uint32_t env = d.env_id_base + (uint32_t)i;
+    const float origin[3] = {0.0f, 0.0f, 0.0f};
+    race_generate_ring(d, env, episode, 0, origin, ring0);
     // R/dronelib.h:250-290 init_drone(size ~ U(0.05, 0.8), dr = 0.1)
     float u[16];
 #pragma unroll
@@ -273,101 +282,88 @@ __device__ __noinline__ void race_generate_episode(const RaceDev &d, int i, uint
     }
 }
 
-__device__ __forceinline__ void race_store_params(const RaceDev &d, int i, const float p[13]) {
+// the ring that follows `ring` (index r-1, just passed) in episode `episode` of env i
+__device__ __noinline__ void race_next_ring(const RaceDev &d, int i, uint32_t episode, int r, float ring[6]) {
+    const float prev[3] = {ring[0], ring[1], ring[2]};
+    race_generate_ring(d, d.env_id_base + (uint32_t)i, episode, r, prev, ring);
+}
+
+__device__ __forceinline__ void race_store_params(const RaceDev &d, int i, const float p[13], uint32_t episode) {
     d.P[0 * (size_t)d.ld + i] = make_float4(p[0], p[1], p[2], p[3]);
     d.P[1 * (size_t)d.ld + i] = make_float4(p[4], p[5], p[6], p[7]);
     d.P[2 * (size_t)d.ld + i] = make_float4(p[8], p[9], p[10], p[11]);
-    d.PJ[i] = p[12];
+    reinterpret_cast<float2 *>(&d.T[i])[0] = make_float2(p[12], __uint_as_float(episode));
 }
 
-// Generate episode `episode` of env i into the env's PREPARED slot (next params, next spawn,
-// ring buffer tb) and publish it by tagging the slot with the episode number.
-__device__ __forceinline__ void race_fill_slot(const RaceDev &d, int i, uint32_t episode, int tb) {
+// Generate episode `episode` of env i into the env's PREPARED slot (next params, spawn, ring 0)
+// and publish it by tagging the slot with the episode number.
+__device__ __forceinline__ void race_fill_slot(const RaceDev &d, int i, uint32_t episode) {
     float p[13], spawn[3], ring0[6];
-    race_generate_episode(d, i, episode, tb, p, spawn, ring0);
+    race_generate_episode(d, i, episode, p, spawn, ring0);
     d.N[0 * (size_t)d.ld + i] = make_float4(p[0], p[1], p[2], p[3]);
     d.N[1 * (size_t)d.ld + i] = make_float4(p[4], p[5], p[6], p[7]);
     d.N[2 * (size_t)d.ld + i] = make_float4(p[8], p[9], p[10], p[11]);
-    d.NJ[i] = p[12];
-    d.NS[i] = make_float4(spawn[0], spawn[1], spawn[2], 0.0f);
-    __threadfence();
-    d.SLOT_EP[i] = episode;
+    d.NS[i] = make_float4(spawn[0], spawn[1], spawn[2], p[12]);
+    d.NR0[i] = make_float4(ring0[0], ring0[1], ring0[2], ring0[3]);
+    d.NR1[i] = make_float4(ring0[4], ring0[5], __uint_as_float(episode), 0.0f); // (n.y, n.z, tag, -)
 }
 
-// Generate episode `episode` in place as the LIVE episode of env i (rings into buffer tb, params
-// into P, fresh state, current ring, observation row).  Only used when the prepared slot cannot
-// be trusted (see race_begin_episode) and by vec_reset.
+// Generate episode `episode` in place as the LIVE episode of env i (params into P, fresh state,
+// current ring, observation row).  Used when the prepared slot cannot be trusted (see
+// race_adopt_from_smem) and by vec_reset.
 template <bool STRICT>
-__device__ __noinline__ void race_begin_generated(const RaceDev &d, int i, uint32_t episode, int tb, float *obs_row) {
+__device__ __noinline__ void race_begin_generated(const RaceDev &d, int i, uint32_t episode, float *obs_row) {
     float p[13], spawn[3], ring0[6], s[17];
-    race_generate_episode(d, i, episode, tb, p, spawn, ring0);
+    race_generate_episode(d, i, episode, p, spawn, ring0);
 #pragma unroll
     for (int k = 0; k < 17; k++) s[k] = 0.0f;
     s[6] = 1.0f;
     s[0] = spawn[0]; s[1] = spawn[1]; s[2] = spawn[2];
-    race_store_params(d, i, p);
-    race_store_state(d, i, s, 0, tb << 30, 0.0f);
+    race_store_params(d, i, p, episode);
+    race_store_state(d, i, s, 0, 0, 0.0f);
     race_store_current_ring(d, i, ring0);
     race_observe<STRICT>(s, p[10], ring0, obs_row);
 }
 
-// Parity hook (B2D_RESET_INJECT): the next episode is the oracle's post-reset state from the payload.
+// Parity hook (B2D_RESET_INJECT): the next episode is the oracle's post-reset state from the
+// payload; its rings are kept in the external ring arrays X0/X1.
 template <bool STRICT>
-__device__ __noinline__ void race_inject_episode(const RaceDev &d, int i, int par, float *obs_row) {
+__device__ __noinline__ void race_inject_episode(const RaceDev &d, int i, uint32_t episode, float *obs_row) {
     const float *b = d.payload + (size_t)i * (33 + 6 * d.max_rings);
     float s[17];
 #pragma unroll
     for (int k = 0; k < 17; k++) s[k] = b[k];
-    race_store_params(d, i, b + 17);
+    race_store_params(d, i, b + 17, episode);
     const int tick = (int)b[30], ring_idx = (int)b[31];
-    const size_t gbase = (size_t)par * d.max_rings * d.ld + i;
     for (int r = 0; r < d.max_rings; r++) {
         const float *g = b + 33 + 6 * r;
-        d.G0[gbase + (size_t)r * d.ld] = make_float4(g[0], g[1], g[2], g[3]);
-        d.G1[gbase + (size_t)r * d.ld] = make_float2(g[4], g[5]);
+        d.X0[(size_t)r * d.ld + i] = make_float4(g[0], g[1], g[2], g[3]);
+        d.X1[(size_t)r * d.ld + i] = make_float2(g[4], g[5]);
     }
     const float *g = b + 33 + 6 * (ring_idx < d.max_rings ? ring_idx : 0);
-    race_store_state(d, i, s, tick, ring_idx | (par << 30), b[32]);
+    race_store_state(d, i, s, tick, ring_idx | RING_EXTERNAL, b[32]);
     race_store_current_ring(d, i, g);
     race_observe<STRICT>(s, b[27], g, obs_row);
 }
-
-// ---------------------------------------------------------------- TMA bulk store helpers
-__device__ __forceinline__ void tma_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_1d(void *gdst, const void *ssrc, uint32_t bytes) {
-    uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------- async copy helpers
 __device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async8(void *sdst, const void *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *sdst, const void *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-// all but the N most recent bulk (TMA) store groups have fully completed (writes performed)
-template <int N> __device__ __forceinline__ void tma_store_wait_done() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
 // per-warp shared memory:
 //   stage  11 float4 per lane: inputs of the NEXT tile, in flight while the current tile computes
-//   obs    the 32x29 observation tile of the current tile (source of the TMA bulk store)
-//   adopt  7 float4 per lane: the prepared episode of a lane whose env just finished, in
+//   obs    the 32x29 observation tile of the current tile (staging for the coalesced store)
+//   adopt  6 float4 per lane: the prepared episode of a lane whose env just finished, in
 //          flight while the NEXT tile computes
-constexpr int RACE_STAGE_SLOTS = 11; // act, S0..S4, P0..P2, C0, (j_mot | - | C1.x C1.y)
-constexpr int RACE_ADOPT_SLOTS = 7;  // N0..N2, spawn, ring0 (pos,n.x), (n.y n.z j_mot -), (EP SLOT_EP - -)
+constexpr int RACE_STAGE_SLOTS = 11; // act, S0..S4, P0..P2, C0, T
+constexpr int RACE_ADOPT_SLOTS = 6;  // N0..N2, (spawn, j_mot), ring0 (pos,n.x), (n.y, n.z, episode tag, -)
 constexpr int RACE_STAGE_BYTES = RACE_STAGE_SLOTS * 32 * 16;
 constexpr int RACE_TILE_BYTES = 32 * RACE_OBS * 4;
 constexpr int RACE_WARP_SMEM = RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_SLOTS * 32 * 16;
-constexpr int RACE_SMEM_BYTES = (RACE_BLOCK / 32) * RACE_WARP_SMEM;
+constexpr int RACE_SMEM_BYTES = RACE_WARPS * RACE_WARP_SMEM;
 
 __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *stage, int lane, int i) {
     const size_t ld = d.ld;
@@ -377,202 +373,190 @@ __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *sta
 #pragma unroll
     for (int k = 0; k < 3; k++) cp_async16(&stage[(6 + k) * 32 + lane], &d.P[k * ld + i]);
     cp_async16(&stage[9 * 32 + lane], &d.C0[i]);
-    float *tail = reinterpret_cast<float *>(&stage[10 * 32 + lane]);
-    cp_async4(tail, &d.PJ[i]);
-    cp_async8(tail + 2, &d.C1[i]);
+    cp_async16(&stage[10 * 32 + lane], &d.T[i]);
 }
 
-// the prepared episode of env i (ring buffer par^1 holds its rings) -> this lane's adopt slots
-__device__ __forceinline__ void race_prefetch_slot(const RaceDev &d, float4 *adopt, int lane, int i, int par) {
+// the prepared episode of env i -> this lane's adopt slots
+__device__ __forceinline__ void race_prefetch_slot(const RaceDev &d, float4 *adopt, int lane, int i) {
     const size_t ld = d.ld;
-    const size_t g = (size_t)(par ^ 1) * d.max_rings * ld + i;
 #pragma unroll
     for (int k = 0; k < 3; k++) cp_async16(&adopt[k * 32 + lane], &d.N[k * ld + i]);
     cp_async16(&adopt[3 * 32 + lane], &d.NS[i]);
-    cp_async16(&adopt[4 * 32 + lane], &d.G0[g]);
-    float *t5 = reinterpret_cast<float *>(&adopt[5 * 32 + lane]);
-    cp_async8(t5, &d.G1[g]);
-    cp_async4(t5 + 2, &d.NJ[i]);
-    uint32_t *t6 = reinterpret_cast<uint32_t *>(&adopt[6 * 32 + lane]);
-    cp_async4(t6, &d.EP[i]);
-    cp_async4(t6 + 1, &d.SLOT_EP[i]);
+    cp_async16(&adopt[4 * 32 + lane], &d.NR0[i]);
+    cp_async16(&adopt[5 * 32 + lane], &d.NR1[i]);
 }
 
-// A finished env starts its next episode: ADOPT the prepared slot (already copied into this
-// lane's adopt slots): the two ring buffers swap roles, params / spawn / ring 0 are installed,
-// the first observation row is written, and the consumed slot is described for the refill
-// pass of the next launch.  The slot was restocked by an earlier launch; its episode tag is
-// verified anyway and a mismatch (possible only if state was edited from outside mid-flight)
-// falls back to generating the episode in place: same function of (seed, env, episode number).
+// A finished env starts episode `want`: ADOPT the prepared slot (already copied into this
+// lane's adopt slots): params / spawn / ring 0 are installed and the first observation row is
+// written.  The slot's episode tag is verified; on a mismatch (slot not restocked yet: an env
+// finishing again within a step or two, a full refill ring, or state edited from outside) or
+// when the caller already knows the slot may be mid-rewrite (`trust` false) the episode is
+// generated in place instead: same pure function of (seed, env, episode number).
 template <bool STRICT>
-__device__ __forceinline__ uint2 race_adopt_from_smem(const RaceDev &d, const float4 *adopt, int lane, int i, int par,
-                                                      float *obs_row) {
+__device__ __forceinline__ void race_adopt_from_smem(const RaceDev &d, const float4 *adopt, int lane, int i,
+                                                     uint32_t want, bool trust, float *obs_row) {
     const size_t ld = d.ld;
-    const int npar = par ^ 1;
     const float4 a = adopt[0 * 32 + lane], b = adopt[1 * 32 + lane], c = adopt[2 * 32 + lane];
-    const float4 sp = adopt[3 * 32 + lane], r0 = adopt[4 * 32 + lane], t5 = adopt[5 * 32 + lane];
-    const uint4 t6 = reinterpret_cast<const uint4 *>(adopt)[6 * 32 + lane];
-    const uint32_t want = t6.x + 1u;
-    if (t6.y == want) {
+    const float4 sp = adopt[3 * 32 + lane], r0 = adopt[4 * 32 + lane], r1 = adopt[5 * 32 + lane];
+    if (trust && __float_as_uint(r1.z) == want) {
         float s[17];
 #pragma unroll
         for (int k = 0; k < 17; k++) s[k] = 0.0f;
         s[6] = 1.0f;
         s[0] = sp.x; s[1] = sp.y; s[2] = sp.z;
-        const float ring0[6] = {r0.x, r0.y, r0.z, r0.w, t5.x, t5.y};
+        const float ring0[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
         d.P[0 * ld + i] = a;
         d.P[1 * ld + i] = b;
         d.P[2 * ld + i] = c;
-        d.PJ[i] = t5.z;
-        race_store_state(d, i, s, 0, npar << 30, 0.0f);
+        reinterpret_cast<float2 *>(&d.T[i])[0] = make_float2(sp.w, __uint_as_float(want));
+        race_store_state(d, i, s, 0, 0, 0.0f);
         race_store_current_ring(d, i, ring0);
         race_observe<STRICT>(s, c.z, ring0, obs_row);
     } else {
-        race_begin_generated<STRICT>(d, i, want, npar, obs_row);
+        race_begin_generated<STRICT>(d, i, want, obs_row);
     }
-    d.EP[i] = want;
-    return make_uint2((uint32_t)i | ((uint32_t)par << 31), want + 1u);
-}
-
-// ---------------------------------------------------------------- queues
-__device__ __forceinline__ uint2 *race_queue(const RaceDev &d, unsigned int which, int shard) {
-    return d.refill + ((size_t)which * QUEUE_ENV_SHARDS + shard) * d.queue_cap;
-}
-// tile shard s owns tiles [s*per, min((s+1)*per, ntiles))
-__device__ __forceinline__ int race_tiles_per_shard(int ntiles) { return (ntiles + QUEUE_TILE_SHARDS - 1) / QUEUE_TILE_SHARDS; }
-
-// Blocking claim with stealing (lane 0 only): used once the warp's home shard ran dry.
-__device__ __noinline__ int race_claim_tile_slow(Ctl *ctl, int home, int ntiles) {
-    const int per = race_tiles_per_shard(ntiles);
-    for (int k = 1; k < QUEUE_TILE_SHARDS; k++) {
-        const int s = (home + k) % QUEUE_TILE_SHARDS;
-        const int end = min((s + 1) * per, ntiles);
-        if ((int)*((volatile unsigned int *)&ctl->tile_next[s].v) < end) {
-            const int t = (int)atomicAdd(&ctl->tile_next[s].v, 1u);
-            if (t < end) return t;
-        }
-    }
-    return ntiles;
 }
 
 // ---------------------------------------------------------------- the step kernel
-// ONE launch per vec_step.  Persistent grid (one resident set of CTAs per SM), RACE_BLOCK
-// threads each; every warp is independent and never waits on another.
-//   prologue: the first warps regenerate the prepared slots consumed in the previous step (32
-//     slots per warp, every lane busy: Philox + trig, ~3000 dependent instructions),
-//     overlapped with the other warps' stepping.
-//   main loop: warps pull tiles of 32 envs (one env per lane) from sharded atomic tile
-//     counters, so late starters simply take fewer tiles.  Everything with memory latency is
-//     software-pipelined one tile deep and costs no registers:
-//       * the inputs of the warp's next tile stream into shared memory with cp.async while
-//         the current tile computes (~1000 FP32 instructions per lane);
-//       * the tile after that is being claimed (atomic in flight);
-//       * a lane whose env finished streams the env's prepared next episode into shared
-//         memory and installs it one tile later (no dependent-load stall, no second kernel).
-//     Each warp stages its 32 observation rows in its own shared-memory tile and ships them
-//     as one 3,712-byte TMA bulk store (row-major [N,29] rows are 116 B, not a multiple of 16,
-//     so per-lane vector stores cannot be coalesced).  Episode statistics are summed per CTA
-//     in shared memory and flushed by whichever warp of the CTA finishes last.
+// ONE launch per vec_step.  Persistent grid (RACE_MIN_CTAS resident CTAs per SM), RACE_WARPS
+// warps each; a warp owns one tile of 32 envs at a time (one env per lane).
+//
+// Tile order.  CTA c owns tiles c, c+G, c+2G, ... (G = grid size; the same CTA owns the same
+// envs in every launch) and its warps draw them through a SHARED-MEMORY ticket, so a warp that
+// spent time restocking episode slots simply takes fewer tiles.  Across the grid the warps
+// sweep every array as one contiguous frontier, which is what DRAM wants (sharded dynamic
+// claims ran 4% slower with 16 frontiers and 50% slower with 256).
+//
+// Everything with memory latency is software-pipelined one tile deep and costs no registers:
+//   * the inputs of the warp's next tile stream into shared memory (cp.async) while the
+//     current tile computes (~1000 FP32 instructions per lane);
+//   * a lane whose env finished streams the env's prepared next episode into shared memory
+//     and installs it one tile later (no dependent-load stall, no second kernel).
+// Observation rows ([N,29] row-major, 116 B: not a multiple of 16) are staged per warp in
+// shared memory and leave as lane-consecutive float4 stores, 512 B per instruction.
+//
+// Restocking.  Installing an episode consumes the env's prepared slot; the slot is described
+// by an entry in the CTA's refill ring (shared memory).  Whenever 32 entries are waiting, the
+// next warp that finishes a tile regenerates them in one pass with every lane busy (Philox +
+// trig, ~7800 instructions).  One pass at a time per CTA and FIFO order, so two generations for
+// the same env never interleave.  Fewer than 32 entries left at the end of a launch are carried
+// to the next one (d.carry); an env listed there may have its slot rewritten while the next
+// launch runs, so if it finishes again meanwhile it is generated in place (`s_pending`).
+// Enqueueing is best effort: a full ring drops the entry and the tag check covers it later.
+//
+// No global atomic in this kernel returns a value (see Ctl).
 template <bool STRICT>
 __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(const __grid_constant__ RaceDev d) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ int s_done;
     __shared__ int s_acc[8];
+    __shared__ unsigned int s_ticket;             // tile tickets handed out so far in this CTA
+    __shared__ unsigned int s_q_head, s_q_tail;   // refill ring: entries [tail, head), monotonic
+    __shared__ unsigned int s_q_lock;             // one refill pass at a time
+    __shared__ unsigned int s_npending;           // carried-over entries whose slots are not restocked yet
+    __shared__ unsigned int s_pending[RACE_CARRY];
+    __shared__ uint2 s_queue[RACE_QUEUE_CAP];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    if (tid < 8) s_acc[tid] = 0;
-    if (tid == 8) s_done = 0;
-    __syncthreads();
+    const int G = gridDim.x;
+    const int ntiles = (d.n + 31) >> 5;
+    const bool inject = d.reset_mode == 1; // B2D_RESET_INJECT (parity hook)
     float4 *stage = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM);
     float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES);
     float4 *adopt = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES + RACE_TILE_BYTES);
     float *my_row = tile_obs + lane * RACE_OBS;
-    const int warps_total = gridDim.x * (RACE_BLOCK / 32);
-    const int gw = blockIdx.x * (RACE_BLOCK / 32) + warp;
-    const int ntiles = (d.n + 31) >> 5;
-    const uint32_t epoch = d.ctl->epoch + 1u;
-    const bool inject = d.reset_mode == 1; // B2D_RESET_INJECT (parity hook)
 
-    // claim the first tiles from the warp's home shard; two further claims stay in flight so a
-    // claim's round trip to L2 has two whole tiles to complete
-    const unsigned int src = (epoch - 1u) & 1u;
-    const int home = gw % QUEUE_TILE_SHARDS;
-    const int home_end = min((home + 1) * race_tiles_per_shard(ntiles), ntiles);
-    int tile = 0, next = 0, claim_a = 0, claim_b = 0; // raw claims (lane 0); resolved when they become `next`
-    if (lane == 0) {
-        tile = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
-        next = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
-        claim_a = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
-        if (tile >= home_end) tile = race_claim_tile_slow(d.ctl, home, ntiles);
+    // Launch overlap (b2d_vec_step_tape): the next launch of this kernel may begin while this one
+    // drains; its CTA c owns the same envs as this CTA c and waits for exactly this CTA's flag.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (d.chain_wait) {
+        if (tid == 0) {
+            unsigned int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(d.chain + blockIdx.x) : "memory");
+                if (seen != d.seq - 1u) __nanosleep(64);
+            } while (seen != d.seq - 1u);
+        }
+        __syncthreads();
     }
-    tile = __shfl_sync(0xffffffffu, tile, 0);
+
+    // the first two tickets of every warp are static, so the first loads leave before any barrier
+    int tile = warp * G + blockIdx.x;
+    int next = (RACE_WARPS + warp) * G + blockIdx.x;
     if (tile < ntiles && tile * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, tile * 32 + lane);
     cp_async_commit(); // group: inputs of the first tile
     cp_async_commit(); // group: (empty) adoption loads "of the tile before the first"
 
-    // ---- prologue: restock the prepared slots consumed during step epoch-1
-    {
-        const unsigned int stride = (unsigned int)max(warps_total / QUEUE_ENV_SHARDS, 1) * 32u;
-        // with fewer warps than shards a warp walks several shards; the warps beyond a whole
-        // multiple of the shard count would only repeat chunks, so they skip the prologue
-        const bool spare = warps_total >= QUEUE_ENV_SHARDS && gw >= (warps_total / QUEUE_ENV_SHARDS) * QUEUE_ENV_SHARDS;
-        for (int sh = gw % QUEUE_ENV_SHARDS; sh < QUEUE_ENV_SHARDS && !spare; sh += warps_total) {
-            const unsigned int c = d.ctl->queue_count[src][sh].v;
-            const uint2 *l = race_queue(d, src, sh);
-            for (unsigned int k = (unsigned int)(gw / QUEUE_ENV_SHARDS) * 32u + lane; k < ((c + 31u) & ~31u); k += stride) {
-                if (k < c) {
-                    uint2 e = l[k];
-                    race_fill_slot(d, (int)(e.x & 0x7fffffffu), e.y, (int)(e.x >> 31));
-                }
-            }
+    if (tid < 8) s_acc[tid] = 0;
+    for (int k = tid; k < RACE_QUEUE_CAP; k += RACE_BLOCK) s_queue[k] = make_uint2(QUEUE_EMPTY, 0u);
+    __syncthreads();
+    if (warp == 0) { // entries carried over from the previous launch seed the ring
+        const uint2 e = __ldcg(&d.carry[(size_t)blockIdx.x * RACE_CARRY + lane]);
+        const bool have = e.x != QUEUE_EMPTY && !inject;
+        const unsigned int m = __ballot_sync(0xffffffffu, have);
+        if (have) {
+            const int slot = __popc(m & ((1u << lane) - 1u));
+            s_queue[slot] = e;
+            s_pending[slot] = e.x;
         }
-        __syncwarp();
+        if (lane == 0) {
+            s_done = 0;
+            s_ticket = 2 * RACE_WARPS;
+            s_q_head = (unsigned int)__popc(m);
+            s_q_tail = 0u;
+            s_q_lock = 0u;
+            s_npending = (unsigned int)__popc(m);
+        }
     }
+    __syncthreads();
+
+#if B2D_EXPERIMENT_TIMING
+    long long tm_wait = 0, tm_math = 0, tm_store = 0, tm_adopt = 0, tm_iters = 0, tm_inst = 0, tm_refill = 0;
+    const long long t_begin = clock64();
+#endif
 
     // state carried from one tile to the next
-    bool store_pending = false;      // a TMA store of this warp's observation tile is in flight
-    bool pend_adopt = false;         // this lane's env finished in the previous tile (Philox mode)
-    int pend_i = 0, pend_par = 0;
-    unsigned int pend_m = 0u, pend_base = 0u; // ballot of pend_adopt, refill-queue slot reserved for them
-    int pend_shard = 0;
+    bool pend_adopt = false; // this lane's env finished in the previous tile (Philox mode)
+    bool pend_trust = true;  // ... and its prepared slot cannot be mid-rewrite
+    int pend_i = 0;
+    uint32_t pend_want = 0u; // episode number it starts next
+    unsigned int pend_m = 0u; // ballot of pend_adopt
+    int claim = 0;            // lane 0: ticket for the tile after `next`
 
     while (true) {
         const bool have_tile = tile < ntiles;
         if (!have_tile && pend_m == 0u) break;
-        if (have_tile) {
-            if (lane == 0 && next >= home_end) next = race_claim_tile_slow(d.ctl, home, ntiles);
-            next = __shfl_sync(0xffffffffu, next, 0);
-        }
         const int i = tile * 32 + lane;
         const bool valid = have_tile && i < d.n;
+        B2D_TICK(t0);
         cp_async_wait<1>(); // this tile's inputs have landed (the newest group, adoption loads, may still fly)
+        B2D_TICK(t1);
         const float4 a4 = stage[0 * 32 + lane];
         const float4 q0 = stage[1 * 32 + lane], q1 = stage[2 * 32 + lane], q2 = stage[3 * 32 + lane],
                      q3 = stage[4 * 32 + lane], q4 = stage[5 * 32 + lane];
         const float4 p0 = stage[6 * 32 + lane], p1 = stage[7 * 32 + lane], p2 = stage[8 * 32 + lane];
         const float4 c0 = stage[9 * 32 + lane];
-        const float4 tl = stage[10 * 32 + lane]; // (j_mot, -, C1.x, C1.y)
-        // the previous tile's observation store must have read the tile before it is rewritten
-        if (store_pending && lane == 0) tma_store_wait_read();
+        const float4 tl = stage[10 * 32 + lane]; // (j_mot, episode, ring n.y, ring n.z)
         __syncwarp();
         if (have_tile && next < ntiles && next * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, next * 32 + lane);
         cp_async_commit(); // group: inputs of the next tile
-        if (have_tile && lane == 0) claim_b = (int)atomicAdd(&d.ctl->tile_next[home].v, 1u);
+        if (have_tile && lane == 0) claim = (int)atomicAdd(&s_ticket, 1u); // shared memory: lands within the tile
 
         float s[17];
         float ring[6];
         float mrpm = 1.0f, ep_ret = 0.0f;
-        int tick = 0, ring_idx = 0, par = 0, cause = -1;
+        int tick = 0, ring_idx = 0, ring_ext = 0, cause = -1;
+        const uint32_t episode = __float_as_uint(tl.y);
         if (valid) {
             s[0] = q0.x; s[1] = q0.y; s[2] = q0.z; s[3] = q0.w; s[4] = q1.x; s[5] = q1.y; s[6] = q1.z; s[7] = q1.w;
             s[8] = q2.x; s[9] = q2.y; s[10] = q2.z; s[11] = q2.w; s[12] = q3.x; s[13] = q3.y; s[14] = q3.z; s[15] = q3.w;
             s[16] = q4.x;
             tick = __float_as_int(q4.y) + 1;
             const int ring_word = __float_as_int(q4.z);
-            ring_idx = ring_word & 0x3fffffff;
-            par = (ring_word >> 30) & 1;
+            ring_idx = ring_word & RING_INDEX_MASK;
+            ring_ext = ring_word & RING_EXTERNAL;
             ep_ret = q4.w;
             DroneParams p = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, tl.x};
             mrpm = p2.z;
@@ -590,7 +574,11 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
             if (d.act_out) reinterpret_cast<float4 *>(d.act_out)[i] = make_float4(act[0], act[1], act[2], act[3]);
 
             const float before[3] = {s[0], s[1], s[2]};
+#if B2D_EXPERIMENT_SKIP_MATH
+            s[0] = fmaf(act[0], 1e-6f, s[0]); s[4] += p.mass * 1e-9f; s[13] += act[3];
+#else
             advance_body<STRICT>(s, p, act);
+#endif
 
             // ---- episode logic: R/drone_race.h:165-203
             float reward = 0.0f;
@@ -612,24 +600,23 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
                     cause = ACC_TIMEOUT;
                 } else if (ring_idx == d.max_rings) {
                     cause = ACC_SPARE; // course complete
-                } else if (gate > 0.0f) {
-                    race_load_ring(d, i, par, ring_idx, ring);
+                } else if (gate > 0.0f) { // the next ring becomes the current one
+                    if (ring_ext) race_load_external_ring(d, i, ring_idx, ring);
+                    else race_next_ring(d, i, episode, ring_idx, ring);
                     race_store_current_ring(d, i, ring);
                 }
             }
             d.rew[i] = reward;
             d.term[i] = cause >= 0 ? 1 : 0;
         }
+        B2D_TICK(t2);
 
         // ---- finished lanes book the episode; their next episode is installed one tile later
         const bool finished = cause >= 0;
         const bool adopt_now = finished && !inject;
         const unsigned int m = __ballot_sync(0xffffffffu, adopt_now);
-        const int qshard = tile % QUEUE_ENV_SHARDS;
-        unsigned int base = 0;
-        if (m != 0u && lane == 0) base = atomicAdd(&d.ctl->queue_count[epoch & 1u][qshard].v, (unsigned int)__popc(m));
         if (valid && !finished) {
-            race_store_state(d, i, s, tick, ring_idx | (par << 30), ep_ret);
+            race_store_state(d, i, s, tick, ring_idx | ring_ext, ep_ret);
             race_observe<STRICT>(s, mrpm, ring, my_row);
         }
         if (finished) {
@@ -639,97 +626,159 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
             atomicAdd(&s_acc[ACC_LENGTH], tick);
             atomicAdd(&s_acc[ACC_RINGS], ring_idx);
             if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
-            if (inject) race_inject_episode<STRICT>(d, i, par, my_row);
+            if (inject) race_inject_episode<STRICT>(d, i, episode + 1u, my_row);
         }
         __syncwarp();
 
-        // ---- observations out: one TMA bulk store per full warp tile (rows of lanes that
-        // finished hold stale data here; they are rewritten when the episode is installed)
-        bool stored_now = false;
+        // ---- observations out: the warp's 3,712-byte tile as 232 lane-consecutive float4.
+        // Rows of lanes that finished hold stale data here; they are rewritten when the episode
+        // is installed one tile later.
         if (have_tile) {
             const int rows = min(32, d.n - tile * 32);
+            float *gobs = d.obs + (size_t)tile * 32 * RACE_OBS;
             if (rows == 32) {
-                stored_now = true;
-                if (lane == 0) {
-                    tma_store_fence();
-                    tma_store_1d(d.obs + (size_t)tile * 32 * RACE_OBS, tile_obs, RACE_TILE_BYTES);
-                }
-                store_pending = true;
+                const float4 *src = reinterpret_cast<const float4 *>(tile_obs);
+                float4 *dst = reinterpret_cast<float4 *>(gobs);
+#pragma unroll
+                for (int k = 0; k < 7; k++) __stcs(&dst[k * 32 + lane], src[k * 32 + lane]);
+                if (lane < 8) __stcs(&dst[224 + lane], src[224 + lane]);
             } else {
-                float *gobs = d.obs + (size_t)tile * 32 * RACE_OBS;
                 for (int k = lane; k < rows * RACE_OBS; k += 32) gobs[k] = tile_obs[k];
-                __syncwarp();
             }
+            __syncwarp();
         }
+        B2D_TICK(t3);
 
         // ---- install the next episode of the envs that finished in the PREVIOUS tile
         cp_async_wait<1>(); // their prepared slots have landed (only the next tile's inputs may still fly)
+        B2D_TICK(t4);
         if (pend_m != 0u) {
-            pend_base = __shfl_sync(0xffffffffu, pend_base, 0);
-            // their stale rows went out with the previous tile's bulk store: it must be complete
-            if (lane == 0) {
-                if (stored_now) tma_store_wait_done<1>(); // all but the store issued a moment ago
-                else tma_store_wait_done<0>();
-            }
-            __syncwarp();
+            __syncwarp(); // their stale rows (stored by other lanes one tile ago) are ordered before the rewrite
             if (pend_adopt) {
-                const uint2 e = race_adopt_from_smem<STRICT>(d, adopt, lane, pend_i, pend_par, d.obs + (size_t)pend_i * RACE_OBS);
-                race_queue(d, epoch & 1u, pend_shard)[pend_base + __popc(pend_m & ((1u << lane) - 1u))] = e;
+                race_adopt_from_smem<STRICT>(d, adopt, lane, pend_i, pend_want, pend_trust, d.obs + (size_t)pend_i * RACE_OBS);
+                const uint2 e = make_uint2((uint32_t)pend_i, pend_want + 1u); // the slot is consumed
+                // best-effort enqueue of the consumed slot
+                for (;;) {
+                    const unsigned int h = *(volatile unsigned int *)&s_q_head;
+                    if (h - *(volatile unsigned int *)&s_q_tail >= (unsigned int)RACE_QUEUE_CAP) break; // full: drop
+                    if (atomicCAS(&s_q_head, h, h + 1u) == h) {
+                        volatile uint2 *q = &s_queue[h & (RACE_QUEUE_CAP - 1)];
+                        q->y = e.y; // .x (the non-empty marker) last
+                        q->x = e.x;
+                        break;
+                    }
+                }
             }
             __syncwarp();
         }
-        // ---- and start streaming the prepared slots of the envs that finished in THIS tile
-        if (adopt_now) race_prefetch_slot(d, adopt, lane, i, par);
+        B2D_TICK(t5);
+
+        // ---- restock: 32 waiting entries -> one full-occupancy generation pass by this warp
+        if (!inject) {
+            unsigned int take = QUEUE_EMPTY;
+            if (lane == 0) {
+                const unsigned int tl0 = *(volatile unsigned int *)&s_q_tail;
+                if (*(volatile unsigned int *)&s_q_head - tl0 >= 32u && atomicCAS(&s_q_lock, 0u, 1u) == 0u) {
+                    const unsigned int tl1 = *(volatile unsigned int *)&s_q_tail; // re-read under the lock
+                    if (*(volatile unsigned int *)&s_q_head - tl1 >= 32u) take = tl1;
+                    else atomicExch(&s_q_lock, 0u);
+                }
+            }
+            take = __shfl_sync(0xffffffffu, take, 0);
+            if (take != QUEUE_EMPTY) {
+                volatile uint2 *slot = &s_queue[(take + lane) & (RACE_QUEUE_CAP - 1)];
+                uint2 e;
+                do { // the producer writes the entry right after reserving it
+                    e.x = slot->x;
+                    e.y = slot->y;
+                } while (e.x == QUEUE_EMPTY);
+                slot->x = QUEUE_EMPTY;
+                __syncwarp();
+                if (lane == 0) *(volatile unsigned int *)&s_q_tail = take + 32u; // the 32 ring slots may be reused
+                race_fill_slot(d, (int)e.x, e.y);
+                __threadfence(); // slots complete before the pending list is lifted / the lock is released
+                __syncwarp();
+                if (lane == 0) {
+                    if (take == 0u) *(volatile unsigned int *)&s_npending = 0u; // carried entries sit at the ring's front
+                    atomicExch(&s_q_lock, 0u);
+                }
+            }
+        }
+        B2D_TICK(t6);
+
+        // ---- start streaming the prepared slots of the envs that finished in THIS tile
+        bool trust = true;
+        if (adopt_now) {
+            const unsigned int np = *(volatile unsigned int *)&s_npending;
+            for (unsigned int k = 0; k < np; k++) trust = trust && s_pending[k] != (unsigned int)i;
+            race_prefetch_slot(d, adopt, lane, i);
+        }
         cp_async_commit(); // group: adoption loads of this tile (possibly empty)
         pend_adopt = adopt_now;
+        pend_trust = trust;
         pend_i = i;
-        pend_par = par;
+        pend_want = episode + 1u;
         pend_m = m;
-        pend_base = base;
-        pend_shard = qshard;
-
+#if B2D_EXPERIMENT_TIMING
+        tm_wait += t1 - t0; tm_math += t2 - t1; tm_store += t3 - t2; tm_adopt += t4 - t3; tm_inst += t5 - t4;
+        tm_refill += t6 - t5; tm_iters += 1;
+#endif
         if (have_tile) {
             tile = next;
-            next = claim_a; // claimed two tiles ago
-            claim_a = claim_b;
+            next = __shfl_sync(0xffffffffu, claim, 0) * G + blockIdx.x;
         }
     }
-    if (store_pending && lane == 0) tma_store_wait_read();
+    cp_async_wait<0>();
+
+#if B2D_EXPERIMENT_TIMING
+    if (lane == 0) {
+        atomicAdd(&d.ctl->dbg[0], (unsigned long long)tm_wait); atomicAdd(&d.ctl->dbg[1], (unsigned long long)tm_math);
+        atomicAdd(&d.ctl->dbg[2], (unsigned long long)tm_store); atomicAdd(&d.ctl->dbg[3], (unsigned long long)tm_adopt);
+        atomicAdd(&d.ctl->dbg[4], (unsigned long long)tm_iters); atomicAdd(&d.ctl->dbg[5], (unsigned long long)tm_refill);
+        atomicAdd(&d.ctl->dbg[6], (unsigned long long)(clock64() - t_begin)); atomicAdd(&d.ctl->dbg[7], 1ull);
+        atomicAdd(&d.ctl->dbg[8], (unsigned long long)tm_inst);
+        atomicMax(&d.ctl->dbg[9], (unsigned long long)(clock64() - t_begin));
+    }
+#endif
 
     // ---- CTA epilogue by whichever warp finishes last
     int last = 0;
     __syncwarp();
-    if (lane == 0) {
-        __threadfence_block();
-        last = atomicAdd(&s_done, 1) == RACE_BLOCK / 32 - 1;
-    }
+    __threadfence(); // this warp's state is visible device-wide before the CTA's completion flag can be
+    if (lane == 0) last = atomicAdd(&s_done, 1) == RACE_WARPS - 1;
     last = __shfl_sync(0xffffffffu, last, 0);
     if (last) {
         __threadfence_block();
-        if (lane < 7) {
-            int v = s_acc[lane];
-            if (v != 0) {
-                atomicAdd((unsigned long long *)&d.ctl->acc[lane], (unsigned long long)(long long)v);
-                if (lane == ACC_RINGS)
-                    atomicAdd((unsigned long long *)&d.ctl->score_step[epoch & 1u], (unsigned long long)(long long)v);
-            }
+        // whole passes still waiting (only when slots were consumed faster than they could be restocked)
+        unsigned int tl0 = *(volatile unsigned int *)&s_q_tail;
+        const unsigned int hd = *(volatile unsigned int *)&s_q_head;
+        while (hd - tl0 >= 32u) {
+            const uint2 e = s_queue[(tl0 + lane) & (RACE_QUEUE_CAP - 1)];
+            race_fill_slot(d, (int)e.x, e.y);
+            tl0 += 32u;
         }
-        __syncwarp();
-        // ---- every CTA takes a ticket; the last one closes the step.  No device-scope fence is
-        // needed: everything a CTA publishes is consumed by the NEXT launch, and the closing
-        // writes touch only words no CTA of this launch reads after taking its ticket.
+        // the rest (< 32 entries) is carried to the next launch
+        {
+            uint2 e = make_uint2(QUEUE_EMPTY, 0u);
+            if ((unsigned int)lane < hd - tl0) e = s_queue[(tl0 + lane) & (RACE_QUEUE_CAP - 1)];
+            d.carry[(size_t)blockIdx.x * RACE_CARRY + lane] = e;
+        }
+        if (lane < 7) {
+            const int v = s_acc[lane];
+            if (v != 0) atomicAdd((unsigned long long *)&d.ctl->acc[lane], (unsigned long long)(long long)v);
+            if (lane == ACC_RINGS) d.cta_score[blockIdx.x] = (long long)v;
+        }
+#if B2D_EXPERIMENT_TIMING
         if (lane == 0) {
-            unsigned int t = atomicAdd(&d.ctl->ticket, 1u);
-            if (t == gridDim.x - 1) {
-                d.ctl->score_step[(epoch + 1u) & 1u] = 0;
-                // the queue this launch consumed is the one step epoch+1 appends to
-                for (int q = 0; q < QUEUE_ENV_SHARDS; q++) d.ctl->queue_count[(epoch + 1u) & 1u][q].v = 0;
-                const int per = race_tiles_per_shard(ntiles);
-                for (int q = 0; q < QUEUE_TILE_SHARDS; q++) d.ctl->tile_next[q].v = (unsigned int)(q * per);
-                d.ctl->ticket = 0;
-                __threadfence();
-                d.ctl->epoch = epoch;
-            }
+            atomicAdd(&d.ctl->dbg[10], (unsigned long long)(clock64() - t_begin)); // CTA busy time
+            atomicMax(&d.ctl->dbg[11], (unsigned long long)(clock64() - t_begin));
+        }
+#endif
+        __syncwarp();
+        if (lane == 0) {
+            atomicAdd(&d.ctl->ctas_done, 1u); // result unused: a reduction, not a returning atomic
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(d.chain + blockIdx.x), "r"(d.seq) : "memory");
         }
     }
 }
@@ -740,50 +789,50 @@ __global__ void __launch_bounds__(128) race_reset_kernel(const __grid_constant__
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
     if (d.reset_mode == 1 /* B2D_RESET_INJECT */) {
-        race_inject_episode<true>(d, i, 0, d.obs + (size_t)i * RACE_OBS);
+        race_inject_episode<true>(d, i, 0u, d.obs + (size_t)i * RACE_OBS);
         return;
     }
-    race_begin_generated<true>(d, i, 0u, 0, d.obs + (size_t)i * RACE_OBS);
-    d.EP[i] = 0u;
-    race_fill_slot(d, i, 1u, 1);
+    race_begin_generated<true>(d, i, 0u, d.obs + (size_t)i * RACE_OBS);
+    race_fill_slot(d, i, 1u);
 }
 
-// Refill every slot still queued from the last step now (instead of overlapped with the next
-// step) -- used before state is edited from outside (put_state), so that no refill is in flight
-// while the edited env may finish again.
-__global__ void __launch_bounds__(128) race_drain_kernel(const __grid_constant__ RaceDev d) {
-    const unsigned int src = d.ctl->epoch & 1u;
-    const unsigned int cnt = d.ctl->queue_count[src][blockIdx.y].v;
-    const uint2 *list = race_queue(d, src, blockIdx.y);
-    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
-        uint2 e = list[k];
-        if (e.y != 0xffffffffu) race_fill_slot(d, (int)(e.x & 0x7fffffffu), e.y, (int)(e.x >> 31));
-    }
-}
-__global__ void race_drain_done_kernel(Ctl *ctl) {
-    if (threadIdx.x < QUEUE_ENV_SHARDS) ctl->queue_count[ctl->epoch & 1u][threadIdx.x].v = 0;
+// Restock every slot still listed in the carry-over lists now (instead of during the next
+// step) -- used before state is edited from outside (put_state), so that no refill is pending
+// while an edited env may finish again.  One warp per step CTA.
+__global__ void __launch_bounds__(32) race_drain_kernel(const __grid_constant__ RaceDev d) {
+    uint2 *slot = &d.carry[(size_t)blockIdx.x * RACE_CARRY + threadIdx.x];
+    const uint2 e = *slot;
+    if (e.x != QUEUE_EMPTY) race_fill_slot(d, (int)e.x, e.y);
+    *slot = make_uint2(QUEUE_EMPTY, 0u);
 }
 
-__global__ void race_ctl_reset_kernel(Ctl *ctl, unsigned int epoch, int clear_acc, int ntiles) {
+// (re)initialise the control block: step counter, carry-over lists, optionally the statistics
+__global__ void race_ctl_reset_kernel(Ctl *ctl, uint2 *carry, long long *cta_score, unsigned int steps, unsigned int grid,
+                                      int clear_acc) {
+    for (unsigned int k = threadIdx.x; k < grid * RACE_CARRY; k += blockDim.x) carry[k] = make_uint2(QUEUE_EMPTY, 0u);
+    for (unsigned int k = threadIdx.x; k < grid; k += blockDim.x) cta_score[k] = 0;
     if (threadIdx.x == 0) {
-        ctl->epoch = epoch;
-        ctl->ticket = 0;
-        for (int q = 0; q < QUEUE_ENV_SHARDS; q++) ctl->queue_count[0][q].v = ctl->queue_count[1][q].v = 0;
-        for (int q = 0; q < QUEUE_TILE_SHARDS; q++) ctl->tile_next[q].v = (unsigned int)(q * race_tiles_per_shard(ntiles));
-        ctl->score_step[0] = ctl->score_step[1] = 0;
+        ctl->grid = grid;
+        ctl->ctas_done = steps * grid;
         if (clear_acc) {
             for (int k = 0; k < ACC_COUNT; k++) ctl->acc[k] = 0;
             for (int k = 0; k < 8; k++) ctl->facc[k] = 0.0;
+            for (int k = 0; k < 12; k++) ctl->dbg[k] = 0;
         }
     }
 }
 
 // snapshot + clear for vec_log: out[0..7] = acc, out[8] = score of the last step
-__global__ void race_log_snapshot_kernel(Ctl *ctl, long long *out) {
+__global__ void race_log_snapshot_kernel(Ctl *ctl, long long *cta_score, long long *out) {
+    long long sc = 0;
+    for (unsigned int k = threadIdx.x; k < ctl->grid; k += 32) {
+        sc += cta_score[k];
+        cta_score[k] = 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
     if (threadIdx.x == 0) {
         for (int k = 0; k < ACC_COUNT; k++) { out[k] = ctl->acc[k]; ctl->acc[k] = 0; }
-        out[ACC_COUNT] = ctl->score_step[ctl->epoch & 1u];
-        ctl->score_step[0] = ctl->score_step[1] = 0;
+        out[ACC_COUNT] = sc;
     }
 }
 
@@ -794,8 +843,8 @@ __global__ void __launch_bounds__(128) race_observe_kernel(const RaceDev d) {
     float4 q0 = d.S[0 * ld + i], q1 = d.S[1 * ld + i], q2 = d.S[2 * ld + i], q3 = d.S[3 * ld + i], q4 = d.S[4 * ld + i];
     float s[17] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x};
     float4 c0 = d.C0[i];
-    float2 c1 = d.C1[i];
-    float ring[6] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y};
+    float4 c1 = d.T[i];
+    float ring[6] = {c0.x, c0.y, c0.z, c0.w, c1.z, c1.w};
     race_observe<true>(s, d.P[2 * ld + i].z, ring, d.obs + (size_t)i * RACE_OBS);
 }
 
@@ -812,16 +861,23 @@ __global__ void race_pack_kernel(const RaceDev d, const int *ids, int n, float *
     b[8] = q2.x; b[9] = q2.y; b[10] = q2.z; b[11] = q2.w; b[12] = q3.x; b[13] = q3.y; b[14] = q3.z; b[15] = q3.w;
     b[16] = q4.x;
     b[17] = p0.x; b[18] = p0.y; b[19] = p0.z; b[20] = p0.w; b[21] = p1.x; b[22] = p1.y; b[23] = p1.z; b[24] = p1.w;
-    b[25] = p2.x; b[26] = p2.y; b[27] = p2.z; b[28] = p2.w; b[29] = d.PJ[i];
+    const float4 pj = d.T[i];
+    b[25] = p2.x; b[26] = p2.y; b[27] = p2.z; b[28] = p2.w; b[29] = pj.x;
     const int ring_word = __float_as_int(q4.z);
-    b[30] = (float)__float_as_int(q4.y); b[31] = (float)(ring_word & 0x3fffffff); b[32] = q4.w;
+    b[30] = (float)__float_as_int(q4.y); b[31] = (float)(ring_word & RING_INDEX_MASK); b[32] = q4.w;
+    // all rings of the live episode: stored ones, or the lazily generated chain replayed from ring 0
+    float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     for (int r = 0; r < d.max_rings; r++) {
-        float ring[6];
-        race_load_ring(d, i, (ring_word >> 30) & 1, r, ring);
+        if (ring_word & RING_EXTERNAL) race_load_external_ring(d, i, r, ring);
+        else {
+            const float prev[3] = {ring[0], ring[1], ring[2]};
+            race_generate_ring(d, d.env_id_base + (uint32_t)i, __float_as_uint(pj.y), r, prev, ring);
+        }
         for (int c = 0; c < 6; c++) b[33 + 6 * r + c] = ring[c];
     }
 }
 
+// put_state: the blob's rings become external rings of the env's live episode (X0/X1 must exist)
 __global__ void race_unpack_kernel(const RaceDev d, const int *ids, int n, const float *blobs) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -831,13 +887,12 @@ __global__ void race_unpack_kernel(const RaceDev d, const int *ids, int n, const
     float s[17];
     for (int c = 0; c < 17; c++) s[c] = b[c];
     const int ring_idx = (int)b[31];
-    const int par = (__float_as_int(d.S[4 * ld + i].z) >> 30) & 1; // keep the env's ring-buffer parity
-    race_store_state(d, i, s, (int)b[30], ring_idx | (par << 30), b[32]);
-    race_store_params(d, i, b + 17);
+    race_store_state(d, i, s, (int)b[30], ring_idx | RING_EXTERNAL, b[32]);
+    race_store_params(d, i, b + 17, __float_as_uint(d.T[i].y)); // the episode number is kept
     for (int r = 0; r < d.max_rings; r++) {
         const float *g = b + 33 + 6 * r;
-        d.G0[((size_t)par * d.max_rings + r) * ld + i] = make_float4(g[0], g[1], g[2], g[3]);
-        d.G1[((size_t)par * d.max_rings + r) * ld + i] = make_float2(g[4], g[5]);
+        d.X0[(size_t)r * ld + i] = make_float4(g[0], g[1], g[2], g[3]);
+        d.X1[(size_t)r * ld + i] = make_float2(g[4], g[5]);
     }
     const float *g = b + 33 + 6 * (ring_idx < d.max_rings ? ring_idx : 0);
     race_store_current_ring(d, i, g);

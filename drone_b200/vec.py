@@ -47,6 +47,16 @@ class _Vec:
                 raise ValueError("actions must have shape [num_agents, 4]")
             capi.check(L.b2d_vec_step_from(self.h, C.c_void_p(actions.data_ptr()), _stream_ptr(stream)))
 
+    def step_tape(self, tape, first, steps, stream=None):
+        """`steps` consecutive steps reading actions from a CUDA tape [T, num_agents, 4]
+        (slice (first + k) % T at step k); one kernel launch per step, no host work in between."""
+        if tape.dtype != torch.float32 or not tape.is_cuda or not tape.is_contiguous() or tape.dim() != 3:
+            raise ValueError("tape must be a contiguous float32 CUDA tensor [T, num_agents, 4]")
+        if tape.shape[1] * tape.shape[2] != self.num_agents * 4:
+            raise ValueError("tape slices must have shape [num_agents, 4]")
+        capi.check(capi.lib().b2d_vec_step_tape(self.h, C.c_void_p(tape.data_ptr()), int(tape.shape[0]), int(first),
+                                                int(steps), _stream_ptr(stream)))
+
     def step_host(self, stream=None):
         capi.check(capi.lib().b2d_vec_step_host(self.h, _stream_ptr(stream)))
 

@@ -114,6 +114,12 @@ int b2d_vec_step(b2d_vec *vec, void *cuda_stream);
 /* same, reading this step's actions from another device buffer of the same
  * shape (a policy's output tensor, or one slice of an action tape) */
 int b2d_vec_step_from(b2d_vec *vec, const float *device_actions, void *cuda_stream);
+/* `steps` consecutive vec_steps whose actions come from a device-resident tape
+ * [tape_len][num_agents][4] (step k reads slice (first + k) % tape_len) -- the reference's own
+ * cached-action loop (DR/drone_race.py:83-90) without a host round trip per step.  One kernel
+ * launch per step, each reading and writing the contract buffers like b2d_vec_step; successive
+ * launches may overlap at their edges (env shards are independent between steps). */
+int b2d_vec_step_tape(b2d_vec *vec, const float *device_tape, int tape_len, int first, int steps, void *cuda_stream);
 /* host-buffer form of vec_step for callers that keep the reference's NumPy
  * buffers: copies actions H2D, steps, copies observations/rewards/terminals
  * D2H (chunked and overlapped), then synchronises.  Host pointers default to
