@@ -669,3 +669,582 @@ void orc_race_log(OrcRace *o, float out[9]) {
         }
     }
 }
+
+/* ====================================================================== swarm env
+ * R/drone_swarm/drone_swarm.h:84-497 restated.  GRID = (30, 30, 10), MARGIN = GRID - 1
+ * (R/drone_swarm/dronelib.h:39-44), MAX_DIST = sqrtf(60^2 + 60^2 + 20^2) (:50), HORIZON 1024,
+ * rim hits return -0.0f (:485).
+ *
+ * Agents are processed in index order inside c_step; neighbour queries therefore see the
+ * already-moved (and possibly re-spawned) positions of lower-index agents and the previous
+ * tick's positions of higher-index agents.  The restatement keeps the reference's loop
+ * structure literally, so that order dependence is reproduced by construction.
+ *
+ * Reset sources: libc rand() in the reference's draw order (ORC_RESET_LIBC, incl. the unused
+ * dt-jitter draw per drone per step), the device's Philox stream (ORC_RESET_PHILOX), or
+ * injected draw results (ORC_RESET_INJECT).  In every mode the results of the random draws of a
+ * step can be RECORDED into / READ from per-agent and per-env payload rows:
+ *   agent row [ORC_SWARM_AGENT_PAYLOAD = 41]:
+ *     [0:13] params, [13:16] pos                      of an out-of-bounds respawn (reset_agent)
+ *     [16:29] params, [29:32] pos, [32:35] target_pos, [35:38] target_vel, [38:41] race start pos
+ *                                                     of the env-wide reset (c_reset)
+ *   env row [2 + 6*max_rings]: [0] unused, [1] task, then rings pos(3) normal(3)
+ *   flags: agent bit0 = respawned this step; env bit0 = env-wide reset this step
+ */
+#define S_GX 30.0f
+#define S_GY 30.0f
+#define S_GZ 10.0f
+#define S_MX (S_GX - 1)
+#define S_MY (S_GY - 1)
+#define S_MZ (S_GZ - 1)
+#define S_VT 0.05f
+#define S_HORIZON 1024
+#define S_TASK_RACE 7
+
+enum { AX_SPAWN = 0, AX_TPOS = 3, AX_TVEL = 6, AX_LAST_ABS = 9, AX_LAST_TGT = 10, AX_LAST_COL = 11,
+       AX_RETURN = 12, AX_COLLISIONS = 13, AX_SCORE = 14, AX_N = 15 };
+
+struct OrcSwarm {
+    int n, A, R;
+    float *st;   /* [n][A][17] */
+    float *pr;   /* [n][A][13] */
+    float *ax;   /* [n][A][AX_N] */
+    float *prev; /* [n][A][3] prev_pos of the last move_drone */
+    int *ep_len, *ring_idx; /* [n][A] */
+    int *tick, *task;       /* [n] */
+    float *rings;           /* [n][R][7] pos3 normal3 radius */
+    float *logs;            /* [n][9] */
+    uint32_t key[2], env_id_base;
+    uint32_t *env_episode;  /* [n] env-wide resets so far (Philox counter word) */
+    uint32_t *respawns;     /* [n][A] out-of-bounds respawns so far (Philox counter word) */
+    float *pay_agent;       /* [n*A][41] or NULL */
+    unsigned char *flag_agent;
+    float *pay_env;         /* [n][2+6R] or NULL */
+    unsigned char *flag_env;
+    int seed;
+};
+
+OrcSwarm *orc_swarm_create(int n, int num_agents, int max_rings) {
+    OrcSwarm *o = (OrcSwarm *)calloc(1, sizeof(OrcSwarm));
+    o->n = n; o->A = num_agents; o->R = max_rings;
+    size_t na = (size_t)n * num_agents;
+    o->st = (float *)calloc(na * 17, sizeof(float));
+    o->pr = (float *)calloc(na * P_N, sizeof(float));
+    o->ax = (float *)calloc(na * AX_N, sizeof(float));
+    o->prev = (float *)calloc(na * 3, sizeof(float));
+    o->ep_len = (int *)calloc(na, sizeof(int));
+    o->ring_idx = (int *)calloc(na, sizeof(int));
+    o->tick = (int *)calloc((size_t)n, sizeof(int));
+    o->task = (int *)calloc((size_t)n, sizeof(int));
+    o->rings = (float *)calloc((size_t)n * max_rings * 7, sizeof(float));
+    o->logs = (float *)calloc((size_t)n * 9, sizeof(float));
+    o->env_episode = (uint32_t *)calloc((size_t)n, sizeof(uint32_t));
+    o->respawns = (uint32_t *)calloc(na, sizeof(uint32_t));
+    return o;
+}
+
+void orc_swarm_close(OrcSwarm *o) {
+    if (!o) return;
+    free(o->st); free(o->pr); free(o->ax); free(o->prev); free(o->ep_len); free(o->ring_idx);
+    free(o->tick); free(o->task); free(o->rings); free(o->logs); free(o->env_episode); free(o->respawns);
+    free(o);
+}
+
+void orc_swarm_set_philox(OrcSwarm *o, uint64_t seed, uint32_t env_id_base) {
+    o->key[0] = (uint32_t)seed;
+    o->key[1] = (uint32_t)(seed >> 32);
+    o->env_id_base = env_id_base;
+}
+
+void orc_swarm_set_payload(OrcSwarm *o, float *agent_rows, unsigned char *agent_flags, float *env_rows,
+                           unsigned char *env_flags) {
+    o->pay_agent = agent_rows; o->flag_agent = agent_flags; o->pay_env = env_rows; o->flag_env = env_flags;
+}
+
+/* ---- the swarm's random draws, by source ------------------------------------------------- */
+/* Philox counters: (global env id, who, ordinal, item << 8 | attempt); who = agent index for the
+ * env-wide reset, agent | 0x10000 for a respawn, 0xFFFF0000 for env-level draws (task, rings). */
+typedef struct {
+    const OrcSwarm *o;
+    int mode;
+    uint32_t env, who, ordinal;
+} SwRand;
+
+static void sw_words(const SwRand *r, uint32_t item, uint32_t attempt, uint32_t w[4]) {
+    uint32_t ctr[4] = {r->env, r->who, r->ordinal, (item << 8) | attempt};
+    orc_philox4x32_10(ctr, r->o->key, w);
+}
+
+/* size ~ U(0.1, 0.4) + init_drone's 12 jitters (R/drone_swarm/drone_swarm.h:387-388) */
+static void sw_draw_params(const SwRand *r, float *p) {
+    float size, uj[12];
+    if (r->mode == ORC_RESET_LIBC) {
+        size = libc_rndf(0.1f, 0.4); /* the reference passes the double literal 0.4 -> (float)0.4 */
+        for (int k = 0; k < 12; k++) {
+            float lo, hi;
+            jitter_bounds(k, &lo, &hi);
+            uj[k] = libc_rndf(lo, hi);
+        }
+        params_from_draws(size, uj, 0, p);
+    } else {
+        float draws[16];
+        uint32_t w[4];
+        for (uint32_t k = 0; k < 4; k++) {
+            sw_words(r, k, 0, w);
+            for (int j = 0; j < 4; j++) draws[4 * k + j] = u_from_word(w[j]);
+        }
+        size = lerp_u(0.1f, 0.4f, draws[0]);
+        for (int k = 0; k < 12; k++) {
+            float lo, hi;
+            jitter_bounds(k, &lo, &hi);
+            uj[k] = lerp_u(lo, hi, draws[1 + k]);
+        }
+        params_from_draws(size, uj, 1, p);
+    }
+}
+
+static v3 sw_draw_box(const SwRand *r, uint32_t item, uint32_t attempt, float bx, float by, float bz) {
+    v3 c;
+    if (r->mode == ORC_RESET_LIBC) {
+        c.x = libc_rndf(-bx, bx); c.y = libc_rndf(-by, by); c.z = libc_rndf(-bz, bz);
+    } else {
+        uint32_t w[4];
+        sw_words(r, item, attempt, w);
+        c.x = lerp_u(-bx, bx, u_from_word(w[0]));
+        c.y = lerp_u(-by, by, u_from_word(w[1]));
+        c.z = lerp_u(-bz, bz, u_from_word(w[2]));
+    }
+    return c;
+}
+
+/* ---- helpers mirroring the reference functions ------------------------------------------- */
+#define SW_AG(o, e, a) ((size_t)(e) * (o)->A + (a))
+
+/* R/drone_swarm/drone_swarm.h:107-129: index of the nearest other agent, -1 if alone */
+static int sw_nearest(const OrcSwarm *o, int e, int a) {
+    float min_dist = 999999.0f;
+    int nearest = -1;
+    const float *me = o->st + SW_AG(o, e, a) * 17;
+    for (int j = 0; j < o->A; j++) {
+        if (j == a) continue;
+        const float *ot = o->st + SW_AG(o, e, j) * 17;
+        float dx = me[0] - ot[0], dy = me[1] - ot[1], dz = me[2] - ot[2];
+        float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+        if (dist < min_dist) {
+            min_dist = dist;
+            nearest = j;
+        }
+    }
+    return nearest;
+}
+
+/* R/drone_swarm/drone_swarm.h:335-376 */
+static float sw_compute_reward(OrcSwarm *o, int e, int a, int collision) {
+    size_t k = SW_AG(o, e, a);
+    const float *s = o->st + k * 17;
+    float *x = o->ax + k * AX_N;
+    float dx = s[0] - x[AX_TPOS + 0], dy = s[1] - x[AX_TPOS + 1], dz = s[2] - x[AX_TPOS + 2];
+    float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float max_dist = sqrtf((2 * S_GX) * (2 * S_GX) + (2 * S_GY) * (2 * S_GY) + (2 * S_GZ) * (2 * S_GZ));
+    float dist_reward = (float)(1.0 - (double)(dist / max_dist));
+    float density_reward = 0.0f;
+    if (collision && o->A > 1) {
+        int j = sw_nearest(o, e, a);
+        const float *ot = o->st + SW_AG(o, e, j) * 17;
+        dx = s[0] - ot[0]; dy = s[1] - ot[1]; dz = s[2] - ot[2];
+        float min_dist = sqrtf(dx * dx + dy * dy + dz * dz);
+        if (min_dist < 1.0f) {
+            density_reward = -1.0f;
+            x[AX_COLLISIONS] += 1.0f;
+        }
+    }
+    float abs_reward = dist_reward + density_reward;
+    if (dist_reward < 0.0f && density_reward < 0.0f) abs_reward *= -1.0f;
+    float delta = abs_reward - x[AX_LAST_ABS];
+    x[AX_LAST_COL] = density_reward;
+    x[AX_LAST_TGT] = dist_reward;
+    x[AX_LAST_ABS] = abs_reward;
+    o->ep_len[k] += 1;
+    x[AX_SCORE] += abs_reward;
+    return delta;
+}
+
+/* R/drone_swarm/drone_swarm.h:219-232 */
+static void sw_move_target(float *x) {
+    x[AX_TPOS + 0] += x[AX_TVEL + 0];
+    x[AX_TPOS + 1] += x[AX_TVEL + 1];
+    x[AX_TPOS + 2] += x[AX_TVEL + 2];
+    if (x[AX_TPOS + 0] < -S_GX || x[AX_TPOS + 0] > S_GX) x[AX_TVEL + 0] = -x[AX_TVEL + 0];
+    if (x[AX_TPOS + 1] < -S_GY || x[AX_TPOS + 1] > S_GY) x[AX_TVEL + 1] = -x[AX_TVEL + 1];
+    if (x[AX_TPOS + 2] < -S_GZ || x[AX_TPOS + 2] > S_GZ) x[AX_TVEL + 2] = -x[AX_TVEL + 2];
+}
+
+static void sw_target_idle(OrcSwarm *o, int e, int a, const SwRand *r) {
+    float *x = o->ax + SW_AG(o, e, a) * AX_N;
+    v3 p = sw_draw_box(r, 5, 0, S_MX, S_MY, S_MZ);
+    v3 v = sw_draw_box(r, 6, 0, S_VT, S_VT, S_VT);
+    x[AX_TPOS] = p.x; x[AX_TPOS + 1] = p.y; x[AX_TPOS + 2] = p.z;
+    x[AX_TVEL] = v.x; x[AX_TVEL + 1] = v.y; x[AX_TVEL + 2] = v.z;
+}
+
+/* the closed-form formation targets: R/drone_swarm/drone_swarm.h:246-261 (orbit), :273-281 (cube),
+ * :299-307 (flag).  PI is raylib's float literal; sqrt/cos/sin are the double libm calls. */
+void orc_swarm_formation_target(int task, int idx, int num_agents, float out[3]) {
+    if (task == 2) {
+        float Rr = 8.0f;
+        float phi = 3.14159265358979323846f * (sqrt(5.0f) - 1.0f);
+        float y = 1.0f - 2 * ((float)idx / (float)num_agents);
+        float radius = sqrtf(1.0f - y * y);
+        float theta = phi * idx;
+        float x = cos(theta) * radius;
+        float z = sin(theta) * radius;
+        out[0] = Rr * x; out[1] = Rr * z; out[2] = Rr * y;
+    } else if (task == 4) {
+        float z = idx / 16;
+        idx = idx % 16;
+        float x = (float)(idx % 4);
+        float y = (float)(idx / 4);
+        out[0] = 4 * x - 6; out[1] = 4 * y - 6; out[2] = 4 * z - 6;
+    } else {
+        float x = (float)(idx % 8);
+        float y = (float)(idx / 8);
+        x = 2.0f * x - 7;
+        y = 5 - 1.5f * y;
+        out[0] = 0.0f; out[1] = x; out[2] = y;
+    }
+}
+
+/* R/drone_swarm/drone_swarm.h:234-333 */
+static void sw_set_target(OrcSwarm *o, int e, int a, const SwRand *r) {
+    float *x = o->ax + SW_AG(o, e, a) * AX_N;
+    const float *s = o->st + SW_AG(o, e, a) * 17;
+    const float *x0 = o->ax + SW_AG(o, e, 0) * AX_N;
+    int task = o->task[e];
+    if (task == 0) {
+        sw_target_idle(o, e, a, r);
+        return;
+    }
+    if (task == 3 || task == 5) { /* follow / congo */
+        if (a == 0) {
+            sw_target_idle(o, e, a, r);
+            return;
+        }
+        const float *src = task == 3 ? x0 : o->ax + SW_AG(o, e, a - 1) * AX_N;
+        for (int k = 0; k < 6; k++) x[AX_TPOS + k] = src[AX_TPOS + k];
+        if (task == 5)
+            for (int i = 0; i < 40; i++) sw_move_target(x);
+        return;
+    }
+    if (task == 1) {
+        x[AX_TPOS] = s[0]; x[AX_TPOS + 1] = s[1]; x[AX_TPOS + 2] = s[2];
+    } else if (task == S_TASK_RACE) {
+        const float *g = o->rings + ((size_t)e * o->R + o->ring_idx[SW_AG(o, e, a)]) * 7;
+        x[AX_TPOS] = g[0]; x[AX_TPOS + 1] = g[1]; x[AX_TPOS + 2] = g[2];
+    } else {
+        orc_swarm_formation_target(task, a, o->A, x + AX_TPOS);
+    }
+    x[AX_TVEL] = x[AX_TVEL + 1] = x[AX_TVEL + 2] = 0.0f;
+}
+
+/* R/drone_swarm/drone_swarm.h:378-399; `row` = the 16 floats (params, pos) of the payload to
+ * record into / read from, or NULL */
+static void sw_reset_agent(OrcSwarm *o, int e, int a, const SwRand *r, float *row) {
+    size_t k = SW_AG(o, e, a);
+    float *s = o->st + k * 17, *p = o->pr + k * P_N, *x = o->ax + k * AX_N;
+    x[AX_RETURN] = 0.0f;
+    o->ep_len[k] = 0;
+    x[AX_COLLISIONS] = 0.0f;
+    x[AX_SCORE] = 0.0f;
+    o->ring_idx[k] = 0;
+    zero_motion(s);
+    if (r->mode == ORC_RESET_INJECT) {
+        memcpy(p, row, P_N * sizeof(float));
+        s[0] = row[13]; s[1] = row[14]; s[2] = row[15];
+    } else {
+        sw_draw_params(r, p);
+        v3 c = sw_draw_box(r, 4, 0, S_MX, S_MY, S_MZ);
+        s[0] = c.x; s[1] = c.y; s[2] = c.z;
+        if (row) {
+            memcpy(row, p, P_N * sizeof(float));
+            row[13] = s[0]; row[14] = s[1]; row[15] = s[2];
+        }
+    }
+    o->prev[k * 3] = s[0]; o->prev[k * 3 + 1] = s[1]; o->prev[k * 3 + 2] = s[2];
+    x[AX_SPAWN] = s[0]; x[AX_SPAWN + 1] = s[1]; x[AX_SPAWN + 2] = s[2];
+    sw_compute_reward(o, e, a, o->task[e] != S_TASK_RACE);
+}
+
+/* R/drone_swarm/drone_swarm.h:91-105 */
+static void sw_add_log(OrcSwarm *o, int e, int a, int oob) {
+    size_t k = SW_AG(o, e, a);
+    float *l = o->logs + (size_t)e * 9, *x = o->ax + k * AX_N;
+    l[6] += x[AX_SCORE];
+    l[0] += x[AX_RETURN];
+    l[1] += o->ep_len[k];
+    l[3] += x[AX_COLLISIONS] / (float)o->ep_len[k];
+    l[7] += x[AX_SCORE] / (float)o->ep_len[k];
+    if (oob) l[4] += 1.0f;
+    l[8] += 1.0f;
+    o->ep_len[k] = 0;
+    x[AX_RETURN] = 0.0f;
+}
+
+void orc_swarm_observe(const OrcSwarm *o, int e, float *obs);
+
+/* R/drone_swarm/drone_swarm.h:401-443 */
+static void sw_env_reset(OrcSwarm *o, int e, int mode, int first) {
+    const int A = o->A, R = o->R;
+    float *erow = o->pay_env ? o->pay_env + (size_t)e * (2 + 6 * R) : NULL;
+    if (o->flag_env && mode != ORC_RESET_INJECT) o->flag_env[e] |= 1;
+    o->tick[e] = 0;
+    o->env_episode[e] = first ? 0u : o->env_episode[e] + 1u;
+    SwRand er = {o, mode, o->env_id_base + (uint32_t)e, 0xFFFF0000u, o->env_episode[e]};
+    if (mode == ORC_RESET_LIBC) {
+        if (rand() % 4) o->task[e] = S_TASK_RACE;
+        else o->task[e] = rand() % 7;
+    } else if (mode == ORC_RESET_PHILOX) {
+        uint32_t w[4];
+        sw_words(&er, 0, 0, w);
+        if ((w[0] >> 1) % 4u) o->task[e] = S_TASK_RACE;
+        else o->task[e] = (int)((w[1] >> 1) % 7u);
+    } else {
+        o->task[e] = (int)erow[1];
+    }
+    if (erow && mode != ORC_RESET_INJECT) erow[1] = (float)o->task[e];
+
+    for (int a = 0; a < A; a++) {
+        float *arow = o->pay_agent ? o->pay_agent + SW_AG(o, e, a) * ORC_SWARM_AGENT_PAYLOAD : NULL;
+        SwRand ar = {o, mode, er.env, (uint32_t)a, er.ordinal};
+        sw_reset_agent(o, e, a, &ar, arow ? arow + 16 : NULL);
+        float *x = o->ax + SW_AG(o, e, a) * AX_N;
+        if (mode == ORC_RESET_INJECT) {
+            for (int k = 0; k < 6; k++) x[AX_TPOS + k] = arow[32 + k];
+        } else {
+            sw_set_target(o, e, a, &ar);
+            if (arow) for (int k = 0; k < 6; k++) arow[32 + k] = x[AX_TPOS + k];
+        }
+    }
+    float *rings = o->rings + (size_t)e * R * 7;
+    memset(rings, 0, (size_t)R * 7 * sizeof(float));
+    if (o->task[e] == S_TASK_RACE) {
+        const float lox = -S_GX + 2 * RING_RADIUS, loy = -S_GY + 2 * RING_RADIUS, loz = -S_GZ + 2 * RING_RADIUS;
+        const float min_gap = 2.0f * RING_RADIUS;
+        for (int r = 0; r < R; r++) {
+            float *g = rings + 7 * r;
+            if (mode == ORC_RESET_INJECT) {
+                memcpy(g, erow + 2 + 6 * r, 6 * sizeof(float));
+            } else {
+                for (uint32_t t = 0;; t++) {
+                    v3 c, nrm;
+                    if (mode == ORC_RESET_LIBC) {
+                        c.x = libc_rndf(lox, -lox); c.y = libc_rndf(loy, -loy); c.z = libc_rndf(loz, -loz);
+                        float u1 = libc_rndf(0.0f, 1.0f), u2 = libc_rndf(0.0f, 1.0f), u3 = libc_rndf(0.0f, 1.0f);
+                        nrm = ring_normal_from_u(u1, u2, u3, 0);
+                    } else {
+                        uint32_t w[4], w2[4];
+                        sw_words(&er, 0x10u + 2u * r, t, w);
+                        sw_words(&er, 0x11u + 2u * r, t, w2);
+                        c.x = lerp_u(lox, -lox, u_from_word(w[0]));
+                        c.y = lerp_u(loy, -loy, u_from_word(w[1]));
+                        c.z = lerp_u(loz, -loz, u_from_word(w[2]));
+                        nrm = ring_normal_from_u(u_from_word(w[3]), u_from_word(w2[0]), u_from_word(w2[1]), 1);
+                    }
+                    g[0] = c.x; g[1] = c.y; g[2] = c.z; g[3] = nrm.x; g[4] = nrm.y; g[5] = nrm.z;
+                    if (r == 0) break;
+                    v3 prev = {g[-7], g[-6], g[-5]};
+                    if (!(dist3(c, prev) < min_gap)) break;
+                    if (mode == ORC_RESET_PHILOX && t + 1 >= MAX_ATTEMPTS) break;
+                }
+                if (erow) memcpy(erow + 2 + 6 * r, g, 6 * sizeof(float));
+            }
+            g[6] = RING_RADIUS;
+        }
+        v3 r0 = {rings[0], rings[1], rings[2]};
+        for (int a = 0; a < A; a++) {
+            float *s = o->st + SW_AG(o, e, a) * 17;
+            float *arow = o->pay_agent ? o->pay_agent + SW_AG(o, e, a) * ORC_SWARM_AGENT_PAYLOAD : NULL;
+            if (mode == ORC_RESET_INJECT) {
+                s[0] = arow[38]; s[1] = arow[39]; s[2] = arow[40];
+                continue;
+            }
+            SwRand ar = {o, mode, er.env, (uint32_t)a, er.ordinal};
+            for (uint32_t t = 0;; t++) {
+                v3 c = sw_draw_box(&ar, 7, t, S_MX, S_MY, S_MZ);
+                s[0] = c.x; s[1] = c.y; s[2] = c.z;
+                if (!(dist3(c, r0) < min_gap)) break;
+                if (mode == ORC_RESET_PHILOX && t + 1 >= MAX_ATTEMPTS) break;
+            }
+            if (arow) { arow[38] = s[0]; arow[39] = s[1]; arow[40] = s[2]; }
+        }
+    } else if (erow && mode != ORC_RESET_INJECT) {
+        memset(erow + 2, 0, (size_t)6 * R * sizeof(float));
+    }
+}
+
+/* R/drone_swarm/drone_swarm.h:131-217 for every agent of env e; obs = [A][41] */
+void orc_swarm_observe(const OrcSwarm *o, int e, float *obs) {
+    for (int a = 0; a < o->A; a++) {
+        size_t k = SW_AG(o, e, a);
+        const float *s = o->st + k * 17, *p = o->pr + k * P_N, *x = o->ax + k * AX_N;
+        float *ob = obs + (size_t)a * ORC_SWARM_OBS;
+        q4 q = {s[6], s[7], s[8], s[9]};
+        q4 qi = {q.w, -q.x, -q.y, -q.z};
+        v3 vel = {s[3], s[4], s[5]};
+        v3 vb = qrot(qi, vel);
+        v3 zax = {0.0f, 0.0f, 1.0f};
+        v3 up = qrot(q, zax);
+        int c = 0;
+        ob[c++] = vb.x / K_MAX_VEL; ob[c++] = vb.y / K_MAX_VEL; ob[c++] = vb.z / K_MAX_VEL;
+        ob[c++] = s[10] / K_MAX_OMEGA; ob[c++] = s[11] / K_MAX_OMEGA; ob[c++] = s[12] / K_MAX_OMEGA;
+        ob[c++] = up.x; ob[c++] = up.y; ob[c++] = up.z;
+        ob[c++] = q.w; ob[c++] = q.x; ob[c++] = q.y; ob[c++] = q.z;
+        for (int m = 0; m < 4; m++) ob[c++] = s[13 + m] / p[P_MRPM];
+        ob[c++] = s[0] / S_GX; ob[c++] = s[1] / S_GY; ob[c++] = s[2] / S_GZ;
+        ob[c++] = x[AX_SPAWN] / S_GX; ob[c++] = x[AX_SPAWN + 1] / S_GY; ob[c++] = x[AX_SPAWN + 2] / S_GZ;
+        float dx = x[AX_TPOS] - s[0], dy = x[AX_TPOS + 1] - s[1], dz = x[AX_TPOS + 2] - s[2];
+        ob[c++] = clampf_(dx, -1.0f, 1.0f); ob[c++] = clampf_(dy, -1.0f, 1.0f); ob[c++] = clampf_(dz, -1.0f, 1.0f);
+        ob[c++] = dx / S_GX; ob[c++] = dy / S_GY; ob[c++] = dz / S_GZ;
+        ob[c++] = x[AX_LAST_COL]; ob[c++] = x[AX_LAST_TGT]; ob[c++] = x[AX_LAST_ABS];
+        if (o->A > 1) {
+            const float *ot = o->st + SW_AG(o, e, sw_nearest(o, e, a)) * 17;
+            ob[c++] = clampf_(ot[0] - s[0], -1.0f, 1.0f);
+            ob[c++] = clampf_(ot[1] - s[1], -1.0f, 1.0f);
+            ob[c++] = clampf_(ot[2] - s[2], -1.0f, 1.0f);
+        } else {
+            ob[c++] = 0.0f; ob[c++] = 0.0f; ob[c++] = 0.0f;
+        }
+        if (o->task[e] == S_TASK_RACE) {
+            const float *g = o->rings + ((size_t)e * o->R + o->ring_idx[k]) * 7;
+            v3 d = {g[0] - s[0], g[1] - s[1], g[2] - s[2]};
+            v3 nrm = {g[3], g[4], g[5]};
+            v3 to = qrot(qi, d), bn = qrot(qi, nrm);
+            ob[c++] = to.x / S_GX; ob[c++] = to.y / S_GY; ob[c++] = to.z / S_GZ;
+            ob[c++] = bn.x; ob[c++] = bn.y; ob[c++] = bn.z;
+        } else {
+            for (int m = 0; m < 6; m++) ob[c++] = 0.0f;
+        }
+    }
+}
+
+void orc_swarm_reset(OrcSwarm *o, int mode, int seed, float *obs) {
+    o->seed = seed;
+    for (int e = 0; e < o->n; e++) {
+        if (mode == ORC_RESET_LIBC) srand(e + seed * o->n); /* EB:500-504 */
+        for (int a = 0; a < o->A; a++) o->respawns[SW_AG(o, e, a)] = 0;
+        sw_env_reset(o, e, mode, 1);
+        if (obs) orc_swarm_observe(o, e, obs + SW_AG(o, e, 0) * ORC_SWARM_OBS);
+    }
+}
+
+/* R/drone_swarm/drone_swarm.h:445-497 for env e */
+static void sw_step_env(OrcSwarm *o, int e, int mode, float *actions, float *obs, float *rew, unsigned char *term) {
+    const int A = o->A;
+    o->tick[e] = (o->tick[e] + 1) % S_HORIZON;
+    for (int a = 0; a < A; a++) {
+        size_t k = SW_AG(o, e, a);
+        float *s = o->st + k * 17, *x = o->ax + k * AX_N;
+        rew[k] = 0;
+        term[k] = 0;
+        if (mode == ORC_RESET_LIBC) (void)rand(); /* dt-jitter draw, R/drone_swarm/dronelib.h:440 */
+        o->prev[k * 3] = s[0]; o->prev[k * 3 + 1] = s[1]; o->prev[k * 3 + 2] = s[2];
+        advance_body(s, o->pr + k * P_N, actions + k * 4);
+        int oob = s[0] < -S_GX || s[0] > S_GX || s[1] < -S_GY || s[1] > S_GY || s[2] < -S_GZ || s[2] > S_GZ;
+        sw_move_target(x);
+        float reward;
+        if (o->task[e] == S_TASK_RACE) {
+            const float *g = o->rings + ((size_t)e * o->R + o->ring_idx[k]) * 7;
+            reward = sw_compute_reward(o, e, a, 1);
+            v3 before = {o->prev[k * 3], o->prev[k * 3 + 1], o->prev[k * 3 + 2]};
+            v3 after = {s[0], s[1], s[2]};
+            float passed = gate_event(before, after, g, -0.0f);
+            if (passed > 0) {
+                o->ring_idx[k] = (o->ring_idx[k] + 1) % o->R;
+                o->logs[(size_t)e * 9 + 2] += 1.0f;
+                SwRand none = {o, mode, 0, 0, 0};
+                sw_set_target(o, e, a, &none);
+                sw_compute_reward(o, e, a, 1);
+            }
+            reward += passed;
+        } else {
+            reward = sw_compute_reward(o, e, a, 1);
+        }
+        rew[k] += reward;
+        x[AX_RETURN] += reward;
+        if (oob) {
+            rew[k] -= 1;
+            term[k] = 1;
+            sw_add_log(o, e, a, 1);
+            float *arow = o->pay_agent ? o->pay_agent + k * ORC_SWARM_AGENT_PAYLOAD : NULL;
+            if (o->flag_agent && mode != ORC_RESET_INJECT) o->flag_agent[k] |= 1;
+            o->respawns[k] += 1;
+            SwRand ar = {o, mode, o->env_id_base + (uint32_t)e, (uint32_t)a | 0x10000u, o->respawns[k]};
+            sw_reset_agent(o, e, a, &ar, arow);
+        } else if (o->tick[e] >= S_HORIZON - 1) {
+            term[k] = 1;
+            sw_add_log(o, e, a, 0);
+        }
+    }
+    if (o->tick[e] >= S_HORIZON - 1) sw_env_reset(o, e, mode, 0);
+    orc_swarm_observe(o, e, obs + SW_AG(o, e, 0) * ORC_SWARM_OBS);
+}
+
+void orc_swarm_step(OrcSwarm *o, int mode, float *actions, float *obs, float *rew, unsigned char *term) {
+    if (mode != ORC_RESET_INJECT) {
+        if (o->flag_agent) memset(o->flag_agent, 0, (size_t)o->n * o->A);
+        if (o->flag_env) memset(o->flag_env, 0, (size_t)o->n);
+    }
+    for (int e = 0; e < o->n; e++) sw_step_env(o, e, mode, actions, obs, rew, term);
+}
+
+void orc_swarm_log(OrcSwarm *o, float out[9]) {
+    for (int j = 0; j < 9; j++) out[j] = 0.0f;
+    for (int e = 0; e < o->n; e++) {
+        float *l = o->logs + (size_t)e * 9;
+        for (int j = 0; j < 9; j++) {
+            out[j] += l[j];
+            l[j] = 0.0f;
+        }
+    }
+}
+
+/* blobs: same layouts as oracle/ref_shim_swarm.c */
+void orc_swarm_get_env(const OrcSwarm *o, int e, float *b) {
+    b[0] = (float)o->tick[e];
+    b[1] = (float)o->task[e];
+    for (int r = 0; r < o->R; r++) memcpy(b + 2 + 6 * r, o->rings + ((size_t)e * o->R + r) * 7, 6 * sizeof(float));
+}
+
+void orc_swarm_put_env(OrcSwarm *o, int e, const float *b) {
+    o->tick[e] = (int)b[0];
+    o->task[e] = (int)b[1];
+    for (int r = 0; r < o->R; r++) {
+        float *g = o->rings + ((size_t)e * o->R + r) * 7;
+        memcpy(g, b + 2 + 6 * r, 6 * sizeof(float));
+        g[6] = (g[3] == 0.0f && g[4] == 0.0f && g[5] == 0.0f) ? 0.0f : RING_RADIUS;
+    }
+}
+
+void orc_swarm_get_agent(const OrcSwarm *o, int e, int a, float *b) {
+    size_t k = SW_AG(o, e, a);
+    const float *x = o->ax + k * AX_N;
+    memcpy(b, o->st + k * 17, 17 * sizeof(float));
+    memcpy(b + 17, o->pr + k * P_N, P_N * sizeof(float));
+    memcpy(b + 30, x + AX_SPAWN, 3 * sizeof(float));
+    memcpy(b + 33, x + AX_TPOS, 6 * sizeof(float));
+    b[39] = x[AX_LAST_ABS]; b[40] = x[AX_LAST_TGT]; b[41] = x[AX_LAST_COL];
+    b[42] = x[AX_RETURN]; b[43] = x[AX_COLLISIONS]; b[44] = (float)o->ep_len[k];
+    b[45] = x[AX_SCORE]; b[46] = (float)o->ring_idx[k];
+}
+
+void orc_swarm_put_agent(OrcSwarm *o, int e, int a, const float *b) {
+    size_t k = SW_AG(o, e, a);
+    float *x = o->ax + k * AX_N;
+    memcpy(o->st + k * 17, b, 17 * sizeof(float));
+    memcpy(o->pr + k * P_N, b + 17, P_N * sizeof(float));
+    memcpy(x + AX_SPAWN, b + 30, 3 * sizeof(float));
+    memcpy(x + AX_TPOS, b + 33, 6 * sizeof(float));
+    x[AX_LAST_ABS] = b[39]; x[AX_LAST_TGT] = b[40]; x[AX_LAST_COL] = b[41];
+    x[AX_RETURN] = b[42]; x[AX_COLLISIONS] = b[43]; o->ep_len[k] = (int)b[44];
+    x[AX_SCORE] = b[45]; o->ring_idx[k] = (int)b[46];
+    memcpy(o->prev + k * 3, b, 3 * sizeof(float));
+}

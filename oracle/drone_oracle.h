@@ -66,17 +66,23 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 void orc_sincos_det(float theta, float *s, float *c);
 
 typedef struct OrcSwarm OrcSwarm;
+#define ORC_SWARM_AGENT_PAYLOAD 41 /* see drone_oracle.c "swarm env" for the row layouts */
 OrcSwarm *orc_swarm_create(int n, int num_agents, int max_rings);
 void orc_swarm_close(OrcSwarm *o);
 void orc_swarm_set_philox(OrcSwarm *o, uint64_t seed, uint32_t env_id_base);
+/* rows/flags the draws of each reset/step are recorded into (LIBC/PHILOX) or read from (INJECT) */
+void orc_swarm_set_payload(OrcSwarm *o, float *agent_rows, unsigned char *agent_flags, float *env_rows,
+                           unsigned char *env_flags);
 void orc_swarm_reset(OrcSwarm *o, int mode, int seed, float *obs);
-void orc_swarm_step(OrcSwarm *o, int mode, float *actions, float *obs, float *rew,
-                    unsigned char *term);
+void orc_swarm_step(OrcSwarm *o, int mode, float *actions, float *obs, float *rew, unsigned char *term);
+void orc_swarm_observe(const OrcSwarm *o, int e, float *obs);
 void orc_swarm_log(OrcSwarm *o, float out[9]);
 void orc_swarm_get_env(const OrcSwarm *o, int i, float *blob);
 void orc_swarm_put_env(OrcSwarm *o, int i, const float *blob);
 void orc_swarm_get_agent(const OrcSwarm *o, int i, int a, float *blob);
 void orc_swarm_put_agent(OrcSwarm *o, int i, int a, const float *blob);
+/* closed-form formation targets (task 2 orbit, 4 cube, 6 flag) exactly as the reference computes them */
+void orc_swarm_formation_target(int task, int idx, int num_agents, float out[3]);
 
 #ifdef __cplusplus
 }

@@ -236,3 +236,162 @@ class OrcRace(_Buffers):
         if self.h:
             self.lib.orc_race_close(self.h)
             self.h = None
+
+
+SWARM_AGENT_PAYLOAD = 41
+
+
+class RefSwarm(_Buffers):
+    """The reference's DroneSwarm envs (oracle/_ref/libref_swarm.so), driven like env_binding.h."""
+
+    def __init__(self, n, num_agents, max_rings=5):
+        self.lib = L = C.CDLL(REF_SWARM_SO)
+        L.refswarm_create.restype = C.c_void_p
+        L.refswarm_create.argtypes = [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _up]
+        for name, args in [("refswarm_reset", [C.c_void_p, C.c_int]), ("refswarm_step", [C.c_void_p]),
+                           ("refswarm_step_range", [C.c_void_p, C.c_int, C.c_int]),
+                           ("refswarm_log", [C.c_void_p, _fp]),
+                           ("refswarm_get_env", [C.c_void_p, C.c_int, _fp]),
+                           ("refswarm_put_env", [C.c_void_p, C.c_int, _fp]),
+                           ("refswarm_get_agent", [C.c_void_p, C.c_int, C.c_int, _fp]),
+                           ("refswarm_put_agent", [C.c_void_p, C.c_int, C.c_int, _fp]),
+                           ("refswarm_observe", [C.c_void_p, C.c_int]), ("refswarm_close", [C.c_void_p])]:
+            getattr(L, name).argtypes = args
+            getattr(L, name).restype = None
+        self.n, self.A, self.max_rings = n, num_agents, max_rings
+        self.env_blob = 2 + 6 * max_rings
+        self._alloc(n * num_agents, 41)
+        self.h = L.refswarm_create(n, num_agents, max_rings, _f(self.observations), _f(self.actions),
+                                   _f(self.rewards), _u(self.terminals))
+
+    def reset(self, seed):
+        self.lib.refswarm_reset(self.h, int(seed))
+
+    def step(self, actions=None):
+        if actions is not None:
+            self.actions[:] = actions
+        self.lib.refswarm_step(self.h)
+
+    def log(self):
+        out = np.zeros(9, np.float32)
+        self.lib.refswarm_log(self.h, _f(out))
+        return out
+
+    def get_state(self):
+        """(env blobs [n, 2+6R], agent blobs [n, A, 47])"""
+        env = np.zeros((self.n, self.env_blob), np.float32)
+        ag = np.zeros((self.n, self.A, SWARM_AGENT), np.float32)
+        for e in range(self.n):
+            self.lib.refswarm_get_env(self.h, e, _f(env[e]))
+            for a in range(self.A):
+                self.lib.refswarm_get_agent(self.h, e, a, _f(ag[e, a]))
+        return env, ag
+
+    def put_state(self, env, ag):
+        env = np.ascontiguousarray(env, np.float32)
+        ag = np.ascontiguousarray(ag, np.float32)
+        for e in range(self.n):
+            self.lib.refswarm_put_env(self.h, e, _f(env[e]))
+            for a in range(self.A):
+                self.lib.refswarm_put_agent(self.h, e, a, _f(ag[e, a]))
+
+    def observe(self):
+        for e in range(self.n):
+            self.lib.refswarm_observe(self.h, e)
+
+    def close(self):
+        if self.h:
+            self.lib.refswarm_close(self.h)
+            self.h = None
+
+
+def _orc_swarm():
+    L = _orc()
+    if not getattr(L, "_swarm_bound", False):
+        L.orc_swarm_create.restype = C.c_void_p
+        L.orc_swarm_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.orc_swarm_close.argtypes = [C.c_void_p]
+        L.orc_swarm_set_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+        L.orc_swarm_set_payload.argtypes = [C.c_void_p, _fp, _up, _fp, _up]
+        L.orc_swarm_reset.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp]
+        L.orc_swarm_step.argtypes = [C.c_void_p, C.c_int, _fp, _fp, _fp, _up]
+        L.orc_swarm_observe.argtypes = [C.c_void_p, C.c_int, _fp]
+        L.orc_swarm_log.argtypes = [C.c_void_p, _fp]
+        L.orc_swarm_get_env.argtypes = [C.c_void_p, C.c_int, _fp]
+        L.orc_swarm_put_env.argtypes = [C.c_void_p, C.c_int, _fp]
+        L.orc_swarm_get_agent.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp]
+        L.orc_swarm_put_agent.argtypes = [C.c_void_p, C.c_int, C.c_int, _fp]
+        L.orc_swarm_formation_target.argtypes = [C.c_int, C.c_int, C.c_int, _fp]
+        for f in ("orc_swarm_close", "orc_swarm_set_philox", "orc_swarm_set_payload", "orc_swarm_reset",
+                  "orc_swarm_step", "orc_swarm_observe", "orc_swarm_log", "orc_swarm_get_env", "orc_swarm_put_env",
+                  "orc_swarm_get_agent", "orc_swarm_put_agent", "orc_swarm_formation_target"):
+            getattr(L, f).restype = None
+        L._swarm_bound = True
+    return L
+
+
+class OrcSwarm(_Buffers):
+    """Our CPU restatement of the swarm env (oracle/drone_oracle.c)."""
+
+    def __init__(self, n, num_agents, max_rings=5, seed=0, env_id_base=0):
+        self.lib = L = _orc_swarm()
+        self.n, self.A, self.max_rings = n, num_agents, max_rings
+        self.env_blob = 2 + 6 * max_rings
+        self._alloc(n * num_agents, 41)
+        self.h = L.orc_swarm_create(n, num_agents, max_rings)
+        self.env_id_base = int(env_id_base)
+        L.orc_swarm_set_philox(self.h, int(seed), self.env_id_base)
+        # draw results of the latest reset/step (recorded in LIBC/PHILOX mode, consumed in INJECT mode)
+        self.pay_agent = np.zeros((n * num_agents, SWARM_AGENT_PAYLOAD), np.float32)
+        self.flag_agent = np.zeros(n * num_agents, np.uint8)
+        self.pay_env = np.zeros((n, self.env_blob), np.float32)
+        self.flag_env = np.zeros(n, np.uint8)
+        L.orc_swarm_set_payload(self.h, _f(self.pay_agent), _u(self.flag_agent), _f(self.pay_env), _u(self.flag_env))
+
+    def reset(self, seed=0, mode=RESET_LIBC):
+        if mode == RESET_PHILOX:
+            self.lib.orc_swarm_set_philox(self.h, int(seed), self.env_id_base)
+        self.lib.orc_swarm_reset(self.h, mode, int(seed), _f(self.observations))
+
+    def step(self, actions=None, mode=RESET_LIBC):
+        if actions is not None:
+            self.actions[:] = actions
+        self.lib.orc_swarm_step(self.h, mode, _f(self.actions), _f(self.observations), _f(self.rewards),
+                                _u(self.terminals))
+
+    def log(self):
+        out = np.zeros(9, np.float32)
+        self.lib.orc_swarm_log(self.h, _f(out))
+        return out
+
+    def get_state(self):
+        env = np.zeros((self.n, self.env_blob), np.float32)
+        ag = np.zeros((self.n, self.A, SWARM_AGENT), np.float32)
+        for e in range(self.n):
+            self.lib.orc_swarm_get_env(self.h, e, _f(env[e]))
+            for a in range(self.A):
+                self.lib.orc_swarm_get_agent(self.h, e, a, _f(ag[e, a]))
+        return env, ag
+
+    def put_state(self, env, ag):
+        env = np.ascontiguousarray(env, np.float32)
+        ag = np.ascontiguousarray(ag, np.float32)
+        for e in range(self.n):
+            self.lib.orc_swarm_put_env(self.h, e, _f(env[e]))
+            for a in range(self.A):
+                self.lib.orc_swarm_put_agent(self.h, e, a, _f(ag[e, a]))
+
+    def observe(self):
+        for e in range(self.n):
+            self.lib.orc_swarm_observe(self.h, e, _f(self.observations[e * self.A:(e + 1) * self.A]))
+
+    def close(self):
+        if self.h:
+            self.lib.orc_swarm_close(self.h)
+            self.h = None
+
+
+def formation_target(task, idx, num_agents):
+    out = np.zeros(3, np.float32)
+    _orc_swarm().orc_swarm_formation_target(int(task), int(idx), int(num_agents), _f(out))
+    return out
