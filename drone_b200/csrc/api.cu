@@ -38,7 +38,7 @@ enum { KIND_RACE = 0, KIND_SWARM = 1 };
 struct b2d_vec {
     int kind;
     int device;
-    int num_envs, num_agents /* rows */, obs_dim, blob_floats;
+    int num_envs, num_agents /* rows */, obs_dim, blob_floats, payload_floats;
     int math, write_clamped;
     int step_ctas;
     RaceDev race;
@@ -140,6 +140,7 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
     v->num_envs = v->num_agents = cfg->num_envs;
     v->obs_dim = B2D_RACE_OBS;
     v->blob_floats = B2D_RACE_BLOB + 6 * cfg->max_rings;
+    v->payload_floats = v->blob_floats;
     v->math = cfg->math;
     v->write_clamped = cfg->write_clamped_actions;
     RaceDev &d = v->race;
@@ -186,10 +187,108 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
     return B2D_OK;
 }
 
+// closed-form formation targets of the swarm tasks, evaluated on the host with the reference's own
+// expressions (DS/drone_swarm.h:246-261 orbit, :273-281 cube, :299-307 flag): PI is raylib's float
+// literal, sqrt / cos / sin are the double libm calls.  table[3][A][3]
+static void swarm_formation_table(int A, std::vector<float> &tab) {
+    tab.assign((size_t)3 * A * 3, 0.0f);
+    for (int idx = 0; idx < A; idx++) {
+        {
+            float Rr = 8.0f;
+            // the reference is C: sqrt / cos / sin below are the DOUBLE libm functions (a C++ overload
+            // on float arguments would silently pick sqrtf / cosf / sinf)
+            float phi = (float)((double)3.14159265358979323846f * (sqrt((double)5.0f) - (double)1.0f));
+            float y = 1.0f - 2 * ((float)idx / (float)A);
+            float radius = sqrtf(1.0f - y * y);
+            float theta = phi * idx;
+            float x = (float)(cos((double)theta) * (double)radius);
+            float z = (float)(sin((double)theta) * (double)radius);
+            float *o = &tab[((size_t)0 * A + idx) * 3];
+            o[0] = Rr * x; o[1] = Rr * z; o[2] = Rr * y;
+        }
+        {
+            int i = idx;
+            float z = i / 16;
+            i = i % 16;
+            float x = (float)(i % 4);
+            float y = (float)(i / 4);
+            float *o = &tab[((size_t)1 * A + idx) * 3];
+            o[0] = 4 * x - 6; o[1] = 4 * y - 6; o[2] = 4 * z - 6;
+        }
+        {
+            float x = (float)(idx % 8);
+            float y = (float)(idx / 8);
+            x = 2.0f * x - 7;
+            y = 5 - 1.5f * y;
+            float *o = &tab[((size_t)2 * A + idx) * 3];
+            o[0] = 0.0f; o[1] = x; o[2] = y;
+        }
+    }
+}
+
 extern "C" int b2d_swarm_create(b2d_vec **out, const b2d_swarm_cfg *cfg, const b2d_buffers *ext) {
-    (void)cfg; (void)ext;
-    if (out) *out = nullptr;
-    return fail(B2D_ESTATE, "swarm env not built in this library version");
+    if (!out || !cfg) return fail(B2D_EINVAL, "b2d_swarm_create: null argument");
+    *out = nullptr;
+    if (cfg->num_envs <= 0) return fail(B2D_EINVAL, "num_envs must be greater than 0");
+    if (cfg->num_agents <= 0 || cfg->num_agents > SWARM_BLOCK) return fail(B2D_EINVAL, "num_agents must be in [1, 128]");
+    if (cfg->max_rings <= 0 || cfg->max_rings > 4096) return fail(B2D_EINVAL, "max_rings must be in [1, 4096]");
+    if (cfg->math != B2D_MATH_FAST && cfg->math != B2D_MATH_STRICT) return fail(B2D_EINVAL, "unknown math mode");
+    if ((long long)cfg->num_envs * cfg->num_agents > 0x7fffffffLL / 64) return fail(B2D_EINVAL, "too many agents");
+    int rc = check_ext(ext);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    b2d_vec *v = new (std::nothrow) b2d_vec();
+    if (!v) return fail(B2D_ENOMEM, "out of host memory");
+    v->kind = KIND_SWARM;
+    v->device = cfg->device;
+    v->num_envs = cfg->num_envs;
+    v->num_agents = cfg->num_envs * cfg->num_agents;
+    v->obs_dim = B2D_SWARM_OBS;
+    v->blob_floats = cfg->num_agents * B2D_SWARM_AGENT_BLOB + 2 + 6 * cfg->max_rings;
+    v->payload_floats = cfg->num_agents * B2D_SWARM_AGENT_PAYLOAD + 2 + 6 * cfg->max_rings;
+    v->math = cfg->math;
+    v->write_clamped = cfg->write_clamped_actions;
+    v->step_ctas = 1;
+    memset(&v->race, 0, sizeof(v->race));
+    SwarmDev &d = v->swarm;
+    memset(&d, 0, sizeof(d));
+    d.n = cfg->num_envs;
+    d.A = cfg->num_agents;
+    d.R = d.max_rings = cfg->max_rings;
+    d.rows = v->num_agents;
+    d.ld = (d.rows + 255) / 256 * 256;
+    d.epc = SWARM_BLOCK / d.A;
+    d.key0 = (uint32_t)cfg->seed;
+    d.key1 = (uint32_t)(cfg->seed >> 32);
+    d.env_id_base = cfg->env_id_base;
+    d.reset_mode = B2D_RESET_PHILOX;
+    const size_t ld = d.ld;
+    float *form = nullptr;
+    if ((rc = setup_buffers(v, ext)) || (rc = dev_alloc(v, &d.S, 5 * ld)) || (rc = dev_alloc(v, &d.P, 3 * ld)) ||
+        (rc = dev_alloc(v, &d.T, ld)) || (rc = dev_alloc(v, &d.U, ld)) || (rc = dev_alloc(v, &d.V, ld)) ||
+        (rc = dev_alloc(v, &d.W, ld)) || (rc = dev_alloc(v, &d.E, (size_t)d.n)) ||
+        (rc = dev_alloc(v, &d.G0, (size_t)d.R * d.n)) || (rc = dev_alloc(v, &d.G1, (size_t)d.R * d.n)) ||
+        (rc = dev_alloc(v, &form, (size_t)9 * d.A)) || (rc = dev_alloc(v, &d.ctl, 1)) || (rc = finish_create(v))) {
+        b2d_vec_close(v);
+        return rc;
+    }
+    std::vector<float> tab;
+    swarm_formation_table(d.A, tab);
+    const unsigned int one = 1;
+    if (cudaMemcpy(form, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(&d.ctl->grid, &one, sizeof(one), cudaMemcpyHostToDevice) != cudaSuccess) {
+        b2d_vec_close(v);
+        return fail(B2D_ECUDA, "swarm table upload failed");
+    }
+    d.form = form;
+    d.obs = v->dev.observations;
+    d.act_in = v->dev.actions;
+    d.act_out = v->write_clamped ? v->dev.actions : nullptr;
+    d.rew = v->dev.rewards;
+    d.term = v->dev.terminals;
+    // quaternion identity for every drone so that a put_state-free first step is well defined
+    *out = v;
+    return B2D_OK;
 }
 
 extern "C" int b2d_vec_close(b2d_vec *v) {
@@ -239,6 +338,8 @@ extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
         v->launches += 2;
         return launch_check("race_reset_kernel");
     }
+    if (v->swarm.reset_mode == B2D_RESET_INJECT && !v->swarm.payload) return fail(B2D_ESTATE, "inject mode without a payload");
+    CUDA_TRY(cudaMemsetAsync(&v->swarm.ctl->ctas_done, 0, sizeof(unsigned int), st));
     swarm_vec_reset(v->swarm, seed, st, &v->launches);
     return launch_check("swarm_reset_kernel");
 }
@@ -471,7 +572,7 @@ extern "C" int b2d_get_state(b2d_vec *v, const int *env_ids, int n, float *host_
         CUDA_TRY(cudaMemcpy(v->d_ids_tmp, env_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
     }
     if (v->kind == KIND_RACE) race_pack_kernel<<<(n + 127) / 128, 128>>>(v->race, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
-    else swarm_pack_kernel<<<(n + 127) / 128, 128>>>(v->swarm, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
+    else swarm_pack_kernel<<<(n * v->swarm.A + 127) / 128, 128>>>(v->swarm, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
     v->launches += 1;
     if ((rc = launch_check("pack_kernel"))) return rc;
     CUDA_TRY(cudaMemcpy(host_blobs, v->d_blob_tmp, (size_t)n * v->blob_floats * sizeof(float), cudaMemcpyDeviceToHost));
@@ -495,7 +596,7 @@ extern "C" int b2d_put_state(b2d_vec *v, const int *env_ids, int n, const float 
         v->launches += 1;
     }
     if (v->kind == KIND_RACE) race_unpack_kernel<<<(n + 127) / 128, 128>>>(v->race, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
-    else swarm_unpack_kernel<<<(n + 127) / 128, 128>>>(v->swarm, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
+    else swarm_unpack_kernel<<<(n * v->swarm.A + 127) / 128, 128>>>(v->swarm, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
     v->launches += 1;
     if ((rc = launch_check("unpack_kernel"))) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
@@ -532,7 +633,7 @@ extern "C" int b2d_set_reset_mode(b2d_vec *v, int mode) {
 
 extern "C" int b2d_set_reset_payload(b2d_vec *v, const float *host_payload) {
     if (!v || !host_payload) return fail(B2D_EINVAL, "null argument");
-    const size_t bytes = (size_t)v->num_envs * v->blob_floats * sizeof(float);
+    const size_t bytes = (size_t)v->num_envs * v->payload_floats * sizeof(float);
     if (!v->d_payload) {
         if (cudaMalloc(&v->d_payload, bytes) != cudaSuccess) return fail(B2D_ENOMEM, "cudaMalloc payload");
     }

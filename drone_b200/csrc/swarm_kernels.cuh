@@ -1,23 +1,708 @@
-// swarm_kernels.cuh -- device side of the multi-drone swarm env (placeholder until the
-// warp-per-env kernel lands; b2d_swarm_create reports B2D_ESTATE meanwhile).
+// swarm_kernels.cuh -- device side of the multi-drone swarm env (sm_100a).
+//
+// Reference behaviour restated (R = pufferlib/ocean/drone_swarm):
+//   swarm_kernel            R/drone_swarm.h:445-497 c_step, :401-443 c_reset (+ EB:520-522 vec_step loop)
+//   sw_reward()             R/drone_swarm.h:335-376 compute_reward, :107-129 nearest_drone
+//   sw_observe()            R/drone_swarm.h:131-217 compute_observations
+//   targets                 R/drone_swarm.h:219-333 move_target, set_target_*
+//   respawn / env reset     R/drone_swarm.h:378-443 reset_agent, c_reset
+//   log                     R/drone_swarm.h:91-105  add_log, EB:572-591 vec_log
+//
+// One thread per drone, an env = A consecutive threads of a 128-thread CTA (128/A envs per CTA),
+// so agent rows are contiguous and every state access is a coalesced float4 run.
+//
+// The reference steps the agents of an env one after the other, so what agent i sees of agent j
+// depends on their order: j < i has already moved this tick (and may have been re-spawned after
+// leaving the arena), j > i still sits at its previous-tick position.  Nothing else couples the
+// agents, so the loop is parallelised by publishing three position arrays per env in shared
+// memory -- previous tick (old), moved-and-possibly-respawned (fin), after an env-wide reset
+// (rst / pos) -- and selecting per neighbour by index.  Ties in the nearest-neighbour search go
+// to the lowest index exactly as the reference's strict `<` scan does.
+//
+// Layout in HBM, ld = rows rounded up to 256 (row = env * A + agent):
+//   S float4[5][ld]  pos, vel, quat, omega, rpm (17 f32) + episode_length + ring_idx + episode_return
+//   P float4[3][ld]  12 params;  T float4[ld] (j_mot, respawn count, collisions, score)
+//   U float4[ld] (spawn.xyz, last_abs_reward)  V float4[ld] (target_pos.xyz, last_target_reward)
+//   W float4[ld] (target_vel.xyz, last_collision_reward)
+//   E int4[n] (tick, task, env-reset count, -)   G0 float4[R][n], G1 float2[R][n] rings per env
+// Algorithmic bytes per drone-step: reads 228 (act 16, S 80, P+T 64 of which 52 used, U/V/W 48,
+// ring 24 shared per env) + writes 293 (S 80, V/W/T 48 of which 36 used, obs 164, rew 4, term 1)
+// = 521 B.
 #pragma once
+#include "episode_gen.cuh"
 #include "race_kernels.cuh"
 
 namespace b2d {
 
+constexpr int SWARM_BLOCK = 128;
+constexpr int SWARM_OBS = 41;
+constexpr int SWARM_AGENT_BLOB = 47;
+constexpr int SWARM_AGENT_PAYLOAD = 41; // oracle/drone_oracle.c "swarm env": respawn [0:16], env reset [16:41]
+constexpr int SWARM_HORIZON = 1024;
+constexpr int SWARM_TASK_RACE = 7;
+#define SW_GX 30.0f
+#define SW_GY 30.0f
+#define SW_GZ 10.0f
+
+// float-valued statistics (Ctl::facc): Log field order of R/dronelib.h:52-63
+enum { FACC_RETURN = 0, FACC_LENGTH, FACC_RINGS, FACC_COLLISION, FACC_OOB, FACC_SCORE, FACC_PERF, FACC_N };
+
 struct SwarmDev {
-    int n, num_agents, max_rings;
+    int n, A, R, rows, ld, epc, max_rings;
+    float4 *S, *P, *T, *U, *V, *W;
+    int4 *E;
+    float4 *G0;
+    float2 *G1;
+    const float *form; // [3][A][3] closed-form formation targets (orbit, cube, flag), computed on the host
+    const float *act_in;
+    float *act_out;
+    float *obs;
+    float *rew;
+    unsigned char *term;
     Ctl *ctl;
-    const float *payload;
+    const float *payload; // [n][A*41 + 2 + 6R] draw results (inject mode)
+    uint32_t key0, key1, env_id_base;
     int reset_mode;
 };
 
-__global__ void swarm_log_snapshot_kernel(Ctl *, long long *) {}
-__global__ void swarm_pack_kernel(const SwarmDev, const int *, int, float *) {}
-__global__ void swarm_unpack_kernel(const SwarmDev, const int *, int, const float *) {}
-static inline void swarm_vec_reset(SwarmDev &, uint64_t, cudaStream_t, long long *) {}
-static inline void swarm_vec_step(SwarmDev &, const float *, int, cudaStream_t, long long *) {}
-static inline void swarm_observe_launch(SwarmDev &, cudaStream_t) {}
-static inline void swarm_log_finish(const long long *, float *) {}
+struct SwarmAgent {
+    float s[17];
+    float p[13];
+    float spawn[3], tpos[3], tvel[3];
+    float last_abs, last_tgt, last_col, ep_ret, collisions, score;
+    int ep_len, ring_idx;
+    uint32_t respawns;
+};
+
+__device__ __forceinline__ void sw_load(const SwarmDev &d, int k, SwarmAgent &g) {
+    const size_t ld = d.ld;
+    const float4 q0 = d.S[0 * ld + k], q1 = d.S[1 * ld + k], q2 = d.S[2 * ld + k], q3 = d.S[3 * ld + k], q4 = d.S[4 * ld + k];
+    const float4 p0 = d.P[0 * ld + k], p1 = d.P[1 * ld + k], p2 = d.P[2 * ld + k];
+    const float4 tt = d.T[k], u = d.U[k], v = d.V[k], w = d.W[k];
+    g.s[0] = q0.x; g.s[1] = q0.y; g.s[2] = q0.z; g.s[3] = q0.w; g.s[4] = q1.x; g.s[5] = q1.y; g.s[6] = q1.z; g.s[7] = q1.w;
+    g.s[8] = q2.x; g.s[9] = q2.y; g.s[10] = q2.z; g.s[11] = q2.w; g.s[12] = q3.x; g.s[13] = q3.y; g.s[14] = q3.z; g.s[15] = q3.w;
+    g.s[16] = q4.x;
+    g.ep_len = __float_as_int(q4.y); g.ring_idx = __float_as_int(q4.z); g.ep_ret = q4.w;
+    g.p[0] = p0.x; g.p[1] = p0.y; g.p[2] = p0.z; g.p[3] = p0.w; g.p[4] = p1.x; g.p[5] = p1.y; g.p[6] = p1.z; g.p[7] = p1.w;
+    g.p[8] = p2.x; g.p[9] = p2.y; g.p[10] = p2.z; g.p[11] = p2.w; g.p[12] = tt.x;
+    g.respawns = __float_as_uint(tt.y); g.collisions = tt.z; g.score = tt.w;
+    g.spawn[0] = u.x; g.spawn[1] = u.y; g.spawn[2] = u.z; g.last_abs = u.w;
+    g.tpos[0] = v.x; g.tpos[1] = v.y; g.tpos[2] = v.z; g.last_tgt = v.w;
+    g.tvel[0] = w.x; g.tvel[1] = w.y; g.tvel[2] = w.z; g.last_col = w.w;
+}
+
+__device__ __forceinline__ void sw_store(const SwarmDev &d, int k, const SwarmAgent &g, bool params_too) {
+    const size_t ld = d.ld;
+    d.S[0 * ld + k] = make_float4(g.s[0], g.s[1], g.s[2], g.s[3]);
+    d.S[1 * ld + k] = make_float4(g.s[4], g.s[5], g.s[6], g.s[7]);
+    d.S[2 * ld + k] = make_float4(g.s[8], g.s[9], g.s[10], g.s[11]);
+    d.S[3 * ld + k] = make_float4(g.s[12], g.s[13], g.s[14], g.s[15]);
+    d.S[4 * ld + k] = make_float4(g.s[16], __int_as_float(g.ep_len), __int_as_float(g.ring_idx), g.ep_ret);
+    d.T[k] = make_float4(g.p[12], __uint_as_float(g.respawns), g.collisions, g.score);
+    d.V[k] = make_float4(g.tpos[0], g.tpos[1], g.tpos[2], g.last_tgt);
+    d.W[k] = make_float4(g.tvel[0], g.tvel[1], g.tvel[2], g.last_col);
+    d.U[k] = make_float4(g.spawn[0], g.spawn[1], g.spawn[2], g.last_abs);
+    if (params_too) {
+        d.P[0 * ld + k] = make_float4(g.p[0], g.p[1], g.p[2], g.p[3]);
+        d.P[1 * ld + k] = make_float4(g.p[4], g.p[5], g.p[6], g.p[7]);
+        d.P[2 * ld + k] = make_float4(g.p[8], g.p[9], g.p[10], g.p[11]);
+    }
+}
+
+__device__ __forceinline__ void sw_load_ring(const SwarmDev &d, int e, int r, float ring[6]) {
+    const float4 a = __ldcg(&d.G0[(size_t)r * d.n + e]);
+    const float2 b = __ldcg(&d.G1[(size_t)r * d.n + e]);
+    ring[0] = a.x; ring[1] = a.y; ring[2] = a.z; ring[3] = a.w; ring[4] = b.x; ring[5] = b.y;
+}
+
+// ---- random draws: Philox counters (global env id, who, ordinal, item << 8 | attempt); see
+// oracle/drone_oracle.c sw_words.  who = agent (env-wide reset), agent | 0x10000 (respawn),
+// 0xFFFF0000 (env-level draws).
+__device__ __forceinline__ uint4 sw_words(const SwarmDev &d, uint32_t env, uint32_t who, uint32_t ordinal, uint32_t item,
+                                          uint32_t attempt) {
+    return philox4x32_10(make_uint4(env, who, ordinal, (item << 8) | attempt), d.key0, d.key1);
+}
+
+__device__ __noinline__ void sw_draw_params(const SwarmDev &d, uint32_t env, uint32_t who, uint32_t ordinal, float p[13]) {
+    float u[16];
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+        const uint4 w = sw_words(d, env, who, ordinal, k, 0u);
+        u[4 * k + 0] = unit_from_word(w.x).v; u[4 * k + 1] = unit_from_word(w.y).v;
+        u[4 * k + 2] = unit_from_word(w.z).v; u[4 * k + 3] = unit_from_word(w.w).v;
+    }
+    drone_params_from_draws(u, 0.1f, 0.4f, p); // size ~ U(0.1, 0.4): R/drone_swarm.h:387
+}
+
+__device__ __forceinline__ void sw_draw_box(const SwarmDev &d, uint32_t env, uint32_t who, uint32_t ordinal, uint32_t item,
+                                            uint32_t attempt, float bx, float by, float bz, float out[3]) {
+    const uint4 w = sw_words(d, env, who, ordinal, item, attempt);
+    out[0] = lerp_u(-bx, bx, unit_from_word(w.x)).v;
+    out[1] = lerp_u(-by, by, unit_from_word(w.y)).v;
+    out[2] = lerp_u(-bz, bz, unit_from_word(w.z)).v;
+}
+
+// R/drone_swarm.h:219-232
+__device__ __forceinline__ void sw_move_target(float tp[3], float tv[3]) {
+    tp[0] = __fadd_rn(tp[0], tv[0]); tp[1] = __fadd_rn(tp[1], tv[1]); tp[2] = __fadd_rn(tp[2], tv[2]);
+    if (tp[0] < -SW_GX || tp[0] > SW_GX) tv[0] = -tv[0];
+    if (tp[1] < -SW_GY || tp[1] > SW_GY) tv[1] = -tv[1];
+    if (tp[2] < -SW_GZ || tp[2] > SW_GZ) tv[2] = -tv[2];
+}
+
+// nearest other agent of env (shared-memory base b0, A agents) as seen by agent a standing at
+// `self`: agents below a are read from `lo`, agents above from `hi` (R/drone_swarm.h:107-129).
+// Returns the distance the reference computes; `other` receives the neighbour's position.
+template <bool STRICT>
+__device__ __forceinline__ float sw_nearest(const float (*lo)[SWARM_BLOCK], const float (*hi)[SWARM_BLOCK], int b0, int A, int a,
+                                            const float self[3], float other[3]) {
+    float best = STRICT ? 999999.0f : 999999.0f * 999999.0f;
+    other[0] = other[1] = other[2] = 0.0f;
+    for (int j = 0; j < A; j++) {
+        if (j == a) continue;
+        const float (*src)[SWARM_BLOCK] = j < a ? lo : hi;
+        const float ox = src[0][b0 + j], oy = src[1][b0 + j], oz = src[2][b0 + j];
+        float dist;
+        if constexpr (STRICT) {
+            const xf dx = xf(self[0]) - xf(ox), dy = xf(self[1]) - xf(oy), dz = xf(self[2]) - xf(oz);
+            dist = xsqrt(dx * dx + dy * dy + dz * dz).v;
+        } else {
+            const float dx = self[0] - ox, dy = self[1] - oy, dz = self[2] - oz;
+            dist = dx * dx + dy * dy + dz * dz; // squared: same ordering, no square root per candidate
+        }
+        if (dist < best) {
+            best = dist;
+            other[0] = ox; other[1] = oy; other[2] = oz;
+        }
+    }
+    if constexpr (!STRICT) best = sqrtf(best);
+    return best;
+}
+
+// R/drone_swarm.h:335-376.  Side effects on the agent exactly as the reference's.
+template <bool STRICT>
+__device__ __forceinline__ float sw_reward(SwarmAgent &g, const float self[3], bool collision, int A, float nearest_dist) {
+    float dist_reward;
+    if constexpr (STRICT) {
+        const xf dx = xf(self[0]) - xf(g.tpos[0]), dy = xf(self[1]) - xf(g.tpos[1]), dz = xf(self[2]) - xf(g.tpos[2]);
+        const xf dist = xsqrt(dx * dx + dy * dy + dz * dz);
+        const xf maxd = xsqrt(xf(7600.0f)); // sqrtf(60^2 + 60^2 + 20^2)
+        // (float)(1.0 - (double)(dist / MAX_DIST)) == 1.0f - dist / MAX_DIST: the double difference is exact
+        dist_reward = (xf(1.0f) - dist / maxd).v;
+    } else {
+        const float dx = self[0] - g.tpos[0], dy = self[1] - g.tpos[1], dz = self[2] - g.tpos[2];
+        dist_reward = 1.0f - sqrtf(dx * dx + dy * dy + dz * dz) * 0.011470787f; // 1 / sqrt(7600)
+    }
+    float density_reward = 0.0f;
+    if (collision && A > 1 && nearest_dist < 1.0f) {
+        density_reward = -1.0f;
+        g.collisions = __fadd_rn(g.collisions, 1.0f);
+    }
+    float abs_reward = __fadd_rn(dist_reward, density_reward);
+    if (dist_reward < 0.0f && density_reward < 0.0f) abs_reward = -abs_reward;
+    const float delta = __fsub_rn(abs_reward, g.last_abs);
+    g.last_col = density_reward;
+    g.last_tgt = dist_reward;
+    g.last_abs = abs_reward;
+    g.ep_len += 1;
+    g.score = __fadd_rn(g.score, abs_reward);
+    return delta;
+}
+
+// R/drone_swarm.h:131-217, one agent; `near` = its nearest neighbour's position
+template <bool STRICT>
+__device__ __forceinline__ void sw_observe(const SwarmAgent &g, int A, const float near[3], bool race, const float ring[6],
+                                           float *row, int stride) {
+    float o[SWARM_OBS];
+    if constexpr (STRICT) {
+        Q4<xf> q, qi;
+        q.w = g.s[6]; q.x = g.s[7]; q.y = g.s[8]; q.z = g.s[9];
+        qi.w = q.w; qi.x = -q.x; qi.y = -q.y; qi.z = -q.z;
+        V3<xf> vel, zax;
+        vel.x = g.s[3]; vel.y = g.s[4]; vel.z = g.s[5];
+        zax.x = 0.0f; zax.y = 0.0f; zax.z = 1.0f;
+        const V3<xf> vb = qrot(qi, vel), up = qrot(q, zax);
+        o[0] = (vb.x / xf(B2D_MAX_VEL)).v; o[1] = (vb.y / xf(B2D_MAX_VEL)).v; o[2] = (vb.z / xf(B2D_MAX_VEL)).v;
+        o[3] = (xf(g.s[10]) / xf(B2D_MAX_OMEGA)).v; o[4] = (xf(g.s[11]) / xf(B2D_MAX_OMEGA)).v;
+        o[5] = (xf(g.s[12]) / xf(B2D_MAX_OMEGA)).v;
+        o[6] = up.x.v; o[7] = up.y.v; o[8] = up.z.v;
+        o[9] = g.s[6]; o[10] = g.s[7]; o[11] = g.s[8]; o[12] = g.s[9];
+#pragma unroll
+        for (int m = 0; m < 4; m++) o[13 + m] = (xf(g.s[13 + m]) / xf(g.p[10])).v;
+        o[17] = (xf(g.s[0]) / xf(SW_GX)).v; o[18] = (xf(g.s[1]) / xf(SW_GY)).v; o[19] = (xf(g.s[2]) / xf(SW_GZ)).v;
+        o[20] = (xf(g.spawn[0]) / xf(SW_GX)).v; o[21] = (xf(g.spawn[1]) / xf(SW_GY)).v; o[22] = (xf(g.spawn[2]) / xf(SW_GZ)).v;
+        const xf dx = xf(g.tpos[0]) - xf(g.s[0]), dy = xf(g.tpos[1]) - xf(g.s[1]), dz = xf(g.tpos[2]) - xf(g.s[2]);
+        o[23] = xclamp(dx, -1.0f, 1.0f).v; o[24] = xclamp(dy, -1.0f, 1.0f).v; o[25] = xclamp(dz, -1.0f, 1.0f).v;
+        o[26] = (dx / xf(SW_GX)).v; o[27] = (dy / xf(SW_GY)).v; o[28] = (dz / xf(SW_GZ)).v;
+        o[29] = g.last_col; o[30] = g.last_tgt; o[31] = g.last_abs;
+        if (A > 1) {
+            o[32] = xclamp(xf(near[0]) - xf(g.s[0]), -1.0f, 1.0f).v;
+            o[33] = xclamp(xf(near[1]) - xf(g.s[1]), -1.0f, 1.0f).v;
+            o[34] = xclamp(xf(near[2]) - xf(g.s[2]), -1.0f, 1.0f).v;
+        } else {
+            o[32] = o[33] = o[34] = 0.0f;
+        }
+        if (race) {
+            V3<xf> dd, nn;
+            dd.x = xf(ring[0]) - xf(g.s[0]); dd.y = xf(ring[1]) - xf(g.s[1]); dd.z = xf(ring[2]) - xf(g.s[2]);
+            nn.x = ring[3]; nn.y = ring[4]; nn.z = ring[5];
+            const V3<xf> to = qrot(qi, dd), bn = qrot(qi, nn);
+            o[35] = (to.x / xf(SW_GX)).v; o[36] = (to.y / xf(SW_GY)).v; o[37] = (to.z / xf(SW_GZ)).v;
+            o[38] = bn.x.v; o[39] = bn.y.v; o[40] = bn.z.v;
+        } else {
+#pragma unroll
+            for (int m = 35; m < 41; m++) o[m] = 0.0f;
+        }
+    } else {
+        const float w = g.s[6], x = g.s[7], y = g.s[8], z = g.s[9];
+        const float ww = w * w, xx = x * x, yy = y * y, zz = z * z;
+        const float xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+        const float r00 = (ww + xx) - (yy + zz), r11 = (ww - xx) + (yy - zz), r22 = (ww - xx) - (yy - zz);
+        const float r01 = 2.0f * (xy - wz), r10 = 2.0f * (xy + wz);
+        const float r02 = 2.0f * (xz + wy), r20 = 2.0f * (xz - wy);
+        const float r12 = 2.0f * (yz - wx), r21 = 2.0f * (yz + wx);
+        o[0] = 0.02f * (r00 * g.s[3] + r10 * g.s[4] + r20 * g.s[5]);
+        o[1] = 0.02f * (r01 * g.s[3] + r11 * g.s[4] + r21 * g.s[5]);
+        o[2] = 0.02f * (r02 * g.s[3] + r12 * g.s[4] + r22 * g.s[5]);
+        o[3] = 0.02f * g.s[10]; o[4] = 0.02f * g.s[11]; o[5] = 0.02f * g.s[12];
+        o[6] = r02; o[7] = r12; o[8] = r22;
+        o[9] = w; o[10] = x; o[11] = y; o[12] = z;
+        const float inv = __frcp_rn(g.p[10]);
+#pragma unroll
+        for (int m = 0; m < 4; m++) o[13 + m] = g.s[13 + m] * inv;
+        const float igx = 1.0f / SW_GX, igz = 1.0f / SW_GZ;
+        o[17] = g.s[0] * igx; o[18] = g.s[1] * igx; o[19] = g.s[2] * igz;
+        o[20] = g.spawn[0] * igx; o[21] = g.spawn[1] * igx; o[22] = g.spawn[2] * igz;
+        const float dx = g.tpos[0] - g.s[0], dy = g.tpos[1] - g.s[1], dz = g.tpos[2] - g.s[2];
+        o[23] = fminf(fmaxf(dx, -1.0f), 1.0f); o[24] = fminf(fmaxf(dy, -1.0f), 1.0f); o[25] = fminf(fmaxf(dz, -1.0f), 1.0f);
+        o[26] = dx * igx; o[27] = dy * igx; o[28] = dz * igz;
+        o[29] = g.last_col; o[30] = g.last_tgt; o[31] = g.last_abs;
+        if (A > 1) {
+            o[32] = fminf(fmaxf(near[0] - g.s[0], -1.0f), 1.0f);
+            o[33] = fminf(fmaxf(near[1] - g.s[1], -1.0f), 1.0f);
+            o[34] = fminf(fmaxf(near[2] - g.s[2], -1.0f), 1.0f);
+        } else {
+            o[32] = o[33] = o[34] = 0.0f;
+        }
+        if (race) {
+            const float ex = ring[0] - g.s[0], ey = ring[1] - g.s[1], ez = ring[2] - g.s[2];
+            o[35] = igx * (r00 * ex + r10 * ey + r20 * ez);
+            o[36] = igx * (r01 * ex + r11 * ey + r21 * ez);
+            o[37] = igz * (r02 * ex + r12 * ey + r22 * ez);
+            o[38] = r00 * ring[3] + r10 * ring[4] + r20 * ring[5];
+            o[39] = r01 * ring[3] + r11 * ring[4] + r21 * ring[5];
+            o[40] = r02 * ring[3] + r12 * ring[4] + r22 * ring[5];
+        } else {
+#pragma unroll
+            for (int m = 35; m < 41; m++) o[m] = 0.0f;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < SWARM_OBS; m++) row[m * stride] = o[m];
+}
+
+// R/drone_swarm.h:378-390 minus the reward: statistics zeroed, new drone, at `pos`
+__device__ __forceinline__ void sw_respawn_state(SwarmAgent &g, const float p[13], const float pos[3]) {
+    g.ep_ret = 0.0f;
+    g.ep_len = 0;
+    g.collisions = 0.0f;
+    g.score = 0.0f;
+    g.ring_idx = 0;
+#pragma unroll
+    for (int k = 0; k < 13; k++) g.p[k] = p[k];
+#pragma unroll
+    for (int k = 0; k < 17; k++) g.s[k] = 0.0f;
+    g.s[6] = 1.0f;
+    g.s[0] = pos[0]; g.s[1] = pos[1]; g.s[2] = pos[2];
+    g.spawn[0] = pos[0]; g.spawn[1] = pos[1]; g.spawn[2] = pos[2];
+}
+
+// ---------------------------------------------------------------- the kernel
+// ONLY_RESET = false: one vec_step.  ONLY_RESET = true: vec_reset (every env runs c_reset).
+template <bool STRICT, bool ONLY_RESET>
+__global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constant__ SwarmDev d) {
+    __shared__ float s_old[3][SWARM_BLOCK]; // positions before this tick's move
+    __shared__ float s_fin[3][SWARM_BLOCK]; // after the move, or the respawn position of an agent that left the arena
+    __shared__ float s_rst[3][SWARM_BLOCK]; // first position drawn by an env-wide reset
+    __shared__ float s_pos[3][SWARM_BLOCK]; // final positions of the tick (what the observations see)
+    __shared__ float s_obs[SWARM_BLOCK * SWARM_OBS];
+    __shared__ float s_ring0[SWARM_BLOCK][3];
+    __shared__ float s_facc[8];
+
+    const int t = threadIdx.x;
+    const int A = d.A;
+    const int le = t / A;
+    const int a = t - le * A;
+    const int e = blockIdx.x * d.epc + le;
+    const bool active = le < d.epc && e < d.n;
+    const int b0 = le * A;
+    const int k = e * A + a;
+    const uint32_t genv = d.env_id_base + (uint32_t)e;
+    const bool inject = d.reset_mode == 1;
+    const float *pay_agent = d.payload ? d.payload + (size_t)e * (A * SWARM_AGENT_PAYLOAD + 2 + 6 * d.R) + (size_t)a * SWARM_AGENT_PAYLOAD : nullptr;
+    const float *pay_env = d.payload ? d.payload + (size_t)e * (A * SWARM_AGENT_PAYLOAD + 2 + 6 * d.R) + (size_t)A * SWARM_AGENT_PAYLOAD : nullptr;
+    if (t < 8) s_facc[t] = 0.0f;
+
+    SwarmAgent g;
+    int tick = 0, task = 0;
+    uint32_t env_episode = 0;
+    float reward = 0.0f;
+    int terminal = 0;
+    bool params_dirty = false;
+    bool do_reset = false;
+    if (active) {
+        sw_load(d, k, g);
+        const int4 ev = d.E[e];
+        tick = ev.x; task = ev.y; env_episode = (uint32_t)ev.z;
+        s_old[0][t] = g.s[0]; s_old[1][t] = g.s[1]; s_old[2][t] = g.s[2];
+    }
+
+    if constexpr (!ONLY_RESET) {
+        // ---- phase 1: every drone moves (R/drone_swarm.h:452-461); agents that leave the arena draw their respawn
+        bool oob = false;
+        float rp[13], rpos[3] = {0.0f, 0.0f, 0.0f};
+        if (active) {
+            tick = (tick + 1) % SWARM_HORIZON;
+            const float4 a4 = reinterpret_cast<const float4 *>(d.act_in)[k];
+            float act[4];
+            if constexpr (STRICT) {
+                act[0] = xclamp(xf(a4.x), -1.0f, 1.0f).v; act[1] = xclamp(xf(a4.y), -1.0f, 1.0f).v;
+                act[2] = xclamp(xf(a4.z), -1.0f, 1.0f).v; act[3] = xclamp(xf(a4.w), -1.0f, 1.0f).v;
+            } else {
+                act[0] = fminf(fmaxf(a4.x, -1.0f), 1.0f); act[1] = fminf(fmaxf(a4.y, -1.0f), 1.0f);
+                act[2] = fminf(fmaxf(a4.z, -1.0f), 1.0f); act[3] = fminf(fmaxf(a4.w, -1.0f), 1.0f);
+            }
+            if (d.act_out) reinterpret_cast<float4 *>(d.act_out)[k] = make_float4(act[0], act[1], act[2], act[3]);
+            DroneParams p = {g.p[0], g.p[1], g.p[2], g.p[3], g.p[4], g.p[5], g.p[6], g.p[7], g.p[8], g.p[9], g.p[10], g.p[11], g.p[12]};
+            advance_body<STRICT>(g.s, p, act);
+            oob = g.s[0] < -SW_GX || g.s[0] > SW_GX || g.s[1] < -SW_GY || g.s[1] > SW_GY || g.s[2] < -SW_GZ || g.s[2] > SW_GZ;
+            sw_move_target(g.tpos, g.tvel);
+            if (oob) {
+                if (inject) {
+#pragma unroll
+                    for (int m = 0; m < 13; m++) rp[m] = pay_agent[m];
+                    rpos[0] = pay_agent[13]; rpos[1] = pay_agent[14]; rpos[2] = pay_agent[15];
+                } else {
+                    g.respawns += 1u;
+                    sw_draw_params(d, genv, (uint32_t)a | 0x10000u, g.respawns, rp);
+                    sw_draw_box(d, genv, (uint32_t)a | 0x10000u, g.respawns, 4u, 0u, 29.0f, 29.0f, 9.0f, rpos);
+                }
+            }
+            s_fin[0][t] = oob ? rpos[0] : g.s[0];
+            s_fin[1][t] = oob ? rpos[1] : g.s[1];
+            s_fin[2][t] = oob ? rpos[2] : g.s[2];
+        }
+        __syncthreads();
+
+        // ---- phase 2: rewards, ring logic, respawn bookkeeping (R/drone_swarm.h:463-491)
+        if (active) {
+            const float before[3] = {s_old[0][t], s_old[1][t], s_old[2][t]};
+            const float self[3] = {g.s[0], g.s[1], g.s[2]};
+            float other[3];
+            float nd = 0.0f;
+            if (A > 1) nd = sw_nearest<STRICT>(s_fin, s_old, b0, A, a, self, other);
+            if (task == SWARM_TASK_RACE) {
+                float ring[6];
+                sw_load_ring(d, e, g.ring_idx, ring);
+                reward = sw_reward<STRICT>(g, self, true, A, nd);
+                float passed;
+                if constexpr (STRICT) passed = gate_event<xf>(before, self, ring, -0.0f);
+                else passed = gate_event<float>(before, self, ring, -0.0f);
+                if (passed > 0.0f) {
+                    g.ring_idx = (g.ring_idx + 1) % d.R;
+                    atomicAdd(&s_facc[FACC_RINGS], 1.0f);
+                    sw_load_ring(d, e, g.ring_idx, ring);
+                    g.tpos[0] = ring[0]; g.tpos[1] = ring[1]; g.tpos[2] = ring[2];
+                    g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
+                    sw_reward<STRICT>(g, self, true, A, nd);
+                }
+                reward = __fadd_rn(reward, passed);
+            } else {
+                reward = sw_reward<STRICT>(g, self, true, A, nd);
+            }
+            g.ep_ret = __fadd_rn(g.ep_ret, reward);
+            const bool horizon = tick >= SWARM_HORIZON - 1;
+            if (oob || horizon) { // add_log: R/drone_swarm.h:91-105
+                terminal = 1;
+                const float len = (float)g.ep_len;
+                atomicAdd(&s_facc[FACC_SCORE], g.score);
+                atomicAdd(&s_facc[FACC_RETURN], g.ep_ret);
+                atomicAdd(&s_facc[FACC_LENGTH], len);
+                atomicAdd(&s_facc[FACC_COLLISION], g.collisions / len);
+                atomicAdd(&s_facc[FACC_PERF], g.score / len);
+                if (oob) atomicAdd(&s_facc[FACC_OOB], 1.0f);
+                atomicAdd(&s_facc[FACC_N], 1.0f);
+                g.ep_len = 0;
+                g.ep_ret = 0.0f;
+            }
+            if (oob) {
+                reward = __fsub_rn(reward, 1.0f);
+                sw_respawn_state(g, rp, rpos);
+                params_dirty = true;
+                float nd2 = 0.0f;
+                if (A > 1 && task != SWARM_TASK_RACE) nd2 = sw_nearest<STRICT>(s_fin, s_old, b0, A, a, rpos, other);
+                sw_reward<STRICT>(g, rpos, task != SWARM_TASK_RACE, A, nd2);
+            }
+            do_reset = horizon;
+        }
+    } else {
+        if (active) {
+            s_fin[0][t] = g.s[0]; s_fin[1][t] = g.s[1]; s_fin[2][t] = g.s[2];
+            g.respawns = 0u;
+            do_reset = true;
+        }
+    }
+
+    // ---- phase 3: env-wide reset (R/drone_swarm.h:401-443), every 1023 ticks for all agents of the env at once
+    const int cta_reset = __syncthreads_or(do_reset ? 1 : 0);
+    if (cta_reset) {
+        float first[3] = {0.0f, 0.0f, 0.0f}, np[13];
+        if (do_reset) {
+            tick = 0;
+            env_episode = ONLY_RESET ? 0u : env_episode + 1u;
+            if (inject) {
+                task = (int)pay_env[1];
+#pragma unroll
+                for (int m = 0; m < 13; m++) np[m] = pay_agent[16 + m];
+                first[0] = pay_agent[29]; first[1] = pay_agent[30]; first[2] = pay_agent[31];
+            } else {
+                const uint4 w = sw_words(d, genv, 0xFFFF0000u, env_episode, 0u, 0u);
+                task = ((w.x >> 1) % 4u) ? SWARM_TASK_RACE : (int)((w.y >> 1) % 7u);
+                sw_draw_params(d, genv, (uint32_t)a, env_episode, np);
+                sw_draw_box(d, genv, (uint32_t)a, env_episode, 4u, 0u, 29.0f, 29.0f, 9.0f, first);
+            }
+            s_rst[0][t] = first[0]; s_rst[1][t] = first[1]; s_rst[2][t] = first[2];
+        }
+        __syncthreads();
+        if (do_reset) {
+            // reset_agent: the reward is computed against the STALE target and half-reset neighbours
+            sw_respawn_state(g, np, first);
+            params_dirty = true;
+            float other[3], nd = 0.0f;
+            if (A > 1 && task != SWARM_TASK_RACE) nd = sw_nearest<STRICT>(s_rst, s_fin, b0, A, a, first, other);
+            sw_reward<STRICT>(g, first, task != SWARM_TASK_RACE, A, nd);
+            // set_target: R/drone_swarm.h:234-333
+            if (inject) {
+#pragma unroll
+                for (int m = 0; m < 3; m++) { g.tpos[m] = pay_agent[32 + m]; g.tvel[m] = pay_agent[35 + m]; }
+            } else if (task == 0 || ((task == 3 || task == 5) && a == 0)) {
+                sw_draw_box(d, genv, (uint32_t)a, env_episode, 5u, 0u, 29.0f, 29.0f, 9.0f, g.tpos);
+                sw_draw_box(d, genv, (uint32_t)a, env_episode, 6u, 0u, 0.05f, 0.05f, 0.05f, g.tvel);
+            } else if (task == 3 || task == 5) {
+                // follow: agent 0's idle target; congo: the same target advanced 40 moves per link of the chain
+                sw_draw_box(d, genv, 0u, env_episode, 5u, 0u, 29.0f, 29.0f, 9.0f, g.tpos);
+                sw_draw_box(d, genv, 0u, env_episode, 6u, 0u, 0.05f, 0.05f, 0.05f, g.tvel);
+                if (task == 5)
+                    for (int m = 0; m < 40 * a; m++) sw_move_target(g.tpos, g.tvel);
+            } else if (task == 1) {
+                g.tpos[0] = first[0]; g.tpos[1] = first[1]; g.tpos[2] = first[2];
+                g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
+            } else if (task == SWARM_TASK_RACE) {
+                // rings are regenerated AFTER the targets are set: the target is the previous episode's ring 0
+                float ring[6];
+                sw_load_ring(d, e, 0, ring);
+                g.tpos[0] = ring[0]; g.tpos[1] = ring[1]; g.tpos[2] = ring[2];
+                g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
+            } else {
+                const float *f = d.form + ((size_t)(task == 2 ? 0 : (task == 4 ? 1 : 2)) * A + a) * 3;
+                g.tpos[0] = f[0]; g.tpos[1] = f[1]; g.tpos[2] = f[2];
+                g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
+            }
+        }
+        __syncthreads(); // every agent has read the old ring 0 before the rings are rewritten
+        if (do_reset && a == 0) {
+            float prev[3] = {0.0f, 0.0f, 0.0f};
+            for (int r = 0; r < d.R; r++) {
+                float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                if (task == SWARM_TASK_RACE) {
+                    if (inject) {
+#pragma unroll
+                        for (int m = 0; m < 6; m++) ring[m] = pay_env[2 + 6 * r + m];
+                    } else {
+                        for (uint32_t at = 0; at < RESET_MAX_ATTEMPTS; at++) {
+                            const uint4 wa = sw_words(d, genv, 0xFFFF0000u, env_episode, 0x10u + 2u * r, at);
+                            const uint4 wb = sw_words(d, genv, 0xFFFF0000u, env_episode, 0x11u + 2u * r, at);
+                            ring_from_words(wa, wb, 26.0f, 26.0f, 6.0f, ring);
+                            if (r == 0 || !(dist3_exact(ring, prev) < 4.0f)) break;
+                        }
+                    }
+                }
+                prev[0] = ring[0]; prev[1] = ring[1]; prev[2] = ring[2];
+                d.G0[(size_t)r * d.n + e] = make_float4(ring[0], ring[1], ring[2], ring[3]);
+                d.G1[(size_t)r * d.n + e] = make_float2(ring[4], ring[5]);
+                if (r == 0) { s_ring0[le][0] = ring[0]; s_ring0[le][1] = ring[1]; s_ring0[le][2] = ring[2]; }
+            }
+        }
+        __syncthreads();
+        if (do_reset && task == SWARM_TASK_RACE) {
+            // start at least 2*radius from the first ring; spawn_pos / prev_pos keep the first draw (R/drone_swarm.h:429-439)
+            const float r0[3] = {s_ring0[le][0], s_ring0[le][1], s_ring0[le][2]};
+            float c[3];
+            if (inject) {
+                c[0] = pay_agent[38]; c[1] = pay_agent[39]; c[2] = pay_agent[40];
+            } else {
+                for (uint32_t at = 0; at < RESET_MAX_ATTEMPTS; at++) {
+                    sw_draw_box(d, genv, (uint32_t)a, env_episode, 7u, at, 29.0f, 29.0f, 9.0f, c);
+                    if (!(dist3_exact(c, r0) < 4.0f)) break;
+                }
+            }
+            g.s[0] = c[0]; g.s[1] = c[1]; g.s[2] = c[2];
+        }
+    }
+    if (active) {
+        s_pos[0][t] = g.s[0]; s_pos[1][t] = g.s[1]; s_pos[2][t] = g.s[2];
+    }
+    __syncthreads();
+
+    // ---- phase 4: state out, observations (R/drone_swarm.h:131-217) staged through shared memory
+    if (active) {
+        sw_store(d, k, g, params_dirty);
+        if (a == 0) d.E[e] = make_int4(tick, task, (int)env_episode, 0);
+        if constexpr (!ONLY_RESET) {
+            d.rew[k] = reward;
+            d.term[k] = (unsigned char)terminal;
+        }
+        const float self[3] = {g.s[0], g.s[1], g.s[2]};
+        float near[3] = {0.0f, 0.0f, 0.0f};
+        if (A > 1) sw_nearest<STRICT>(s_pos, s_pos, b0, A, a, self, near);
+        float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (task == SWARM_TASK_RACE) sw_load_ring(d, e, g.ring_idx, ring);
+        sw_observe<STRICT>(g, A, near, task == SWARM_TASK_RACE, ring, s_obs + t * SWARM_OBS, 1);
+    }
+    __syncthreads();
+    {
+        const int rows_here = min(d.epc, d.n - blockIdx.x * d.epc) * A;
+        float *gobs = d.obs + (size_t)blockIdx.x * d.epc * A * SWARM_OBS;
+        for (int m = t; m < rows_here * SWARM_OBS; m += SWARM_BLOCK) __stcs(&gobs[m], s_obs[m]);
+    }
+    if constexpr (!ONLY_RESET) {
+        if (t < 8 && s_facc[t] != 0.0f) atomicAdd(&d.ctl->facc[t], (double)s_facc[t]);
+        if (t == 0 && blockIdx.x == 0) atomicAdd(&d.ctl->ctas_done, 1u);
+    }
+}
+
+// snapshot + clear for vec_log: out[0..7] = the float sums in 2^-20 fixed point, so that the
+// cross-rank reduction is the same integer all-reduce the race env uses
+__global__ void swarm_log_snapshot_kernel(Ctl *ctl, long long *out) {
+    if (threadIdx.x < 8) {
+        out[threadIdx.x] = __double2ll_rn(ctl->facc[threadIdx.x] * 1048576.0);
+        ctl->facc[threadIdx.x] = 0.0;
+    } else if (threadIdx.x < 16) {
+        out[threadIdx.x] = 0;
+    }
+}
+
+// state blobs: per env [A][47] agent blobs (oracle/ref_shim_swarm.c layout) then [2 + 6R] env blob
+__global__ void swarm_pack_kernel(const SwarmDev d, const int *ids, int n, float *blobs) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n * d.A) return;
+    const int slot = j / d.A, a = j - slot * d.A;
+    const int e = ids ? ids[slot] : slot;
+    const int blob = d.A * SWARM_AGENT_BLOB + 2 + 6 * d.R;
+    SwarmAgent g;
+    sw_load(d, e * d.A + a, g);
+    float *b = blobs + (size_t)slot * blob + (size_t)a * SWARM_AGENT_BLOB;
+    for (int m = 0; m < 17; m++) b[m] = g.s[m];
+    for (int m = 0; m < 13; m++) b[17 + m] = g.p[m];
+    for (int m = 0; m < 3; m++) { b[30 + m] = g.spawn[m]; b[33 + m] = g.tpos[m]; b[36 + m] = g.tvel[m]; }
+    b[39] = g.last_abs; b[40] = g.last_tgt; b[41] = g.last_col; b[42] = g.ep_ret; b[43] = g.collisions;
+    b[44] = (float)g.ep_len; b[45] = g.score; b[46] = (float)g.ring_idx;
+    if (a == 0) {
+        float *eb = blobs + (size_t)slot * blob + (size_t)d.A * SWARM_AGENT_BLOB;
+        const int4 ev = d.E[e];
+        eb[0] = (float)ev.x; eb[1] = (float)ev.y;
+        for (int r = 0; r < d.R; r++) sw_load_ring(d, e, r, eb + 2 + 6 * r);
+    }
+}
+
+__global__ void swarm_unpack_kernel(const SwarmDev d, const int *ids, int n, const float *blobs) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n * d.A) return;
+    const int slot = j / d.A, a = j - slot * d.A;
+    const int e = ids ? ids[slot] : slot;
+    const int blob = d.A * SWARM_AGENT_BLOB + 2 + 6 * d.R;
+    const float *b = blobs + (size_t)slot * blob + (size_t)a * SWARM_AGENT_BLOB;
+    SwarmAgent g;
+    const int k = e * d.A + a;
+    g.respawns = __float_as_uint(d.T[k].y);
+    for (int m = 0; m < 17; m++) g.s[m] = b[m];
+    for (int m = 0; m < 13; m++) g.p[m] = b[17 + m];
+    for (int m = 0; m < 3; m++) { g.spawn[m] = b[30 + m]; g.tpos[m] = b[33 + m]; g.tvel[m] = b[36 + m]; }
+    g.last_abs = b[39]; g.last_tgt = b[40]; g.last_col = b[41]; g.ep_ret = b[42]; g.collisions = b[43];
+    g.ep_len = (int)b[44]; g.score = b[45]; g.ring_idx = (int)b[46];
+    sw_store(d, k, g, true);
+    if (a == 0) {
+        const float *eb = blobs + (size_t)slot * blob + (size_t)d.A * SWARM_AGENT_BLOB;
+        d.E[e] = make_int4((int)eb[0], (int)eb[1], d.E[e].z, 0);
+        for (int r = 0; r < d.R; r++) {
+            const float *gg = eb + 2 + 6 * r;
+            d.G0[(size_t)r * d.n + e] = make_float4(gg[0], gg[1], gg[2], gg[3]);
+            d.G1[(size_t)r * d.n + e] = make_float2(gg[4], gg[5]);
+        }
+    }
+}
+
+// observations recomputed from the current state (after put_state)
+template <bool STRICT>
+__global__ void __launch_bounds__(SWARM_BLOCK) swarm_observe_kernel(const __grid_constant__ SwarmDev d) {
+    __shared__ float s_pos[3][SWARM_BLOCK];
+    const int t = threadIdx.x, A = d.A;
+    const int le = t / A, a = t - le * A, e = blockIdx.x * d.epc + le;
+    const bool active = le < d.epc && e < d.n;
+    SwarmAgent g;
+    if (active) {
+        sw_load(d, e * A + a, g);
+        s_pos[0][t] = g.s[0]; s_pos[1][t] = g.s[1]; s_pos[2][t] = g.s[2];
+    }
+    __syncthreads();
+    if (!active) return;
+    const int task = d.E[e].y;
+    const float self[3] = {g.s[0], g.s[1], g.s[2]};
+    float near[3] = {0.0f, 0.0f, 0.0f};
+    if (A > 1) sw_nearest<STRICT>(s_pos, s_pos, le * A, A, a, self, near);
+    float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (task == SWARM_TASK_RACE) sw_load_ring(d, e, g.ring_idx, ring);
+    sw_observe<STRICT>(g, A, near, task == SWARM_TASK_RACE, ring, d.obs + (size_t)(e * A + a) * SWARM_OBS, 1);
+}
+
+// ---------------------------------------------------------------- host-side launch helpers
+static inline int swarm_grid(const SwarmDev &d) { return (d.n + d.epc - 1) / d.epc; }
+
+static inline void swarm_vec_reset(SwarmDev &d, uint64_t seed, cudaStream_t st, long long *launches) {
+    d.key0 = (uint32_t)seed;
+    d.key1 = (uint32_t)(seed >> 32);
+    swarm_kernel<true, true><<<swarm_grid(d), SWARM_BLOCK, 0, st>>>(d);
+    *launches += 1;
+}
+
+static inline void swarm_vec_step(SwarmDev &dev, const float *actions, int math, cudaStream_t st, long long *launches) {
+    SwarmDev d = dev;
+    if (actions) d.act_in = actions;
+    if (math == 1) swarm_kernel<true, false><<<swarm_grid(d), SWARM_BLOCK, 0, st>>>(d);
+    else swarm_kernel<false, false><<<swarm_grid(d), SWARM_BLOCK, 0, st>>>(d);
+    *launches += 1;
+}
+
+static inline void swarm_observe_launch(SwarmDev &d, cudaStream_t st) {
+    swarm_observe_kernel<true><<<swarm_grid(d), SWARM_BLOCK, 0, st>>>(d);
+}
+
+// averaging of vec_log for the swarm (EB:588-591 + DS/binding.c:13-23): sums arrive as doubles
+static inline void swarm_log_finish(const long long *a, float *out) {
+    double f[8];
+    for (int k = 0; k < 8; k++) f[k] = (double)a[k] / 1048576.0;
+    const double n = f[FACC_N];
+    for (int k = 0; k < 9; k++) out[k] = 0.0f;
+    if (n == 0.0) return;
+    out[0] = (float)(f[FACC_RETURN] / n);
+    out[1] = (float)(f[FACC_LENGTH] / n);
+    out[2] = (float)(f[FACC_RINGS] / n);
+    out[3] = (float)(f[FACC_COLLISION] / n);
+    out[4] = (float)(f[FACC_OOB] / n);
+    out[5] = 0.0f;
+    out[6] = (float)(f[FACC_SCORE] / n);
+    out[7] = (float)(f[FACC_PERF] / n);
+    out[8] = (float)n;
+}
 
 } // namespace b2d

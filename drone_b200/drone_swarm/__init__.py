@@ -1,0 +1,1 @@
+from .drone_swarm import DroneSwarm  # noqa: F401

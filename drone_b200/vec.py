@@ -29,6 +29,7 @@ class _Vec:
         L = capi.lib()
         self.num_agents = L.b2d_num_agents(self.h)
         self.blob_floats = L.b2d_state_blob_floats(self.h)
+        self.payload_floats = self.blob_floats
 
     # ---- the hot path -----------------------------------------------------
     def reset(self, seed=0, stream=None):
@@ -109,7 +110,7 @@ class _Vec:
 
     def set_reset_payload(self, payload):
         payload = np.ascontiguousarray(payload, np.float32)
-        assert payload.shape == (self.num_envs, self.blob_floats)
+        assert payload.shape == (self.num_envs, self.payload_floats)
         capi.check(capi.lib().b2d_set_reset_payload(self.h, payload.ctypes.data_as(C.POINTER(C.c_float))))
 
     @property
@@ -223,4 +224,69 @@ class RaceVec(_Vec):
     def _log_dict(self, v):
         # keys and order of DR/binding.c:13-23
         return {"perf": v[7], "score": v[6], "collision_rate": v[3], "oob": v[4], "timeout": v[5],
+                "episode_return": v[0], "episode_length": v[1], "n": v[8]}
+
+
+def _make_buffers(vec, rows, obs_dim, host_buffers):
+    """Contract buffers: torch-owned device tensors adopted by the library (zero-copy), or the
+    caller's NumPy arrays mirrored by the *_host entry points."""
+    bufs = capi.Buffers()
+    if host_buffers is None:
+        vec.observations = torch.zeros((rows, obs_dim), dtype=torch.float32, device=vec.device)
+        vec.actions = torch.zeros((rows, 4), dtype=torch.float32, device=vec.device)
+        vec.rewards = torch.zeros(rows, dtype=torch.float32, device=vec.device)
+        vec.terminals = torch.zeros(rows, dtype=torch.uint8, device=vec.device)
+        vec.truncations = torch.zeros(rows, dtype=torch.uint8, device=vec.device)
+        for name in ("observations", "actions", "rewards", "terminals", "truncations"):
+            setattr(bufs, name, getattr(vec, name).data_ptr())
+        bufs.location = capi.MEM_DEVICE
+    else:
+        vec.host = host_buffers
+        for name in ("observations", "actions", "rewards", "terminals", "truncations"):
+            setattr(bufs, name, host_buffers[name].ctypes.data)
+        bufs.location = capi.MEM_HOST
+    return bufs
+
+
+class SwarmVec(_Vec):
+    """Device-resident DroneSwarm envs (reference: pufferlib/ocean/drone_swarm)."""
+    obs_dim = 41
+
+    def __init__(self, num_envs, num_drones=64, max_rings=5, seed=0, device="cuda:0", math="fast",
+                 env_id_base=0, write_clamped_actions=False, host_buffers=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("drone_b200 needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device(device)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.num_envs, self.num_drones, self.max_rings = int(num_envs), int(num_drones), int(max_rings)
+        rows = self.num_envs * self.num_drones
+        cfg = capi.SwarmCfg(self.num_envs, self.num_drones, self.max_rings, idx, int(seed) & (2**64 - 1),
+                            int(env_id_base), _math(math), int(bool(write_clamped_actions)))
+        bufs = _make_buffers(self, rows, self.obs_dim, host_buffers)
+        h = C.c_void_p()
+        with torch.cuda.device(idx):
+            torch.cuda.current_stream().synchronize()
+            capi.check(capi.lib().b2d_swarm_create(C.byref(h), C.byref(cfg), C.byref(bufs)))
+        self._adopt(h, self.device)
+        self.payload_floats = self.num_drones * 41 + 2 + 6 * self.max_rings
+        if host_buffers is not None:
+            db = capi.Buffers()
+            capi.check(capi.lib().b2d_get_buffers(self.h, C.byref(db)))
+            self.observations = _alias(db.observations, (rows, self.obs_dim), torch.float32, self.device, self)
+            self.actions = _alias(db.actions, (rows, 4), torch.float32, self.device, self)
+            self.rewards = _alias(db.rewards, (rows,), torch.float32, self.device, self)
+            self.terminals = _alias(db.terminals, (rows,), torch.uint8, self.device, self)
+            self.truncations = _alias(db.truncations, (rows,), torch.uint8, self.device, self)
+
+    def split_state(self, blobs):
+        """state blobs [num_envs, blob] -> (env blobs [n, 2+6R], agent blobs [n, A, 47])"""
+        n, A = blobs.shape[0], self.num_drones
+        return blobs[:, A * 47:].copy(), blobs[:, :A * 47].reshape(n, A, 47).copy()
+
+    def join_state(self, env, ag):
+        return np.concatenate([np.asarray(ag, np.float32).reshape(len(env), -1), np.asarray(env, np.float32)], axis=1)
+
+    def _log_dict(self, v):
+        # keys and order of DS/binding.c:13-23
+        return {"perf": v[7], "score": v[6], "rings_passed": v[2], "collision_rate": v[3], "oob": v[4],
                 "episode_return": v[0], "episode_length": v[1], "n": v[8]}

@@ -34,6 +34,7 @@ extern "C" {
 #define B2D_LOG_FIELDS 9     /* DR/dronelib.h:52-63 */
 #define B2D_RACE_BLOB 33     /* + 6*max_rings floats, see b2d_get_state */
 #define B2D_SWARM_AGENT_BLOB 47
+#define B2D_SWARM_AGENT_PAYLOAD 41 /* per-agent draw results of the swarm reset payload */
 
 typedef struct b2d_vec b2d_vec; /* replaces VecEnv, EB:262-265 */
 
@@ -167,7 +168,15 @@ int b2d_observe(b2d_vec *vec, void *cuda_stream);
 /* ---- parity / configuration hooks --------------------------------------------- */
 int b2d_set_math(b2d_vec *vec, int math);
 int b2d_set_reset_mode(b2d_vec *vec, int reset_mode);
-/* host_payload: [num_envs][state blob] next-episode states for B2D_RESET_INJECT (copied; synchronous) */
+/* host_payload for B2D_RESET_INJECT (copied; synchronous).
+ *   race:  [num_envs][state blob]: the post-reset state an env takes when it terminates this step.
+ *   swarm: [num_envs][num_agents*41 + 2 + 6*max_rings]: the RESULTS of the random draws of this step:
+ *          per agent [0:13] params [13:16] pos of an out-of-bounds respawn (DS/drone_swarm.h:378-399),
+ *          [16:29] params [29:32] pos [32:35] target_pos [35:38] target_vel [38:41] race start pos of an
+ *          env-wide reset (DS/drone_swarm.h:401-443); then per env [0] unused [1] task, rings pos(3) normal(3).
+ * Swarm state blob (b2d_get_state / b2d_put_state) per env: [num_agents][47] (pos vel quat omega rpms |
+ * 13 params | spawn_pos target_pos target_vel | last_abs last_target last_collision reward |
+ * episode_return collisions episode_length score ring_idx) then [2 + 6*max_rings] (tick, task, rings). */
 int b2d_set_reset_payload(b2d_vec *vec, const float *host_payload);
 int b2d_set_step_count(b2d_vec *vec, uint32_t steps);
 

@@ -64,6 +64,60 @@ def race_golden(n, T, seed, max_rings=10, max_moves=1000, tape_seed=1234, scale=
     return g
 
 
+def swarm_golden(n, A, T, seed, max_rings=5, tape_seed=77, scale=1.2):
+    """Swarm vectors.  Outputs come from the unmodified reference (RefSwarm).  The results of its
+    random draws (respawns, env-wide resets) are not observable from outside c_step, so they are
+    taken from the CPU restatement run on the same libc stream right after, which must reproduce
+    the reference's outputs bit for bit at every step before its draws are accepted."""
+    tape = action_tape(n * A, seed=tape_seed, scale=scale)
+    ref = po.RefSwarm(n, A, max_rings)
+    ref.reset(seed)
+    init_obs = ref.observations.copy()
+    term = np.zeros((T, n * A), np.uint8)
+    rew = np.zeros((T, n * A), np.float32)
+    oh = np.zeros((T, n * A), np.uint32)
+    obs_full, obs_steps = [], []
+    for t in range(T):
+        ref.step(tape[t % len(tape)])
+        term[t], rew[t], oh[t] = ref.terminals, ref.rewards, row_hash(ref.observations)
+        if t in OBS_STEPS or t in (1022, 1023, 1024) or t == T - 1:
+            obs_steps.append(t)
+            obs_full.append(ref.observations.copy())
+    fin_env, fin_ag = ref.get_state()
+    log = ref.log()
+    ref.close()
+
+    orc = po.OrcSwarm(n, A, max_rings)
+    orc.reset(seed, mode=po.RESET_LIBC)
+    assert np.array_equal(orc.observations.view(np.uint32), init_obs.view(np.uint32))
+    pay0 = np.concatenate([orc.pay_agent.reshape(n, -1), orc.pay_env], axis=1)
+    ev_t, ev_row, ev_pay, er_t, er_env, er_pay = [], [], [], [], [], []
+    for t in range(T):
+        orc.step(tape[t % len(tape)], mode=po.RESET_LIBC)
+        assert np.array_equal(row_hash(orc.observations), oh[t]), f"restatement diverged from the reference at step {t}"
+        assert np.array_equal(orc.rewards.view(np.uint32), rew[t].view(np.uint32)) and np.array_equal(orc.terminals, term[t])
+        envs = np.flatnonzero(orc.flag_env)
+        rows = np.flatnonzero(orc.flag_agent | np.repeat(orc.flag_env, A))
+        if len(rows):
+            ev_t += [t] * len(rows)
+            ev_row += rows.tolist()
+            ev_pay.append(orc.pay_agent[rows].copy())
+        if len(envs):
+            er_t += [t] * len(envs)
+            er_env += envs.tolist()
+            er_pay.append(orc.pay_env[envs].copy())
+    e2, a2 = orc.get_state()
+    assert np.array_equal(e2.view(np.uint32), fin_env.view(np.uint32)) and np.array_equal(a2.view(np.uint32), fin_ag.view(np.uint32))
+    orc.close()
+    return dict(meta=np.array([n, A, T, seed, max_rings], np.int64), tape=tape, init_obs=init_obs, init_payload=pay0,
+                term=term, rew=rew, obs_hash=oh, obs_steps=np.array(obs_steps, np.int32), obs_full=np.array(obs_full),
+                ev_t=np.array(ev_t, np.int32), ev_row=np.array(ev_row, np.int32),
+                ev_pay=np.concatenate(ev_pay) if ev_pay else np.zeros((0, po.SWARM_AGENT_PAYLOAD), np.float32),
+                er_t=np.array(er_t, np.int32), er_env=np.array(er_env, np.int32),
+                er_pay=np.concatenate(er_pay) if er_pay else np.zeros((0, 2 + 6 * max_rings), np.float32),
+                final_env=fin_env, final_agents=fin_ag, log=log)
+
+
 if __name__ == "__main__":
     if not po.have_ref():
         po.build(quiet=False)
@@ -75,3 +129,11 @@ if __name__ == "__main__":
         g = race_golden(**kw)
         np.savez_compressed(os.path.join(HERE, name), **g)
         print(name, "resets:", len(g["ev_t"]), "bytes:", os.path.getsize(os.path.join(HERE, name)))
+    for name, kw in [("swarm_n4_A8_T1100_seed3.npz", dict(n=4, A=8, T=1100, seed=3)),
+                     ("swarm_n3_A16_T1060_seed12.npz", dict(n=3, A=16, T=1060, seed=12, max_rings=3)),
+                     ("swarm_n6_A1_T1040_seed5.npz", dict(n=6, A=1, T=1040, seed=5)),
+                     ("swarm_n2_A64_T300_seed21.npz", dict(n=2, A=64, T=300, seed=21))]:
+        g = swarm_golden(**kw)
+        np.savez_compressed(os.path.join(HERE, name), **g)
+        print(name, "respawn rows:", len(g["ev_t"]), "env resets:", len(g["er_t"]), "tasks:", g["final_env"][:, 1],
+              "bytes:", os.path.getsize(os.path.join(HERE, name)))
