@@ -119,15 +119,17 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
-def cpu_sample(steps_budget_s=20.0, kind="reference"):
+def cpu_sample(steps_budget_s=20.0, kind="reference", drones=0):
     """Bounded CPU sample of the same workload shape (rank 0, N=1 only)."""
     from oracle import cpu_worker
     procs = cpu_worker.host_cores()
-    probe = cpu_worker.run(procs, procs * 2048, 20, 5, kind)
+    per = 2048 if not drones else max(1, 2048 // drones)
+    probe = cpu_worker.run(procs, procs * per, 20, 5, kind, drones=drones)
     rate = probe["env_steps_per_s"]
-    envs = procs * 4096
-    steps = int(max(50, min(2000, rate * steps_budget_s / envs)))
-    res = cpu_worker.run(procs, envs, steps, 20, kind)
+    envs = procs * per * 2
+    units = envs * max(drones, 1)
+    steps = int(max(50, min(2000, rate * steps_budget_s / units)))
+    res = cpu_worker.run(procs, envs, steps, 20, kind, drones=drones)
     return res
 
 

@@ -46,6 +46,7 @@ SYMBOLS = {
     "b2d_vec_step_from": (C.c_int, [_P, _P, _P]),
     "b2d_vec_step_tape": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "b2d_vec_step_host": (C.c_int, [_P, _P]),
+    "b2d_vec_step_host_from": (C.c_int, [_P, _P, _P]),
     "b2d_vec_reset_host": (C.c_int, [_P, C.c_uint64, _P]),
     "b2d_vec_log": (C.c_int, [_P, C.POINTER(C.c_float), _P]),
     "b2d_vec_log_begin": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(C.c_int)]),

@@ -49,6 +49,7 @@ struct b2d_vec {
     // host mirrors for the *_host entry points
     b2d_buffers host;
     bool has_host;
+    bool registered[5];
     std::vector<void *> allocs; // state arrays etc.
     float *d_payload;
     float *d_blob_tmp;
@@ -107,7 +108,19 @@ static int setup_buffers(b2d_vec *v, const b2d_buffers *ext) {
     if (ext_dev && ext->truncations) v->dev.truncations = ext->truncations;
     else if ((rc = dev_alloc(v, &v->dev.truncations, rows))) return rc;
     v->has_host = ext && ext->location == B2D_MEM_HOST;
-    if (v->has_host) v->host = *ext;
+    if (v->has_host) {
+        v->host = *ext;
+        // page-lock the caller's buffers for the life of the handle (they must outlive it anyway:
+        // ownership as in the reference).  Already-pinned memory reports an error that is ignored.
+        void *ptrs[5] = {ext->observations, ext->actions, ext->rewards, ext->terminals, ext->truncations};
+        const size_t bytes[5] = {rows * v->obs_dim * 4, rows * 16, rows * 4, rows, rows};
+        for (int k = 0; k < 5; k++) {
+            v->registered[k] = false;
+            if (!ptrs[k]) continue;
+            if (cudaHostRegister(ptrs[k], bytes[k], cudaHostRegisterDefault) == cudaSuccess) v->registered[k] = true;
+            else cudaGetLastError();
+        }
+    }
     return B2D_OK;
 }
 
@@ -306,6 +319,11 @@ extern "C" int b2d_vec_close(b2d_vec *v) {
                 (double)h[10] / (w / RACE_WARPS), (double)h[11]);
     }
 #endif
+    if (v->has_host) {
+        void *ptrs[5] = {v->host.observations, v->host.actions, v->host.rewards, v->host.terminals, v->host.truncations};
+        for (int k = 0; k < 5; k++)
+            if (v->registered[k] && ptrs[k]) cudaHostUnregister(ptrs[k]);
+    }
     for (void *p : v->allocs) cudaFree(p);
     if (v->d_payload) cudaFree(v->d_payload);
     if (v->d_blob_tmp) cudaFree(v->d_blob_tmp);
@@ -347,12 +365,20 @@ extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
 // One launch of the step kernel.  `overlap`: the launch is made programmatically dependent on the
 // previous launch in the stream, which the caller guarantees is the previous step of this handle
 // (b2d_vec_step_tape); every CTA then waits for its own predecessor only (race_step_kernel).
-static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool overlap = false) {
+static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool overlap = false, int chunk = 0, int chunks = 1) {
     if (v->kind == KIND_RACE) {
         RaceDev d = v->race;
         if (actions) d.act_in = actions;
         d.seq = ++v->seq;
         d.chain_wait = overlap ? 1 : 0;
+        {   // tiles of this launch: the whole vector, or chunk `chunk` of `chunks` (host-buffer pipeline)
+            const int ntiles = (d.n + 31) / 32;
+            const int per = (ntiles + chunks - 1) / chunks;
+            d.tile_begin = chunk * per;
+            d.tile_end = chunk * per + per < ntiles ? chunk * per + per : ntiles;
+            d.count_step = chunk == chunks - 1;
+            d.score_add = chunk > 0;
+        }
         cudaEvent_t pe[2] = {nullptr, nullptr};
         if (v->profile) {
             for (int k = 0; k < 2; k++) { cudaEventCreate(&pe[k]); v->prof_events.push_back(pe[k]); }
@@ -412,33 +438,56 @@ extern "C" int b2d_vec_step_tape(b2d_vec *v, const float *device_tape, int tape_
     return B2D_OK;
 }
 
-// Host-buffer step: one kernel (it is far shorter than the PCIe transfers); the D2H of
-// observations is split across two copy streams so both DMA engines stay busy.
-extern "C" int b2d_vec_step_host(b2d_vec *v, void *stream) {
-    if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
-    if (!v->has_host) return fail(B2D_ESTATE, "handle was not created with host buffers");
-    cudaStream_t st = (cudaStream_t)stream;
+// Host-buffer step.  The PCIe transfers dominate (16 B in, 121 B out per env against a kernel of
+// 80 us per million envs), so the step is issued as a pipeline over chunks of the env range:
+// actions of chunk j+1 go up and its tiles are stepped while the results of chunk j come down on
+// the copy streams.  `host_actions` (optional) are copied into the caller-visible action buffer
+// like the reference's wrapper does (`self.actions[:] = actions`), chunk by chunk, so that the
+// 1 ms CPU copy of 16 MB hides behind the transfers as well.
+static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st) {
     const size_t rows = (size_t)v->num_agents;
-    CUDA_TRY(cudaMemcpyAsync(v->dev.actions, v->host.actions, rows * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = step_impl(v, nullptr, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(v->ev_step, st));
-    // rewards/terminals (+clamped actions) on copy stream 0, observations split over both
-    const size_t half = (rows / 2) * v->obs_dim;
-    const size_t total = rows * v->obs_dim;
-    for (int k = 0; k < 2; k++) CUDA_TRY(cudaStreamWaitEvent(v->copy_streams[k], v->ev_step, 0));
-    CUDA_TRY(cudaMemcpyAsync(v->host.observations, v->dev.observations, half * sizeof(float), cudaMemcpyDeviceToHost, v->copy_streams[0]));
-    CUDA_TRY(cudaMemcpyAsync(v->host.observations + half, v->dev.observations + half, (total - half) * sizeof(float), cudaMemcpyDeviceToHost, v->copy_streams[1]));
-    CUDA_TRY(cudaMemcpyAsync(v->host.rewards, v->dev.rewards, rows * sizeof(float), cudaMemcpyDeviceToHost, v->copy_streams[0]));
-    CUDA_TRY(cudaMemcpyAsync(v->host.terminals, v->dev.terminals, rows, cudaMemcpyDeviceToHost, v->copy_streams[1]));
-    if (v->write_clamped)
-        CUDA_TRY(cudaMemcpyAsync(v->host.actions, v->dev.actions, rows * 4 * sizeof(float), cudaMemcpyDeviceToHost, v->copy_streams[0]));
+    const bool copy_in = host_actions && host_actions != v->host.actions;
+    int chunks = 1;
+    if (v->kind == KIND_RACE && rows >= (1u << 17)) chunks = rows >= (1u << 19) ? 8 : 4;
+    const size_t tiles = (rows + 31) / 32, per_tiles = (tiles + chunks - 1) / chunks;
+    for (int j = 0; j < chunks; j++) {
+        const size_t r0 = (size_t)j * per_tiles * 32;
+        if (r0 >= rows) break;
+        const size_t r1 = r0 + per_tiles * 32 < rows ? r0 + per_tiles * 32 : rows;
+        const size_t nr = r1 - r0;
+        cudaStream_t cs = v->copy_streams[j & 1];
+        // the CPU copy of this chunk's actions overlaps the transfers of the chunks already in flight
+        if (copy_in) memcpy(v->host.actions + r0 * 4, host_actions + r0 * 4, nr * 4 * sizeof(float));
+        CUDA_TRY(cudaMemcpyAsync(v->dev.actions + r0 * 4, v->host.actions + r0 * 4, nr * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+        int rc = step_impl(v, nullptr, st, false, j, chunks);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(v->ev_step, st));
+        CUDA_TRY(cudaStreamWaitEvent(cs, v->ev_step, 0));
+        CUDA_TRY(cudaMemcpyAsync(v->host.observations + r0 * v->obs_dim, v->dev.observations + r0 * v->obs_dim,
+                                 nr * v->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(v->host.rewards + r0, v->dev.rewards + r0, nr * sizeof(float), cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(v->host.terminals + r0, v->dev.terminals + r0, nr, cudaMemcpyDeviceToHost, cs));
+        if (v->write_clamped)
+            CUDA_TRY(cudaMemcpyAsync(v->host.actions + r0 * 4, v->dev.actions + r0 * 4, nr * 4 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    }
     for (int k = 0; k < 2; k++) {
         CUDA_TRY(cudaEventRecord(v->ev_copy[k], v->copy_streams[k]));
         CUDA_TRY(cudaStreamWaitEvent(st, v->ev_copy[k], 0));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     return B2D_OK;
+}
+
+extern "C" int b2d_vec_step_host(b2d_vec *v, void *stream) {
+    if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    if (!v->has_host) return fail(B2D_ESTATE, "handle was not created with host buffers");
+    return step_host_impl(v, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int b2d_vec_step_host_from(b2d_vec *v, const float *host_actions, void *stream) {
+    if (!v || !host_actions) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    if (!v->has_host) return fail(B2D_ESTATE, "handle was not created with host buffers");
+    return step_host_impl(v, host_actions, (cudaStream_t)stream);
 }
 
 extern "C" int b2d_vec_reset_host(b2d_vec *v, uint64_t seed, void *stream) {

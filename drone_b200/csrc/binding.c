@@ -52,6 +52,7 @@ typedef struct EnvH {
     BufSet bufs;
     int seed;
     int max_rings, max_moves, num_agents;
+    int device, env_id_base, math, write_clamped; /* optional kwargs (placement / arithmetic), kept for vectorize() */
     VecH *parent; /* set by vectorize(); or a private 1-env vec for env_reset/env_step */
     int index;
     int owns_parent;
@@ -246,8 +247,25 @@ static int parse_env_kwargs(PyObject *kwargs, int *max_rings, int *max_moves, in
     return 0;
 }
 
+typedef struct {
+    int device, env_id_base, math, write_clamped;
+} Extra;
+
+/* placement / arithmetic kwargs that have no counterpart in the reference: device=0, env_id_base=0,
+ * math="fast"|"strict", write_clamped_actions=0.  The reference clamps the shared action buffer in
+ * place (DR/dronelib.h:437); the step uses the clamped values either way, but storing them back
+ * (16 B/env, plus a D2H copy for NumPy callers) is opt-in. */
+static Extra parse_extra(PyObject *kwargs) {
+    Extra x;
+    x.device = opt_int(kwargs, "device", 0);
+    x.env_id_base = opt_int(kwargs, "env_id_base", 0);
+    x.math = opt_int(kwargs, "math", B2D_MATH_FAST);
+    x.write_clamped = opt_int(kwargs, "write_clamped_actions", 0);
+    return x;
+}
+
 static VecH *make_vec(const FiveBufs *f, int num_envs, int seed, int max_rings, int max_moves, int num_agents,
-                      PyObject *kwargs) {
+                      Extra x) {
     b2d_buffers ext;
     ext.observations = (float *)f->ptr[0];
     ext.actions = (float *)f->ptr[1];
@@ -267,11 +285,11 @@ static VecH *make_vec(const FiveBufs *f, int num_envs, int seed, int max_rings, 
     cfg.num_envs = num_envs;
     cfg.num_agents = num_agents;
     cfg.max_rings = max_rings;
-    cfg.device = opt_int(kwargs, "device", 0);
+    cfg.device = x.device;
     cfg.seed = (uint64_t)(int64_t)seed;
-    cfg.env_id_base = (uint32_t)opt_int(kwargs, "env_id_base", 0);
-    cfg.math = opt_int(kwargs, "math", B2D_MATH_FAST);
-    cfg.write_clamped_actions = opt_int(kwargs, "write_clamped_actions", 0);
+    cfg.env_id_base = (uint32_t)x.env_id_base;
+    cfg.math = x.math;
+    cfg.write_clamped_actions = x.write_clamped;
     (void)max_moves;
     Py_BEGIN_ALLOW_THREADS rc = b2d_swarm_create(&vh->vec, &cfg, &ext);
     Py_END_ALLOW_THREADS
@@ -281,14 +299,11 @@ static VecH *make_vec(const FiveBufs *f, int num_envs, int seed, int max_rings, 
     cfg.num_envs = num_envs;
     cfg.max_rings = max_rings;
     cfg.max_moves = max_moves;
-    cfg.device = opt_int(kwargs, "device", 0);
+    cfg.device = x.device;
     cfg.seed = (uint64_t)(int64_t)seed;
-    cfg.env_id_base = (uint32_t)opt_int(kwargs, "env_id_base", 0);
-    cfg.math = opt_int(kwargs, "math", B2D_MATH_FAST);
-    /* the reference clamps the shared action buffer in place (DR/dronelib.h:437); the step uses
-     * the clamped values either way, but storing them back (16 B/env, plus a D2H copy for NumPy
-     * callers) is opt-in: write_clamped_actions=1 */
-    cfg.write_clamped_actions = opt_int(kwargs, "write_clamped_actions", 0);
+    cfg.env_id_base = (uint32_t)x.env_id_base;
+    cfg.math = x.math;
+    cfg.write_clamped_actions = x.write_clamped;
     (void)num_agents;
     Py_BEGIN_ALLOW_THREADS rc = b2d_race_create(&vh->vec, &cfg, &ext);
     Py_END_ALLOW_THREADS
@@ -363,7 +378,11 @@ static PyObject *env_init(PyObject *self, PyObject *args, PyObject *kwargs) {
     env->bufs.obs = f.ptr[0]; env->bufs.act = f.ptr[1]; env->bufs.rew = f.ptr[2];
     env->bufs.term = f.ptr[3]; env->bufs.trunc = f.ptr[4];
     env->bufs.location = f.location;
-    env->bufs.device = opt_int(kwargs, "device", 0);
+    {
+        Extra x = parse_extra(kwargs);
+        env->device = x.device; env->env_id_base = x.env_id_base; env->math = x.math; env->write_clamped = x.write_clamped;
+    }
+    env->bufs.device = env->device;
     env->bufs.rows = f.rows[0];
     return PyLong_FromVoidPtr(env);
 }
@@ -374,7 +393,8 @@ static int env_materialise(EnvH *env) {
     f.ptr[0] = env->bufs.obs; f.ptr[1] = env->bufs.act; f.ptr[2] = env->bufs.rew;
     f.ptr[3] = env->bufs.term; f.ptr[4] = env->bufs.trunc;
     f.location = env->bufs.location;
-    VecH *vh = make_vec(&f, 1, env->seed, env->max_rings, env->max_moves, env->num_agents, NULL);
+    Extra x = {env->device, env->env_id_base, env->math, env->write_clamped};
+    VecH *vh = make_vec(&f, 1, env->seed, env->max_rings, env->max_moves, env->num_agents, x);
     if (!vh) return -1;
     env->parent = vh;
     env->index = 0;
@@ -540,7 +560,7 @@ static PyObject *vec_init(PyObject *self, PyObject *args, PyObject *kwargs) {
         PyErr_SetString(PyExc_ValueError, "buffers are smaller than num_envs rows");
         return NULL;
     }
-    VecH *vh = make_vec(&f, num_envs, seed, max_rings, max_moves, num_agents, kwargs);
+    VecH *vh = make_vec(&f, num_envs, seed, max_rings, max_moves, num_agents, parse_extra(kwargs));
     if (!vh) return NULL;
     return PyLong_FromVoidPtr(vh);
 }
@@ -593,7 +613,8 @@ static PyObject *vectorize(PyObject *self, PyObject *args) {
     f.ptr[0] = e0->bufs.obs; f.ptr[1] = e0->bufs.act; f.ptr[2] = e0->bufs.rew;
     f.ptr[3] = e0->bufs.term; f.ptr[4] = e0->bufs.trunc;
     f.location = e0->bufs.location;
-    VecH *vh = make_vec(&f, (int)num_envs, e0->seed, e0->max_rings, e0->max_moves, e0->num_agents, NULL);
+    Extra x0 = {e0->device, e0->env_id_base, e0->math, e0->write_clamped};
+    VecH *vh = make_vec(&f, (int)num_envs, e0->seed, e0->max_rings, e0->max_moves, e0->num_agents, x0);
     if (!vh) {
         free(envs);
         return NULL;
@@ -633,6 +654,38 @@ static PyObject *vec_step(PyObject *self, PyObject *args) {
     VecH *vh = unpack_vecenv(args);
     if (!vh) return NULL;
     if (vec_step_impl(vh) < 0) return NULL;
+    Py_RETURN_NONE;
+}
+
+/* extension: vec_step_actions(vec, actions) == `buffer_actions[:] = actions; vec_step(vec)` of the
+ * reference wrappers (DR/drone_race.py:59-62) in one call for NumPy-buffer handles: the copy into
+ * the shared action buffer runs on several cores with the GIL released. */
+static PyObject *vec_step_actions(PyObject *self, PyObject *args) {
+    if (PyTuple_Size(args) != 2) {
+        PyErr_SetString(PyExc_TypeError, "vec_step_actions requires 2 arguments");
+        return NULL;
+    }
+    VecH *vh = unpack_vecenv(args);
+    if (!vh) return NULL;
+    PyObject *o = PyTuple_GetItem(args, 1);
+    if (vh->location != B2D_MEM_HOST || !PyObject_TypeCheck(o, &PyArray_Type)) {
+        PyErr_SetString(PyExc_TypeError, "vec_step_actions needs a NumPy-buffer handle and a NumPy array");
+        return NULL;
+    }
+    PyArrayObject *a = (PyArrayObject *)o;
+    if (!PyArray_ISCONTIGUOUS(a) || PyArray_TYPE(a) != NPY_FLOAT32 ||
+        PyArray_SIZE(a) != (npy_intp)b2d_num_agents(vh->vec) * 4) {
+        PyErr_SetString(PyExc_ValueError, "actions must be a contiguous float32 array of shape [num_agents, 4]");
+        return NULL;
+    }
+    int rc;
+    const float *src = (const float *)PyArray_DATA(a);
+    Py_BEGIN_ALLOW_THREADS rc = b2d_vec_step_host_from(vh->vec, src, vh->stream);
+    Py_END_ALLOW_THREADS
+    if (rc != B2D_OK) {
+        set_b2d_error(rc);
+        return NULL;
+    }
     Py_RETURN_NONE;
 }
 
@@ -774,6 +827,7 @@ static PyMethodDef methods[] = {
     {"vec_render", vec_render, METH_VARARGS, "Render the vector of environments"},
     {"vec_close", vec_close, METH_VARARGS, "Close the vector of environments"},
     {"shared", (PyCFunction)my_shared, METH_VARARGS | METH_KEYWORDS, "Shared state"},
+    {"vec_step_actions", vec_step_actions, METH_VARARGS, "Copy actions into the shared buffer and step"},
     {"vec_handle", vec_handle, METH_VARARGS, "Raw b2d_vec* of a vector handle"},
     {"vec_set_stream", vec_set_stream, METH_VARARGS, "Set the CUDA stream of a vector handle"},
     {"vec_buffers", vec_buffers, METH_VARARGS, "Device pointers of the contract buffers"},

@@ -87,6 +87,9 @@ struct RaceDev {
     uint2 *carry;        // [grid][RACE_CARRY] refill entries a CTA did not get to (env, episode)
     unsigned int *chain; // [grid] sequence number of the last launch CTA c completed
     long long *cta_score; // [grid] sum of score over the episodes CTA c saw end in the LAST step (R/drone_race.h:160)
+    int tile_begin, tile_end; // tiles [begin, end) stepped by this launch (host-buffer steps are issued in chunks)
+    int count_step;      // 1: this launch completes a vec_step (the last chunk): bump the step counter
+    int score_add;       // 1: add to cta_score instead of overwriting it (chunks after the first)
     uint32_t seq;        // sequence number of this launch (host counter, +1 per launch)
     int chain_wait;      // 1: launched programmatically dependent on launch seq-1 of this kernel: CTA c
                          //    starts as soon as CTA c of that launch is done (see b2d_vec_step_tape)
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int G = gridDim.x;
-    const int ntiles = (d.n + 31) >> 5;
+    const int ntiles = min((d.n + 31) >> 5, d.tile_end);
     const bool inject = d.reset_mode == 1; // B2D_RESET_INJECT (parity hook)
     float4 *stage = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM);
     float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES);
@@ -483,8 +486,10 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     }
 
     // the first two tickets of every warp are static, so the first loads leave before any barrier
-    int tile = warp * G + blockIdx.x;
-    int next = (RACE_WARPS + warp) * G + blockIdx.x;
+    // CTA c owns the tiles congruent to c modulo G, whatever range a launch covers
+    const int first_tile = d.tile_begin + (int)((blockIdx.x + G - d.tile_begin % G) % G);
+    int tile = warp * G + first_tile;
+    int next = (RACE_WARPS + warp) * G + first_tile;
     if (tile < ntiles && tile * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, tile * 32 + lane);
     cp_async_commit(); // group: inputs of the first tile
     cp_async_commit(); // group: (empty) adoption loads "of the tile before the first"
@@ -725,7 +730,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
 #endif
         if (have_tile) {
             tile = next;
-            next = __shfl_sync(0xffffffffu, claim, 0) * G + blockIdx.x;
+            next = __shfl_sync(0xffffffffu, claim, 0) * G + first_tile;
         }
     }
     cp_async_wait<0>();
@@ -766,7 +771,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         if (lane < 7) {
             const int v = s_acc[lane];
             if (v != 0) atomicAdd((unsigned long long *)&d.ctl->acc[lane], (unsigned long long)(long long)v);
-            if (lane == ACC_RINGS) d.cta_score[blockIdx.x] = (long long)v;
+            if (lane == ACC_RINGS) d.cta_score[blockIdx.x] = (long long)v + (d.score_add ? d.cta_score[blockIdx.x] : 0ll);
         }
 #if B2D_EXPERIMENT_TIMING
         if (lane == 0) {
@@ -776,7 +781,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
 #endif
         __syncwarp();
         if (lane == 0) {
-            atomicAdd(&d.ctl->ctas_done, 1u); // result unused: a reduction, not a returning atomic
+            if (d.count_step) atomicAdd(&d.ctl->ctas_done, 1u); // result unused: a reduction, not a returning atomic
             __threadfence();
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(d.chain + blockIdx.x), "r"(d.seq) : "memory");
         }

@@ -154,27 +154,32 @@ __device__ __forceinline__ void sw_move_target(float tp[3], float tv[3]) {
 // `self`: agents below a are read from `lo`, agents above from `hi` (R/drone_swarm.h:107-129).
 // Returns the distance the reference computes; `other` receives the neighbour's position.
 template <bool STRICT>
-__device__ __forceinline__ float sw_nearest(const float (*lo)[SWARM_BLOCK], const float (*hi)[SWARM_BLOCK], int b0, int A, int a,
-                                            const float self[3], float other[3]) {
-    float best = STRICT ? 999999.0f : 999999.0f * 999999.0f;
-    other[0] = other[1] = other[2] = 0.0f;
-    for (int j = 0; j < A; j++) {
-        if (j == a) continue;
-        const float (*src)[SWARM_BLOCK] = j < a ? lo : hi;
-        const float ox = src[0][b0 + j], oy = src[1][b0 + j], oz = src[2][b0 + j];
+__device__ __forceinline__ void sw_nearest_scan(const float4 *src, int j0, int j1, const float self[3], float &best, float4 &who) {
+    for (int j = j0; j < j1; j++) {
+        const float4 o = src[j];
         float dist;
         if constexpr (STRICT) {
-            const xf dx = xf(self[0]) - xf(ox), dy = xf(self[1]) - xf(oy), dz = xf(self[2]) - xf(oz);
+            const xf dx = xf(self[0]) - xf(o.x), dy = xf(self[1]) - xf(o.y), dz = xf(self[2]) - xf(o.z);
             dist = xsqrt(dx * dx + dy * dy + dz * dz).v;
         } else {
-            const float dx = self[0] - ox, dy = self[1] - oy, dz = self[2] - oz;
+            const float dx = self[0] - o.x, dy = self[1] - o.y, dz = self[2] - o.z;
             dist = dx * dx + dy * dy + dz * dz; // squared: same ordering, no square root per candidate
         }
         if (dist < best) {
             best = dist;
-            other[0] = ox; other[1] = oy; other[2] = oz;
+            who = o;
         }
     }
+}
+
+template <bool STRICT>
+__device__ __forceinline__ float sw_nearest(const float4 *lo, const float4 *hi, int b0, int A, int a, const float self[3],
+                                            float other[3]) {
+    float best = STRICT ? 999999.0f : 999999.0f * 999999.0f;
+    float4 who = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    sw_nearest_scan<STRICT>(lo + b0, 0, a, self, best, who);     // ascending index, strict '<': lowest index wins ties
+    sw_nearest_scan<STRICT>(hi + b0, a + 1, A, self, best, who);
+    other[0] = who.x; other[1] = who.y; other[2] = who.z;
     if constexpr (!STRICT) best = sqrtf(best);
     return best;
 }
@@ -321,10 +326,10 @@ __device__ __forceinline__ void sw_respawn_state(SwarmAgent &g, const float p[13
 // ONLY_RESET = false: one vec_step.  ONLY_RESET = true: vec_reset (every env runs c_reset).
 template <bool STRICT, bool ONLY_RESET>
 __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constant__ SwarmDev d) {
-    __shared__ float s_old[3][SWARM_BLOCK]; // positions before this tick's move
-    __shared__ float s_fin[3][SWARM_BLOCK]; // after the move, or the respawn position of an agent that left the arena
-    __shared__ float s_rst[3][SWARM_BLOCK]; // first position drawn by an env-wide reset
-    __shared__ float s_pos[3][SWARM_BLOCK]; // final positions of the tick (what the observations see)
+    __shared__ float4 s_old[SWARM_BLOCK]; // positions before this tick's move
+    __shared__ float4 s_fin[SWARM_BLOCK]; // after the move, or the respawn position of an agent that left the arena
+    __shared__ float4 s_rst[SWARM_BLOCK]; // first position drawn by an env-wide reset
+    __shared__ float4 s_pos[SWARM_BLOCK]; // final positions of the tick (what the observations see)
     __shared__ float s_obs[SWARM_BLOCK * SWARM_OBS];
     __shared__ float s_ring0[SWARM_BLOCK][3];
     __shared__ float s_facc[8];
@@ -354,7 +359,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         sw_load(d, k, g);
         const int4 ev = d.E[e];
         tick = ev.x; task = ev.y; env_episode = (uint32_t)ev.z;
-        s_old[0][t] = g.s[0]; s_old[1][t] = g.s[1]; s_old[2][t] = g.s[2];
+        s_old[t] = make_float4(g.s[0], g.s[1], g.s[2], 0.0f);
     }
 
     if constexpr (!ONLY_RESET) {
@@ -388,15 +393,14 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                     sw_draw_box(d, genv, (uint32_t)a | 0x10000u, g.respawns, 4u, 0u, 29.0f, 29.0f, 9.0f, rpos);
                 }
             }
-            s_fin[0][t] = oob ? rpos[0] : g.s[0];
-            s_fin[1][t] = oob ? rpos[1] : g.s[1];
-            s_fin[2][t] = oob ? rpos[2] : g.s[2];
+            s_fin[t] = oob ? make_float4(rpos[0], rpos[1], rpos[2], 0.0f) : make_float4(g.s[0], g.s[1], g.s[2], 0.0f);
         }
         __syncthreads();
 
         // ---- phase 2: rewards, ring logic, respawn bookkeeping (R/drone_swarm.h:463-491)
         if (active) {
-            const float before[3] = {s_old[0][t], s_old[1][t], s_old[2][t]};
+            const float4 o4 = s_old[t];
+            const float before[3] = {o4.x, o4.y, o4.z};
             const float self[3] = {g.s[0], g.s[1], g.s[2]};
             float other[3];
             float nd = 0.0f;
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         }
     } else {
         if (active) {
-            s_fin[0][t] = g.s[0]; s_fin[1][t] = g.s[1]; s_fin[2][t] = g.s[2];
+            s_fin[t] = make_float4(g.s[0], g.s[1], g.s[2], 0.0f);
             g.respawns = 0u;
             do_reset = true;
         }
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                 sw_draw_params(d, genv, (uint32_t)a, env_episode, np);
                 sw_draw_box(d, genv, (uint32_t)a, env_episode, 4u, 0u, 29.0f, 29.0f, 9.0f, first);
             }
-            s_rst[0][t] = first[0]; s_rst[1][t] = first[1]; s_rst[2][t] = first[2];
+            s_rst[t] = make_float4(first[0], first[1], first[2], 0.0f);
         }
         __syncthreads();
         if (do_reset) {
@@ -550,7 +554,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         }
     }
     if (active) {
-        s_pos[0][t] = g.s[0]; s_pos[1][t] = g.s[1]; s_pos[2][t] = g.s[2];
+        s_pos[t] = make_float4(g.s[0], g.s[1], g.s[2], 0.0f);
     }
     __syncthreads();
 
@@ -645,14 +649,14 @@ __global__ void swarm_unpack_kernel(const SwarmDev d, const int *ids, int n, con
 // observations recomputed from the current state (after put_state)
 template <bool STRICT>
 __global__ void __launch_bounds__(SWARM_BLOCK) swarm_observe_kernel(const __grid_constant__ SwarmDev d) {
-    __shared__ float s_pos[3][SWARM_BLOCK];
+    __shared__ float4 s_pos[SWARM_BLOCK];
     const int t = threadIdx.x, A = d.A;
     const int le = t / A, a = t - le * A, e = blockIdx.x * d.epc + le;
     const bool active = le < d.epc && e < d.n;
     SwarmAgent g;
     if (active) {
         sw_load(d, e * A + a, g);
-        s_pos[0][t] = g.s[0]; s_pos[1][t] = g.s[1]; s_pos[2][t] = g.s[2];
+        s_pos[t] = make_float4(g.s[0], g.s[1], g.s[2], 0.0f);
     }
     __syncthreads();
     if (!active) return;

@@ -80,7 +80,8 @@ class DroneRace(PufferEnv):
                     self.rewards[env_num:(env_num + 1)],
                     self.terminals[env_num:(env_num + 1)],
                     self.truncations[env_num:(env_num + 1)],
-                    env_num, report_interval=self.report_interval, **kwargs))
+                    env_num, report_interval=self.report_interval, device=device, math=math,
+                    env_id_base=env_id_base, **kwargs))
             self._env_handles = c_envs
             self.c_envs = binding.vectorize(*c_envs)
         else:
@@ -112,11 +113,16 @@ class DroneRace(PufferEnv):
         if self.buffers == "device":
             if actions is not self.actions:
                 self.actions.copy_(actions)
+        self.tick += 1
+        if self.buffers == "device":
+            binding.vec_step(self.c_envs)
+        elif (isinstance(actions, np.ndarray) and actions.dtype == np.float32 and actions.flags.c_contiguous
+                and actions.shape == self.actions.shape):
+            # `self.actions[:] = actions; vec_step` in one call (the copy runs on several cores)
+            binding.vec_step_actions(self.c_envs, actions)
         else:
             self.actions[:] = actions
-
-        self.tick += 1
-        binding.vec_step(self.c_envs)
+            binding.vec_step(self.c_envs)
 
         info = []
         if self.tick % self.report_interval == 0:

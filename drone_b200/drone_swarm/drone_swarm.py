@@ -55,7 +55,8 @@ class DroneSwarm(PufferEnv):
                 sl = slice(i * num_drones, (i + 1) * num_drones)
                 c_envs.append(binding.env_init(self.observations[sl], self.actions[sl], self.rewards[sl],
                                                self.terminals[sl], self.truncations[sl], i,
-                                               num_agents=num_drones, max_rings=max_rings))
+                                               num_agents=num_drones, max_rings=max_rings, device=device, math=math,
+                                               env_id_base=env_id_base))
             self._env_handles = c_envs
             self.c_envs = binding.vectorize(*c_envs)
         else:
@@ -73,11 +74,16 @@ class DroneSwarm(PufferEnv):
         if self.buffers == "device":
             if actions is not self.actions:
                 self.actions.copy_(actions)
+        self.tick += 1
+        if self.buffers == "device":
+            binding.vec_step(self.c_envs)
+        elif (isinstance(actions, np.ndarray) and actions.dtype == np.float32 and actions.flags.c_contiguous
+                and actions.shape == self.actions.shape):
+            # `self.actions[:] = actions; vec_step` in one call (the copy runs on several cores)
+            binding.vec_step_actions(self.c_envs, actions)
         else:
             self.actions[:] = actions
-
-        self.tick += 1
-        binding.vec_step(self.c_envs)
+            binding.vec_step(self.c_envs)
 
         info = []
         if self.tick % self.report_interval == 0:

@@ -25,16 +25,18 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 
 
-def _worker(rank, n, steps, warmup, kind, seed, barrier, out):
+def _worker(rank, n, steps, warmup, kind, seed, barrier, out, drones=0):
     from oracle import pyoracle as po
+    if drones:  # swarm: n envs of `drones` agents (pufferlib/ocean/drone_swarm), max_rings=10
+        env = po.RefSwarm(n, drones, 10) if kind == "reference" else po.OrcSwarm(n, drones, 10)
+    else:
+        env = po.RefRace(n) if kind == "reference" else po.OrcRace(n)
     if kind == "reference":
-        env = po.RefRace(n)
         step = env.step
     else:
-        env = po.OrcRace(n)
         step = lambda a: env.step(a, mode=po.RESET_LIBC)  # noqa: E731
     rng = np.random.default_rng(1234 + rank)
-    tape = rng.uniform(-1.0, 1.0, size=(16, n, 4)).astype(np.float32)
+    tape = rng.uniform(-1.0, 1.0, size=(16, n * max(drones, 1), 4)).astype(np.float32)
     env.reset(seed)
     for t in range(warmup):
         step(tape[t % 16])
@@ -47,8 +49,9 @@ def _worker(rank, n, steps, warmup, kind, seed, barrier, out):
     env.close()
 
 
-def run(procs, envs, steps, warmup, kind="reference", seed=0):
-    """Total `envs` split over `procs` processes; returns a result dict."""
+def run(procs, envs, steps, warmup, kind="reference", seed=0, drones=0):
+    """Total `envs` split over `procs` processes; returns a result dict.  drones > 0 selects the
+    swarm env (envs x drones agents); env_steps_per_s then counts drone-steps."""
     from oracle import pyoracle as po
     if kind == "reference" and not po.have_ref():
         kind = "port"
@@ -58,7 +61,7 @@ def run(procs, envs, steps, warmup, kind="reference", seed=0):
     ctx = mp.get_context("spawn")
     barrier = ctx.Barrier(procs)
     out = ctx.Queue()
-    ps = [ctx.Process(target=_worker, args=(r, per, steps, warmup, kind, seed, barrier, out)) for r in range(procs)]
+    ps = [ctx.Process(target=_worker, args=(r, per, steps, warmup, kind, seed, barrier, out, drones)) for r in range(procs)]
     for p in ps:
         p.start()
     res = [out.get() for _ in ps]
@@ -66,6 +69,9 @@ def run(procs, envs, steps, warmup, kind="reference", seed=0):
         p.join()
     wall = max(r[1] for r in res)
     total = per * procs
+    if drones:
+        return {"env_steps_per_s": total * drones * steps / wall, "procs": procs, "envs": total, "steps": steps,
+                "wall_s": wall, "kind": kind, "drones": drones}
     return {"env_steps_per_s": total * steps / wall, "procs": procs, "envs": total, "steps": steps,
             "wall_s": wall, "kind": kind}
 

@@ -160,6 +160,9 @@ def test_create_argument_validation_happens_before_cuda():
     for cfg in (capi.RaceCfg(0, 10, 1000, 0, 0, 0, 0, 0), capi.RaceCfg(8, 0, 1000, 0, 0, 0, 0, 0),
                 capi.RaceCfg(8, 10, 0, 0, 0, 0, 0, 0), capi.RaceCfg(8, 10, 10, 0, 0, 0, 7, 0)):
         assert lib.b2d_race_create(C.byref(h), C.byref(cfg), None) == capi.B2D_EINVAL
+    for scfg in (capi.SwarmCfg(4, 0, 5, 0, 0, 0, 0, 0), capi.SwarmCfg(4, 129, 5, 0, 0, 0, 0, 0),
+                 capi.SwarmCfg(0, 8, 5, 0, 0, 0, 0, 0), capi.SwarmCfg(4, 8, 0, 0, 0, 0, 0, 0)):
+        assert lib.b2d_swarm_create(C.byref(h), C.byref(scfg), None) == capi.B2D_EINVAL
     assert lib.b2d_race_create(None, None, None) == capi.B2D_EINVAL
     assert lib.b2d_vec_step(None, None) == capi.B2D_EINVAL
     assert lib.b2d_vec_close(None) == capi.B2D_EINVAL
