@@ -1,0 +1,117 @@
+"""On-device rollout: policy forward, action sampling and the env step alternate on one stream
+with no host synchronisation; a K-step collection is captured once in a CUDA graph and replayed.
+
+This is the device-resident counterpart of PuffeRL.evaluate (pufferlib/pufferl.py:214-314) for
+envs whose buffers already live on the GPU: what that loop does per step -- recv (obs, reward,
+done), `policy.forward_eval`, `sample_logits` on a Normal (pufferlib/pytorch.py:189-199), store
+(obs, action, logprob, reward clamped to [-1, 1], done, value), clip the action to the action
+space, send -- happens here without the per-step `.to(device)` / `.cpu().numpy()` round trips
+(pufferl.py:240-243,292) that cap any GPU env at ~1e6 steps/s.  The policy is plain torch (library
+GEMMs); the env step is the CUDA kernel behind `vec.step()`.
+
+Experience is stored time-major, [horizon, num_agents, ...], so every store is one contiguous
+write; `segments()` returns the reference's [num_agents, horizon, ...] views.
+"""
+import math
+
+import torch
+from torch import nn
+
+
+class DronePolicy(nn.Module):
+    """pufferlib.models.Default for a Box action space (models.py:41-63,86-98): Linear(obs,128) + GELU,
+    mean head (std 0.01 init), state-independent log-std parameter, value head."""
+
+    def __init__(self, obs_dim=29, act_dim=4, hidden_size=128):
+        super().__init__()
+        self.encoder = nn.Sequential(nn.Linear(obs_dim, hidden_size), nn.GELU())
+        self.decoder_mean = nn.Linear(hidden_size, act_dim)
+        self.decoder_logstd = nn.Parameter(torch.zeros(1, act_dim))
+        self.value = nn.Linear(hidden_size, 1)
+        nn.init.orthogonal_(self.encoder[0].weight, math.sqrt(2))
+        nn.init.orthogonal_(self.decoder_mean.weight, 0.01)
+        nn.init.orthogonal_(self.value.weight, 1.0)
+        for lin in (self.encoder[0], self.decoder_mean, self.value):
+            nn.init.constant_(lin.bias, 0.0)
+
+    def forward_eval(self, observations, state=None):
+        hidden = self.encoder(observations.float())
+        mean = self.decoder_mean(hidden)
+        return mean, self.decoder_logstd.expand_as(mean), self.value(hidden)
+
+    forward = forward_eval
+
+
+class DeviceRollout:
+    def __init__(self, vec, policy, horizon=128, use_graph=True, deterministic=False, autocast=None):
+        self.vec, self.policy, self.horizon = vec, policy, int(horizon)
+        self.deterministic, self.autocast = deterministic, autocast
+        n, dev = vec.num_agents, vec.device
+        k = self.horizon
+        self.observations = torch.zeros((k, n, vec.obs_dim), dtype=torch.float32, device=dev)
+        self.actions = torch.zeros((k, n, 4), dtype=torch.float32, device=dev)
+        self.logprobs = torch.zeros((k, n), dtype=torch.float32, device=dev)
+        self.rewards = torch.zeros((k, n), dtype=torch.float32, device=dev)
+        self.terminals = torch.zeros((k, n), dtype=torch.float32, device=dev)
+        self.values = torch.zeros((k, n), dtype=torch.float32, device=dev)
+        self.graph = None
+        self.use_graph = use_graph
+        self.env_steps = 0
+
+    @torch.no_grad()
+    def _one_step(self, k):
+        vec = self.vec
+        obs = vec.observations
+        self.observations[k].copy_(obs)
+        torch.clamp(vec.rewards, -1.0, 1.0, out=self.rewards[k])          # pufferl.py:260
+        self.terminals[k].copy_(vec.terminals)                              # d.float(), pufferl.py:281
+        if self.autocast is not None:
+            with torch.autocast("cuda", dtype=self.autocast):
+                mean, logstd, value = self.policy.forward_eval(obs)
+            mean, value = mean.float(), value.float()
+        else:
+            mean, logstd, value = self.policy.forward_eval(obs)
+        if self.deterministic:
+            action = mean
+            self.logprobs[k].copy_((-logstd - 0.5 * math.log(2.0 * math.pi)).sum(1))
+        else:
+            noise = torch.randn_like(mean)
+            action = torch.addcmul(mean, logstd.exp(), noise)               # Normal(mean, std).sample()
+            self.logprobs[k].copy_((-0.5 * noise * noise - logstd - 0.5 * math.log(2.0 * math.pi)).sum(1))
+        self.actions[k].copy_(action)
+        self.values[k].copy_(value.flatten())
+        torch.clamp(action, -1.0, 1.0, out=vec.actions)                     # np.clip to the action space, pufferl.py:293-294
+        vec.step()
+
+    @torch.no_grad()
+    def _collect_eager(self):
+        for k in range(self.horizon):
+            self._one_step(k)
+
+    @torch.no_grad()
+    def collect(self):
+        """One horizon of experience.  Asynchronous: returns after enqueueing (graph replay)."""
+        if not self.use_graph:
+            self._collect_eager()
+        else:
+            if self.graph is None:
+                side = torch.cuda.Stream(device=self.vec.device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):  # warm-up outside capture (cuBLAS workspaces, lazy inits)
+                    for _ in range(2):
+                        self._one_step(0)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                self.env_steps += 2
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._collect_eager()
+            self.graph.replay()
+        self.env_steps += self.horizon
+        return self
+
+    def segments(self):
+        """The reference's experience layout [segments = num_agents, horizon, ...] (views)."""
+        t = lambda x: x.transpose(0, 1)  # noqa: E731
+        return dict(observations=t(self.observations), actions=t(self.actions), logprobs=t(self.logprobs),
+                    rewards=t(self.rewards), terminals=t(self.terminals), values=t(self.values))
