@@ -63,3 +63,21 @@ def test_box_space_behaviour():
     assert s.shape == (4,) and s.dtype == np.float32 and b.contains(s)
     j = pe.joint_space(b, 5)
     assert j.shape == (5, 4) and float(j.low.min()) == -1.0
+
+
+def test_registry_names_and_native_backend_rules():
+    """pufferlib/ocean/environment.py:167-177 and pufferlib/vector.py:618-639 for the drone envs."""
+    from drone_b200 import registry
+    assert registry.env_creator("puffer_drone_race").__name__ == "DroneRace"
+    assert registry.env_creator("puffer_drone_swarm").__name__ == "DroneSwarm"
+    with pytest.raises(pe.APIUsageError):
+        registry.env_creator("drone_race")
+    with pytest.raises(pe.APIUsageError):
+        registry.env_creator("puffer_breakout")
+    with pytest.raises(pe.APIUsageError):
+        registry.make("puffer_drone_race", backend="Multiprocessing")
+    with pytest.raises(pe.APIUsageError):
+        registry.make("puffer_drone_race", num_envs=2)
+    with pytest.raises(pe.APIUsageError):
+        registry.make("puffer_drone_race", num_envs=0)
+    assert registry.ENV_DEFAULTS["drone_swarm"] == dict(num_envs=16, num_drones=64, max_rings=10)

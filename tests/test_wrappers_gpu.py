@@ -170,3 +170,17 @@ def test_host_buffer_pipeline_equals_device_path():
     assert vec.step_count == T
     env.close()
     vec.close()
+
+
+def test_registry_make_builds_the_ini_default_envs():
+    from drone_b200 import registry
+    env = registry.make("puffer_drone_swarm", env_kwargs=dict(num_envs=4), seed=3)
+    assert env.num_agents == 4 * 64 and env.observations.shape == (256, 41)  # drone_swarm.ini: 64 drones
+    obs, _ = env.reset(3)
+    env.step(np.zeros((256, 4), np.float32))
+    assert np.isfinite(env.observations).all()
+    env.close()
+    env = registry.make("puffer_drone_race", env_kwargs=dict(num_envs=64, buffers="device"))
+    env.reset(0)
+    assert env.observations.is_cuda and env.num_agents == 64
+    env.close()
