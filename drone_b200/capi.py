@@ -66,6 +66,8 @@ SYMBOLS = {
     "b2d_set_reset_payload": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "b2d_set_step_count": (C.c_int, [_P, C.c_uint32]),
     "b2d_profile_kernels": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
+    "b2d_puff_advantage": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_longlong, C.c_longlong,
+                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _P]),
     "b2d_last_error": (C.c_char_p, []),
     "b2d_version": (C.c_int, []),
 }

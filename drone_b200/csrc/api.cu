@@ -7,6 +7,7 @@
 #include "../../include/b200drone.h"
 #include "race_kernels.cuh"
 #include "swarm_kernels.cuh"
+#include "advantage_kernels.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -720,6 +721,26 @@ extern "C" int b2d_profile_kernels(b2d_vec *v, int enable, float out_us[3]) {
         out_us[2] = (float)n;
     }
     return B2D_OK;
+}
+
+// ---------------------------------------------------------------- advantage (trainer side)
+extern "C" int b2d_puff_advantage(const float *values, const float *rewards, const float *dones, const float *importance,
+                                  float *advantages, float *abs_sum, int num_rows, int horizon, long long row_stride,
+                                  long long t_stride, float gamma, float lambda, float rho_clip, float c_clip, int math,
+                                  void *stream) {
+    if (!values || !rewards || !dones || !importance || !advantages) return fail(B2D_EINVAL, "b2d_puff_advantage: null tensor");
+    if (num_rows < 0 || horizon < 0 || row_stride <= 0 || t_stride <= 0) return fail(B2D_EINVAL, "b2d_puff_advantage: bad shape");
+    if (math != B2D_MATH_FAST && math != B2D_MATH_STRICT) return fail(B2D_EINVAL, "unknown math mode");
+    if (num_rows == 0) return B2D_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (num_rows + 255) / 256;
+    if (math == B2D_MATH_STRICT)
+        puff_advantage_kernel<true><<<grid, 256, 0, st>>>(values, rewards, dones, importance, advantages, abs_sum, num_rows, horizon,
+                                                          row_stride, t_stride, gamma, lambda, rho_clip, c_clip);
+    else
+        puff_advantage_kernel<false><<<grid, 256, 0, st>>>(values, rewards, dones, importance, advantages, abs_sum, num_rows, horizon,
+                                                           row_stride, t_stride, gamma, lambda, rho_clip, c_clip);
+    return launch_check("puff_advantage_kernel");
 }
 
 extern "C" const char *b2d_last_error(void) { return g_err; }

@@ -187,6 +187,19 @@ int b2d_set_step_count(b2d_vec *vec, uint32_t steps);
  * enable=0 synchronises and returns mean microseconds {step kernel, adopt kernel, steps timed}. */
 int b2d_profile_kernels(b2d_vec *vec, int enable, float out_us[3]);
 
+/* ---- trainer-side helper -------------------------------------------
+ * replaces torch.ops.pufferlib.compute_puff_advantage (extensions/cuda/pufferlib.cu:41-82 and its
+ * CPU twin extensions/pufferlib.cpp:28-41,63-72): GAE with V-trace clipping, backwards in time per
+ * row.  Device pointers to float32 tensors addressed as x[row * row_stride + t * t_stride]:
+ * row-major [segments, horizon] (row_stride = horizon, t_stride = 1, the reference's layout) or
+ * time-major [horizon, num_agents] (row_stride = 1, t_stride = num_agents, coalesced).
+ * advantages[., horizon-1] is not written (as in the reference).  abs_sum (optional, [num_rows]) gets
+ * sum_t |advantage| per row, the priority PuffeRL.train computes next (pufferl.py:342). */
+int b2d_puff_advantage(const float *values, const float *rewards, const float *dones, const float *importance,
+                       float *advantages, float *abs_sum, int num_rows, int horizon, long long row_stride,
+                       long long t_stride, float gamma, float lambda, float rho_clip, float c_clip, int math,
+                       void *cuda_stream);
+
 const char *b2d_last_error(void);
 int b2d_version(void);
 

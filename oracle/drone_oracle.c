@@ -1248,3 +1248,28 @@ void orc_swarm_put_agent(OrcSwarm *o, int e, int a, const float *b) {
     x[AX_SCORE] = b[45]; o->ring_idx[k] = (int)b[46];
     memcpy(o->prev + k * 3, b, 3 * sizeof(float));
 }
+
+/* ====================================================================== advantage
+ * pufferlib/extensions/pufferlib.cpp:28-41 (puff_advantage_row) and :63-72 (puff_advantage),
+ * restated with the same strides interface as b2d_puff_advantage.  Built with -ffp-contract=off
+ * like the reference's CPU build (no FMA on baseline x86-64). */
+void orc_puff_advantage(const float *values, const float *rewards, const float *dones, const float *importance,
+                        float *advantages, float *abs_sum, int num_rows, int horizon, long long row_stride,
+                        long long t_stride, float gamma, float lambda, float rho_clip, float c_clip) {
+    for (int row = 0; row < num_rows; row++) {
+        long long base = (long long)row * row_stride;
+        float lastpufferlam = 0;
+        float prio = 0.0f;
+        for (int t = horizon - 2; t >= 0; t--) {
+            long long at = base + (long long)t * t_stride, an = at + t_stride;
+            float nextnonterminal = 1.0 - dones[an];
+            float rho_t = fminf(importance[at], rho_clip);
+            float c_t = fminf(importance[at], c_clip);
+            float delta = rho_t * (rewards[an] + gamma * values[an] * nextnonterminal - values[at]);
+            lastpufferlam = delta + gamma * lambda * c_t * lastpufferlam * nextnonterminal;
+            advantages[at] = lastpufferlam;
+            prio += fabsf(lastpufferlam);
+        }
+        if (abs_sum) abs_sum[row] = prio;
+    }
+}

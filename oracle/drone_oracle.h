@@ -84,6 +84,11 @@ void orc_swarm_put_agent(OrcSwarm *o, int i, int a, const float *blob);
 /* closed-form formation targets (task 2 orbit, 4 cube, 6 flag) exactly as the reference computes them */
 void orc_swarm_formation_target(int task, int idx, int num_agents, float out[3]);
 
+/* pufferlib/extensions/pufferlib.cpp:28-41,63-72 with explicit strides (x[row*row_stride + t*t_stride]) */
+void orc_puff_advantage(const float *values, const float *rewards, const float *dones, const float *importance,
+                        float *advantages, float *abs_sum, int num_rows, int horizon, long long row_stride,
+                        long long t_stride, float gamma, float lambda, float rho_clip, float c_clip);
+
 #ifdef __cplusplus
 }
 #endif

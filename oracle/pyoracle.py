@@ -395,3 +395,24 @@ def formation_target(task, idx, num_agents):
     out = np.zeros(3, np.float32)
     _orc_swarm().orc_swarm_formation_target(int(task), int(idx), int(num_agents), _f(out))
     return out
+
+
+def puff_advantage(values, rewards, dones, importance, gamma, lam, rho_clip, c_clip, time_major=False):
+    """The reference's CPU advantage (pufferlib.cpp:28-41,63-72) on float32 NumPy arrays.
+    Returns (advantages, sum_t |adv| per row)."""
+    L = _orc()
+    L.orc_puff_advantage.restype = None
+    L.orc_puff_advantage.argtypes = [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_longlong, C.c_longlong,
+                                     C.c_float, C.c_float, C.c_float, C.c_float]
+    a = [np.ascontiguousarray(x, np.float32) for x in (values, rewards, dones, importance)]
+    if time_major:
+        horizon, rows = a[0].shape
+        rs, ts = 1, rows
+    else:
+        rows, horizon = a[0].shape
+        rs, ts = horizon, 1
+    adv = np.zeros_like(a[0])
+    prio = np.zeros(rows, np.float32)
+    L.orc_puff_advantage(_f(a[0]), _f(a[1]), _f(a[2]), _f(a[3]), _f(adv), _f(prio), rows, horizon, rs, ts,
+                         gamma, lam, rho_clip, c_clip)
+    return adv, prio
