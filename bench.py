@@ -288,7 +288,7 @@ def main():
         e2e = {"value": total_envs * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": total_envs * 16,
                "d2h_bytes_per_step": total_envs * (116 + 4 + 1), "steps": e2e_steps,
                "ms_per_step": dt / e2e_steps * 1e3,
-               "api": "drone_b200.drone_race.DroneRace(buffers='host').step(np.ndarray) -> binding.vec_step -> b2d_vec_step_host",
+               "api": "drone_b200.drone_race.DroneRace(buffers='host').step(np.ndarray) -> binding.vec_step_actions -> b2d_vec_step_host_from",
                "checksum": float(np.abs(obs).sum(dtype=np.float64))}
         env.close()
 
