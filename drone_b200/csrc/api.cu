@@ -188,6 +188,9 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
     }
     race_ctl_reset_kernel<<<1, 256>>>(d.ctl, d.carry, d.cta_score, 0u, (unsigned int)v->step_ctas, 1);
     cudaDeviceSynchronize();
+#if B2D_EXPERIMENT_TIMING
+    cudaMalloc(&d.trace, (size_t)v->step_ctas * 4 * sizeof(unsigned long long));
+#endif
     d.obs = v->dev.observations;
     d.act_in = v->dev.actions;
     d.act_out = v->write_clamped ? v->dev.actions : nullptr;
@@ -316,6 +319,17 @@ extern "C" int b2d_vec_close(b2d_vec *v) {
         const double it = (double)h[4], w = (double)h[7];
         fprintf(stderr, "[b2d timing] per tile iteration (cycles): wait_inputs %.0f  compute %.0f  store %.0f  wait_adopt %.0f  install %.0f  refill %.0f | per warp-launch: total %.0f  iterations %.2f\n",
                 h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[8] / it, h[5] / it, h[6] / w, it / w);
+        if (getenv("B2D_TRACE_FILE")) {
+            std::vector<unsigned long long> tr((size_t)v->step_ctas * 4);
+            cudaMemcpy(tr.data(), v->race.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
+            FILE *f = fopen(getenv("B2D_TRACE_FILE"), "w");
+            if (f) {
+                fprintf(f, "cta,smid,entry_ns,go_ns,done_ns\n");
+                for (int c = 0; c < v->step_ctas; c++)
+                    fprintf(f, "%d,%llu,%llu,%llu,%llu\n", c, tr[c * 4], tr[c * 4 + 1], tr[c * 4 + 2], tr[c * 4 + 3]);
+                fclose(f);
+            }
+        }
         fprintf(stderr, "[b2d timing] slowest warp loop %.0f cycles; CTA busy: mean %.0f, slowest %.0f cycles (any launch)\n", (double)h[9],
                 (double)h[10] / (w / RACE_WARPS), (double)h[11]);
     }

@@ -102,6 +102,9 @@ struct RaceDev {
     const float *payload; // [n][33+6R] next-episode blobs (inject mode)
     uint32_t key0, key1, env_id_base;
     int reset_mode; // b2d_reset_mode
+#if B2D_EXPERIMENT_TIMING
+    unsigned long long *trace; // [grid][4] (smid, CTA entry ns, first tile ns, CTA done ns) of the last launch
+#endif
 };
 
 // ---------------------------------------------------------------- observations
@@ -474,6 +477,10 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     // Launch overlap (b2d_vec_step_tape): the next launch of this kernel may begin while this one
     // drains; its CTA c owns the same envs as this CTA c and waits for exactly this CTA's flag.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#if B2D_EXPERIMENT_TIMING
+    unsigned long long tr_entry = 0, tr_go = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_entry));
+#endif
     if (d.chain_wait) {
         if (tid == 0) {
             unsigned int seen;
@@ -485,6 +492,9 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         __syncthreads();
     }
 
+#if B2D_EXPERIMENT_TIMING
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_go));
+#endif
     // the first two tickets of every warp are static, so the first loads leave before any barrier
     // CTA c owns the tiles congruent to c modulo G, whatever range a launch covers
     const int first_tile = d.tile_begin + (int)((blockIdx.x + G - d.tile_begin % G) % G);
@@ -701,7 +711,10 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
                 __syncwarp();
                 if (lane == 0) *(volatile unsigned int *)&s_q_tail = take + 32u; // the 32 ring slots may be reused
                 race_fill_slot(d, (int)e.x, e.y);
-                __threadfence(); // slots complete before the pending list is lifted / the lock is released
+                // Slots complete before the pending list is lifted / the lock is released.  The readers
+                // this orders against are warps of THIS CTA (CTA scope: a device-scope fence here was
+                // measured at ~10 us under load); the next launch is ordered by the epilogue's fence.
+                __threadfence_block();
                 __syncwarp();
                 if (lane == 0) {
                     if (take == 0u) *(volatile unsigned int *)&s_npending = 0u; // carried entries sit at the ring's front
@@ -777,6 +790,12 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         if (lane == 0) {
             atomicAdd(&d.ctl->dbg[10], (unsigned long long)(clock64() - t_begin)); // CTA busy time
             atomicMax(&d.ctl->dbg[11], (unsigned long long)(clock64() - t_begin));
+            unsigned long long tr_done;
+            unsigned int smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_done));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            d.trace[blockIdx.x * 4 + 0] = smid; d.trace[blockIdx.x * 4 + 1] = tr_entry;
+            d.trace[blockIdx.x * 4 + 2] = tr_go; d.trace[blockIdx.x * 4 + 3] = tr_done;
         }
 #endif
         __syncwarp();

@@ -91,6 +91,47 @@ __device__ __forceinline__ void sw_load(const SwarmDev &d, int k, SwarmAgent &g)
     g.tvel[0] = w.x; g.tvel[1] = w.y; g.tvel[2] = w.z; g.last_col = w.w;
 }
 
+// Inputs of one agent for one step, staged in shared memory by cp.async one tile ahead of their
+// use (slot s of thread t at stage[s * SWARM_BLOCK + t]: conflict-free, thread-private).
+constexpr int SW_STAGE_SLOTS = 14; // act, S0..S4, P0..P2, T, U, V, W, E
+constexpr int SW_STAGE_BYTES = SW_STAGE_SLOTS * SWARM_BLOCK * 16;
+constexpr int SW_DYN_SMEM = SW_STAGE_BYTES + SWARM_BLOCK * SWARM_OBS * 4;
+
+__device__ __forceinline__ void sw_prefetch(const SwarmDev &d, float4 *stage, int t, int e, int k) {
+    const size_t ld = d.ld;
+    cp_async16(&stage[0 * SWARM_BLOCK + t], reinterpret_cast<const float4 *>(d.act_in) + k);
+#pragma unroll
+    for (int m = 0; m < 5; m++) cp_async16(&stage[(1 + m) * SWARM_BLOCK + t], &d.S[m * ld + k]);
+#pragma unroll
+    for (int m = 0; m < 3; m++) cp_async16(&stage[(6 + m) * SWARM_BLOCK + t], &d.P[m * ld + k]);
+    cp_async16(&stage[9 * SWARM_BLOCK + t], &d.T[k]);
+    cp_async16(&stage[10 * SWARM_BLOCK + t], &d.U[k]);
+    cp_async16(&stage[11 * SWARM_BLOCK + t], &d.V[k]);
+    cp_async16(&stage[12 * SWARM_BLOCK + t], &d.W[k]);
+    cp_async16(&stage[13 * SWARM_BLOCK + t], &d.E[e]);
+}
+
+__device__ __forceinline__ void sw_load_staged(const float4 *stage, int t, SwarmAgent &g, float4 &a4, int4 &ev) {
+    a4 = stage[0 * SWARM_BLOCK + t];
+    const float4 q0 = stage[1 * SWARM_BLOCK + t], q1 = stage[2 * SWARM_BLOCK + t], q2 = stage[3 * SWARM_BLOCK + t],
+                 q3 = stage[4 * SWARM_BLOCK + t], q4 = stage[5 * SWARM_BLOCK + t];
+    const float4 p0 = stage[6 * SWARM_BLOCK + t], p1 = stage[7 * SWARM_BLOCK + t], p2 = stage[8 * SWARM_BLOCK + t];
+    const float4 tt = stage[9 * SWARM_BLOCK + t], u = stage[10 * SWARM_BLOCK + t], v = stage[11 * SWARM_BLOCK + t],
+                 w = stage[12 * SWARM_BLOCK + t];
+    const float4 e4 = stage[13 * SWARM_BLOCK + t];
+    ev = make_int4(__float_as_int(e4.x), __float_as_int(e4.y), __float_as_int(e4.z), __float_as_int(e4.w));
+    g.s[0] = q0.x; g.s[1] = q0.y; g.s[2] = q0.z; g.s[3] = q0.w; g.s[4] = q1.x; g.s[5] = q1.y; g.s[6] = q1.z; g.s[7] = q1.w;
+    g.s[8] = q2.x; g.s[9] = q2.y; g.s[10] = q2.z; g.s[11] = q2.w; g.s[12] = q3.x; g.s[13] = q3.y; g.s[14] = q3.z; g.s[15] = q3.w;
+    g.s[16] = q4.x;
+    g.ep_len = __float_as_int(q4.y); g.ring_idx = __float_as_int(q4.z); g.ep_ret = q4.w;
+    g.p[0] = p0.x; g.p[1] = p0.y; g.p[2] = p0.z; g.p[3] = p0.w; g.p[4] = p1.x; g.p[5] = p1.y; g.p[6] = p1.z; g.p[7] = p1.w;
+    g.p[8] = p2.x; g.p[9] = p2.y; g.p[10] = p2.z; g.p[11] = p2.w; g.p[12] = tt.x;
+    g.respawns = __float_as_uint(tt.y); g.collisions = tt.z; g.score = tt.w;
+    g.spawn[0] = u.x; g.spawn[1] = u.y; g.spawn[2] = u.z; g.last_abs = u.w;
+    g.tpos[0] = v.x; g.tpos[1] = v.y; g.tpos[2] = v.z; g.last_tgt = v.w;
+    g.tvel[0] = w.x; g.tvel[1] = w.y; g.tvel[2] = w.z; g.last_col = w.w;
+}
+
 __device__ __forceinline__ void sw_store(const SwarmDev &d, int k, const SwarmAgent &g, bool params_too) {
     const size_t ld = d.ld;
     d.S[0 * ld + k] = make_float4(g.s[0], g.s[1], g.s[2], g.s[3]);
@@ -150,38 +191,112 @@ __device__ __forceinline__ void sw_move_target(float tp[3], float tv[3]) {
     if (tp[2] < -SW_GZ || tp[2] > SW_GZ) tv[2] = -tv[2];
 }
 
-// nearest other agent of env (shared-memory base b0, A agents) as seen by agent a standing at
-// `self`: agents below a are read from `lo`, agents above from `hi` (R/drone_swarm.h:107-129).
-// Returns the distance the reference computes; `other` receives the neighbour's position.
-template <bool STRICT>
-__device__ __forceinline__ void sw_nearest_scan(const float4 *src, int j0, int j1, const float self[3], float &best, float4 &who) {
-    for (int j = j0; j < j1; j++) {
-        const float4 o = src[j];
-        float dist;
-        if constexpr (STRICT) {
-            const xf dx = xf(self[0]) - xf(o.x), dy = xf(self[1]) - xf(o.y), dz = xf(self[2]) - xf(o.z);
-            dist = xsqrt(dx * dx + dy * dy + dz * dz).v;
-        } else {
-            const float dx = self[0] - o.x, dy = self[1] - o.y, dz = self[2] - o.z;
-            dist = dx * dx + dy * dy + dz * dz; // squared: same ordering, no square root per candidate
-        }
-        if (dist < best) {
-            best = dist;
-            who = o;
-        }
-    }
-}
+// Positions of the CTA's agents in shared memory, one array per coordinate so that two
+// neighbouring candidates load as one 64-bit word per coordinate and their squared distances
+// come out of packed FP32x2 instructions (sm_100: add/mul/fma.f32x2, each half an IEEE
+// round-to-nearest op, so the strict path stays bit-exact).
+//
+// WINDOW LAYOUT.  The reference steps the agents of an env in index order, so agent a sees agents
+// j < a where they stand NOW (array `lo`) and agents j > a where they stood BEFORE (array `hi`).
+// Each env keeps its position arrays back to back, hi first: [hi_0 .. hi_{A-1} | lo_0 .. lo_{A-1}],
+// so the A - 1 candidates of agent a are the CONTIGUOUS window positions a+1 .. a+A-1 (hi_{a+1} ..
+// hi_{A-1}, then lo_0 .. lo_{a-1}): one linear sweep, no per-candidate array select, no self test.
+// Three arrays in a row [old | fin | rst] serve the step scan (hi = old, lo = fin: window at 0) and
+// the env-reset scan (hi = fin, lo = rst: window at A); the observation scan uses [pos | pos].
+// Envs sit 3A floats apart, which also spreads the envs of one warp over different banks.
+constexpr int SW_WIN = 3 * SWARM_BLOCK;
+struct SwarmWin {
+    float x[SW_WIN], y[SW_WIN], z[SW_WIN];
+    __device__ __forceinline__ void put(int i, float px, float py, float pz) { x[i] = px; y[i] = py; z[i] = pz; }
+};
 
+// Nearest other agent of agent a standing at `self` (R/drone_swarm.h:107-129); w = &win.x[window
+// start of the env].  Returns the distance the reference computes; `other` = that agent's position.
+//
+// STRICT: ascending index, strict '<' on the reference's sqrtf values (lowest index wins ties);
+// the root is taken only for a candidate whose SQUARED distance beats the best so far (sqrtf is
+// monotonic, nothing else can win): a handful of roots per sweep instead of A - 1.
+// Fast: the window sweep above, two candidates per iteration; the winner is the minimum of
+// (squared distance with its 7 low mantissa bits replaced by the window offset) taken with one
+// 3-input integer min per pair.  Candidates closer than 1.5e-5 relative in squared distance may
+// therefore swap (the tests count such flips); the returned distance is recomputed exactly.
 template <bool STRICT>
-__device__ __forceinline__ float sw_nearest(const float4 *lo, const float4 *hi, int b0, int A, int a, const float self[3],
-                                            float other[3]) {
-    float best = STRICT ? 999999.0f : 999999.0f * 999999.0f;
-    float4 who = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    sw_nearest_scan<STRICT>(lo + b0, 0, a, self, best, who);     // ascending index, strict '<': lowest index wins ties
-    sw_nearest_scan<STRICT>(hi + b0, a + 1, A, self, best, who);
-    other[0] = who.x; other[1] = who.y; other[2] = who.z;
-    if constexpr (!STRICT) best = sqrtf(best);
-    return best;
+__device__ __forceinline__ float sw_nearest(const float *w, int A, int a, const float self[3], float other[3]) {
+    other[0] = other[1] = other[2] = 0.0f;
+    if constexpr (STRICT) {
+        float best2 = __int_as_float(0x7f800000), bestd = 999999.0f;
+        int idx = -1;
+        auto consider = [&](int j, float v) {
+            if (j != a && v < best2) {
+                const float r = xsqrt(xf(v)).v;
+                if (r < bestd) { bestd = r; best2 = v; idx = j; }
+            }
+        };
+        if ((A & 1) == 0) {
+#pragma unroll 2
+            for (int j = 0; j < A; j += 2) {
+                const float *src = w + (j < a ? A : 0) + j; // a pair never straddles a: the element at a is skipped
+                const float2 ox = *reinterpret_cast<const float2 *>(src);
+                const float2 oy = *reinterpret_cast<const float2 *>(src + SW_WIN);
+                const float2 oz = *reinterpret_cast<const float2 *>(src + 2 * SW_WIN);
+                const float2 dx = __fadd2_rn(ox, make_float2(-self[0], -self[0])), dy = __fadd2_rn(oy, make_float2(-self[1], -self[1])),
+                             dz = __fadd2_rn(oz, make_float2(-self[2], -self[2]));
+                const float2 d2 = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
+                consider(j, d2.x);
+                consider(j + 1, d2.y);
+            }
+        } else {
+            for (int j = 0; j < A; j++) {
+                const float *src = w + (j < a ? A : 0) + j;
+                const float dx = __fsub_rn(src[0], self[0]), dy = __fsub_rn(src[SW_WIN], self[1]), dz = __fsub_rn(src[2 * SW_WIN], self[2]);
+                consider(j, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+            }
+        }
+        if (idx >= 0) {
+            const float *src = w + (idx < a ? A : 0) + idx;
+            other[0] = src[0]; other[1] = src[SW_WIN]; other[2] = src[2 * SW_WIN];
+        }
+        return bestd;
+    } else {
+        constexpr unsigned int KEY_NONE = 0x7f800000u, CODE_MASK = 127u;
+        unsigned int best = KEY_NONE;
+        int a2 = a;
+        if ((A & 1) == 0) {
+            a2 = a & ~1;
+            {   // the other agent of a's own pair: code 1
+                const float *src = w + ((a & 1) ? A + a - 1 : a + 1);
+                const float dx = src[0] - self[0], dy = src[SW_WIN] - self[1], dz = src[2 * SW_WIN] - self[2];
+                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                best = min(best, (__float_as_uint(d2) & ~CODE_MASK) | 1u);
+            }
+            const float2 nx = make_float2(-self[0], -self[0]), ny = make_float2(-self[1], -self[1]), nz = make_float2(-self[2], -self[2]);
+            const float *src = w + a2;
+#pragma unroll 4
+            for (int c = 2; c < A; c += 2) { // window offsets c, c + 1 from a's pair
+                const float2 ox = *reinterpret_cast<const float2 *>(src + c);
+                const float2 oy = *reinterpret_cast<const float2 *>(src + c + SW_WIN);
+                const float2 oz = *reinterpret_cast<const float2 *>(src + c + 2 * SW_WIN);
+                const float2 dx = __fadd2_rn(ox, nx), dy = __fadd2_rn(oy, ny), dz = __fadd2_rn(oz, nz);
+                const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                const unsigned int k0 = (__float_as_uint(d2.x) & ~CODE_MASK) | (unsigned int)c;
+                const unsigned int k1 = (__float_as_uint(d2.y) & ~CODE_MASK) | (unsigned int)(c + 1);
+                best = __vimin3_u32(best, k0, k1);
+            }
+        } else {
+            for (int c = 1; c < A; c++) { // odd A: one candidate at a time, window offsets from a itself
+                const float *src = w + a + c;
+                const float dx = src[0] - self[0], dy = src[SW_WIN] - self[1], dz = src[2 * SW_WIN] - self[2];
+                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                best = min(best, (__float_as_uint(d2) & ~CODE_MASK) | (unsigned int)c);
+            }
+        }
+        if (best >= KEY_NONE) return 999999.0f;
+        const int code = (int)(best & CODE_MASK);
+        const float *src = ((A & 1) == 0 && code == 1) ? w + ((a & 1) ? A + a - 1 : a + 1) : w + a2 + code;
+        other[0] = src[0]; other[1] = src[SW_WIN]; other[2] = src[2 * SW_WIN];
+        const float dx = other[0] - self[0], dy = other[1] - self[1], dz = other[2] - self[2];
+        return sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    }
 }
 
 // R/drone_swarm.h:335-376.  Side effects on the agent exactly as the reference's.
@@ -324,28 +439,45 @@ __device__ __forceinline__ void sw_respawn_state(SwarmAgent &g, const float p[13
 
 // ---------------------------------------------------------------- the kernel
 // ONLY_RESET = false: one vec_step.  ONLY_RESET = true: vec_reset (every env runs c_reset).
+//
+// A tile = the SWARM_BLOCK / A envs one CTA steps together.  The step launch is persistent (a few
+// resident CTAs per SM, CTA c takes tiles c, c + grid, ...): while a tile computes (~2-3 k
+// instructions per agent) the 14 input words of the CTA's next tile stream into shared memory
+// with cp.async, so no warp ever waits on a global load at the top of a tile.
 template <bool STRICT, bool ONLY_RESET>
 __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constant__ SwarmDev d) {
-    __shared__ float4 s_old[SWARM_BLOCK]; // positions before this tick's move
-    __shared__ float4 s_fin[SWARM_BLOCK]; // after the move, or the respawn position of an agent that left the arena
-    __shared__ float4 s_rst[SWARM_BLOCK]; // first position drawn by an env-wide reset
-    __shared__ float4 s_pos[SWARM_BLOCK]; // final positions of the tick (what the observations see)
-    __shared__ float s_obs[SWARM_BLOCK * SWARM_OBS];
+    // per env (3A floats apart): [old | fin | rst] = before this tick's move | after the move, or the respawn
+    // position of an agent that left the arena | first position drawn by an env-wide reset
+    __shared__ __align__(16) SwarmWin s_trail;
+    __shared__ __align__(16) SwarmWin s_now; // per env [pos | pos]: final positions of the tick (what the observations see)
     __shared__ float s_ring0[SWARM_BLOCK][3];
     __shared__ float s_facc[8];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    float4 *stage = reinterpret_cast<float4 *>(s_dyn);                       // step launches only
+    float *s_obs = reinterpret_cast<float *>(s_dyn + (ONLY_RESET ? 0 : SW_STAGE_BYTES));
 
     const int t = threadIdx.x;
     const int A = d.A;
     const int le = t / A;
     const int a = t - le * A;
-    const int e = blockIdx.x * d.epc + le;
+    const int w0 = le * 3 * A; // this env's windows
+    const bool inject = d.reset_mode == 1;
+    const int ntiles = (d.n + d.epc - 1) / d.epc;
+    const size_t pay_stride = (size_t)A * SWARM_AGENT_PAYLOAD + 2 + 6 * d.R;
+
+    if constexpr (!ONLY_RESET) {
+        const int e0 = blockIdx.x * d.epc + le;
+        if ((int)blockIdx.x < ntiles && le < d.epc && e0 < d.n) sw_prefetch(d, stage, t, e0, e0 * A + a);
+        cp_async_commit();
+    }
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int e = tile * d.epc + le;
     const bool active = le < d.epc && e < d.n;
-    const int b0 = le * A;
     const int k = e * A + a;
     const uint32_t genv = d.env_id_base + (uint32_t)e;
-    const bool inject = d.reset_mode == 1;
-    const float *pay_agent = d.payload ? d.payload + (size_t)e * (A * SWARM_AGENT_PAYLOAD + 2 + 6 * d.R) + (size_t)a * SWARM_AGENT_PAYLOAD : nullptr;
-    const float *pay_env = d.payload ? d.payload + (size_t)e * (A * SWARM_AGENT_PAYLOAD + 2 + 6 * d.R) + (size_t)A * SWARM_AGENT_PAYLOAD : nullptr;
+    const float *pay_agent = d.payload ? d.payload + (size_t)e * pay_stride + (size_t)a * SWARM_AGENT_PAYLOAD : nullptr;
+    const float *pay_env = d.payload ? d.payload + (size_t)e * pay_stride + (size_t)A * SWARM_AGENT_PAYLOAD : nullptr;
     if (t < 8) s_facc[t] = 0.0f;
 
     SwarmAgent g;
@@ -355,12 +487,25 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
     int terminal = 0;
     bool params_dirty = false;
     bool do_reset = false;
-    if (active) {
-        sw_load(d, k, g);
-        const int4 ev = d.E[e];
-        tick = ev.x; task = ev.y; env_episode = (uint32_t)ev.z;
-        s_old[t] = make_float4(g.s[0], g.s[1], g.s[2], 0.0f);
+    float4 a4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if constexpr (ONLY_RESET) {
+        if (active) {
+            sw_load(d, k, g);
+            const int4 ev = d.E[e];
+            tick = ev.x; task = ev.y; env_episode = (uint32_t)ev.z;
+        }
+    } else {
+        cp_async_wait<0>(); // this thread's staged inputs of this tile have landed
+        if (active) {
+            int4 ev;
+            sw_load_staged(stage, t, g, a4, ev);
+            tick = ev.x; task = ev.y; env_episode = (uint32_t)ev.z;
+        }
+        const int tn = tile + gridDim.x, en = tn * d.epc + le;
+        if (tn < ntiles && le < d.epc && en < d.n) sw_prefetch(d, stage, t, en, en * A + a); // slots are thread-private
+        cp_async_commit();
     }
+    if (active) s_trail.put(w0 + a, g.s[0], g.s[1], g.s[2]);
 
     if constexpr (!ONLY_RESET) {
         // ---- phase 1: every drone moves (R/drone_swarm.h:452-461); agents that leave the arena draw their respawn
@@ -368,7 +513,6 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         float rp[13], rpos[3] = {0.0f, 0.0f, 0.0f};
         if (active) {
             tick = (tick + 1) % SWARM_HORIZON;
-            const float4 a4 = reinterpret_cast<const float4 *>(d.act_in)[k];
             float act[4];
             if constexpr (STRICT) {
                 act[0] = xclamp(xf(a4.x), -1.0f, 1.0f).v; act[1] = xclamp(xf(a4.y), -1.0f, 1.0f).v;
@@ -393,18 +537,18 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                     sw_draw_box(d, genv, (uint32_t)a | 0x10000u, g.respawns, 4u, 0u, 29.0f, 29.0f, 9.0f, rpos);
                 }
             }
-            s_fin[t] = oob ? make_float4(rpos[0], rpos[1], rpos[2], 0.0f) : make_float4(g.s[0], g.s[1], g.s[2], 0.0f);
+            if (oob) s_trail.put(w0 + A + a, rpos[0], rpos[1], rpos[2]);
+            else s_trail.put(w0 + A + a, g.s[0], g.s[1], g.s[2]);
         }
         __syncthreads();
 
         // ---- phase 2: rewards, ring logic, respawn bookkeeping (R/drone_swarm.h:463-491)
         if (active) {
-            const float4 o4 = s_old[t];
-            const float before[3] = {o4.x, o4.y, o4.z};
+            const float before[3] = {s_trail.x[w0 + a], s_trail.y[w0 + a], s_trail.z[w0 + a]};
             const float self[3] = {g.s[0], g.s[1], g.s[2]};
             float other[3];
             float nd = 0.0f;
-            if (A > 1) nd = sw_nearest<STRICT>(s_fin, s_old, b0, A, a, self, other);
+            if (A > 1) nd = sw_nearest<STRICT>(&s_trail.x[w0], A, a, self, other);
             if (task == SWARM_TASK_RACE) {
                 float ring[6];
                 sw_load_ring(d, e, g.ring_idx, ring);
@@ -444,14 +588,14 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                 sw_respawn_state(g, rp, rpos);
                 params_dirty = true;
                 float nd2 = 0.0f;
-                if (A > 1 && task != SWARM_TASK_RACE) nd2 = sw_nearest<STRICT>(s_fin, s_old, b0, A, a, rpos, other);
+                if (A > 1 && task != SWARM_TASK_RACE) nd2 = sw_nearest<STRICT>(&s_trail.x[w0], A, a, rpos, other);
                 sw_reward<STRICT>(g, rpos, task != SWARM_TASK_RACE, A, nd2);
             }
             do_reset = horizon;
         }
     } else {
         if (active) {
-            s_fin[t] = make_float4(g.s[0], g.s[1], g.s[2], 0.0f);
+            s_trail.put(w0 + A + a, g.s[0], g.s[1], g.s[2]);
             g.respawns = 0u;
             do_reset = true;
         }
@@ -475,7 +619,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                 sw_draw_params(d, genv, (uint32_t)a, env_episode, np);
                 sw_draw_box(d, genv, (uint32_t)a, env_episode, 4u, 0u, 29.0f, 29.0f, 9.0f, first);
             }
-            s_rst[t] = make_float4(first[0], first[1], first[2], 0.0f);
+            s_trail.put(w0 + 2 * A + a, first[0], first[1], first[2]);
         }
         __syncthreads();
         if (do_reset) {
@@ -483,7 +627,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             sw_respawn_state(g, np, first);
             params_dirty = true;
             float other[3], nd = 0.0f;
-            if (A > 1 && task != SWARM_TASK_RACE) nd = sw_nearest<STRICT>(s_rst, s_fin, b0, A, a, first, other);
+            if (A > 1 && task != SWARM_TASK_RACE) nd = sw_nearest<STRICT>(&s_trail.x[w0 + A], A, a, first, other);
             sw_reward<STRICT>(g, first, task != SWARM_TASK_RACE, A, nd);
             // set_target: R/drone_swarm.h:234-333
             if (inject) {
@@ -554,7 +698,8 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         }
     }
     if (active) {
-        s_pos[t] = make_float4(g.s[0], g.s[1], g.s[2], 0.0f);
+        s_now.put(w0 + a, g.s[0], g.s[1], g.s[2]);
+        s_now.put(w0 + A + a, g.s[0], g.s[1], g.s[2]);
     }
     __syncthreads();
 
@@ -568,21 +713,32 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         }
         const float self[3] = {g.s[0], g.s[1], g.s[2]};
         float near[3] = {0.0f, 0.0f, 0.0f};
-        if (A > 1) sw_nearest<STRICT>(s_pos, s_pos, b0, A, a, self, near);
+        if (A > 1) sw_nearest<STRICT>(&s_now.x[w0], A, a, self, near);
         float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
         if (task == SWARM_TASK_RACE) sw_load_ring(d, e, g.ring_idx, ring);
         sw_observe<STRICT>(g, A, near, task == SWARM_TASK_RACE, ring, s_obs + t * SWARM_OBS, 1);
     }
     __syncthreads();
     {
-        const int rows_here = min(d.epc, d.n - blockIdx.x * d.epc) * A;
-        float *gobs = d.obs + (size_t)blockIdx.x * d.epc * A * SWARM_OBS;
-        for (int m = t; m < rows_here * SWARM_OBS; m += SWARM_BLOCK) __stcs(&gobs[m], s_obs[m]);
+        const int rows_here = min(d.epc, d.n - tile * d.epc) * A;
+        float *gobs = d.obs + (size_t)tile * d.epc * A * SWARM_OBS;
+        if ((rows_here & 3) == 0 && (((size_t)tile * d.epc * A) & 3) == 0) { // 16-byte aligned tile: float4 stores
+            const float4 *src = reinterpret_cast<const float4 *>(s_obs);
+            float4 *dst = reinterpret_cast<float4 *>(gobs);
+            for (int m = t; m < rows_here * SWARM_OBS / 4; m += SWARM_BLOCK) __stcs(&dst[m], src[m]);
+        } else {
+            for (int m = t; m < rows_here * SWARM_OBS; m += SWARM_BLOCK) __stcs(&gobs[m], s_obs[m]);
+        }
     }
     if constexpr (!ONLY_RESET) {
         if (t < 8 && s_facc[t] != 0.0f) atomicAdd(&d.ctl->facc[t], (double)s_facc[t]);
-        if (t == 0 && blockIdx.x == 0) atomicAdd(&d.ctl->ctas_done, 1u);
+        if (t == 0 && tile == 0) atomicAdd(&d.ctl->ctas_done, 1u);
     }
+    // the next tile's first barrier (after its phase 1) separates this tile's readers of the
+    // shared arrays from their next writers, except the old / fin arrays, which are last read before this
+    // tile's final barriers
+  }
+  if constexpr (!ONLY_RESET) cp_async_wait<0>();
 }
 
 // snapshot + clear for vec_log: out[0..7] = the float sums in 2^-20 fixed point, so that the
@@ -649,21 +805,22 @@ __global__ void swarm_unpack_kernel(const SwarmDev d, const int *ids, int n, con
 // observations recomputed from the current state (after put_state)
 template <bool STRICT>
 __global__ void __launch_bounds__(SWARM_BLOCK) swarm_observe_kernel(const __grid_constant__ SwarmDev d) {
-    __shared__ float4 s_pos[SWARM_BLOCK];
+    __shared__ __align__(16) SwarmWin s_now;
     const int t = threadIdx.x, A = d.A;
-    const int le = t / A, a = t - le * A, e = blockIdx.x * d.epc + le;
+    const int le = t / A, a = t - le * A, e = blockIdx.x * d.epc + le, w0 = le * 3 * A;
     const bool active = le < d.epc && e < d.n;
     SwarmAgent g;
     if (active) {
         sw_load(d, e * A + a, g);
-        s_pos[t] = make_float4(g.s[0], g.s[1], g.s[2], 0.0f);
+        s_now.put(w0 + a, g.s[0], g.s[1], g.s[2]);
+        s_now.put(w0 + A + a, g.s[0], g.s[1], g.s[2]);
     }
     __syncthreads();
     if (!active) return;
     const int task = d.E[e].y;
     const float self[3] = {g.s[0], g.s[1], g.s[2]};
     float near[3] = {0.0f, 0.0f, 0.0f};
-    if (A > 1) sw_nearest<STRICT>(s_pos, s_pos, le * A, A, a, self, near);
+    if (A > 1) sw_nearest<STRICT>(&s_now.x[w0], A, a, self, near);
     float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     if (task == SWARM_TASK_RACE) sw_load_ring(d, e, g.ring_idx, ring);
     sw_observe<STRICT>(g, A, near, task == SWARM_TASK_RACE, ring, d.obs + (size_t)(e * A + a) * SWARM_OBS, 1);
@@ -675,15 +832,35 @@ static inline int swarm_grid(const SwarmDev &d) { return (d.n + d.epc - 1) / d.e
 static inline void swarm_vec_reset(SwarmDev &d, uint64_t seed, cudaStream_t st, long long *launches) {
     d.key0 = (uint32_t)seed;
     d.key1 = (uint32_t)(seed >> 32);
-    swarm_kernel<true, true><<<swarm_grid(d), SWARM_BLOCK, 0, st>>>(d);
+    swarm_kernel<true, true><<<swarm_grid(d), SWARM_BLOCK, SWARM_BLOCK * SWARM_OBS * 4, st>>>(d);
     *launches += 1;
+}
+
+// persistent step grid: every resident CTA slot of the device, or one CTA per tile when there are fewer tiles
+static inline int swarm_step_grid(const SwarmDev &d, int math) {
+    static int per_sm[2] = {0, 0}, sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(swarm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM);
+        cudaFuncSetAttribute(swarm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM);
+        cudaFuncSetAttribute(swarm_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(swarm_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], swarm_kernel<false, false>, SWARM_BLOCK, SW_DYN_SMEM);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], swarm_kernel<true, false>, SWARM_BLOCK, SW_DYN_SMEM);
+        for (int m = 0; m < 2; m++) if (per_sm[m] < 1) per_sm[m] = 1;
+    }
+    const int tiles = swarm_grid(d), slots = sms * per_sm[math == 1 ? 1 : 0];
+    return tiles < slots ? tiles : slots;
 }
 
 static inline void swarm_vec_step(SwarmDev &dev, const float *actions, int math, cudaStream_t st, long long *launches) {
     SwarmDev d = dev;
     if (actions) d.act_in = actions;
-    if (math == 1) swarm_kernel<true, false><<<swarm_grid(d), SWARM_BLOCK, 0, st>>>(d);
-    else swarm_kernel<false, false><<<swarm_grid(d), SWARM_BLOCK, 0, st>>>(d);
+    const int grid = swarm_step_grid(d, math);
+    if (math == 1) swarm_kernel<true, false><<<grid, SWARM_BLOCK, SW_DYN_SMEM, st>>>(d);
+    else swarm_kernel<false, false><<<grid, SWARM_BLOCK, SW_DYN_SMEM, st>>>(d);
     *launches += 1;
 }
 
