@@ -14,6 +14,7 @@ B2D_OK, B2D_EINVAL, B2D_ENOMEM, B2D_ECUDA, B2D_ESTATE = 0, -1, -2, -3, -4
 MATH_FAST, MATH_STRICT = 0, 1
 RESET_PHILOX, RESET_INJECT = 0, 1
 MEM_DEVICE, MEM_HOST = 0, 1
+POLICY_FP32, POLICY_TF32 = 0, 1
 LOG_FIELDS = ("episode_return", "episode_length", "rings_passed", "collision_rate", "oob",
               "timeout", "score", "perf", "n")  # DR/dronelib.h:52-63
 
@@ -33,6 +34,19 @@ class SwarmCfg(C.Structure):
     _fields_ = [("num_envs", C.c_int), ("num_agents", C.c_int), ("max_rings", C.c_int),
                 ("device", C.c_int), ("seed", C.c_uint64), ("env_id_base", C.c_uint32),
                 ("math", C.c_int), ("write_clamped_actions", C.c_int)]
+
+
+class PolicyWeights(C.Structure):
+    _fields_ = [("encoder_weight", C.c_void_p), ("encoder_bias", C.c_void_p), ("decoder_mean_weight", C.c_void_p),
+                ("decoder_mean_bias", C.c_void_p), ("decoder_logstd", C.c_void_p), ("value_weight", C.c_void_p),
+                ("value_bias", C.c_void_p), ("hidden", C.c_int), ("precision", C.c_int)]
+
+
+class PolicyIO(C.Structure):
+    _fields_ = [("observations", C.c_void_p), ("rewards", C.c_void_p), ("terminals", C.c_void_p),
+                ("env_actions", C.c_void_p), ("store_observations", C.c_void_p), ("store_actions", C.c_void_p),
+                ("store_logprobs", C.c_void_p), ("store_rewards", C.c_void_p), ("store_terminals", C.c_void_p),
+                ("store_values", C.c_void_p), ("rows", C.c_int), ("obs_dim", C.c_int), ("row_id_base", C.c_uint32)]
 
 
 # every symbol include/b200drone.h declares: name -> (restype, argtypes)
@@ -68,6 +82,7 @@ SYMBOLS = {
     "b2d_profile_kernels": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
     "b2d_puff_advantage": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_longlong, C.c_longlong,
                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _P]),
+    "b2d_policy_act": (C.c_int, [C.POINTER(PolicyWeights), C.POINTER(PolicyIO), C.c_uint64, _P, C.c_int, _P]),
     "b2d_last_error": (C.c_char_p, []),
     "b2d_version": (C.c_int, []),
 }

@@ -8,6 +8,7 @@
 #include "race_kernels.cuh"
 #include "swarm_kernels.cuh"
 #include "advantage_kernels.cuh"
+#include "policy_kernels.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -755,6 +756,87 @@ extern "C" int b2d_puff_advantage(const float *values, const float *rewards, con
         puff_advantage_kernel<false><<<grid, 256, 0, st>>>(values, rewards, dones, importance, advantages, abs_sum, num_rows, horizon,
                                                            row_stride, t_stride, gamma, lambda, rho_clip, c_clip);
     return launch_check("puff_advantage_kernel");
+}
+
+// ---------------------------------------------------------------- fused policy step (rollout side)
+template <class K> static int policy_launch(K kernel, int slot, int threads, int warps, size_t smem, const PolicyArgs &a, cudaStream_t st) {
+    static int grid_for[4][64] = {{0}};
+    static size_t smem_for[4][64] = {{0}};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(B2D_EINVAL, "device ordinal out of range");
+    if (grid_for[slot][dev] == 0 || smem_for[slot][dev] != smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, sms = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (per_sm < 1) return fail(B2D_ECUDA, "policy kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+        grid_for[slot][dev] = per_sm * sms;
+        smem_for[slot][dev] = smem;
+    }
+    const int tiles = (a.rows + POL_TILE - 1) / POL_TILE;
+    int grid = (tiles + warps - 1) / warps;
+    if (grid > grid_for[slot][dev]) grid = grid_for[slot][dev];
+    kernel<<<grid, threads, smem, st>>>(a);
+    return launch_check("policy_act_kernel");
+}
+
+static size_t policy_smem_fp32(int D, int H) { return ((size_t)D * H + 7 * (size_t)H + (size_t)POL_WARPS * POL_TILE * D) * sizeof(float); }
+static size_t policy_smem_tf32(int D, int H, int warps) {
+    const size_t nt = H / 8, ks = (D + 7) / 8;
+    return nt * ks * 256 + nt * 256 + (size_t)H * 4 + (size_t)warps * POL_TILE * (D + 8) * 4;
+}
+
+extern "C" int b2d_policy_act(const b2d_policy_weights *w, const b2d_policy_io *io, uint64_t noise_seed,
+                              unsigned int *device_counter, int deterministic, void *stream) {
+    if (!w || !io) return fail(B2D_EINVAL, "b2d_policy_act: null argument");
+    if (!w->encoder_weight || !w->encoder_bias || !w->decoder_mean_weight || !w->decoder_mean_bias || !w->decoder_logstd ||
+        !w->value_weight || !w->value_bias)
+        return fail(B2D_EINVAL, "b2d_policy_act: null weight tensor");
+    if (w->hidden < 8 || w->hidden > 256 || (w->hidden & 7)) return fail(B2D_EINVAL, "b2d_policy_act: hidden must be a multiple of 8 in [8, 256]");
+    if (w->precision != B2D_POLICY_FP32 && w->precision != B2D_POLICY_TF32) return fail(B2D_EINVAL, "b2d_policy_act: unknown precision");
+    if (!io->observations || !io->rewards || !io->terminals || !io->env_actions) return fail(B2D_EINVAL, "b2d_policy_act: null env buffer");
+    if (!device_counter) return fail(B2D_EINVAL, "b2d_policy_act: null call counter");
+    if (io->rows < 0) return fail(B2D_EINVAL, "b2d_policy_act: negative row count");
+    if (io->obs_dim != B2D_RACE_OBS && io->obs_dim != B2D_SWARM_OBS) return fail(B2D_EINVAL, "b2d_policy_act: obs_dim must be 29 or 41");
+    if (((uintptr_t)io->env_actions & 15) || ((uintptr_t)io->store_actions & 15))
+        return fail(B2D_EINVAL, "b2d_policy_act: action buffers must be 16-byte aligned");
+    if (io->rows == 0) return B2D_OK;
+    PolicyArgs a;
+    a.enc_w = w->encoder_weight;
+    a.enc_b = w->encoder_bias;
+    a.mean_w = w->decoder_mean_weight;
+    a.mean_b = w->decoder_mean_bias;
+    a.logstd = w->decoder_logstd;
+    a.value_w = w->value_weight;
+    a.value_b = w->value_bias;
+    a.hidden = w->hidden;
+    a.obs = io->observations;
+    a.rew = io->rewards;
+    a.term = io->terminals;
+    a.env_act = io->env_actions;
+    a.st_obs = io->store_observations;
+    a.st_act = io->store_actions;
+    a.st_logp = io->store_logprobs;
+    a.st_rew = io->store_rewards;
+    a.st_term = io->store_terminals;
+    a.st_val = io->store_values;
+    a.rows = io->rows;
+    a.row_id_base = io->row_id_base;
+    a.seed_lo = (uint32_t)noise_seed;
+    a.seed_hi = (uint32_t)(noise_seed >> 32);
+    a.counter = device_counter;
+    a.deterministic = deterministic ? 1 : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int H = a.hidden;
+    if (w->precision == B2D_POLICY_TF32) {
+        if (io->obs_dim == B2D_RACE_OBS)
+            return policy_launch(policy_act_tf32_kernel<B2D_RACE_OBS, 8, 4>, 2, 256, 8, policy_smem_tf32(B2D_RACE_OBS, H, 8), a, st);
+        return policy_launch(policy_act_tf32_kernel<B2D_SWARM_OBS, 4, 2>, 3, 128, 4, policy_smem_tf32(B2D_SWARM_OBS, H, 4), a, st);
+    }
+    if (io->obs_dim == B2D_RACE_OBS)
+        return policy_launch(policy_act_kernel<B2D_RACE_OBS>, 0, POL_THREADS, POL_WARPS, policy_smem_fp32(B2D_RACE_OBS, H), a, st);
+    return policy_launch(policy_act_kernel<B2D_SWARM_OBS>, 1, POL_THREADS, POL_WARPS, policy_smem_fp32(B2D_SWARM_OBS, H), a, st);
 }
 
 extern "C" const char *b2d_last_error(void) { return g_err; }

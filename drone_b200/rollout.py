@@ -6,8 +6,11 @@ envs whose buffers already live on the GPU: what that loop does per step -- recv
 done), `policy.forward_eval`, `sample_logits` on a Normal (pufferlib/pytorch.py:189-199), store
 (obs, action, logprob, reward clamped to [-1, 1], done, value), clip the action to the action
 space, send -- happens here without the per-step `.to(device)` / `.cpu().numpy()` round trips
-(pufferl.py:240-243,292) that cap any GPU env at ~1e6 steps/s.  The policy is plain torch (library
-GEMMs); the env step is the CUDA kernel behind `vec.step()`.
+(pufferl.py:240-243,292) that cap any GPU env at ~1e6 steps/s.  Per step there are two kernels:
+the fused policy step (`policy_impl="fused"`, drone_b200.policy / csrc/policy_kernels.cuh: MLP,
+sampling, log-prob, experience stores and action clip in one launch) and the env step behind
+`vec.step()`.  `policy_impl="torch"` keeps the same loop on plain torch ops (library GEMMs) -- the
+form any other policy class uses, and the fused kernel's cross-check in the tests.
 
 Experience is stored time-major, [horizon, num_agents, ...], so every store is one contiguous
 write; `segments()` returns the reference's [num_agents, horizon, ...] views.
@@ -43,9 +46,21 @@ class DronePolicy(nn.Module):
 
 
 class DeviceRollout:
-    def __init__(self, vec, policy, horizon=128, use_graph=True, deterministic=False, autocast=None):
+    def __init__(self, vec, policy, horizon=128, use_graph=True, deterministic=False, autocast=None,
+                 policy_impl="auto", noise_seed=0, precision="tf32"):
         self.vec, self.policy, self.horizon = vec, policy, int(horizon)
         self.deterministic, self.autocast = deterministic, autocast
+        if policy_impl == "auto":
+            policy_impl = "fused" if (isinstance(policy, DronePolicy) and autocast is None) else "torch"
+        if policy_impl not in ("fused", "torch"):
+            raise ValueError("policy_impl must be 'auto', 'fused' or 'torch'")
+        self.policy_impl = policy_impl
+        self.fused = None
+        if policy_impl == "fused":
+            from .policy import FusedPolicyStep
+            self.fused = FusedPolicyStep(policy, vec.observations, vec.rewards, vec.terminals, vec.actions,
+                                         noise_seed=noise_seed, row_id_base=getattr(vec, "row_id_base", 0),
+                                         deterministic=deterministic, precision=precision)
         n, dev = vec.num_agents, vec.device
         k = self.horizon
         self.observations = torch.zeros((k, n, vec.obs_dim), dtype=torch.float32, device=dev)
@@ -61,6 +76,11 @@ class DeviceRollout:
     @torch.no_grad()
     def _one_step(self, k):
         vec = self.vec
+        if self.fused is not None:
+            self.fused.act(self.observations[k], self.actions[k], self.logprobs[k], self.rewards[k], self.terminals[k],
+                           self.values[k])
+            vec.step()
+            return
         obs = vec.observations
         self.observations[k].copy_(obs)
         torch.clamp(vec.rewards, -1.0, 1.0, out=self.rewards[k])          # pufferl.py:260

@@ -182,6 +182,7 @@ class RaceVec(_Vec):
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.num_envs = int(num_envs)
         self.max_rings, self.max_moves = int(max_rings), int(max_moves)
+        self.row_id_base = int(env_id_base)  # global id of row 0 (policy noise stream, drone_b200.policy)
         cfg = capi.RaceCfg(self.num_envs, self.max_rings, self.max_moves, idx, int(seed) & (2**64 - 1),
                            int(env_id_base), _math(math), int(bool(write_clamped_actions)))
         n = self.num_envs
@@ -260,6 +261,7 @@ class SwarmVec(_Vec):
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.num_envs, self.num_drones, self.max_rings = int(num_envs), int(num_drones), int(max_rings)
         rows = self.num_envs * self.num_drones
+        self.row_id_base = int(env_id_base) * self.num_drones
         cfg = capi.SwarmCfg(self.num_envs, self.num_drones, self.max_rings, idx, int(seed) & (2**64 - 1),
                             int(env_id_base), _math(math), int(bool(write_clamped_actions)))
         bufs = _make_buffers(self, rows, self.obs_dim, host_buffers)

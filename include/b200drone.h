@@ -200,6 +200,56 @@ int b2d_puff_advantage(const float *values, const float *rewards, const float *d
                        long long t_stride, float gamma, float lambda, float rho_clip, float c_clip, int math,
                        void *cuda_stream);
 
+/* ---- rollout-side helper -------------------------------------------
+ * One kernel for everything PuffeRL.evaluate does per step between vecenv.recv() and
+ * vecenv.send() for a Box action space (pufferl.py:229-296): forward_eval of
+ * pufferlib.models.Default (models.py:41-98: Linear(obs_dim, hidden) + GELU, mean head,
+ * state-independent log-std, value head), sample_logits on Normal(mean, exp(logstd))
+ * (pytorch.py:189-199), reward clamp to [-1, 1] (pufferl.py:260), the experience stores
+ * (pufferl.py:270-281) and the clip of the action to the action space (pufferl.py:292-294).
+ * All pointers are device memory, float32 unless stated, torch nn.Linear layouts. */
+typedef enum b2d_policy_precision {
+    B2D_POLICY_FP32 = 0, /* both Linear layers in float32 FMAs on the CUDA cores (|error| ~1e-6 vs float64) */
+    B2D_POLICY_TF32 = 1  /* both Linear layers as TF32 tensor-core GEMMs with float32 accumulation: what the reference
+                            itself runs on a GPU (torch.set_float32_matmul_precision('high'), pufferl.py:55) */
+} b2d_policy_precision;
+
+typedef struct b2d_policy_weights {
+    const float *encoder_weight;      /* [hidden, obs_dim] */
+    const float *encoder_bias;        /* [hidden] */
+    const float *decoder_mean_weight; /* [4, hidden] */
+    const float *decoder_mean_bias;   /* [4] */
+    const float *decoder_logstd;      /* [4] */
+    const float *value_weight;        /* [1, hidden] */
+    const float *value_bias;          /* [1] */
+    int hidden;                       /* multiple of 8, <= 256 */
+    int precision;                    /* b2d_policy_precision */
+} b2d_policy_weights;
+
+typedef struct b2d_policy_io {
+    const float *observations;      /* [rows, obs_dim] the env's observation buffer */
+    const float *rewards;           /* [rows] */
+    const unsigned char *terminals; /* [rows] u8 */
+    float *env_actions;             /* [rows, 4] out: clip(action, -1, 1), the env's action buffer */
+    /* experience row of this step, each optional (NULL = not stored) */
+    float *store_observations;      /* [rows, obs_dim] */
+    float *store_actions;           /* [rows, 4] the unclipped sample */
+    float *store_logprobs;          /* [rows] */
+    float *store_rewards;           /* [rows] clamped to [-1, 1] */
+    float *store_terminals;         /* [rows] as float */
+    float *store_values;            /* [rows] */
+    int rows;
+    int obs_dim;                    /* B2D_RACE_OBS or B2D_SWARM_OBS */
+    uint32_t row_id_base;           /* global id of row 0 (multi-GPU shards draw the noise of their global rows) */
+} b2d_policy_io;
+
+/* noise: Philox4x32-10 keyed by noise_seed, counter (global row, call number), Box-Muller.  The call
+ * number lives in `device_counter` (two zero-initialised uint32 owned by the caller; word 0 = calls
+ * completed) and is advanced by the kernel, so a CUDA-graph replay draws fresh noise.
+ * deterministic != 0: action = mean.  Stream-ordered, capturable. */
+int b2d_policy_act(const b2d_policy_weights *weights, const b2d_policy_io *io, uint64_t noise_seed,
+                   unsigned int *device_counter, int deterministic, void *cuda_stream);
+
 const char *b2d_last_error(void);
 int b2d_version(void);
 
