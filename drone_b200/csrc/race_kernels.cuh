@@ -54,7 +54,14 @@ constexpr int RACE_LD_ALIGN = 256; // row padding of the SoA arrays
 constexpr int RACE_OBS = 29;
 constexpr int RESET_MAX_ATTEMPTS = 16;
 constexpr int RACE_QUEUE_CAP = 256;            // refill ring of one CTA (entries, power of two)
-constexpr int RACE_CARRY = 32;                 // refill entries a CTA may carry over to the next launch
+constexpr int RACE_CARRY = 128;                // refill entries a CTA may carry over to the next launch
+constexpr int RACE_INSTALL_AGE = 8;             // tiles a finished env waits at most for its install pass to start
+constexpr int RACE_FUSED_MIN_TILES = RACE_INSTALL_AGE + 3; // tiles per warp a fused launch needs (see race_step_kernel)
+constexpr int RACE_TAPE_CHUNK = 250;            // vec_steps per fused tape launch at most
+constexpr int RACE_BALANCE_ROUNDS = 0;          // tile-list rebalancing rounds at the start of a handle's life (api.cu)
+constexpr int RACE_BALANCE_STEPS = 16;          // steps per measured launch while rebalancing
+constexpr int RACE_BALANCE_MIN_STEPS = 4;       // a launch shorter than this is not used as a measurement
+constexpr int RACE_INSTALL_CAP = 128;           // per-warp list of envs waiting for their next episode (install pass at 32)
 constexpr unsigned int QUEUE_EMPTY = 0xffffffffu;
 
 // integer episode-statistics accumulators (all race Log fields are integer valued)
@@ -74,16 +81,16 @@ struct Ctl {
 
 struct RaceDev {
     int n, ld, max_rings, max_moves;
-    float4 *S;
-    float4 *P;
-    float4 *C0;          // current ring (pos.xyz, n.x)
-    float4 *T;           // (j_mot, live episode number as bits, current ring n.y, n.z)
+    float4 *S;           // the hot state, 10 float4 per env: S0..S4, P0..P2, C0, T (see race_at)
     float4 *X0;          // external rings [R][ld] (injected episodes / put_state); allocated on first use
     float2 *X1;
     float4 *N;           // prepared next episode: params 0..11
     float4 *NS;          //   (spawn.xyz, j_mot)
     float4 *NR0;         //   ring 0 (pos.xyz, n.x)
     float4 *NR1;         //   (n.y, n.z, episode tag as bits, -)
+    const int *tile_list; // [ntiles] the tiles of CTA 0, CTA 1, ... (ascending within a CTA)
+    const int *tile_off;  // [grid + 1] where each CTA's tiles start in tile_list
+    unsigned long long *cta_ns; // [grid] wall time CTA c spent in the last launch (ns)
     uint2 *carry;        // [grid][RACE_CARRY] refill entries a CTA did not get to (env, episode)
     unsigned int *chain; // [grid] sequence number of the last launch CTA c completed
     long long *cta_score; // [grid] sum of score over the episodes CTA c saw end in the LAST step (R/drone_race.h:160)
@@ -93,7 +100,10 @@ struct RaceDev {
     uint32_t seq;        // sequence number of this launch (host counter, +1 per launch)
     int chain_wait;      // 1: launched programmatically dependent on launch seq-1 of this kernel: CTA c
                          //    starts as soon as CTA c of that launch is done (see b2d_vec_step_tape)
-    const float *act_in; // [n][4] actions read this step
+    const float *act_in; // [n][4] actions read this step; base of the action tape when steps > 1
+    int install_age;     // an install pass starts when its oldest entry has waited this many tiles (or 16 are listed)
+    int steps;           // vec_steps done by this launch (> 1: fused tape launch, see race_step_kernel)
+    int tape_len, tape_first; // step s reads slice (tape_first + s) % tape_len of the tape (slice = n*4 floats)
     float *act_out;      // [n][4] clamped actions written back, or nullptr
     float *obs;          // [n][29]
     float *rew;          // [n]
@@ -106,6 +116,25 @@ struct RaceDev {
     unsigned long long *trace; // [grid][4] (smid, CTA entry ns, first tile ns, CTA done ns) of the last launch
 #endif
 };
+
+// ---------------------------------------------------------------- hot-state addressing
+// The ten float4 a step reads per env (S0..S4, P0..P2, C0, T = slots 0..9).
+//   tiled (default): float4[tile][10][32] -- the 5 KB a warp reads for a tile, and the 2.5 KB of
+//     state it writes back, are ONE contiguous run in HBM, whatever the other warps are doing
+//   planar: ten separate float4[ld] planes -- a warp touches ten 512-byte pieces per tile, which is
+//     only DRAM-friendly while all warps sweep the planes as one tight frontier
+#ifndef B2D_RACE_TILED
+#define B2D_RACE_TILED 1
+#endif
+constexpr int RACE_HOT_SLOTS = 10;
+enum { SLOT_S = 0, SLOT_P = 5, SLOT_C0 = 8, SLOT_T = 9 };
+__device__ __forceinline__ float4 *race_at(const RaceDev &d, int slot, int i) {
+#if B2D_RACE_TILED
+    return d.S + ((((size_t)(i >> 5)) * RACE_HOT_SLOTS + (size_t)slot) << 5) + (i & 31);
+#else
+    return d.S + (size_t)slot * d.ld + i;
+#endif
+}
 
 // ---------------------------------------------------------------- observations
 // s: 17-float body state; ring: pos(3) normal(3); row: 29 floats (stride 1)
@@ -171,11 +200,11 @@ constexpr int RING_INDEX_MASK = RING_EXTERNAL - 1;
 
 __device__ __forceinline__ void race_store_state(const RaceDev &d, int i, const float s[17], int tick, int ring_word,
                                                  float ep_ret) {
-    d.S[0 * (size_t)d.ld + i] = make_float4(s[0], s[1], s[2], s[3]);
-    d.S[1 * (size_t)d.ld + i] = make_float4(s[4], s[5], s[6], s[7]);
-    d.S[2 * (size_t)d.ld + i] = make_float4(s[8], s[9], s[10], s[11]);
-    d.S[3 * (size_t)d.ld + i] = make_float4(s[12], s[13], s[14], s[15]);
-    d.S[4 * (size_t)d.ld + i] = make_float4(s[16], __int_as_float(tick), __int_as_float(ring_word), ep_ret);
+    *race_at(d, SLOT_S + 0, i) = make_float4(s[0], s[1], s[2], s[3]);
+    *race_at(d, SLOT_S + 1, i) = make_float4(s[4], s[5], s[6], s[7]);
+    *race_at(d, SLOT_S + 2, i) = make_float4(s[8], s[9], s[10], s[11]);
+    *race_at(d, SLOT_S + 3, i) = make_float4(s[12], s[13], s[14], s[15]);
+    *race_at(d, SLOT_S + 4, i) = make_float4(s[16], __int_as_float(tick), __int_as_float(ring_word), ep_ret);
 }
 
 __device__ __forceinline__ void race_load_external_ring(const RaceDev &d, int i, int r, float ring[6]) {
@@ -185,8 +214,8 @@ __device__ __forceinline__ void race_load_external_ring(const RaceDev &d, int i,
 }
 
 __device__ __forceinline__ void race_store_current_ring(const RaceDev &d, int i, const float ring[6]) {
-    d.C0[i] = make_float4(ring[0], ring[1], ring[2], ring[3]);
-    reinterpret_cast<float2 *>(&d.T[i])[1] = make_float2(ring[4], ring[5]);
+    *race_at(d, SLOT_C0, i) = make_float4(ring[0], ring[1], ring[2], ring[3]);
+    reinterpret_cast<float2 *>(race_at(d, SLOT_T, i))[1] = make_float2(ring[4], ring[5]);
 }
 
 // ---------------------------------------------------------------- episode generator
@@ -295,10 +324,10 @@ __device__ __noinline__ void race_next_ring(const RaceDev &d, int i, uint32_t ep
 }
 
 __device__ __forceinline__ void race_store_params(const RaceDev &d, int i, const float p[13], uint32_t episode) {
-    d.P[0 * (size_t)d.ld + i] = make_float4(p[0], p[1], p[2], p[3]);
-    d.P[1 * (size_t)d.ld + i] = make_float4(p[4], p[5], p[6], p[7]);
-    d.P[2 * (size_t)d.ld + i] = make_float4(p[8], p[9], p[10], p[11]);
-    reinterpret_cast<float2 *>(&d.T[i])[0] = make_float2(p[12], __uint_as_float(episode));
+    *race_at(d, SLOT_P + 0, i) = make_float4(p[0], p[1], p[2], p[3]);
+    *race_at(d, SLOT_P + 1, i) = make_float4(p[4], p[5], p[6], p[7]);
+    *race_at(d, SLOT_P + 2, i) = make_float4(p[8], p[9], p[10], p[11]);
+    reinterpret_cast<float2 *>(race_at(d, SLOT_T, i))[0] = make_float2(p[12], __uint_as_float(episode));
 }
 
 // Generate episode `episode` of env i into the env's PREPARED slot (next params, spawn, ring 0)
@@ -362,24 +391,27 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // per-warp shared memory:
 //   stage  11 float4 per lane: inputs of the NEXT tile, in flight while the current tile computes
 //   obs    the 32x29 observation tile of the current tile (staging for the coalesced store)
-//   adopt  6 float4 per lane: the prepared episode of a lane whose env just finished, in
-//          flight while the NEXT tile computes
+//   adopt  6 float4 per lane: the prepared episodes of the envs of an install pass, in flight
+//          while a tile computes
+//   list   up to RACE_INSTALL_CAP (env, episode) pairs: envs of this warp's tiles that finished and
+//          wait for their next episode (see race_step_kernel)
 constexpr int RACE_STAGE_SLOTS = 11; // act, S0..S4, P0..P2, C0, T
 constexpr int RACE_ADOPT_SLOTS = 6;  // N0..N2, (spawn, j_mot), ring0 (pos,n.x), (n.y, n.z, episode tag, -)
 constexpr int RACE_STAGE_BYTES = RACE_STAGE_SLOTS * 32 * 16;
 constexpr int RACE_TILE_BYTES = 32 * RACE_OBS * 4;
-constexpr int RACE_WARP_SMEM = RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_SLOTS * 32 * 16;
+constexpr int RACE_ADOPT_BYTES = RACE_ADOPT_SLOTS * 32 * 16;
+constexpr int RACE_WARP_SMEM = RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_BYTES + RACE_INSTALL_CAP * 8;
 constexpr int RACE_SMEM_BYTES = RACE_WARPS * RACE_WARP_SMEM;
 
-__device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *stage, int lane, int i) {
+__device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, const float *act, float4 *stage, int lane, int i) {
     const size_t ld = d.ld;
-    cp_async16(&stage[0 * 32 + lane], reinterpret_cast<const float4 *>(d.act_in) + i);
+    cp_async16(&stage[0 * 32 + lane], reinterpret_cast<const float4 *>(act) + i);
 #pragma unroll
-    for (int k = 0; k < 5; k++) cp_async16(&stage[(1 + k) * 32 + lane], &d.S[k * ld + i]);
+    for (int k = 0; k < 5; k++) cp_async16(&stage[(1 + k) * 32 + lane], race_at(d, SLOT_S + k, i));
 #pragma unroll
-    for (int k = 0; k < 3; k++) cp_async16(&stage[(6 + k) * 32 + lane], &d.P[k * ld + i]);
-    cp_async16(&stage[9 * 32 + lane], &d.C0[i]);
-    cp_async16(&stage[10 * 32 + lane], &d.T[i]);
+    for (int k = 0; k < 3; k++) cp_async16(&stage[(6 + k) * 32 + lane], race_at(d, SLOT_P + k, i));
+    cp_async16(&stage[9 * 32 + lane], race_at(d, SLOT_C0, i));
+    cp_async16(&stage[10 * 32 + lane], race_at(d, SLOT_T, i));
 }
 
 // the prepared episode of env i -> this lane's adopt slots
@@ -397,7 +429,8 @@ __device__ __forceinline__ void race_prefetch_slot(const RaceDev &d, float4 *ado
 // written.  The slot's episode tag is verified; on a mismatch (slot not restocked yet: an env
 // finishing again within a step or two, a full refill ring, or state edited from outside) or
 // when the caller already knows the slot may be mid-rewrite (`trust` false) the episode is
-// generated in place instead: same pure function of (seed, env, episode number).
+// generated in place instead: same pure function of (seed, env, episode number).  Called from
+// install passes only: every active lane holds a different finished env.
 template <bool STRICT>
 __device__ __forceinline__ void race_adopt_from_smem(const RaceDev &d, const float4 *adopt, int lane, int i,
                                                      uint32_t want, bool trust, float *obs_row) {
@@ -411,10 +444,10 @@ __device__ __forceinline__ void race_adopt_from_smem(const RaceDev &d, const flo
         s[6] = 1.0f;
         s[0] = sp.x; s[1] = sp.y; s[2] = sp.z;
         const float ring0[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
-        d.P[0 * ld + i] = a;
-        d.P[1 * ld + i] = b;
-        d.P[2 * ld + i] = c;
-        reinterpret_cast<float2 *>(&d.T[i])[0] = make_float2(sp.w, __uint_as_float(want));
+        *race_at(d, SLOT_P + 0, i) = a;
+        *race_at(d, SLOT_P + 1, i) = b;
+        *race_at(d, SLOT_P + 2, i) = c;
+        reinterpret_cast<float2 *>(race_at(d, SLOT_T, i))[0] = make_float2(sp.w, __uint_as_float(want));
         race_store_state(d, i, s, 0, 0, 0.0f);
         race_store_current_ring(d, i, ring0);
         race_observe<STRICT>(s, c.z, ring0, obs_row);
@@ -424,31 +457,51 @@ __device__ __forceinline__ void race_adopt_from_smem(const RaceDev &d, const flo
 }
 
 // ---------------------------------------------------------------- the step kernel
-// ONE launch per vec_step.  Persistent grid (RACE_MIN_CTAS resident CTAs per SM), RACE_WARPS
-// warps each; a warp owns one tile of 32 envs at a time (one env per lane).
+// ONE launch per vec_step -- or per run of vec_steps when the actions are already on the device
+// (d.steps > 1, b2d_vec_step_tape).  Persistent grid (RACE_MIN_CTAS resident CTAs per SM),
+// RACE_WARPS warps each; a warp owns one tile of 32 envs at a time (one env per lane).
 //
 // Tile order.  CTA c owns tiles c, c+G, c+2G, ... (G = grid size; the same CTA owns the same
-// envs in every launch) and its warps draw them through a SHARED-MEMORY ticket, so a warp that
-// spent time restocking episode slots simply takes fewer tiles.  Across the grid the warps
-// sweep every array as one contiguous frontier, which is what DRAM wants (sharded dynamic
-// claims ran 4% slower with 16 frontiers and 50% slower with 256).
+// envs in every launch).  Across the grid the warps sweep every array as one contiguous
+// frontier, which is what DRAM wants (sharded dynamic claims ran 4% slower with 16 frontiers and
+// 50% slower with 256).
+//   * single step: the CTA's warps draw its tiles through a SHARED-MEMORY ticket, so a warp that
+//     spent time restocking episode slots simply takes fewer tiles.
+//   * fused steps: warp w owns the CTA's tiles w, w+W, w+2W, ... for the whole launch and walks
+//     them step after step.  Envs are independent and a warp only ever reads state it wrote
+//     itself, so there is NO barrier of any kind between steps -- not across the grid, not in
+//     the CTA: the memory pipeline never drains, the first-tile latency and the straggler tail
+//     of a launch are paid once per launch instead of once per step, and a warp that restocks
+//     slots catches up over the following steps.
 //
-// Everything with memory latency is software-pipelined one tile deep and costs no registers:
-//   * the inputs of the warp's next tile stream into shared memory (cp.async) while the
-//     current tile computes (~1000 FP32 instructions per lane);
-//   * a lane whose env finished streams the env's prepared next episode into shared memory
-//     and installs it one tile later (no dependent-load stall, no second kernel).
+// The inputs of the warp's next tile stream into shared memory (cp.async) while the current
+// tile computes (~1000 FP32 instructions per lane): no register cost, no dependent-load stall.
 // Observation rows ([N,29] row-major, 116 B: not a multiple of 16) are staged per warp in
 // shared memory and leave as lane-consecutive float4 stores, 512 B per instruction.
+//
+// Auto-reset costs warp time in proportion to the envs that finish, not to the tiles that
+// contain one.  About 2.5 % of the envs finish per step, i.e. more than half of all tiles hold
+// a finished env; installing its next episode right there kept 31 lanes idle for ~1500 cycles
+// (measured: 21 % of the warps' time).  Instead a finished lane only appends (env, next
+// episode) to its WARP's install list in shared memory.  When 16 are listed or the oldest has
+// waited RACE_INSTALL_AGE tiles, the warp starts an INSTALL PASS with a different finished env
+// on every lane: the prepared slots are gathered by cp.async while the next tile computes and
+// installed one tile later (params, spawn state, ring 0, first observation row).  The list is
+// private to the warp: no atomics, and the row an env's tile store left behind is overwritten
+// in program order by the same warp.  Leftovers are installed before the launch ends, so every
+// vec_step leaves the reset observation in place like the reference's c_step does.
+// Fused steps add one rule: an env listed in step t is installed before its tile's inputs for
+// step t+1 are prefetched (RACE_INSTALL_AGE <= tiles per warp - 3, enforced by the host).
 //
 // Restocking.  Installing an episode consumes the env's prepared slot; the slot is described
 // by an entry in the CTA's refill ring (shared memory).  Whenever 32 entries are waiting, the
 // next warp that finishes a tile regenerates them in one pass with every lane busy (Philox +
-// trig, ~7800 instructions).  One pass at a time per CTA and FIFO order, so two generations for
-// the same env never interleave.  Fewer than 32 entries left at the end of a launch are carried
-// to the next one (d.carry); an env listed there may have its slot rewritten while the next
-// launch runs, so if it finishes again meanwhile it is generated in place (`s_pending`).
-// Enqueueing is best effort: a full ring drops the entry and the tag check covers it later.
+// trig).  One pass at a time per CTA and FIFO order, so two generations for the same env never
+// interleave.  What is left at the end of a launch (up to RACE_CARRY entries) is carried to
+// the next launch (d.carry) and regenerated there in between tiles; an env listed there may
+// have its slot rewritten while that launch runs, so if it finishes again before its pass is
+// done it is generated in place (`s_pending`).  Enqueueing is best effort: a full ring drops
+// the entry and the tag check covers it later.
 //
 // No global atomic in this kernel returns a value (see Ctl).
 template <bool STRICT>
@@ -456,22 +509,22 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ int s_done;
     __shared__ int s_acc[8];
+    __shared__ int s_score;                       // sum of score over the episodes that ended in the launch's last step
     __shared__ unsigned int s_ticket;             // tile tickets handed out so far in this CTA
     __shared__ unsigned int s_q_head, s_q_tail;   // refill ring: entries [tail, head), monotonic
     __shared__ unsigned int s_q_lock;             // one refill pass at a time
-    __shared__ unsigned int s_npending;           // carried-over entries whose slots are not restocked yet
+    __shared__ unsigned int s_pend_lo, s_pend_hi; // carried-over entries [lo, hi) of s_pending are not restocked yet
     __shared__ unsigned int s_pending[RACE_CARRY];
     __shared__ uint2 s_queue[RACE_QUEUE_CAP];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int G = gridDim.x;
-    const int ntiles = min((d.n + 31) >> 5, d.tile_end);
     const bool inject = d.reset_mode == 1; // B2D_RESET_INJECT (parity hook)
     float4 *stage = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM);
     float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES);
     float4 *adopt = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES + RACE_TILE_BYTES);
+    uint2 *ilist = reinterpret_cast<uint2 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_BYTES);
     float *my_row = tile_obs + lane * RACE_OBS;
 
     // Launch overlap (b2d_vec_step_tape): the next launch of this kernel may begin while this one
@@ -495,34 +548,66 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
 #if B2D_EXPERIMENT_TIMING
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_go));
 #endif
+    unsigned long long t_go;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_go));
+    // This CTA's tiles: an ascending list (d.tile_list), the same in every launch until the host
+    // rebalances it.  A launch covers the tiles in [tile_begin, tile_end): ordinals [o_lo, o_hi).
+    const int *my_tiles = d.tile_list + __ldg(&d.tile_off[blockIdx.x]);
+    int o_lo = 0, o_hi = __ldg(&d.tile_off[blockIdx.x + 1]) - __ldg(&d.tile_off[blockIdx.x]);
+    if (d.tile_begin > 0 || d.tile_end < ((d.n + 31) >> 5)) { // a chunk of the vector (host-buffer pipeline)
+        int below_begin = 0, below_end = 0;
+        for (int k = lane; k < o_hi; k += 32) {
+            const int t = __ldg(&my_tiles[k]);
+            below_begin += t < d.tile_begin;
+            below_end += t < d.tile_end;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            below_begin += __shfl_xor_sync(0xffffffffu, below_begin, o);
+            below_end += __shfl_xor_sync(0xffffffffu, below_end, o);
+        }
+        o_lo = below_begin;
+        o_hi = below_end;
+    }
+    constexpr int NO_TILE = 0x7fffffff;
+    const bool fused = d.steps > 1;
+    const size_t tape_stride = (size_t)d.n * 4;
     // the first two tickets of every warp are static, so the first loads leave before any barrier
-    // CTA c owns the tiles congruent to c modulo G, whatever range a launch covers
-    const int first_tile = d.tile_begin + (int)((blockIdx.x + G - d.tile_begin % G) % G);
-    int tile = warp * G + first_tile;
-    int next = (RACE_WARPS + warp) * G + first_tile;
-    if (tile < ntiles && tile * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, tile * 32 + lane);
+    int ord = o_lo + warp, nord = o_lo + RACE_WARPS + warp;      // ordinals (in the CTA's list) of `tile` and `next`
+    int tstep = 0, nstep = 0;                                    // which step of the launch they belong to
+    if (fused && nord >= o_hi) { nord = ord; nstep = 1; }
+    int tile = ord < o_hi ? __ldg(&my_tiles[ord]) : NO_TILE;     // the tile being stepped
+    int next = nord < o_hi ? __ldg(&my_tiles[nord]) : NO_TILE;   // the tile after it
+    const float *act_cur = d.act_in + (size_t)(d.tape_first % d.tape_len) * tape_stride;
+    if (tile != NO_TILE && tile * 32 + lane < d.n) race_prefetch_tile(d, act_cur, stage, lane, tile * 32 + lane);
     cp_async_commit(); // group: inputs of the first tile
-    cp_async_commit(); // group: (empty) adoption loads "of the tile before the first"
 
     if (tid < 8) s_acc[tid] = 0;
+    if (tid == 8) s_score = 0;
     for (int k = tid; k < RACE_QUEUE_CAP; k += RACE_BLOCK) s_queue[k] = make_uint2(QUEUE_EMPTY, 0u);
     __syncthreads();
-    if (warp == 0) { // entries carried over from the previous launch seed the ring
-        const uint2 e = __ldcg(&d.carry[(size_t)blockIdx.x * RACE_CARRY + lane]);
-        const bool have = e.x != QUEUE_EMPTY && !inject;
-        const unsigned int m = __ballot_sync(0xffffffffu, have);
-        if (have) {
-            const int slot = __popc(m & ((1u << lane) - 1u));
-            s_queue[slot] = e;
-            s_pending[slot] = e.x;
+    {   // entries carried over from the previous launch seed the ring (stored compacted: [0, count) valid)
+        int carried = 0;
+        for (int base = 0; base < RACE_CARRY; base += RACE_BLOCK) {
+            const int k = base + tid;
+            bool have = false;
+            if (k < RACE_CARRY) {
+                const uint2 e = __ldcg(&d.carry[(size_t)blockIdx.x * RACE_CARRY + k]);
+                have = e.x != QUEUE_EMPTY && !inject;
+                if (have) {
+                    s_queue[k] = e;
+                    s_pending[k] = e.x;
+                }
+            }
+            carried += __syncthreads_count(have);
         }
-        if (lane == 0) {
+        if (tid == 0) {
             s_done = 0;
             s_ticket = 2 * RACE_WARPS;
-            s_q_head = (unsigned int)__popc(m);
+            s_q_head = (unsigned int)carried;
             s_q_tail = 0u;
             s_q_lock = 0u;
-            s_npending = (unsigned int)__popc(m);
+            s_pend_lo = 0u;
+            s_pend_hi = (unsigned int)carried;
         }
     }
     __syncthreads();
@@ -532,22 +617,79 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     const long long t_begin = clock64();
 #endif
 
-    // state carried from one tile to the next
-    bool pend_adopt = false; // this lane's env finished in the previous tile (Philox mode)
-    bool pend_trust = true;  // ... and its prepared slot cannot be mid-rewrite
-    int pend_i = 0;
-    uint32_t pend_want = 0u; // episode number it starts next
-    unsigned int pend_m = 0u; // ballot of pend_adopt
-    int claim = 0;            // lane 0: ticket for the tile after `next`
+    int claim = 0;    // lane 0: ticket for the tile after `next` (single step)
+    int listed = 0;   // entries in this warp's install list (warp-uniform)
+    int age = 0;      // tiles since the list was last empty
+    int inflight = 0; // the first `inflight` entries of the list have their prepared slots on the way (cp.async)
+    unsigned int trust_m = 0u; // ... and these of them may adopt the slot (see s_pending)
+    const int install_age = d.install_age;
 
-    while (true) {
-        const bool have_tile = tile < ntiles;
-        if (!have_tile && pend_m == 0u) break;
+    // Install the `inflight` envs at the front of the list (their slots have landed), one per lane.
+    auto install_pass = [&]() {
+        const int cnt = inflight;
+        uint2 e = make_uint2(0u, 0u);
+        if (lane < cnt) {
+            e = ilist[lane];
+            race_adopt_from_smem<STRICT>(d, adopt, lane, (int)e.x, e.y, (trust_m >> lane) & 1u, d.obs + (size_t)e.x * RACE_OBS);
+        }
+        __syncwarp();
+        // the consumed slots go to the CTA's refill ring: one reservation per pass, best effort
+        unsigned int base = QUEUE_EMPTY;
+        if (lane == 0) {
+            for (;;) {
+                const unsigned int h = *(volatile unsigned int *)&s_q_head;
+                if (h - *(volatile unsigned int *)&s_q_tail + (unsigned int)cnt > (unsigned int)RACE_QUEUE_CAP) break; // full: drop
+                if (atomicCAS(&s_q_head, h, h + (unsigned int)cnt) == h) {
+                    base = h;
+                    break;
+                }
+            }
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < cnt && base != QUEUE_EMPTY) {
+            volatile uint2 *q = &s_queue[(base + (unsigned int)lane) & (RACE_QUEUE_CAP - 1)];
+            q->y = e.y + 1u; // .x (the non-empty marker) last
+            q->x = e.x;
+        }
+        // the rest of the list moves to the front
+        const int rest = listed - cnt; // < RACE_INSTALL_CAP - 32
+        uint2 mv[RACE_INSTALL_CAP / 32 - 1];
+#pragma unroll
+        for (int k = 0; k < RACE_INSTALL_CAP / 32 - 1; k++)
+            if (lane + 32 * k < rest) mv[k] = ilist[cnt + lane + 32 * k];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < RACE_INSTALL_CAP / 32 - 1; k++)
+            if (lane + 32 * k < rest) ilist[lane + 32 * k] = mv[k];
+        __syncwarp();
+        listed = rest;
+        inflight = 0;
+        if (rest == 0) age = 0;
+    };
+    // Start gathering the prepared slots of (up to 32 of) the listed envs.
+    auto install_gather = [&]() {
+        const int cnt = min(listed, 32);
+        bool trust = true;
+        if (lane < cnt) {
+            const uint32_t ei = ilist[lane].x;
+            // a carried-over entry for this env whose slot is not restocked yet: the slot may be mid-rewrite
+            const unsigned int lo = *(volatile unsigned int *)&s_pend_lo, hi = *(volatile unsigned int *)&s_pend_hi;
+            for (unsigned int k = lo; k < hi; k++) trust = trust && s_pending[k] != ei;
+            race_prefetch_slot(d, adopt, lane, (int)ei);
+        }
+        trust_m = __ballot_sync(0xffffffffu, trust);
+        inflight = cnt;
+    };
+
+    while (tile != NO_TILE && tstep < d.steps) {
         const int i = tile * 32 + lane;
-        const bool valid = have_tile && i < d.n;
+        const bool valid = i < d.n;
         B2D_TICK(t0);
-        cp_async_wait<1>(); // this tile's inputs have landed (the newest group, adoption loads, may still fly)
+        cp_async_wait<0>(); // this tile's inputs (and the slots of a started install pass) have landed
         B2D_TICK(t1);
+        if (inflight) install_pass();
+        if (listed > 0 && (listed >= 16 || age >= install_age)) install_gather();
+        B2D_TICK(t1b);
         const float4 a4 = stage[0 * 32 + lane];
         const float4 q0 = stage[1 * 32 + lane], q1 = stage[2 * 32 + lane], q2 = stage[3 * 32 + lane],
                      q3 = stage[4 * 32 + lane], q4 = stage[5 * 32 + lane];
@@ -555,9 +697,12 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         const float4 c0 = stage[9 * 32 + lane];
         const float4 tl = stage[10 * 32 + lane]; // (j_mot, episode, ring n.y, ring n.z)
         __syncwarp();
-        if (have_tile && next < ntiles && next * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, next * 32 + lane);
-        cp_async_commit(); // group: inputs of the next tile
-        if (have_tile && lane == 0) claim = (int)atomicAdd(&s_ticket, 1u); // shared memory: lands within the tile
+        if (next != NO_TILE && nstep < d.steps && next * 32 + lane < d.n) {
+            const float *act_next = d.act_in + (size_t)((d.tape_first + nstep) % d.tape_len) * tape_stride;
+            race_prefetch_tile(d, act_next, stage, lane, next * 32 + lane);
+        }
+        cp_async_commit(); // group: inputs of the next tile + the slots of an install pass
+        if (!fused && lane == 0) claim = (int)atomicAdd(&s_ticket, 1u); // shared memory: lands within the tile
 
         float s[17];
         float ring[6];
@@ -626,7 +771,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         }
         B2D_TICK(t2);
 
-        // ---- finished lanes book the episode; their next episode is installed one tile later
+        // ---- finished lanes book the episode and list the env for its next one
         const bool finished = cause >= 0;
         const bool adopt_now = finished && !inject;
         const unsigned int m = __ballot_sync(0xffffffffu, adopt_now);
@@ -641,14 +786,17 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
             atomicAdd(&s_acc[ACC_LENGTH], tick);
             atomicAdd(&s_acc[ACC_RINGS], ring_idx);
             if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
+            if (tstep == d.steps - 1) atomicAdd(&s_score, ring_idx);
             if (inject) race_inject_episode<STRICT>(d, i, episode + 1u, my_row);
+            else ilist[listed + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)i, episode + 1u);
         }
+        listed += __popc(m);
+        if (listed > 0) age += 1;
         __syncwarp();
 
         // ---- observations out: the warp's 3,712-byte tile as 232 lane-consecutive float4.
-        // Rows of lanes that finished hold stale data here; they are rewritten when the episode
-        // is installed one tile later.
-        if (have_tile) {
+        // Rows of lanes that finished hold stale data here; they are rewritten by the install pass.
+        {
             const int rows = min(32, d.n - tile * 32);
             float *gobs = d.obs + (size_t)tile * 32 * RACE_OBS;
             if (rows == 32) {
@@ -663,30 +811,6 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
             __syncwarp();
         }
         B2D_TICK(t3);
-
-        // ---- install the next episode of the envs that finished in the PREVIOUS tile
-        cp_async_wait<1>(); // their prepared slots have landed (only the next tile's inputs may still fly)
-        B2D_TICK(t4);
-        if (pend_m != 0u) {
-            __syncwarp(); // their stale rows (stored by other lanes one tile ago) are ordered before the rewrite
-            if (pend_adopt) {
-                race_adopt_from_smem<STRICT>(d, adopt, lane, pend_i, pend_want, pend_trust, d.obs + (size_t)pend_i * RACE_OBS);
-                const uint2 e = make_uint2((uint32_t)pend_i, pend_want + 1u); // the slot is consumed
-                // best-effort enqueue of the consumed slot
-                for (;;) {
-                    const unsigned int h = *(volatile unsigned int *)&s_q_head;
-                    if (h - *(volatile unsigned int *)&s_q_tail >= (unsigned int)RACE_QUEUE_CAP) break; // full: drop
-                    if (atomicCAS(&s_q_head, h, h + 1u) == h) {
-                        volatile uint2 *q = &s_queue[h & (RACE_QUEUE_CAP - 1)];
-                        q->y = e.y; // .x (the non-empty marker) last
-                        q->x = e.x;
-                        break;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        B2D_TICK(t5);
 
         // ---- restock: 32 waiting entries -> one full-occupancy generation pass by this warp
         if (!inject) {
@@ -711,42 +835,51 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
                 __syncwarp();
                 if (lane == 0) *(volatile unsigned int *)&s_q_tail = take + 32u; // the 32 ring slots may be reused
                 race_fill_slot(d, (int)e.x, e.y);
-                // Slots complete before the pending list is lifted / the lock is released.  The readers
+                // Slots complete before the pending range shrinks / the lock is released.  The readers
                 // this orders against are warps of THIS CTA (CTA scope: a device-scope fence here was
                 // measured at ~10 us under load); the next launch is ordered by the epilogue's fence.
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0) {
-                    if (take == 0u) *(volatile unsigned int *)&s_npending = 0u; // carried entries sit at the ring's front
+                    // carried entries sit at the ring's front, in s_pending order
+                    const unsigned int hi = *(volatile unsigned int *)&s_pend_hi;
+                    if (take < hi) *(volatile unsigned int *)&s_pend_lo = min(hi, take + 32u);
                     atomicExch(&s_q_lock, 0u);
                 }
             }
         }
         B2D_TICK(t6);
-
-        // ---- start streaming the prepared slots of the envs that finished in THIS tile
-        bool trust = true;
-        if (adopt_now) {
-            const unsigned int np = *(volatile unsigned int *)&s_npending;
-            for (unsigned int k = 0; k < np; k++) trust = trust && s_pending[k] != (unsigned int)i;
-            race_prefetch_slot(d, adopt, lane, i);
-        }
-        cp_async_commit(); // group: adoption loads of this tile (possibly empty)
-        pend_adopt = adopt_now;
-        pend_trust = trust;
-        pend_i = i;
-        pend_want = episode + 1u;
-        pend_m = m;
 #if B2D_EXPERIMENT_TIMING
-        tm_wait += t1 - t0; tm_math += t2 - t1; tm_store += t3 - t2; tm_adopt += t4 - t3; tm_inst += t5 - t4;
-        tm_refill += t6 - t5; tm_iters += 1;
+        tm_wait += t1 - t0; tm_inst += t1b - t1; tm_math += t2 - t1b; tm_store += t3 - t2;
+        tm_refill += t6 - t3; tm_iters += 1;
 #endif
-        if (have_tile) {
-            tile = next;
-            next = __shfl_sync(0xffffffffu, claim, 0) * G + first_tile;
+        tile = next;
+        tstep = nstep;
+        ord = nord;
+        if (fused) {
+            nord = ord + RACE_WARPS;
+            if (nord >= o_hi) { nord = o_lo + warp; nstep = tstep + 1; }
+        } else {
+            nord = o_lo + __shfl_sync(0xffffffffu, claim, 0);
         }
+        next = nord < o_hi ? __ldg(&my_tiles[nord]) : NO_TILE; // one address for the whole warp; needed a tile from now
     }
-    cp_async_wait<0>();
+    {   // every env that finished in this launch starts its next episode in this launch
+        B2D_TICK(t7);
+        cp_async_wait<0>();
+        while (inflight || listed > 0) {
+            if (inflight) install_pass();
+            if (listed > 0) {
+                install_gather();
+                cp_async_commit();
+                cp_async_wait<0>();
+            }
+        }
+        B2D_TICK(t8);
+#if B2D_EXPERIMENT_TIMING
+        tm_adopt += t8 - t7;
+#endif
+    }
 
 #if B2D_EXPERIMENT_TIMING
     if (lane == 0) {
@@ -767,24 +900,24 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     last = __shfl_sync(0xffffffffu, last, 0);
     if (last) {
         __threadfence_block();
-        // whole passes still waiting (only when slots were consumed faster than they could be restocked)
+        // more waiting than can be carried (only when slots were consumed much faster than usual): generate now
         unsigned int tl0 = *(volatile unsigned int *)&s_q_tail;
         const unsigned int hd = *(volatile unsigned int *)&s_q_head;
-        while (hd - tl0 >= 32u) {
+        while (hd - tl0 > (unsigned int)RACE_CARRY) {
             const uint2 e = s_queue[(tl0 + lane) & (RACE_QUEUE_CAP - 1)];
             race_fill_slot(d, (int)e.x, e.y);
             tl0 += 32u;
         }
-        // the rest (< 32 entries) is carried to the next launch
-        {
+        // the rest is carried to the next launch, compacted at the front of the CTA's list
+        for (unsigned int k = (unsigned int)lane; k < (unsigned int)RACE_CARRY; k += 32u) {
             uint2 e = make_uint2(QUEUE_EMPTY, 0u);
-            if ((unsigned int)lane < hd - tl0) e = s_queue[(tl0 + lane) & (RACE_QUEUE_CAP - 1)];
-            d.carry[(size_t)blockIdx.x * RACE_CARRY + lane] = e;
+            if (k < hd - tl0) e = s_queue[(tl0 + k) & (RACE_QUEUE_CAP - 1)];
+            d.carry[(size_t)blockIdx.x * RACE_CARRY + k] = e;
         }
         if (lane < 7) {
             const int v = s_acc[lane];
             if (v != 0) atomicAdd((unsigned long long *)&d.ctl->acc[lane], (unsigned long long)(long long)v);
-            if (lane == ACC_RINGS) d.cta_score[blockIdx.x] = (long long)v + (d.score_add ? d.cta_score[blockIdx.x] : 0ll);
+            if (lane == ACC_RINGS) d.cta_score[blockIdx.x] = (long long)s_score + (d.score_add ? d.cta_score[blockIdx.x] : 0ll);
         }
 #if B2D_EXPERIMENT_TIMING
         if (lane == 0) {
@@ -800,7 +933,11 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
 #endif
         __syncwarp();
         if (lane == 0) {
-            if (d.count_step) atomicAdd(&d.ctl->ctas_done, 1u); // result unused: a reduction, not a returning atomic
+            // per-CTA wall time of this launch: what the host balances the tile lists with (b2d_vec_step_tape)
+            unsigned long long t_done;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_done));
+            d.cta_ns[blockIdx.x] = t_done - t_go;
+            if (d.count_step) atomicAdd(&d.ctl->ctas_done, (unsigned int)d.steps); // result unused: a reduction, not a returning atomic
             __threadfence();
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(d.chain + blockIdx.x), "r"(d.seq) : "memory");
         }
@@ -822,8 +959,8 @@ __global__ void __launch_bounds__(128) race_reset_kernel(const __grid_constant__
 
 // Restock every slot still listed in the carry-over lists now (instead of during the next
 // step) -- used before state is edited from outside (put_state), so that no refill is pending
-// while an edited env may finish again.  One warp per step CTA.
-__global__ void __launch_bounds__(32) race_drain_kernel(const __grid_constant__ RaceDev d) {
+// while an edited env may finish again.  One thread per carry entry.
+__global__ void __launch_bounds__(RACE_CARRY) race_drain_kernel(const __grid_constant__ RaceDev d) {
     uint2 *slot = &d.carry[(size_t)blockIdx.x * RACE_CARRY + threadIdx.x];
     const uint2 e = *slot;
     if (e.x != QUEUE_EMPTY) race_fill_slot(d, (int)e.x, e.y);
@@ -864,12 +1001,12 @@ __global__ void __launch_bounds__(128) race_observe_kernel(const RaceDev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
     const size_t ld = d.ld;
-    float4 q0 = d.S[0 * ld + i], q1 = d.S[1 * ld + i], q2 = d.S[2 * ld + i], q3 = d.S[3 * ld + i], q4 = d.S[4 * ld + i];
+    float4 q0 = *race_at(d, SLOT_S + 0, i), q1 = *race_at(d, SLOT_S + 1, i), q2 = *race_at(d, SLOT_S + 2, i), q3 = *race_at(d, SLOT_S + 3, i), q4 = *race_at(d, SLOT_S + 4, i);
     float s[17] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x};
-    float4 c0 = d.C0[i];
-    float4 c1 = d.T[i];
+    float4 c0 = *race_at(d, SLOT_C0, i);
+    float4 c1 = *race_at(d, SLOT_T, i);
     float ring[6] = {c0.x, c0.y, c0.z, c0.w, c1.z, c1.w};
-    race_observe<true>(s, d.P[2 * ld + i].z, ring, d.obs + (size_t)i * RACE_OBS);
+    race_observe<true>(s, race_at(d, SLOT_P + 2, i)->z, ring, d.obs + (size_t)i * RACE_OBS);
 }
 
 // blob layout: include/b200drone.h b2d_get_state
@@ -879,13 +1016,13 @@ __global__ void race_pack_kernel(const RaceDev d, const int *ids, int n, float *
     const int i = ids ? ids[k] : k;
     const size_t ld = d.ld;
     float *b = blobs + (size_t)k * (33 + 6 * d.max_rings);
-    float4 q0 = d.S[0 * ld + i], q1 = d.S[1 * ld + i], q2 = d.S[2 * ld + i], q3 = d.S[3 * ld + i], q4 = d.S[4 * ld + i];
-    float4 p0 = d.P[0 * ld + i], p1 = d.P[1 * ld + i], p2 = d.P[2 * ld + i];
+    float4 q0 = *race_at(d, SLOT_S + 0, i), q1 = *race_at(d, SLOT_S + 1, i), q2 = *race_at(d, SLOT_S + 2, i), q3 = *race_at(d, SLOT_S + 3, i), q4 = *race_at(d, SLOT_S + 4, i);
+    float4 p0 = *race_at(d, SLOT_P + 0, i), p1 = *race_at(d, SLOT_P + 1, i), p2 = *race_at(d, SLOT_P + 2, i);
     b[0] = q0.x; b[1] = q0.y; b[2] = q0.z; b[3] = q0.w; b[4] = q1.x; b[5] = q1.y; b[6] = q1.z; b[7] = q1.w;
     b[8] = q2.x; b[9] = q2.y; b[10] = q2.z; b[11] = q2.w; b[12] = q3.x; b[13] = q3.y; b[14] = q3.z; b[15] = q3.w;
     b[16] = q4.x;
     b[17] = p0.x; b[18] = p0.y; b[19] = p0.z; b[20] = p0.w; b[21] = p1.x; b[22] = p1.y; b[23] = p1.z; b[24] = p1.w;
-    const float4 pj = d.T[i];
+    const float4 pj = *race_at(d, SLOT_T, i);
     b[25] = p2.x; b[26] = p2.y; b[27] = p2.z; b[28] = p2.w; b[29] = pj.x;
     const int ring_word = __float_as_int(q4.z);
     b[30] = (float)__float_as_int(q4.y); b[31] = (float)(ring_word & RING_INDEX_MASK); b[32] = q4.w;
@@ -912,7 +1049,7 @@ __global__ void race_unpack_kernel(const RaceDev d, const int *ids, int n, const
     for (int c = 0; c < 17; c++) s[c] = b[c];
     const int ring_idx = (int)b[31];
     race_store_state(d, i, s, (int)b[30], ring_idx | RING_EXTERNAL, b[32]);
-    race_store_params(d, i, b + 17, __float_as_uint(d.T[i].y)); // the episode number is kept
+    race_store_params(d, i, b + 17, __float_as_uint(race_at(d, SLOT_T, i)->y)); // the episode number is kept
     for (int r = 0; r < d.max_rings; r++) {
         const float *g = b + 33 + 6 * r;
         d.X0[(size_t)r * ld + i] = make_float4(g[0], g[1], g[2], g[3]);
