@@ -342,7 +342,7 @@ extern "C" int b2d_vec_close(b2d_vec *v) {
         unsigned long long h[12];
         cudaMemcpy(h, v->race.ctl->dbg, sizeof(h), cudaMemcpyDeviceToHost);
         const double it = (double)h[4], w = (double)h[7];
-        fprintf(stderr, "[b2d timing] per tile iteration (cycles): wait_inputs %.0f  compute %.0f  store %.0f  tail_install %.0f  install %.0f  refill %.0f | per warp-launch: total %.0f  iterations %.2f\n",
+        fprintf(stderr, "[b2d timing] per tile iteration (cycles): wait_inputs %.0f  compute %.0f  store %.0f  tail_install+loop_end %.0f  install %.0f  refill %.0f | per warp-launch: total %.0f  iterations %.2f\n",
                 h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[8] / it, h[5] / it, h[6] / w, it / w);
         if (getenv("B2D_TRACE_FILE")) {
             std::vector<unsigned long long> tr((size_t)v->step_ctas * 4);

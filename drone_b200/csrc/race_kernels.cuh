@@ -56,7 +56,8 @@ constexpr int RESET_MAX_ATTEMPTS = 16;
 constexpr int RACE_QUEUE_CAP = 256;            // refill ring of one CTA (entries, power of two)
 constexpr int RACE_CARRY = 128;                // refill entries a CTA may carry over to the next launch
 constexpr int RACE_INSTALL_AGE = 8;             // tiles a finished env waits at most for its install pass to start
-constexpr int RACE_FUSED_MIN_TILES = RACE_INSTALL_AGE + 3; // tiles per warp a fused launch needs (see race_step_kernel)
+constexpr int RACE_FUSED_MIN_TILES = RACE_INSTALL_AGE + 6; // tiles per warp a fused launch needs (see race_step_kernel)
+constexpr int RACE_PASS = 16;                  // envs per install pass (half a warp: the gather buffer is 1.5 KB per warp)
 constexpr int RACE_TAPE_CHUNK = 250;            // vec_steps per fused tape launch at most
 constexpr int RACE_BALANCE_ROUNDS = 0;          // tile-list rebalancing rounds at the start of a handle's life (api.cu)
 constexpr int RACE_BALANCE_STEPS = 16;          // steps per measured launch while rebalancing
@@ -389,7 +390,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // per-warp shared memory:
-//   stage  11 float4 per lane: inputs of the NEXT tile, in flight while the current tile computes
+//   stage  2 x 11 float4 per lane: inputs of the NEXT TWO tiles, in flight while the current tile computes
 //   obs    the 32x29 observation tile of the current tile (staging for the coalesced store)
 //   adopt  6 float4 per lane: the prepared episodes of the envs of an install pass, in flight
 //          while a tile computes
@@ -399,8 +400,9 @@ constexpr int RACE_STAGE_SLOTS = 11; // act, S0..S4, P0..P2, C0, T
 constexpr int RACE_ADOPT_SLOTS = 6;  // N0..N2, (spawn, j_mot), ring0 (pos,n.x), (n.y, n.z, episode tag, -)
 constexpr int RACE_STAGE_BYTES = RACE_STAGE_SLOTS * 32 * 16;
 constexpr int RACE_TILE_BYTES = 32 * RACE_OBS * 4;
-constexpr int RACE_ADOPT_BYTES = RACE_ADOPT_SLOTS * 32 * 16;
-constexpr int RACE_WARP_SMEM = RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_BYTES + RACE_INSTALL_CAP * 8;
+constexpr int RACE_ADOPT_BYTES = RACE_ADOPT_SLOTS * RACE_PASS * 16;
+constexpr int RACE_DEPTH = 2; // tiles whose inputs are in flight per warp
+constexpr int RACE_WARP_SMEM = RACE_DEPTH * RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_BYTES + RACE_INSTALL_CAP * 8;
 constexpr int RACE_SMEM_BYTES = RACE_WARPS * RACE_WARP_SMEM;
 
 __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, const float *act, float4 *stage, int lane, int i) {
@@ -418,10 +420,10 @@ __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, const float
 __device__ __forceinline__ void race_prefetch_slot(const RaceDev &d, float4 *adopt, int lane, int i) {
     const size_t ld = d.ld;
 #pragma unroll
-    for (int k = 0; k < 3; k++) cp_async16(&adopt[k * 32 + lane], &d.N[k * ld + i]);
-    cp_async16(&adopt[3 * 32 + lane], &d.NS[i]);
-    cp_async16(&adopt[4 * 32 + lane], &d.NR0[i]);
-    cp_async16(&adopt[5 * 32 + lane], &d.NR1[i]);
+    for (int k = 0; k < 3; k++) cp_async16(&adopt[k * RACE_PASS + lane], &d.N[k * ld + i]);
+    cp_async16(&adopt[3 * RACE_PASS + lane], &d.NS[i]);
+    cp_async16(&adopt[4 * RACE_PASS + lane], &d.NR0[i]);
+    cp_async16(&adopt[5 * RACE_PASS + lane], &d.NR1[i]);
 }
 
 // A finished env starts episode `want`: ADOPT the prepared slot (already copied into this
@@ -435,8 +437,8 @@ template <bool STRICT>
 __device__ __forceinline__ void race_adopt_from_smem(const RaceDev &d, const float4 *adopt, int lane, int i,
                                                      uint32_t want, bool trust, float *obs_row) {
     const size_t ld = d.ld;
-    const float4 a = adopt[0 * 32 + lane], b = adopt[1 * 32 + lane], c = adopt[2 * 32 + lane];
-    const float4 sp = adopt[3 * 32 + lane], r0 = adopt[4 * 32 + lane], r1 = adopt[5 * 32 + lane];
+    const float4 a = adopt[0 * RACE_PASS + lane], b = adopt[1 * RACE_PASS + lane], c = adopt[2 * RACE_PASS + lane];
+    const float4 sp = adopt[3 * RACE_PASS + lane], r0 = adopt[4 * RACE_PASS + lane], r1 = adopt[5 * RACE_PASS + lane];
     if (trust && __float_as_uint(r1.z) == want) {
         float s[17];
 #pragma unroll
@@ -522,9 +524,9 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     const int warp = tid >> 5;
     const bool inject = d.reset_mode == 1; // B2D_RESET_INJECT (parity hook)
     float4 *stage = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM);
-    float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES);
-    float4 *adopt = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES + RACE_TILE_BYTES);
-    uint2 *ilist = reinterpret_cast<uint2 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_BYTES);
+    float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_DEPTH * RACE_STAGE_BYTES);
+    float4 *adopt = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_DEPTH * RACE_STAGE_BYTES + RACE_TILE_BYTES);
+    uint2 *ilist = reinterpret_cast<uint2 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_DEPTH * RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_BYTES);
     float *my_row = tile_obs + lane * RACE_OBS;
 
     // Launch overlap (b2d_vec_step_tape): the next launch of this kernel may begin while this one
@@ -571,15 +573,35 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     constexpr int NO_TILE = 0x7fffffff;
     const bool fused = d.steps > 1;
     const size_t tape_stride = (size_t)d.n * 4;
-    // the first two tickets of every warp are static, so the first loads leave before any barrier
-    int ord = o_lo + warp, nord = o_lo + RACE_WARPS + warp;      // ordinals (in the CTA's list) of `tile` and `next`
-    int tstep = 0, nstep = 0;                                    // which step of the launch they belong to
-    if (fused && nord >= o_hi) { nord = ord; nstep = 1; }
-    int tile = ord < o_hi ? __ldg(&my_tiles[ord]) : NO_TILE;     // the tile being stepped
-    int next = nord < o_hi ? __ldg(&my_tiles[nord]) : NO_TILE;   // the tile after it
-    const float *act_cur = d.act_in + (size_t)(d.tape_first % d.tape_len) * tape_stride;
-    if (tile != NO_TILE && tile * 32 + lane < d.n) race_prefetch_tile(d, act_cur, stage, lane, tile * 32 + lane);
+    // the first four tickets of every warp are static, so the first loads leave before any barrier
+    // ordinals (in the CTA's list) of `tile` (being stepped), `next` and `nn` (the two after it), and their steps
+    // (`n3` is only looked up one tile early: its list entry is a global load of its own)
+    int ord = o_lo + warp, nord = ord + RACE_WARPS, nnord = nord + RACE_WARPS, n3ord = nnord + RACE_WARPS;
+    int tstep = 0, nstep = 0, nnstep = 0, n3step = 0;
+    if (fused) {
+        if (nord >= o_hi) { nord = o_lo + warp; nstep = 1; }
+        nnord = nord + RACE_WARPS;
+        nnstep = nstep;
+        if (nnord >= o_hi) { nnord = o_lo + warp; nnstep = nstep + 1; }
+        n3ord = nnord + RACE_WARPS;
+        n3step = nnstep;
+        if (n3ord >= o_hi) { n3ord = o_lo + warp; n3step = nnstep + 1; }
+    }
+    int tile = ord < o_hi ? __ldg(&my_tiles[ord]) : NO_TILE;
+    int next = nord < o_hi ? __ldg(&my_tiles[nord]) : NO_TILE;
+    int nn = nnord < o_hi ? __ldg(&my_tiles[nnord]) : NO_TILE;
+    // n3 is loaded unconditionally (clamped ordinal) and its validity travels separately, so that nothing
+    // consumes the load before the next tile's end: a select on the value stalled ~2300 cycles per tile
+    const int o_last = max(o_hi - 1, 0);
+    bool n3ok = n3ord < o_hi;
+    int n3 = __ldg(&my_tiles[min(n3ord, o_last)]);
+    auto act_of = [&](int step) { return d.act_in + (size_t)((d.tape_first + step) % d.tape_len) * tape_stride; };
+    if (tile != NO_TILE && tile * 32 + lane < d.n) race_prefetch_tile(d, act_of(0), stage, lane, tile * 32 + lane);
     cp_async_commit(); // group: inputs of the first tile
+    if (next != NO_TILE && nstep < d.steps && next * 32 + lane < d.n)
+        race_prefetch_tile(d, act_of(nstep), stage + RACE_STAGE_SLOTS * 32, lane, next * 32 + lane);
+    cp_async_commit(); // group: inputs of the second tile
+    int cb = 0; // which stage buffer holds `tile`
 
     if (tid < 8) s_acc[tid] = 0;
     if (tid == 8) s_score = 0;
@@ -602,7 +624,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         }
         if (tid == 0) {
             s_done = 0;
-            s_ticket = 2 * RACE_WARPS;
+            s_ticket = 4 * RACE_WARPS;
             s_q_head = (unsigned int)carried;
             s_q_tail = 0u;
             s_q_lock = 0u;
@@ -613,6 +635,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     __syncthreads();
 
 #if B2D_EXPERIMENT_TIMING
+    long long tm_gap = 0, tm_prev = 0;
     long long tm_wait = 0, tm_math = 0, tm_store = 0, tm_adopt = 0, tm_iters = 0, tm_inst = 0, tm_refill = 0;
     const long long t_begin = clock64();
 #endif
@@ -621,8 +644,13 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     int listed = 0;   // entries in this warp's install list (warp-uniform)
     int age = 0;      // tiles since the list was last empty
     int inflight = 0; // the first `inflight` entries of the list have their prepared slots on the way (cp.async)
+    int gather_age = 0; // tiles since that gather was committed (its group has landed for sure at 2)
+    bool took_all = false; // that gather covers everything that was listed when it started
     unsigned int trust_m = 0u; // ... and these of them may adopt the slot (see s_pending)
     const int install_age = d.install_age;
+    // fused launches: a tile's inputs for the next step are prefetched (tiles per warp - 2) tiles after it was
+    // stepped; an env listed then must be installed by then (see the header comment)
+    const int install_all_age = (o_hi - o_lo) / RACE_WARPS - 3;
 
     // Install the `inflight` envs at the front of the list (their slots have landed), one per lane.
     auto install_pass = [&]() {
@@ -664,11 +692,13 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         __syncwarp();
         listed = rest;
         inflight = 0;
+        // what is left was listed after the gather started if the gather took the whole list
         if (rest == 0) age = 0;
+        else if (took_all) age = min(age, gather_age);
     };
     // Start gathering the prepared slots of (up to 32 of) the listed envs.
     auto install_gather = [&]() {
-        const int cnt = min(listed, 32);
+        const int cnt = min(listed, RACE_PASS);
         bool trust = true;
         if (lane < cnt) {
             const uint32_t ei = ilist[lane].x;
@@ -679,29 +709,51 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         }
         trust_m = __ballot_sync(0xffffffffu, trust);
         inflight = cnt;
+        took_all = cnt == listed;
+        gather_age = 0;
+    };
+    // Install everything that is listed, now (the gathers' latency is exposed).
+    auto install_all = [&]() {
+        cp_async_wait<0>();
+        while (inflight || listed > 0) {
+            if (inflight) install_pass();
+            if (listed > 0) {
+                install_gather();
+                cp_async_commit();
+                cp_async_wait<0>();
+            }
+        }
     };
 
     while (tile != NO_TILE && tstep < d.steps) {
         const int i = tile * 32 + lane;
         const bool valid = i < d.n;
         B2D_TICK(t0);
-        cp_async_wait<0>(); // this tile's inputs (and the slots of a started install pass) have landed
+#if B2D_EXPERIMENT_TIMING
+        if (tm_prev) tm_gap += t0 - tm_prev;
+#endif
+        cp_async_wait<1>(); // this tile's inputs have landed (the newest group, the next tile's, may still fly)
         B2D_TICK(t1);
-        if (inflight) install_pass();
-        if (listed > 0 && (listed >= 16 || age >= install_age)) install_gather();
+        // a gather committed two tiles ago has landed too (groups complete in order)
+        if (inflight) gather_age += 1;
+        if (inflight && gather_age >= 2) install_pass();
+        // bursts (most of a tile finishing, tile after tile) and, in a fused launch, an env whose tile is
+        // about to be prefetched for the next step: install everything now
+        if (listed >= RACE_INSTALL_CAP - 64 || (fused && listed > 0 && age >= install_all_age)) install_all();
+        if (!inflight && listed > 0 && (listed >= RACE_PASS || age >= install_age)) install_gather();
         B2D_TICK(t1b);
-        const float4 a4 = stage[0 * 32 + lane];
-        const float4 q0 = stage[1 * 32 + lane], q1 = stage[2 * 32 + lane], q2 = stage[3 * 32 + lane],
-                     q3 = stage[4 * 32 + lane], q4 = stage[5 * 32 + lane];
-        const float4 p0 = stage[6 * 32 + lane], p1 = stage[7 * 32 + lane], p2 = stage[8 * 32 + lane];
-        const float4 c0 = stage[9 * 32 + lane];
-        const float4 tl = stage[10 * 32 + lane]; // (j_mot, episode, ring n.y, ring n.z)
+        float4 *cur = stage + cb * (RACE_STAGE_SLOTS * 32);
+        const float4 a4 = cur[0 * 32 + lane];
+        const float4 q0 = cur[1 * 32 + lane], q1 = cur[2 * 32 + lane], q2 = cur[3 * 32 + lane],
+                     q3 = cur[4 * 32 + lane], q4 = cur[5 * 32 + lane];
+        const float4 p0 = cur[6 * 32 + lane], p1 = cur[7 * 32 + lane], p2 = cur[8 * 32 + lane];
+        const float4 c0 = cur[9 * 32 + lane];
+        const float4 tl = cur[10 * 32 + lane]; // (j_mot, episode, ring n.y, ring n.z)
         __syncwarp();
-        if (next != NO_TILE && nstep < d.steps && next * 32 + lane < d.n) {
-            const float *act_next = d.act_in + (size_t)((d.tape_first + nstep) % d.tape_len) * tape_stride;
-            race_prefetch_tile(d, act_next, stage, lane, next * 32 + lane);
-        }
-        cp_async_commit(); // group: inputs of the next tile + the slots of an install pass
+        if (nn != NO_TILE && nnstep < d.steps && nn * 32 + lane < d.n)
+            race_prefetch_tile(d, act_of(nnstep), cur, lane, nn * 32 + lane);
+        cp_async_commit(); // group: inputs of the tile after the next + the slots of an install pass
+        cb ^= 1;
         if (!fused && lane == 0) claim = (int)atomicAdd(&s_ticket, 1u); // shared memory: lands within the tile
 
         float s[17];
@@ -852,29 +904,26 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
 #if B2D_EXPERIMENT_TIMING
         tm_wait += t1 - t0; tm_inst += t1b - t1; tm_math += t2 - t1b; tm_store += t3 - t2;
         tm_refill += t6 - t3; tm_iters += 1;
+        tm_prev = clock64();
 #endif
         tile = next;
         tstep = nstep;
-        ord = nord;
+        next = nn;
+        nstep = nnstep;
+        nn = n3ok ? n3 : NO_TILE;
+        nnstep = n3step;
         if (fused) {
-            nord = ord + RACE_WARPS;
-            if (nord >= o_hi) { nord = o_lo + warp; nstep = tstep + 1; }
+            n3ord += RACE_WARPS;
+            if (n3ord >= o_hi) { n3ord = o_lo + warp; n3step += 1; }
         } else {
-            nord = o_lo + __shfl_sync(0xffffffffu, claim, 0);
+            n3ord = o_lo + __shfl_sync(0xffffffffu, claim, 0);
         }
-        next = nord < o_hi ? __ldg(&my_tiles[nord]) : NO_TILE; // one address for the whole warp; needed a tile from now
+        n3ok = n3ord < o_hi;
+        n3 = __ldg(&my_tiles[min(n3ord, o_last)]); // one address for the whole warp; consumed a tile from now
     }
     {   // every env that finished in this launch starts its next episode in this launch
         B2D_TICK(t7);
-        cp_async_wait<0>();
-        while (inflight || listed > 0) {
-            if (inflight) install_pass();
-            if (listed > 0) {
-                install_gather();
-                cp_async_commit();
-                cp_async_wait<0>();
-            }
-        }
+        install_all();
         B2D_TICK(t8);
 #if B2D_EXPERIMENT_TIMING
         tm_adopt += t8 - t7;
@@ -884,7 +933,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
 #if B2D_EXPERIMENT_TIMING
     if (lane == 0) {
         atomicAdd(&d.ctl->dbg[0], (unsigned long long)tm_wait); atomicAdd(&d.ctl->dbg[1], (unsigned long long)tm_math);
-        atomicAdd(&d.ctl->dbg[2], (unsigned long long)tm_store); atomicAdd(&d.ctl->dbg[3], (unsigned long long)tm_adopt);
+        atomicAdd(&d.ctl->dbg[2], (unsigned long long)tm_store); atomicAdd(&d.ctl->dbg[3], (unsigned long long)(tm_adopt + tm_gap));
         atomicAdd(&d.ctl->dbg[4], (unsigned long long)tm_iters); atomicAdd(&d.ctl->dbg[5], (unsigned long long)tm_refill);
         atomicAdd(&d.ctl->dbg[6], (unsigned long long)(clock64() - t_begin)); atomicAdd(&d.ctl->dbg[7], 1ull);
         atomicAdd(&d.ctl->dbg[8], (unsigned long long)tm_inst);
