@@ -16,8 +16,6 @@
 #include <cstring>
 #include <new>
 #include <vector>
-#include <algorithm>
-#include <utility>
 
 using namespace b2d;
 
@@ -38,8 +36,6 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 enum { KIND_RACE = 0, KIND_SWARM = 1 };
-struct b2d_vec;
-static int race_upload_tile_lists(b2d_vec *v);
 
 struct b2d_vec {
     int kind;
@@ -66,11 +62,6 @@ struct b2d_vec {
     double h_flog_out[8];
     long long launches;
     uint32_t seq; // step-kernel launches so far (RaceDev::seq)
-    // race: which CTA steps which tiles (balanced against measured per-CTA time, see race_rebalance)
-    std::vector<int> tiles_per_cta;
-    int balance_rounds;  // rebalancing rounds done
-    int balance_steps;   // steps in the launch whose per-CTA times are waiting in RaceDev::cta_ns (0: none)
-    bool chain_broken;   // the tile lists changed: the next launch must not overlap its predecessor
     cudaStream_t copy_streams[2];
     cudaEvent_t ev_step, ev_copy[2];
     // optional per-kernel timing (b2d_profile_kernels): event triples of the profiled steps
@@ -184,35 +175,19 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
         const int ntiles = (cfg->num_envs + 31) / 32;
         int step_ctas = (ntiles + warps_per_cta - 1) / warps_per_cta;
         if (step_ctas > sms * RACE_MIN_CTAS) step_ctas = sms * RACE_MIN_CTAS;
-        // test hook: a small grid gives every warp many tiles at small N (exercises the fused tape launches)
-        if (const char *e = getenv("B2D_RACE_STEP_CTAS")) {
-            const int want = atoi(e);
-            if (want > 0 && want < step_ctas) step_ctas = want;
-        }
         v->step_ctas = step_ctas;
     }
     const size_t ld = d.ld;
     if ((rc = setup_buffers(v, ext)) || (rc = dev_alloc(v, &d.S, RACE_HOT_SLOTS * ld)) ||
         (rc = dev_alloc(v, &d.N, 3 * ld)) || (rc = dev_alloc(v, &d.NS, ld)) || (rc = dev_alloc(v, &d.NR0, ld)) ||
         (rc = dev_alloc(v, &d.NR1, ld)) || (rc = dev_alloc(v, &d.carry, (size_t)v->step_ctas * RACE_CARRY)) ||
-        (rc = dev_alloc(v, &d.chain, (size_t)v->step_ctas)) ||
-        (rc = dev_alloc(v, (int **)&d.tile_list, (size_t)(cfg->num_envs + 31) / 32)) ||
-        (rc = dev_alloc(v, (int **)&d.tile_off, (size_t)v->step_ctas + 1)) || (rc = dev_alloc(v, &d.cta_ns, (size_t)v->step_ctas)) || (rc = dev_alloc(v, &d.cta_score, (size_t)v->step_ctas)) ||
+        (rc = dev_alloc(v, &d.chain, (size_t)v->step_ctas)) || (rc = dev_alloc(v, &d.cta_score, (size_t)v->step_ctas)) ||
         (rc = dev_alloc(v, &d.ctl, 1)) || (rc = finish_create(v))) {
         b2d_vec_close(v);
         return rc;
     }
     race_ctl_reset_kernel<<<1, 256>>>(d.ctl, d.carry, d.cta_score, 0u, (unsigned int)v->step_ctas, 1);
     cudaDeviceSynchronize();
-    {   // equal lists to begin with
-        const int ntiles = (cfg->num_envs + 31) / 32, G = v->step_ctas;
-        v->tiles_per_cta.assign(G, ntiles / G);
-        for (int c = 0; c < ntiles % G; c++) v->tiles_per_cta[c] += 1;
-        if ((rc = race_upload_tile_lists(v))) {
-            b2d_vec_close(v);
-            return rc;
-        }
-    }
 #if B2D_EXPERIMENT_TIMING
     cudaMalloc(&d.trace, (size_t)v->step_ctas * 4 * sizeof(unsigned long long));
 #endif
@@ -342,7 +317,7 @@ extern "C" int b2d_vec_close(b2d_vec *v) {
         unsigned long long h[12];
         cudaMemcpy(h, v->race.ctl->dbg, sizeof(h), cudaMemcpyDeviceToHost);
         const double it = (double)h[4], w = (double)h[7];
-        fprintf(stderr, "[b2d timing] per tile iteration (cycles): wait_inputs %.0f  compute %.0f  store %.0f  tail_install+loop_end %.0f  install %.0f  refill %.0f | per warp-launch: total %.0f  iterations %.2f\n",
+        fprintf(stderr, "[b2d timing] per tile iteration (cycles): wait_inputs %.0f  compute %.0f  store %.0f  wait_adopt %.0f  install %.0f  refill %.0f | per warp-launch: total %.0f  iterations %.2f\n",
                 h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[8] / it, h[5] / it, h[6] / w, it / w);
         if (getenv("B2D_TRACE_FILE")) {
             std::vector<unsigned long long> tr((size_t)v->step_ctas * 4);
@@ -402,120 +377,15 @@ extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
     return launch_check("swarm_reset_kernel");
 }
 
-// ---------------------------------------------------------------- race: tile ownership
-// CTA c steps the tiles of its list, the same ones in every launch (its warps read only state the
-// CTA wrote itself: no ordering between CTAs, launches may overlap per CTA).  The lists interleave
-// proportionally -- the k-th of CTA c's W_c tiles sits at position (k + 1/2) / W_c of the vector --
-// so at any moment the grid works on one narrow band of every array (DRAM row locality), whatever
-// the weights.  Equal weights give the plain round-robin c, c+G, c+2G, ...
-static int race_upload_tile_lists(b2d_vec *v) {
-    const int G = v->step_ctas, ntiles = (v->race.n + 31) / 32;
-    std::vector<std::pair<double, int>> key;
-    key.reserve(ntiles);
-    for (int c = 0; c < G; c++)
-        for (int k = 0; k < v->tiles_per_cta[c]; k++) key.emplace_back((k + 0.5) / v->tiles_per_cta[c], c);
-    std::stable_sort(key.begin(), key.end()); // ties: by CTA, then by k (emplace order)
-    std::vector<int> off(G + 1, 0), fill(G, 0), list(ntiles);
-    for (int c = 0; c < G; c++) off[c + 1] = off[c] + v->tiles_per_cta[c];
-    for (int t = 0; t < ntiles; t++) {
-        const int c = key[t].second;
-        list[off[c] + fill[c]++] = t;
-    }
-    CUDA_TRY(cudaMemcpy((void *)v->race.tile_list, list.data(), sizeof(int) * ntiles, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy((void *)v->race.tile_off, off.data(), sizeof(int) * (G + 1), cudaMemcpyHostToDevice));
-    return B2D_OK;
-}
-
-static int race_min_tiles_per_warp(const b2d_vec *v) {
-    int m = 1 << 30;
-    for (int w : v->tiles_per_cta) m = w < m ? w : m;
-    return m / RACE_WARPS;
-}
-
-// SMs do not step tiles equally fast (per-SM HBM bandwidth depends on where the SM sits: measured
-// 69..88 us for the same 74 tiles), and CTA c lands on the same SM in every launch, so equal
-// lists leave the fast SMs idle for the last fifth of every launch.  After a fused tape launch the
-// per-CTA wall times are read back and the list lengths are made proportional to the measured
-// rates (damped, clamped to +-35 % of the mean).  Which CTA steps an env never changes a result.
-// Called with the stream idle; refill entries carried per CTA are restocked first (they name envs
-// the CTA may no longer own) and the per-CTA launch chain is cut.
-static int race_rebalance(b2d_vec *v, cudaStream_t st) {
-    const int G = v->step_ctas, ntiles = (v->race.n + 31) / 32;
-    CUDA_TRY(cudaStreamSynchronize(st));
-    std::vector<unsigned long long> ns(G);
-    CUDA_TRY(cudaMemcpy(ns.data(), v->race.cta_ns, sizeof(unsigned long long) * G, cudaMemcpyDeviceToHost));
-    if (getenv("B2D_BALANCE_DEBUG")) {
-        unsigned long long lo = ~0ull, hi = 0, sum = 0;
-        int clo = 1 << 30, chi = 0;
-        for (int c = 0; c < G; c++) {
-            lo = ns[c] < lo ? ns[c] : lo; hi = ns[c] > hi ? ns[c] : hi; sum += ns[c];
-            clo = v->tiles_per_cta[c] < clo ? v->tiles_per_cta[c] : clo; chi = v->tiles_per_cta[c] > chi ? v->tiles_per_cta[c] : chi;
-        }
-        fprintf(stderr, "[b2d balance] round %d: %d steps measured, per-CTA us min %.1f mean %.1f max %.1f; tiles per CTA %d..%d\n",
-                v->balance_rounds, v->balance_steps, lo / 1e3, sum / 1e3 / G, hi / 1e3, clo, chi);
-        if (const char *f = getenv("B2D_BALANCE_DUMP")) {
-            FILE *fp = fopen(f, "a");
-            if (fp) {
-                for (int c = 0; c < G; c++) fprintf(fp, "%d,%d,%d,%llu\n", v->balance_rounds, c, v->tiles_per_cta[c], ns[c]);
-                fclose(fp);
-            }
-        }
-    }
-    v->balance_steps = 0;
-    std::vector<double> want(G);
-    double sum = 0.0;
-    for (int c = 0; c < G; c++) {
-        if (ns[c] == 0) return B2D_OK; // no measurement
-        want[c] = (double)v->tiles_per_cta[c] / (double)ns[c];
-        sum += want[c];
-    }
-    const double mean = (double)ntiles / G, damp = v->balance_rounds == 0 ? 1.0 : 0.6;
-    double total = 0.0;
-    for (int c = 0; c < G; c++) {
-        double w = want[c] / sum * ntiles;
-        w = v->tiles_per_cta[c] + damp * (w - v->tiles_per_cta[c]);
-        w = w < 0.65 * mean ? 0.65 * mean : (w > 1.35 * mean ? 1.35 * mean : w);
-        want[c] = w;
-        total += w;
-    }
-    // largest-remainder rounding to exactly ntiles
-    std::vector<int> cnt(G);
-    std::vector<std::pair<double, int>> frac(G);
-    int given = 0;
-    for (int c = 0; c < G; c++) {
-        const double w = want[c] / total * ntiles;
-        cnt[c] = (int)w;
-        frac[c] = {-(w - cnt[c]), c};
-        given += cnt[c];
-    }
-    std::sort(frac.begin(), frac.end());
-    for (int k = 0; k < ntiles - given; k++) cnt[frac[k % G].second] += 1;
-    v->balance_rounds += 1;
-    for (int c = 0; c < G; c++)
-        if (cnt[c] / RACE_WARPS < RACE_FUSED_MIN_TILES) return B2D_OK; // would break the fused-launch rule: keep the lists
-    race_drain_kernel<<<v->step_ctas, RACE_CARRY, 0, st>>>(v->race);
-    CUDA_TRY(cudaStreamSynchronize(st));
-    v->tiles_per_cta = cnt;
-    v->chain_broken = true;
-    return race_upload_tile_lists(v);
-}
-
 // One launch of the step kernel.  `overlap`: the launch is made programmatically dependent on the
 // previous launch in the stream, which the caller guarantees is the previous step of this handle
 // (b2d_vec_step_tape); every CTA then waits for its own predecessor only (race_step_kernel).
-static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool overlap = false, int chunk = 0, int chunks = 1,
-                     int steps = 1, int tape_len = 1, int tape_first = 0) {
+static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool overlap = false, int chunk = 0, int chunks = 1) {
     if (v->kind == KIND_RACE) {
         RaceDev d = v->race;
         if (actions) d.act_in = actions;
-        d.steps = steps; // > 1: `actions` is the base of a tape and the launch walks `steps` slices of it
-        d.tape_len = tape_len;
-        d.tape_first = tape_first;
-        d.install_age = RACE_INSTALL_AGE;
         d.seq = ++v->seq;
-        v->balance_steps = 0;
-        d.chain_wait = overlap && !v->chain_broken ? 1 : 0;
-        v->chain_broken = false;
+        d.chain_wait = overlap ? 1 : 0;
         {   // tiles of this launch: the whole vector, or chunk `chunk` of `chunks` (host-buffer pipeline)
             const int ntiles = (d.n + 31) / 32;
             const int per = (ntiles + chunks - 1) / chunks;
@@ -539,7 +409,7 @@ static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool ove
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = d.chain_wait ? 1 : 0;
+        cfg.numAttrs = overlap ? 1 : 0;
         cudaError_t e = v->math == B2D_MATH_STRICT ? cudaLaunchKernelEx(&cfg, race_step_kernel<true>, d)
                                                    : cudaLaunchKernelEx(&cfg, race_step_kernel<false>, d);
         if (e != cudaSuccess) return fail(B2D_ECUDA, "race_step_kernel launch: %s", cudaGetErrorString(e));
@@ -562,15 +432,11 @@ extern "C" int b2d_vec_step_from(b2d_vec *v, const float *device_actions, void *
     return step_impl(v, device_actions, (cudaStream_t)stream);
 }
 
-// K steps over an action tape that is already on the device.
-// Race: the steps are FUSED into launches of up to RACE_TAPE_CHUNK steps each (race_step_kernel,
-// "fused steps": every warp walks its own tiles step after step, no barrier between steps), when
-// every warp owns at least RACE_FUSED_MIN_TILES tiles; smaller vectors get one launch per step.
-// Launches after the first are allowed to overlap the tail of their predecessor (programmatic
-// dependent launch + per-CTA completion flags): CTA c of a launch needs only CTA c of the launch
-// before it, so a straggling CTA does not idle the whole GPU between launches.  Inside a stream
-// capture the launches are plain (the sequence numbers the flags carry are host state a graph
-// replay would not advance).  B2D_TAPE_FUSED=0 in the environment forces one launch per step.
+// K steps over an action tape that is already on the device.  The launches after the first are
+// allowed to overlap the tail of their predecessor (programmatic dependent launch + per-CTA
+// completion flags): CTA c of step t+1 needs only CTA c of step t, so a straggling CTA no longer
+// idles the whole GPU between steps.  Inside a stream capture the launches are plain (the
+// sequence numbers the flags carry are host state a graph replay would not advance).
 extern "C" int b2d_vec_step_tape(b2d_vec *v, const float *device_tape, int tape_len, int first, int steps, void *stream) {
     if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
     if (!device_tape || ((uintptr_t)device_tape & 15u) || tape_len <= 0 || first < 0 || steps < 0)
@@ -579,34 +445,6 @@ extern "C" int b2d_vec_step_tape(b2d_vec *v, const float *device_tape, int tape_
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
     const size_t stride = (size_t)v->num_agents * 4;
-    if (v->kind == KIND_RACE) {
-        const int ntiles = (v->race.n + 31) / 32;
-        const char *env = getenv("B2D_TAPE_FUSED");
-        (void)ntiles;
-        const bool fused = race_min_tiles_per_warp(v) >= RACE_FUSED_MIN_TILES && !(env && env[0] == '0');
-        if (fused) {
-            int chunk = RACE_TAPE_CHUNK, rounds = RACE_BALANCE_ROUNDS;
-            if (const char *e = getenv("B2D_TAPE_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
-            if (const char *e = getenv("B2D_RACE_BALANCE")) rounds = atoi(e);
-            const bool capturing = cap != cudaStreamCaptureStatusNone;
-            for (int k = 0; k < steps;) {
-                // the first launches of a handle are short and measured: their per-CTA times balance the lists
-                const bool learn = !capturing && v->balance_rounds < rounds;
-                if (learn && v->balance_steps >= RACE_BALANCE_MIN_STEPS) {
-                    int rc = race_rebalance(v, st);
-                    if (rc) return rc;
-                    continue;
-                }
-                int m = steps - k < chunk ? steps - k : chunk;
-                if (learn && m > RACE_BALANCE_STEPS) m = RACE_BALANCE_STEPS;
-                int rc = step_impl(v, device_tape, st, k > 0 && !capturing && !learn, 0, 1, m, tape_len, (first + k) % tape_len);
-                if (rc) return rc;
-                v->balance_steps = capturing ? 0 : m;
-                k += m;
-            }
-            return B2D_OK;
-        }
-    }
     for (int k = 0; k < steps; k++) {
         const float *a = device_tape + (size_t)((first + k) % tape_len) * stride;
         int rc = step_impl(v, a, st, k > 0 && cap == cudaStreamCaptureStatusNone && v->kind == KIND_RACE);
@@ -818,7 +656,7 @@ extern "C" int b2d_put_state(b2d_vec *v, const int *env_ids, int n, const float 
     }
     CUDA_TRY(cudaMemcpy(v->d_blob_tmp, host_blobs, (size_t)n * v->blob_floats * sizeof(float), cudaMemcpyHostToDevice));
     if (v->kind == KIND_RACE) { // no prepared-slot refill may be in flight once states are edited
-        race_drain_kernel<<<v->step_ctas, RACE_CARRY>>>(v->race);
+        race_drain_kernel<<<v->step_ctas, 32>>>(v->race);
         v->launches += 1;
     }
     if (v->kind == KIND_RACE) race_unpack_kernel<<<(n + 127) / 128, 128>>>(v->race, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);

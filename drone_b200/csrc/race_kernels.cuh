@@ -7,7 +7,8 @@
 //   log accumulation       R/drone_race.h:61-70   add_log, EB:572-591 vec_log
 //
 // Layout in HBM (ld = num_envs rounded up to 256; lane i touches element i of
-// every array, so each warp access is one contiguous 512-byte float4 run):
+// every array, so each warp access is one contiguous 512-byte float4 run; S, P, C0 and T are
+// interleaved per tile of 32 envs, see race_at):
 //   S  float4[5][ld]  (px,py,pz,vx) (vy,vz,qw,qx) (qy,qz,wx,wy) (wz,r0,r1,r2) (r3,tick,ring word,ep_return)
 //                     ring word = ring_idx | (rings are external) << 30
 //   P  float4[3][ld]  (mass,ixx,iyy,izz) (arm,k_thrust,k_ang_damp,k_drag) (b_drag,gravity,max_rpm,k_mot)
@@ -54,15 +55,7 @@ constexpr int RACE_LD_ALIGN = 256; // row padding of the SoA arrays
 constexpr int RACE_OBS = 29;
 constexpr int RESET_MAX_ATTEMPTS = 16;
 constexpr int RACE_QUEUE_CAP = 256;            // refill ring of one CTA (entries, power of two)
-constexpr int RACE_CARRY = 128;                // refill entries a CTA may carry over to the next launch
-constexpr int RACE_INSTALL_AGE = 8;             // tiles a finished env waits at most for its install pass to start
-constexpr int RACE_FUSED_MIN_TILES = RACE_INSTALL_AGE + 6; // tiles per warp a fused launch needs (see race_step_kernel)
-constexpr int RACE_PASS = 16;                  // envs per install pass (half a warp: the gather buffer is 1.5 KB per warp)
-constexpr int RACE_TAPE_CHUNK = 250;            // vec_steps per fused tape launch at most
-constexpr int RACE_BALANCE_ROUNDS = 0;          // tile-list rebalancing rounds at the start of a handle's life (api.cu)
-constexpr int RACE_BALANCE_STEPS = 16;          // steps per measured launch while rebalancing
-constexpr int RACE_BALANCE_MIN_STEPS = 4;       // a launch shorter than this is not used as a measurement
-constexpr int RACE_INSTALL_CAP = 128;           // per-warp list of envs waiting for their next episode (install pass at 32)
+constexpr int RACE_CARRY = 32;                 // refill entries a CTA may carry over to the next launch
 constexpr unsigned int QUEUE_EMPTY = 0xffffffffu;
 
 // integer episode-statistics accumulators (all race Log fields are integer valued)
@@ -89,9 +82,6 @@ struct RaceDev {
     float4 *NS;          //   (spawn.xyz, j_mot)
     float4 *NR0;         //   ring 0 (pos.xyz, n.x)
     float4 *NR1;         //   (n.y, n.z, episode tag as bits, -)
-    const int *tile_list; // [ntiles] the tiles of CTA 0, CTA 1, ... (ascending within a CTA)
-    const int *tile_off;  // [grid + 1] where each CTA's tiles start in tile_list
-    unsigned long long *cta_ns; // [grid] wall time CTA c spent in the last launch (ns)
     uint2 *carry;        // [grid][RACE_CARRY] refill entries a CTA did not get to (env, episode)
     unsigned int *chain; // [grid] sequence number of the last launch CTA c completed
     long long *cta_score; // [grid] sum of score over the episodes CTA c saw end in the LAST step (R/drone_race.h:160)
@@ -101,10 +91,7 @@ struct RaceDev {
     uint32_t seq;        // sequence number of this launch (host counter, +1 per launch)
     int chain_wait;      // 1: launched programmatically dependent on launch seq-1 of this kernel: CTA c
                          //    starts as soon as CTA c of that launch is done (see b2d_vec_step_tape)
-    const float *act_in; // [n][4] actions read this step; base of the action tape when steps > 1
-    int install_age;     // an install pass starts when its oldest entry has waited this many tiles (or 16 are listed)
-    int steps;           // vec_steps done by this launch (> 1: fused tape launch, see race_step_kernel)
-    int tape_len, tape_first; // step s reads slice (tape_first + s) % tape_len of the tape (slice = n*4 floats)
+    const float *act_in; // [n][4] actions read this step
     float *act_out;      // [n][4] clamped actions written back, or nullptr
     float *obs;          // [n][29]
     float *rew;          // [n]
@@ -122,8 +109,7 @@ struct RaceDev {
 // The ten float4 a step reads per env (S0..S4, P0..P2, C0, T = slots 0..9).
 //   tiled (default): float4[tile][10][32] -- the 5 KB a warp reads for a tile, and the 2.5 KB of
 //     state it writes back, are ONE contiguous run in HBM, whatever the other warps are doing
-//   planar: ten separate float4[ld] planes -- a warp touches ten 512-byte pieces per tile, which is
-//     only DRAM-friendly while all warps sweep the planes as one tight frontier
+//   planar (B2D_RACE_TILED=0): ten float4[ld] planes -- a warp touches ten 512-byte pieces per tile
 #ifndef B2D_RACE_TILED
 #define B2D_RACE_TILED 1
 #endif
@@ -390,24 +376,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // per-warp shared memory:
-//   stage  2 x 11 float4 per lane: inputs of the NEXT TWO tiles, in flight while the current tile computes
+//   stage  11 float4 per lane: inputs of the NEXT tile, in flight while the current tile computes
 //   obs    the 32x29 observation tile of the current tile (staging for the coalesced store)
-//   adopt  6 float4 per lane: the prepared episodes of the envs of an install pass, in flight
-//          while a tile computes
-//   list   up to RACE_INSTALL_CAP (env, episode) pairs: envs of this warp's tiles that finished and
-//          wait for their next episode (see race_step_kernel)
+//   adopt  6 float4 per lane: the prepared episode of a lane whose env just finished, in
+//          flight while the NEXT tile computes
 constexpr int RACE_STAGE_SLOTS = 11; // act, S0..S4, P0..P2, C0, T
 constexpr int RACE_ADOPT_SLOTS = 6;  // N0..N2, (spawn, j_mot), ring0 (pos,n.x), (n.y, n.z, episode tag, -)
 constexpr int RACE_STAGE_BYTES = RACE_STAGE_SLOTS * 32 * 16;
 constexpr int RACE_TILE_BYTES = 32 * RACE_OBS * 4;
-constexpr int RACE_ADOPT_BYTES = RACE_ADOPT_SLOTS * RACE_PASS * 16;
-constexpr int RACE_DEPTH = 2; // tiles whose inputs are in flight per warp
-constexpr int RACE_WARP_SMEM = RACE_DEPTH * RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_BYTES + RACE_INSTALL_CAP * 8;
+constexpr int RACE_WARP_SMEM = RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_SLOTS * 32 * 16;
 constexpr int RACE_SMEM_BYTES = RACE_WARPS * RACE_WARP_SMEM;
 
-__device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, const float *act, float4 *stage, int lane, int i) {
-    const size_t ld = d.ld;
-    cp_async16(&stage[0 * 32 + lane], reinterpret_cast<const float4 *>(act) + i);
+__device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *stage, int lane, int i) {
+    cp_async16(&stage[0 * 32 + lane], reinterpret_cast<const float4 *>(d.act_in) + i);
 #pragma unroll
     for (int k = 0; k < 5; k++) cp_async16(&stage[(1 + k) * 32 + lane], race_at(d, SLOT_S + k, i));
 #pragma unroll
@@ -420,10 +401,10 @@ __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, const float
 __device__ __forceinline__ void race_prefetch_slot(const RaceDev &d, float4 *adopt, int lane, int i) {
     const size_t ld = d.ld;
 #pragma unroll
-    for (int k = 0; k < 3; k++) cp_async16(&adopt[k * RACE_PASS + lane], &d.N[k * ld + i]);
-    cp_async16(&adopt[3 * RACE_PASS + lane], &d.NS[i]);
-    cp_async16(&adopt[4 * RACE_PASS + lane], &d.NR0[i]);
-    cp_async16(&adopt[5 * RACE_PASS + lane], &d.NR1[i]);
+    for (int k = 0; k < 3; k++) cp_async16(&adopt[k * 32 + lane], &d.N[k * ld + i]);
+    cp_async16(&adopt[3 * 32 + lane], &d.NS[i]);
+    cp_async16(&adopt[4 * 32 + lane], &d.NR0[i]);
+    cp_async16(&adopt[5 * 32 + lane], &d.NR1[i]);
 }
 
 // A finished env starts episode `want`: ADOPT the prepared slot (already copied into this
@@ -431,14 +412,12 @@ __device__ __forceinline__ void race_prefetch_slot(const RaceDev &d, float4 *ado
 // written.  The slot's episode tag is verified; on a mismatch (slot not restocked yet: an env
 // finishing again within a step or two, a full refill ring, or state edited from outside) or
 // when the caller already knows the slot may be mid-rewrite (`trust` false) the episode is
-// generated in place instead: same pure function of (seed, env, episode number).  Called from
-// install passes only: every active lane holds a different finished env.
+// generated in place instead: same pure function of (seed, env, episode number).
 template <bool STRICT>
 __device__ __forceinline__ void race_adopt_from_smem(const RaceDev &d, const float4 *adopt, int lane, int i,
                                                      uint32_t want, bool trust, float *obs_row) {
-    const size_t ld = d.ld;
-    const float4 a = adopt[0 * RACE_PASS + lane], b = adopt[1 * RACE_PASS + lane], c = adopt[2 * RACE_PASS + lane];
-    const float4 sp = adopt[3 * RACE_PASS + lane], r0 = adopt[4 * RACE_PASS + lane], r1 = adopt[5 * RACE_PASS + lane];
+    const float4 a = adopt[0 * 32 + lane], b = adopt[1 * 32 + lane], c = adopt[2 * 32 + lane];
+    const float4 sp = adopt[3 * 32 + lane], r0 = adopt[4 * 32 + lane], r1 = adopt[5 * 32 + lane];
     if (trust && __float_as_uint(r1.z) == want) {
         float s[17];
 #pragma unroll
@@ -459,51 +438,31 @@ __device__ __forceinline__ void race_adopt_from_smem(const RaceDev &d, const flo
 }
 
 // ---------------------------------------------------------------- the step kernel
-// ONE launch per vec_step -- or per run of vec_steps when the actions are already on the device
-// (d.steps > 1, b2d_vec_step_tape).  Persistent grid (RACE_MIN_CTAS resident CTAs per SM),
-// RACE_WARPS warps each; a warp owns one tile of 32 envs at a time (one env per lane).
+// ONE launch per vec_step.  Persistent grid (RACE_MIN_CTAS resident CTAs per SM), RACE_WARPS
+// warps each; a warp owns one tile of 32 envs at a time (one env per lane).
 //
 // Tile order.  CTA c owns tiles c, c+G, c+2G, ... (G = grid size; the same CTA owns the same
-// envs in every launch).  Across the grid the warps sweep every array as one contiguous
-// frontier, which is what DRAM wants (sharded dynamic claims ran 4% slower with 16 frontiers and
-// 50% slower with 256).
-//   * single step: the CTA's warps draw its tiles through a SHARED-MEMORY ticket, so a warp that
-//     spent time restocking episode slots simply takes fewer tiles.
-//   * fused steps: warp w owns the CTA's tiles w, w+W, w+2W, ... for the whole launch and walks
-//     them step after step.  Envs are independent and a warp only ever reads state it wrote
-//     itself, so there is NO barrier of any kind between steps -- not across the grid, not in
-//     the CTA: the memory pipeline never drains, the first-tile latency and the straggler tail
-//     of a launch are paid once per launch instead of once per step, and a warp that restocks
-//     slots catches up over the following steps.
+// envs in every launch) and its warps draw them through a SHARED-MEMORY ticket, so a warp that
+// spent time restocking episode slots simply takes fewer tiles.  Across the grid the warps
+// sweep every array as one contiguous frontier, which is what DRAM wants (sharded dynamic
+// claims ran 4% slower with 16 frontiers and 50% slower with 256).
 //
-// The inputs of the warp's next tile stream into shared memory (cp.async) while the current
-// tile computes (~1000 FP32 instructions per lane): no register cost, no dependent-load stall.
+// Everything with memory latency is software-pipelined one tile deep and costs no registers:
+//   * the inputs of the warp's next tile stream into shared memory (cp.async) while the
+//     current tile computes (~1000 FP32 instructions per lane);
+//   * a lane whose env finished streams the env's prepared next episode into shared memory
+//     and installs it one tile later (no dependent-load stall, no second kernel).
 // Observation rows ([N,29] row-major, 116 B: not a multiple of 16) are staged per warp in
 // shared memory and leave as lane-consecutive float4 stores, 512 B per instruction.
-//
-// Auto-reset costs warp time in proportion to the envs that finish, not to the tiles that
-// contain one.  About 2.5 % of the envs finish per step, i.e. more than half of all tiles hold
-// a finished env; installing its next episode right there kept 31 lanes idle for ~1500 cycles
-// (measured: 21 % of the warps' time).  Instead a finished lane only appends (env, next
-// episode) to its WARP's install list in shared memory.  When 16 are listed or the oldest has
-// waited RACE_INSTALL_AGE tiles, the warp starts an INSTALL PASS with a different finished env
-// on every lane: the prepared slots are gathered by cp.async while the next tile computes and
-// installed one tile later (params, spawn state, ring 0, first observation row).  The list is
-// private to the warp: no atomics, and the row an env's tile store left behind is overwritten
-// in program order by the same warp.  Leftovers are installed before the launch ends, so every
-// vec_step leaves the reset observation in place like the reference's c_step does.
-// Fused steps add one rule: an env listed in step t is installed before its tile's inputs for
-// step t+1 are prefetched (RACE_INSTALL_AGE <= tiles per warp - 3, enforced by the host).
 //
 // Restocking.  Installing an episode consumes the env's prepared slot; the slot is described
 // by an entry in the CTA's refill ring (shared memory).  Whenever 32 entries are waiting, the
 // next warp that finishes a tile regenerates them in one pass with every lane busy (Philox +
-// trig).  One pass at a time per CTA and FIFO order, so two generations for the same env never
-// interleave.  What is left at the end of a launch (up to RACE_CARRY entries) is carried to
-// the next launch (d.carry) and regenerated there in between tiles; an env listed there may
-// have its slot rewritten while that launch runs, so if it finishes again before its pass is
-// done it is generated in place (`s_pending`).  Enqueueing is best effort: a full ring drops
-// the entry and the tag check covers it later.
+// trig, ~7800 instructions).  One pass at a time per CTA and FIFO order, so two generations for
+// the same env never interleave.  Fewer than 32 entries left at the end of a launch are carried
+// to the next one (d.carry); an env listed there may have its slot rewritten while the next
+// launch runs, so if it finishes again meanwhile it is generated in place (`s_pending`).
+// Enqueueing is best effort: a full ring drops the entry and the tag check covers it later.
 //
 // No global atomic in this kernel returns a value (see Ctl).
 template <bool STRICT>
@@ -511,22 +470,22 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ int s_done;
     __shared__ int s_acc[8];
-    __shared__ int s_score;                       // sum of score over the episodes that ended in the launch's last step
     __shared__ unsigned int s_ticket;             // tile tickets handed out so far in this CTA
     __shared__ unsigned int s_q_head, s_q_tail;   // refill ring: entries [tail, head), monotonic
     __shared__ unsigned int s_q_lock;             // one refill pass at a time
-    __shared__ unsigned int s_pend_lo, s_pend_hi; // carried-over entries [lo, hi) of s_pending are not restocked yet
+    __shared__ unsigned int s_npending;           // carried-over entries whose slots are not restocked yet
     __shared__ unsigned int s_pending[RACE_CARRY];
     __shared__ uint2 s_queue[RACE_QUEUE_CAP];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const int G = gridDim.x;
+    const int ntiles = min((d.n + 31) >> 5, d.tile_end);
     const bool inject = d.reset_mode == 1; // B2D_RESET_INJECT (parity hook)
     float4 *stage = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM);
-    float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_DEPTH * RACE_STAGE_BYTES);
-    float4 *adopt = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_DEPTH * RACE_STAGE_BYTES + RACE_TILE_BYTES);
-    uint2 *ilist = reinterpret_cast<uint2 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_DEPTH * RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_BYTES);
+    float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES);
+    float4 *adopt = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES + RACE_TILE_BYTES);
     float *my_row = tile_obs + lane * RACE_OBS;
 
     // Launch overlap (b2d_vec_step_tape): the next launch of this kernel may begin while this one
@@ -550,211 +509,69 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
 #if B2D_EXPERIMENT_TIMING
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_go));
 #endif
-    unsigned long long t_go;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_go));
-    // This CTA's tiles: an ascending list (d.tile_list), the same in every launch until the host
-    // rebalances it.  A launch covers the tiles in [tile_begin, tile_end): ordinals [o_lo, o_hi).
-    const int *my_tiles = d.tile_list + __ldg(&d.tile_off[blockIdx.x]);
-    int o_lo = 0, o_hi = __ldg(&d.tile_off[blockIdx.x + 1]) - __ldg(&d.tile_off[blockIdx.x]);
-    if (d.tile_begin > 0 || d.tile_end < ((d.n + 31) >> 5)) { // a chunk of the vector (host-buffer pipeline)
-        int below_begin = 0, below_end = 0;
-        for (int k = lane; k < o_hi; k += 32) {
-            const int t = __ldg(&my_tiles[k]);
-            below_begin += t < d.tile_begin;
-            below_end += t < d.tile_end;
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            below_begin += __shfl_xor_sync(0xffffffffu, below_begin, o);
-            below_end += __shfl_xor_sync(0xffffffffu, below_end, o);
-        }
-        o_lo = below_begin;
-        o_hi = below_end;
-    }
-    constexpr int NO_TILE = 0x7fffffff;
-    const bool fused = d.steps > 1;
-    const size_t tape_stride = (size_t)d.n * 4;
-    // the first four tickets of every warp are static, so the first loads leave before any barrier
-    // ordinals (in the CTA's list) of `tile` (being stepped), `next` and `nn` (the two after it), and their steps
-    // (`n3` is only looked up one tile early: its list entry is a global load of its own)
-    int ord = o_lo + warp, nord = ord + RACE_WARPS, nnord = nord + RACE_WARPS, n3ord = nnord + RACE_WARPS;
-    int tstep = 0, nstep = 0, nnstep = 0, n3step = 0;
-    if (fused) {
-        if (nord >= o_hi) { nord = o_lo + warp; nstep = 1; }
-        nnord = nord + RACE_WARPS;
-        nnstep = nstep;
-        if (nnord >= o_hi) { nnord = o_lo + warp; nnstep = nstep + 1; }
-        n3ord = nnord + RACE_WARPS;
-        n3step = nnstep;
-        if (n3ord >= o_hi) { n3ord = o_lo + warp; n3step = nnstep + 1; }
-    }
-    int tile = ord < o_hi ? __ldg(&my_tiles[ord]) : NO_TILE;
-    int next = nord < o_hi ? __ldg(&my_tiles[nord]) : NO_TILE;
-    int nn = nnord < o_hi ? __ldg(&my_tiles[nnord]) : NO_TILE;
-    // n3 is loaded unconditionally (clamped ordinal) and its validity travels separately, so that nothing
-    // consumes the load before the next tile's end: a select on the value stalled ~2300 cycles per tile
-    const int o_last = max(o_hi - 1, 0);
-    bool n3ok = n3ord < o_hi;
-    int n3 = __ldg(&my_tiles[min(n3ord, o_last)]);
-    auto act_of = [&](int step) { return d.act_in + (size_t)((d.tape_first + step) % d.tape_len) * tape_stride; };
-    if (tile != NO_TILE && tile * 32 + lane < d.n) race_prefetch_tile(d, act_of(0), stage, lane, tile * 32 + lane);
+    // the first two tickets of every warp are static, so the first loads leave before any barrier
+    // CTA c owns the tiles congruent to c modulo G, whatever range a launch covers
+    const int first_tile = d.tile_begin + (int)((blockIdx.x + G - d.tile_begin % G) % G);
+    int tile = warp * G + first_tile;
+    int next = (RACE_WARPS + warp) * G + first_tile;
+    if (tile < ntiles && tile * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, tile * 32 + lane);
     cp_async_commit(); // group: inputs of the first tile
-    if (next != NO_TILE && nstep < d.steps && next * 32 + lane < d.n)
-        race_prefetch_tile(d, act_of(nstep), stage + RACE_STAGE_SLOTS * 32, lane, next * 32 + lane);
-    cp_async_commit(); // group: inputs of the second tile
-    int cb = 0; // which stage buffer holds `tile`
+    cp_async_commit(); // group: (empty) adoption loads "of the tile before the first"
 
     if (tid < 8) s_acc[tid] = 0;
-    if (tid == 8) s_score = 0;
     for (int k = tid; k < RACE_QUEUE_CAP; k += RACE_BLOCK) s_queue[k] = make_uint2(QUEUE_EMPTY, 0u);
     __syncthreads();
-    {   // entries carried over from the previous launch seed the ring (stored compacted: [0, count) valid)
-        int carried = 0;
-        for (int base = 0; base < RACE_CARRY; base += RACE_BLOCK) {
-            const int k = base + tid;
-            bool have = false;
-            if (k < RACE_CARRY) {
-                const uint2 e = __ldcg(&d.carry[(size_t)blockIdx.x * RACE_CARRY + k]);
-                have = e.x != QUEUE_EMPTY && !inject;
-                if (have) {
-                    s_queue[k] = e;
-                    s_pending[k] = e.x;
-                }
-            }
-            carried += __syncthreads_count(have);
+    if (warp == 0) { // entries carried over from the previous launch seed the ring
+        const uint2 e = __ldcg(&d.carry[(size_t)blockIdx.x * RACE_CARRY + lane]);
+        const bool have = e.x != QUEUE_EMPTY && !inject;
+        const unsigned int m = __ballot_sync(0xffffffffu, have);
+        if (have) {
+            const int slot = __popc(m & ((1u << lane) - 1u));
+            s_queue[slot] = e;
+            s_pending[slot] = e.x;
         }
-        if (tid == 0) {
+        if (lane == 0) {
             s_done = 0;
-            s_ticket = 4 * RACE_WARPS;
-            s_q_head = (unsigned int)carried;
+            s_ticket = 2 * RACE_WARPS;
+            s_q_head = (unsigned int)__popc(m);
             s_q_tail = 0u;
             s_q_lock = 0u;
-            s_pend_lo = 0u;
-            s_pend_hi = (unsigned int)carried;
+            s_npending = (unsigned int)__popc(m);
         }
     }
     __syncthreads();
 
 #if B2D_EXPERIMENT_TIMING
-    long long tm_gap = 0, tm_prev = 0;
     long long tm_wait = 0, tm_math = 0, tm_store = 0, tm_adopt = 0, tm_iters = 0, tm_inst = 0, tm_refill = 0;
     const long long t_begin = clock64();
 #endif
 
-    int claim = 0;    // lane 0: ticket for the tile after `next` (single step)
-    int listed = 0;   // entries in this warp's install list (warp-uniform)
-    int age = 0;      // tiles since the list was last empty
-    int inflight = 0; // the first `inflight` entries of the list have their prepared slots on the way (cp.async)
-    int gather_age = 0; // tiles since that gather was committed (its group has landed for sure at 2)
-    bool took_all = false; // that gather covers everything that was listed when it started
-    unsigned int trust_m = 0u; // ... and these of them may adopt the slot (see s_pending)
-    const int install_age = d.install_age;
-    // fused launches: a tile's inputs for the next step are prefetched (tiles per warp - 2) tiles after it was
-    // stepped; an env listed then must be installed by then (see the header comment)
-    const int install_all_age = (o_hi - o_lo) / RACE_WARPS - 3;
+    // state carried from one tile to the next
+    bool pend_adopt = false; // this lane's env finished in the previous tile (Philox mode)
+    bool pend_trust = true;  // ... and its prepared slot cannot be mid-rewrite
+    int pend_i = 0;
+    uint32_t pend_want = 0u; // episode number it starts next
+    unsigned int pend_m = 0u; // ballot of pend_adopt
+    int claim = 0;            // lane 0: ticket for the tile after `next`
 
-    // Install the `inflight` envs at the front of the list (their slots have landed), one per lane.
-    auto install_pass = [&]() {
-        const int cnt = inflight;
-        uint2 e = make_uint2(0u, 0u);
-        if (lane < cnt) {
-            e = ilist[lane];
-            race_adopt_from_smem<STRICT>(d, adopt, lane, (int)e.x, e.y, (trust_m >> lane) & 1u, d.obs + (size_t)e.x * RACE_OBS);
-        }
-        __syncwarp();
-        // the consumed slots go to the CTA's refill ring: one reservation per pass, best effort
-        unsigned int base = QUEUE_EMPTY;
-        if (lane == 0) {
-            for (;;) {
-                const unsigned int h = *(volatile unsigned int *)&s_q_head;
-                if (h - *(volatile unsigned int *)&s_q_tail + (unsigned int)cnt > (unsigned int)RACE_QUEUE_CAP) break; // full: drop
-                if (atomicCAS(&s_q_head, h, h + (unsigned int)cnt) == h) {
-                    base = h;
-                    break;
-                }
-            }
-        }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane < cnt && base != QUEUE_EMPTY) {
-            volatile uint2 *q = &s_queue[(base + (unsigned int)lane) & (RACE_QUEUE_CAP - 1)];
-            q->y = e.y + 1u; // .x (the non-empty marker) last
-            q->x = e.x;
-        }
-        // the rest of the list moves to the front
-        const int rest = listed - cnt; // < RACE_INSTALL_CAP - 32
-        uint2 mv[RACE_INSTALL_CAP / 32 - 1];
-#pragma unroll
-        for (int k = 0; k < RACE_INSTALL_CAP / 32 - 1; k++)
-            if (lane + 32 * k < rest) mv[k] = ilist[cnt + lane + 32 * k];
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < RACE_INSTALL_CAP / 32 - 1; k++)
-            if (lane + 32 * k < rest) ilist[lane + 32 * k] = mv[k];
-        __syncwarp();
-        listed = rest;
-        inflight = 0;
-        // what is left was listed after the gather started if the gather took the whole list
-        if (rest == 0) age = 0;
-        else if (took_all) age = min(age, gather_age);
-    };
-    // Start gathering the prepared slots of (up to 32 of) the listed envs.
-    auto install_gather = [&]() {
-        const int cnt = min(listed, RACE_PASS);
-        bool trust = true;
-        if (lane < cnt) {
-            const uint32_t ei = ilist[lane].x;
-            // a carried-over entry for this env whose slot is not restocked yet: the slot may be mid-rewrite
-            const unsigned int lo = *(volatile unsigned int *)&s_pend_lo, hi = *(volatile unsigned int *)&s_pend_hi;
-            for (unsigned int k = lo; k < hi; k++) trust = trust && s_pending[k] != ei;
-            race_prefetch_slot(d, adopt, lane, (int)ei);
-        }
-        trust_m = __ballot_sync(0xffffffffu, trust);
-        inflight = cnt;
-        took_all = cnt == listed;
-        gather_age = 0;
-    };
-    // Install everything that is listed, now (the gathers' latency is exposed).
-    auto install_all = [&]() {
-        cp_async_wait<0>();
-        while (inflight || listed > 0) {
-            if (inflight) install_pass();
-            if (listed > 0) {
-                install_gather();
-                cp_async_commit();
-                cp_async_wait<0>();
-            }
-        }
-    };
-
-    while (tile != NO_TILE && tstep < d.steps) {
+    while (true) {
+        const bool have_tile = tile < ntiles;
+        if (!have_tile && pend_m == 0u) break;
         const int i = tile * 32 + lane;
-        const bool valid = i < d.n;
+        const bool valid = have_tile && i < d.n;
         B2D_TICK(t0);
-#if B2D_EXPERIMENT_TIMING
-        if (tm_prev) tm_gap += t0 - tm_prev;
-#endif
-        cp_async_wait<1>(); // this tile's inputs have landed (the newest group, the next tile's, may still fly)
+        cp_async_wait<1>(); // this tile's inputs have landed (the newest group, adoption loads, may still fly)
         B2D_TICK(t1);
-        // a gather committed two tiles ago has landed too (groups complete in order)
-        if (inflight) gather_age += 1;
-        if (inflight && gather_age >= 2) install_pass();
-        // bursts (most of a tile finishing, tile after tile) and, in a fused launch, an env whose tile is
-        // about to be prefetched for the next step: install everything now
-        if (listed >= RACE_INSTALL_CAP - 64 || (fused && listed > 0 && age >= install_all_age)) install_all();
-        if (!inflight && listed > 0 && (listed >= RACE_PASS || age >= install_age)) install_gather();
-        B2D_TICK(t1b);
-        float4 *cur = stage + cb * (RACE_STAGE_SLOTS * 32);
-        const float4 a4 = cur[0 * 32 + lane];
-        const float4 q0 = cur[1 * 32 + lane], q1 = cur[2 * 32 + lane], q2 = cur[3 * 32 + lane],
-                     q3 = cur[4 * 32 + lane], q4 = cur[5 * 32 + lane];
-        const float4 p0 = cur[6 * 32 + lane], p1 = cur[7 * 32 + lane], p2 = cur[8 * 32 + lane];
-        const float4 c0 = cur[9 * 32 + lane];
-        const float4 tl = cur[10 * 32 + lane]; // (j_mot, episode, ring n.y, ring n.z)
+        const float4 a4 = stage[0 * 32 + lane];
+        const float4 q0 = stage[1 * 32 + lane], q1 = stage[2 * 32 + lane], q2 = stage[3 * 32 + lane],
+                     q3 = stage[4 * 32 + lane], q4 = stage[5 * 32 + lane];
+        const float4 p0 = stage[6 * 32 + lane], p1 = stage[7 * 32 + lane], p2 = stage[8 * 32 + lane];
+        const float4 c0 = stage[9 * 32 + lane];
+        const float4 tl = stage[10 * 32 + lane]; // (j_mot, episode, ring n.y, ring n.z)
         __syncwarp();
-        if (nn != NO_TILE && nnstep < d.steps && nn * 32 + lane < d.n)
-            race_prefetch_tile(d, act_of(nnstep), cur, lane, nn * 32 + lane);
-        cp_async_commit(); // group: inputs of the tile after the next + the slots of an install pass
-        cb ^= 1;
-        if (!fused && lane == 0) claim = (int)atomicAdd(&s_ticket, 1u); // shared memory: lands within the tile
+        if (have_tile && next < ntiles && next * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, next * 32 + lane);
+        cp_async_commit(); // group: inputs of the next tile
+        if (have_tile && lane == 0) claim = (int)atomicAdd(&s_ticket, 1u); // shared memory: lands within the tile
 
         float s[17];
         float ring[6];
@@ -823,7 +640,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         }
         B2D_TICK(t2);
 
-        // ---- finished lanes book the episode and list the env for its next one
+        // ---- finished lanes book the episode; their next episode is installed one tile later
         const bool finished = cause >= 0;
         const bool adopt_now = finished && !inject;
         const unsigned int m = __ballot_sync(0xffffffffu, adopt_now);
@@ -838,17 +655,14 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
             atomicAdd(&s_acc[ACC_LENGTH], tick);
             atomicAdd(&s_acc[ACC_RINGS], ring_idx);
             if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
-            if (tstep == d.steps - 1) atomicAdd(&s_score, ring_idx);
             if (inject) race_inject_episode<STRICT>(d, i, episode + 1u, my_row);
-            else ilist[listed + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)i, episode + 1u);
         }
-        listed += __popc(m);
-        if (listed > 0) age += 1;
         __syncwarp();
 
         // ---- observations out: the warp's 3,712-byte tile as 232 lane-consecutive float4.
-        // Rows of lanes that finished hold stale data here; they are rewritten by the install pass.
-        {
+        // Rows of lanes that finished hold stale data here; they are rewritten when the episode
+        // is installed one tile later.
+        if (have_tile) {
             const int rows = min(32, d.n - tile * 32);
             float *gobs = d.obs + (size_t)tile * 32 * RACE_OBS;
             if (rows == 32) {
@@ -863,6 +677,30 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
             __syncwarp();
         }
         B2D_TICK(t3);
+
+        // ---- install the next episode of the envs that finished in the PREVIOUS tile
+        cp_async_wait<1>(); // their prepared slots have landed (only the next tile's inputs may still fly)
+        B2D_TICK(t4);
+        if (pend_m != 0u) {
+            __syncwarp(); // their stale rows (stored by other lanes one tile ago) are ordered before the rewrite
+            if (pend_adopt) {
+                race_adopt_from_smem<STRICT>(d, adopt, lane, pend_i, pend_want, pend_trust, d.obs + (size_t)pend_i * RACE_OBS);
+                const uint2 e = make_uint2((uint32_t)pend_i, pend_want + 1u); // the slot is consumed
+                // best-effort enqueue of the consumed slot
+                for (;;) {
+                    const unsigned int h = *(volatile unsigned int *)&s_q_head;
+                    if (h - *(volatile unsigned int *)&s_q_tail >= (unsigned int)RACE_QUEUE_CAP) break; // full: drop
+                    if (atomicCAS(&s_q_head, h, h + 1u) == h) {
+                        volatile uint2 *q = &s_queue[h & (RACE_QUEUE_CAP - 1)];
+                        q->y = e.y; // .x (the non-empty marker) last
+                        q->x = e.x;
+                        break;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        B2D_TICK(t5);
 
         // ---- restock: 32 waiting entries -> one full-occupancy generation pass by this warp
         if (!inject) {
@@ -887,53 +725,47 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
                 __syncwarp();
                 if (lane == 0) *(volatile unsigned int *)&s_q_tail = take + 32u; // the 32 ring slots may be reused
                 race_fill_slot(d, (int)e.x, e.y);
-                // Slots complete before the pending range shrinks / the lock is released.  The readers
+                // Slots complete before the pending list is lifted / the lock is released.  The readers
                 // this orders against are warps of THIS CTA (CTA scope: a device-scope fence here was
                 // measured at ~10 us under load); the next launch is ordered by the epilogue's fence.
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0) {
-                    // carried entries sit at the ring's front, in s_pending order
-                    const unsigned int hi = *(volatile unsigned int *)&s_pend_hi;
-                    if (take < hi) *(volatile unsigned int *)&s_pend_lo = min(hi, take + 32u);
+                    if (take == 0u) *(volatile unsigned int *)&s_npending = 0u; // carried entries sit at the ring's front
                     atomicExch(&s_q_lock, 0u);
                 }
             }
         }
         B2D_TICK(t6);
-#if B2D_EXPERIMENT_TIMING
-        tm_wait += t1 - t0; tm_inst += t1b - t1; tm_math += t2 - t1b; tm_store += t3 - t2;
-        tm_refill += t6 - t3; tm_iters += 1;
-        tm_prev = clock64();
-#endif
-        tile = next;
-        tstep = nstep;
-        next = nn;
-        nstep = nnstep;
-        nn = n3ok ? n3 : NO_TILE;
-        nnstep = n3step;
-        if (fused) {
-            n3ord += RACE_WARPS;
-            if (n3ord >= o_hi) { n3ord = o_lo + warp; n3step += 1; }
-        } else {
-            n3ord = o_lo + __shfl_sync(0xffffffffu, claim, 0);
+
+        // ---- start streaming the prepared slots of the envs that finished in THIS tile
+        bool trust = true;
+        if (adopt_now) {
+            const unsigned int np = *(volatile unsigned int *)&s_npending;
+            for (unsigned int k = 0; k < np; k++) trust = trust && s_pending[k] != (unsigned int)i;
+            race_prefetch_slot(d, adopt, lane, i);
         }
-        n3ok = n3ord < o_hi;
-        n3 = __ldg(&my_tiles[min(n3ord, o_last)]); // one address for the whole warp; consumed a tile from now
-    }
-    {   // every env that finished in this launch starts its next episode in this launch
-        B2D_TICK(t7);
-        install_all();
-        B2D_TICK(t8);
+        cp_async_commit(); // group: adoption loads of this tile (possibly empty)
+        pend_adopt = adopt_now;
+        pend_trust = trust;
+        pend_i = i;
+        pend_want = episode + 1u;
+        pend_m = m;
 #if B2D_EXPERIMENT_TIMING
-        tm_adopt += t8 - t7;
+        tm_wait += t1 - t0; tm_math += t2 - t1; tm_store += t3 - t2; tm_adopt += t4 - t3; tm_inst += t5 - t4;
+        tm_refill += t6 - t5; tm_iters += 1;
 #endif
+        if (have_tile) {
+            tile = next;
+            next = __shfl_sync(0xffffffffu, claim, 0) * G + first_tile;
+        }
     }
+    cp_async_wait<0>();
 
 #if B2D_EXPERIMENT_TIMING
     if (lane == 0) {
         atomicAdd(&d.ctl->dbg[0], (unsigned long long)tm_wait); atomicAdd(&d.ctl->dbg[1], (unsigned long long)tm_math);
-        atomicAdd(&d.ctl->dbg[2], (unsigned long long)tm_store); atomicAdd(&d.ctl->dbg[3], (unsigned long long)(tm_adopt + tm_gap));
+        atomicAdd(&d.ctl->dbg[2], (unsigned long long)tm_store); atomicAdd(&d.ctl->dbg[3], (unsigned long long)tm_adopt);
         atomicAdd(&d.ctl->dbg[4], (unsigned long long)tm_iters); atomicAdd(&d.ctl->dbg[5], (unsigned long long)tm_refill);
         atomicAdd(&d.ctl->dbg[6], (unsigned long long)(clock64() - t_begin)); atomicAdd(&d.ctl->dbg[7], 1ull);
         atomicAdd(&d.ctl->dbg[8], (unsigned long long)tm_inst);
@@ -949,24 +781,24 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     last = __shfl_sync(0xffffffffu, last, 0);
     if (last) {
         __threadfence_block();
-        // more waiting than can be carried (only when slots were consumed much faster than usual): generate now
+        // whole passes still waiting (only when slots were consumed faster than they could be restocked)
         unsigned int tl0 = *(volatile unsigned int *)&s_q_tail;
         const unsigned int hd = *(volatile unsigned int *)&s_q_head;
-        while (hd - tl0 > (unsigned int)RACE_CARRY) {
+        while (hd - tl0 >= 32u) {
             const uint2 e = s_queue[(tl0 + lane) & (RACE_QUEUE_CAP - 1)];
             race_fill_slot(d, (int)e.x, e.y);
             tl0 += 32u;
         }
-        // the rest is carried to the next launch, compacted at the front of the CTA's list
-        for (unsigned int k = (unsigned int)lane; k < (unsigned int)RACE_CARRY; k += 32u) {
+        // the rest (< 32 entries) is carried to the next launch
+        {
             uint2 e = make_uint2(QUEUE_EMPTY, 0u);
-            if (k < hd - tl0) e = s_queue[(tl0 + k) & (RACE_QUEUE_CAP - 1)];
-            d.carry[(size_t)blockIdx.x * RACE_CARRY + k] = e;
+            if ((unsigned int)lane < hd - tl0) e = s_queue[(tl0 + lane) & (RACE_QUEUE_CAP - 1)];
+            d.carry[(size_t)blockIdx.x * RACE_CARRY + lane] = e;
         }
         if (lane < 7) {
             const int v = s_acc[lane];
             if (v != 0) atomicAdd((unsigned long long *)&d.ctl->acc[lane], (unsigned long long)(long long)v);
-            if (lane == ACC_RINGS) d.cta_score[blockIdx.x] = (long long)s_score + (d.score_add ? d.cta_score[blockIdx.x] : 0ll);
+            if (lane == ACC_RINGS) d.cta_score[blockIdx.x] = (long long)v + (d.score_add ? d.cta_score[blockIdx.x] : 0ll);
         }
 #if B2D_EXPERIMENT_TIMING
         if (lane == 0) {
@@ -982,11 +814,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
 #endif
         __syncwarp();
         if (lane == 0) {
-            // per-CTA wall time of this launch: what the host balances the tile lists with (b2d_vec_step_tape)
-            unsigned long long t_done;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_done));
-            d.cta_ns[blockIdx.x] = t_done - t_go;
-            if (d.count_step) atomicAdd(&d.ctl->ctas_done, (unsigned int)d.steps); // result unused: a reduction, not a returning atomic
+            if (d.count_step) atomicAdd(&d.ctl->ctas_done, 1u); // result unused: a reduction, not a returning atomic
             __threadfence();
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(d.chain + blockIdx.x), "r"(d.seq) : "memory");
         }
@@ -1008,8 +836,8 @@ __global__ void __launch_bounds__(128) race_reset_kernel(const __grid_constant__
 
 // Restock every slot still listed in the carry-over lists now (instead of during the next
 // step) -- used before state is edited from outside (put_state), so that no refill is pending
-// while an edited env may finish again.  One thread per carry entry.
-__global__ void __launch_bounds__(RACE_CARRY) race_drain_kernel(const __grid_constant__ RaceDev d) {
+// while an edited env may finish again.  One warp per step CTA.
+__global__ void __launch_bounds__(32) race_drain_kernel(const __grid_constant__ RaceDev d) {
     uint2 *slot = &d.carry[(size_t)blockIdx.x * RACE_CARRY + threadIdx.x];
     const uint2 e = *slot;
     if (e.x != QUEUE_EMPTY) race_fill_slot(d, (int)e.x, e.y);
@@ -1049,7 +877,6 @@ __global__ void race_log_snapshot_kernel(Ctl *ctl, long long *cta_score, long lo
 __global__ void __launch_bounds__(128) race_observe_kernel(const RaceDev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
-    const size_t ld = d.ld;
     float4 q0 = *race_at(d, SLOT_S + 0, i), q1 = *race_at(d, SLOT_S + 1, i), q2 = *race_at(d, SLOT_S + 2, i), q3 = *race_at(d, SLOT_S + 3, i), q4 = *race_at(d, SLOT_S + 4, i);
     float s[17] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x};
     float4 c0 = *race_at(d, SLOT_C0, i);
@@ -1063,7 +890,6 @@ __global__ void race_pack_kernel(const RaceDev d, const int *ids, int n, float *
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int i = ids ? ids[k] : k;
-    const size_t ld = d.ld;
     float *b = blobs + (size_t)k * (33 + 6 * d.max_rings);
     float4 q0 = *race_at(d, SLOT_S + 0, i), q1 = *race_at(d, SLOT_S + 1, i), q2 = *race_at(d, SLOT_S + 2, i), q3 = *race_at(d, SLOT_S + 3, i), q4 = *race_at(d, SLOT_S + 4, i);
     float4 p0 = *race_at(d, SLOT_P + 0, i), p1 = *race_at(d, SLOT_P + 1, i), p2 = *race_at(d, SLOT_P + 2, i);

@@ -297,71 +297,3 @@ def test_step_tape_equals_single_steps(oracle, n):
         cpu.close()
     a.close()
     b.close()
-
-
-@pytest.mark.parametrize("max_moves", [1, 3, 60])
-def test_fused_tape_launch_bit_exact_vs_port(oracle, monkeypatch, max_moves):
-    """Fused tape launches (one launch walks many vec_steps, no barrier between steps) on a
-    2-CTA grid so that every warp owns ~20 tiles at small N.  max_moves=1 makes every env finish
-    every step (install lists full on every tile), 3 keeps the refill ring saturated, 60 is the
-    ordinary mix.  Result == separate vec_steps == the CPU restatement, every word."""
-    from drone_b200.vec import RaceVec
-    monkeypatch.setenv("B2D_RACE_STEP_CTAS", "2")
-    monkeypatch.setenv("B2D_RACE_BALANCE", "0")
-    n, T, seed = 5003, 70, 23
-    tape = _tape(n, scale=1.0)
-    dtape = torch.from_numpy(tape).cuda()
-    a = RaceVec(n, max_moves=max_moves, math="strict", seed=seed)
-    b = RaceVec(n, max_moves=max_moves, math="strict", seed=seed)
-    a.reset(seed)
-    b.reset(seed)
-    for t in range(T):
-        a.step(dtape[t % 16])
-    l0 = b.kernel_launches
-    b.step_tape(dtape, 0, 33)
-    b.step_tape(dtape, 33 % 16, T - 33)
-    torch.cuda.synchronize()
-    assert b.kernel_launches - l0 == 2, "tape calls were not fused into one launch each"
-    assert a.step_count == b.step_count == T
-    cpu = oracle.OrcRace(n, max_moves=max_moves, seed=seed)
-    cpu.reset(seed, mode=oracle.RESET_PHILOX)
-    for t in range(T):
-        cpu.step(tape[t % 16], mode=oracle.RESET_PHILOX)
-    for name, v in (("single", a), ("fused", b)):
-        assert np.array_equal(_bits(v.get_state()), _bits(cpu.get_state())), name
-        assert np.array_equal(_bits(v.observations.cpu().numpy()), _bits(cpu.observations)), name
-        assert np.array_equal(v.terminals.cpu().numpy(), cpu.terminals), name
-        assert np.array_equal(_bits(v.rewards.cpu().numpy()), _bits(cpu.rewards)), name
-    la, lb, ref = a.log(), b.log(), cpu.log()
-    assert la == lb and lb["n"] == float(ref[8])
-    cpu.close()
-    a.close()
-    b.close()
-
-
-@pytest.mark.parametrize("math", ["strict", "fast"])
-def test_fused_tape_launch_full_grid(math, monkeypatch):
-    """Full-size grid (444 CTAs): 800,001 envs give every warp >= 14 tiles, so the tape is fused.
-    Must equal the same steps issued one launch at a time, bit for bit, in both math modes."""
-    from drone_b200.vec import RaceVec
-    monkeypatch.setenv("B2D_RACE_BALANCE", "0")
-    n, T, seed = 800001, 48, 5
-    g = torch.Generator().manual_seed(77)
-    dtape = (torch.rand((16, n, 4), generator=g) * 2.0 - 1.0).cuda()
-    a = RaceVec(n, max_moves=25, math=math, seed=seed)
-    b = RaceVec(n, max_moves=25, math=math, seed=seed)
-    a.reset(seed)
-    b.reset(seed)
-    for t in range(T):
-        a.step(dtape[t % 16])
-    l0 = b.kernel_launches
-    b.step_tape(dtape, 0, T)
-    torch.cuda.synchronize()
-    assert b.kernel_launches - l0 == 1
-    assert np.array_equal(_bits(a.get_state()), _bits(b.get_state()))
-    assert torch.equal(a.observations.view(torch.int32), b.observations.view(torch.int32))
-    assert torch.equal(a.terminals, b.terminals) and torch.equal(a.rewards.view(torch.int32), b.rewards.view(torch.int32))
-    la, lb = a.log(), b.log()
-    assert la == lb and la["n"] > n
-    a.close()
-    b.close()
