@@ -17,6 +17,17 @@ import bench  # noqa: E402  (ClockSampler, measured_peaks, cpu_sample)
 ALGO_BYTES_PER_DRONE_STEP = 521
 
 
+def swarm_traffic(args):
+    """DRAM bytes per launch from the committed ncu --set full capture (only for the captured shape)."""
+    if args.drones != 64 or args.envs != 65536 or args.math != "fast":
+        return None
+    try:
+        p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "roofline_traffic.json")
+        return json.load(open(p)).get("swarm_kernel_fast_A64_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--drones", type=int, default=64)
@@ -62,7 +73,7 @@ def main():
                                    f"(4 x U(-1,1)), step-only incl. respawns and the 1023-tick env-wide reset (BASELINE.json configs[2])",
                        "rows": rows, "l2": f"working set {rows * 521 / 1e6:.0f} MB per step > 126 MB L2"},
             "episode_stats": stats, "clocks": sampler.summary(), "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": swarm_traffic(args),
                          "kernel": f"swarm_kernel<{args.math}>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_DRONE_STEP * rows,
                          "avg_launch_us": ms / args.steps * 1e3, "peak_source": peak_src}}
     vec.close()
