@@ -380,19 +380,19 @@ extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
 // One launch of the step kernel.  `overlap`: the launch is made programmatically dependent on the
 // previous launch in the stream, which the caller guarantees is the previous step of this handle
 // (b2d_vec_step_tape); every CTA then waits for its own predecessor only (race_step_kernel).
-static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool overlap = false, int chunk = 0, int chunks = 1) {
+static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool overlap = false, int tile_begin = 0,
+                     int tile_end = -1, bool first_chunk = true, bool last_chunk = true) {
     if (v->kind == KIND_RACE) {
         RaceDev d = v->race;
         if (actions) d.act_in = actions;
         d.seq = ++v->seq;
         d.chain_wait = overlap ? 1 : 0;
-        {   // tiles of this launch: the whole vector, or chunk `chunk` of `chunks` (host-buffer pipeline)
+        {   // tiles of this launch: the whole vector, or one chunk of it (host-buffer pipeline)
             const int ntiles = (d.n + 31) / 32;
-            const int per = (ntiles + chunks - 1) / chunks;
-            d.tile_begin = chunk * per;
-            d.tile_end = chunk * per + per < ntiles ? chunk * per + per : ntiles;
-            d.count_step = chunk == chunks - 1;
-            d.score_add = chunk > 0;
+            d.tile_begin = tile_begin;
+            d.tile_end = tile_end < 0 || tile_end > ntiles ? ntiles : tile_end;
+            d.count_step = last_chunk;
+            d.score_add = !first_chunk;
         }
         cudaEvent_t pe[2] = {nullptr, nullptr};
         if (v->profile) {
@@ -464,17 +464,24 @@ static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st
     const bool copy_in = host_actions && host_actions != v->host.actions;
     int chunks = 1;
     if (v->kind == KIND_RACE && rows >= (1u << 17)) chunks = rows >= (1u << 19) ? 8 : 4;
+    // chunk boundaries in tiles; the first chunk is split 1:3 so that the first results start coming
+    // down after 1/32 of the vector instead of 1/8 (the pipeline's lead-in is pure latency)
     const size_t tiles = (rows + 31) / 32, per_tiles = (tiles + chunks - 1) / chunks;
-    for (int j = 0; j < chunks; j++) {
-        const size_t r0 = (size_t)j * per_tiles * 32;
-        if (r0 >= rows) break;
-        const size_t r1 = r0 + per_tiles * 32 < rows ? r0 + per_tiles * 32 : rows;
+    std::vector<size_t> bnd;
+    bnd.push_back(0);
+    if (chunks > 1 && per_tiles >= 4) bnd.push_back(per_tiles / 4);
+    for (int j = 1; j < chunks && (size_t)j * per_tiles < tiles; j++) bnd.push_back((size_t)j * per_tiles);
+    bnd.push_back(tiles);
+    const int nchunks = (int)bnd.size() - 1;
+    for (int j = 0; j < nchunks; j++) {
+        const size_t r0 = bnd[j] * 32;
+        const size_t r1 = bnd[j + 1] * 32 < rows ? bnd[j + 1] * 32 : rows;
         const size_t nr = r1 - r0;
         cudaStream_t cs = v->copy_streams[j & 1];
         // the CPU copy of this chunk's actions overlaps the transfers of the chunks already in flight
         if (copy_in) memcpy(v->host.actions + r0 * 4, host_actions + r0 * 4, nr * 4 * sizeof(float));
         CUDA_TRY(cudaMemcpyAsync(v->dev.actions + r0 * 4, v->host.actions + r0 * 4, nr * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
-        int rc = step_impl(v, nullptr, st, false, j, chunks);
+        int rc = step_impl(v, nullptr, st, false, (int)bnd[j], (int)bnd[j + 1], j == 0, j == nchunks - 1);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(v->ev_step, st));
         CUDA_TRY(cudaStreamWaitEvent(cs, v->ev_step, 0));
