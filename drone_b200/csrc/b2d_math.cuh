@@ -29,6 +29,21 @@ __device__ __forceinline__ xf xclamp(xf a, float lo, float hi) {
     return a.v < lo ? xf(lo) : (a.v > hi ? xf(hi) : a);
 }
 
+// Fast policy only: one MUFU each (rcp.approx <= 1 ulp, rsqrt.approx <= 2 ulp), no denormal /
+// special-case fix-up code.  Arguments on the fast path are masses, inertias, motor constants and
+// squared quaternion norms: always normal, positive numbers.  (__frcp_rn costs ~10 instructions,
+// rsqrtf ~9; six reciprocals and four normalisations per env-step were 10 % of the issue count.)
+__device__ __forceinline__ float approx_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float approx_rsqrt(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ float fval(xf a) { return a.v; }
 __device__ __forceinline__ float fval(float a) { return a; }
 __device__ __forceinline__ xf tsqrt(xf a) { return xsqrt(a); }

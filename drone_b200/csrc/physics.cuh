@@ -162,7 +162,7 @@ __device__ __forceinline__ void advance_body_strict(float s[17], const DronePara
 struct FastConsts {
     float inv_mass, inv_ixx, inv_iyy, inv_izz, inv_kmot;
     float d_yz, d_zx, d_xy; // inertia differences of the gyroscopic term
-    float want[4];
+    float want_k[4]; // commanded rpm / k_mot
 };
 
 __device__ __forceinline__ void rates_fast(const Body<float> &b, const DroneParams &p, const FastConsts &c,
@@ -172,7 +172,7 @@ __device__ __forceinline__ void rates_fast(const Body<float> &b, const DronePara
     float t2 = p.kt * (b.rpm[2] * b.rpm[2]);
     float t3 = p.kt * (b.rpm[3] * b.rpm[3]);
 #pragma unroll
-    for (int m = 0; m < 4; m++) k.drpm[m] = c.inv_kmot * (c.want[m] - b.rpm[m]);
+    for (int m = 0; m < 4; m++) k.drpm[m] = fmaf(-c.inv_kmot, b.rpm[m], c.want_k[m]); // (want - rpm) / k_mot
     const float lift = (t0 + t1) + (t2 + t3);
     const Q4<float> &q = b.q;
     // q (0,0,0,L) q* = L * third column of the (unnormalised) rotation matrix
@@ -197,7 +197,7 @@ __device__ __forceinline__ void rates_fast(const Body<float> &b, const DronePara
 
 __device__ __forceinline__ void qnormalize_fast(Q4<float> &q) {
     float n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
-    float inv = n2 > 0.0f ? rsqrtf(n2) : 1.0f;
+    float inv = n2 > 0.0f ? approx_rsqrt(n2) : 1.0f;
     q.w *= inv; q.x *= inv; q.y *= inv; q.z *= inv;
 }
 
@@ -222,15 +222,16 @@ __device__ __forceinline__ void advance_body_fast(float s[17], const DroneParams
 #pragma unroll
     for (int m = 0; m < 4; m++) b.rpm[m] = s[13 + m];
     FastConsts c;
-    c.inv_mass = __frcp_rn(p.mass);
-    c.inv_ixx = __frcp_rn(p.ixx);
-    c.inv_iyy = __frcp_rn(p.iyy);
-    c.inv_izz = __frcp_rn(p.izz);
-    c.inv_kmot = __frcp_rn(p.kmot);
+    c.inv_mass = approx_rcp(p.mass);
+    c.inv_ixx = approx_rcp(p.ixx);
+    c.inv_iyy = approx_rcp(p.iyy);
+    c.inv_izz = approx_rcp(p.izz);
+    c.inv_kmot = approx_rcp(p.kmot);
     c.d_yz = p.iyy - p.izz; c.d_zx = p.izz - p.ixx; c.d_xy = p.ixx - p.iyy;
     const float half_mrpm = 0.5f * p.mrpm;
+    const float half_mrpm_k = half_mrpm * c.inv_kmot;
 #pragma unroll
-    for (int m = 0; m < 4; m++) c.want[m] = (act[m] + 1.0f) * half_mrpm;
+    for (int m = 0; m < 4; m++) c.want_k[m] = fmaf(act[m], half_mrpm_k, half_mrpm_k);
     const float h = B2D_DT, hh = 0.5f * B2D_DT, h6 = B2D_DT / 6.0f;
 
     Rate<float> k, acc;

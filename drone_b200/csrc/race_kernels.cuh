@@ -40,6 +40,15 @@ namespace b2d {
 #ifndef B2D_EXPERIMENT_SKIP_MATH
 #define B2D_EXPERIMENT_SKIP_MATH 0 // measurement aid: the memory pipeline without the RK4 arithmetic
 #endif
+#ifndef B2D_EXPERIMENT_DOUBLE_MATH
+#define B2D_EXPERIMENT_DOUBLE_MATH 0 // measurement aid: RK4 twice per step, same memory traffic
+#endif
+#ifndef B2D_EXPERIMENT_NO_OBS_STORE
+#define B2D_EXPERIMENT_NO_OBS_STORE 0 // measurement aid: no observation store (-31 % traffic), same arithmetic
+#endif
+#ifndef B2D_EXPERIMENT_NO_RESET
+#define B2D_EXPERIMENT_NO_RESET 0 // measurement aid: episodes never end
+#endif
 #ifndef B2D_EXPERIMENT_TIMING
 #define B2D_EXPERIMENT_TIMING 0 // measurement aid: clock64 sums per phase, printed by b2d_vec_close
 #endif
@@ -115,12 +124,24 @@ struct RaceDev {
 #endif
 constexpr int RACE_HOT_SLOTS = 10;
 enum { SLOT_S = 0, SLOT_P = 5, SLOT_C0 = 8, SLOT_T = 9 };
-__device__ __forceinline__ float4 *race_at(const RaceDev &d, int slot, int i) {
+// address of slot 0 of env i; slot s is race_slot_stride(d) float4 further (a compile-time constant when
+// tiled, so one 64-bit address computation serves all ten slots of an env)
+__device__ __forceinline__ float4 *race_hot(const RaceDev &d, int i) {
 #if B2D_RACE_TILED
-    return d.S + ((((size_t)(i >> 5)) * RACE_HOT_SLOTS + (size_t)slot) << 5) + (i & 31);
+    return d.S + ((size_t)(i >> 5) * (RACE_HOT_SLOTS * 32) + (size_t)(i & 31));
 #else
-    return d.S + (size_t)slot * d.ld + i;
+    return d.S + i;
 #endif
+}
+__device__ __forceinline__ size_t race_slot_stride(const RaceDev &d) {
+#if B2D_RACE_TILED
+    return 32;
+#else
+    return (size_t)d.ld;
+#endif
+}
+__device__ __forceinline__ float4 *race_at(const RaceDev &d, int slot, int i) {
+    return race_hot(d, i) + (size_t)slot * race_slot_stride(d);
 }
 
 // ---------------------------------------------------------------- observations
@@ -174,7 +195,7 @@ __device__ __forceinline__ void race_observe(const float s[17], float mrpm, cons
         row[15] = 0.02f * s[10]; row[16] = 0.02f * s[11]; row[17] = 0.02f * s[12];
         row[18] = r02; row[19] = r12; row[20] = r22;
         row[21] = w; row[22] = x; row[23] = y; row[24] = z;
-        const float inv = __frcp_rn(mrpm);
+        const float inv = approx_rcp(mrpm);
 #pragma unroll
         for (int m = 0; m < 4; m++) row[25 + m] = s[13 + m] * inv;
     }
@@ -187,11 +208,13 @@ constexpr int RING_INDEX_MASK = RING_EXTERNAL - 1;
 
 __device__ __forceinline__ void race_store_state(const RaceDev &d, int i, const float s[17], int tick, int ring_word,
                                                  float ep_ret) {
-    *race_at(d, SLOT_S + 0, i) = make_float4(s[0], s[1], s[2], s[3]);
-    *race_at(d, SLOT_S + 1, i) = make_float4(s[4], s[5], s[6], s[7]);
-    *race_at(d, SLOT_S + 2, i) = make_float4(s[8], s[9], s[10], s[11]);
-    *race_at(d, SLOT_S + 3, i) = make_float4(s[12], s[13], s[14], s[15]);
-    *race_at(d, SLOT_S + 4, i) = make_float4(s[16], __int_as_float(tick), __int_as_float(ring_word), ep_ret);
+    float4 *hot = race_hot(d, i);
+    const size_t st = race_slot_stride(d);
+    hot[(SLOT_S + 0) * st] = make_float4(s[0], s[1], s[2], s[3]);
+    hot[(SLOT_S + 1) * st] = make_float4(s[4], s[5], s[6], s[7]);
+    hot[(SLOT_S + 2) * st] = make_float4(s[8], s[9], s[10], s[11]);
+    hot[(SLOT_S + 3) * st] = make_float4(s[12], s[13], s[14], s[15]);
+    hot[(SLOT_S + 4) * st] = make_float4(s[16], __int_as_float(tick), __int_as_float(ring_word), ep_ret);
 }
 
 __device__ __forceinline__ void race_load_external_ring(const RaceDev &d, int i, int r, float ring[6]) {
@@ -389,12 +412,10 @@ constexpr int RACE_SMEM_BYTES = RACE_WARPS * RACE_WARP_SMEM;
 
 __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *stage, int lane, int i) {
     cp_async16(&stage[0 * 32 + lane], reinterpret_cast<const float4 *>(d.act_in) + i);
+    const float4 *hot = race_hot(d, i);
+    const size_t st = race_slot_stride(d);
 #pragma unroll
-    for (int k = 0; k < 5; k++) cp_async16(&stage[(1 + k) * 32 + lane], race_at(d, SLOT_S + k, i));
-#pragma unroll
-    for (int k = 0; k < 3; k++) cp_async16(&stage[(6 + k) * 32 + lane], race_at(d, SLOT_P + k, i));
-    cp_async16(&stage[9 * 32 + lane], race_at(d, SLOT_C0, i));
-    cp_async16(&stage[10 * 32 + lane], race_at(d, SLOT_T, i));
+    for (int k = 0; k < RACE_HOT_SLOTS; k++) cp_async16(&stage[(1 + k) * 32 + lane], hot + k * st); // stage order = slot order
 }
 
 // the prepared episode of env i -> this lane's adopt slots
@@ -607,33 +628,39 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
             s[0] = fmaf(act[0], 1e-6f, s[0]); s[4] += p.mass * 1e-9f; s[13] += act[3];
 #else
             advance_body<STRICT>(s, p, act);
+#if B2D_EXPERIMENT_DOUBLE_MATH
+            {   // measurement aid: the arithmetic twice, same memory traffic (the second result is folded in at 1e-30)
+                float s2[17];
+#pragma unroll
+                for (int k = 0; k < 17; k++) s2[k] = s[k];
+                advance_body<STRICT>(s2, p, act);
+                s[0] = fmaf(s2[0] + s2[6] + s2[12] + s2[16], 1e-30f, s[0]);
+            }
+#endif
 #endif
 
-            // ---- episode logic: R/drone_race.h:165-203
-            float reward = 0.0f;
+            // ---- episode logic: R/drone_race.h:165-203, as selects (the only branches left are the
+            // rare ones: a plane crossing inside gate_event, a ring pass that needs the next ring)
             const bool oob = s[0] < -10.0f || s[0] > 10.0f || s[1] < -10.0f || s[1] > 10.0f || s[2] < -10.0f || s[2] > 10.0f;
-            if (oob) {
-                reward = -1.0f;
-                ep_ret -= 1.0f;
-                cause = ACC_OOB;
-            } else {
-                float gate;
+            float gate = 0.0f;
+            if (!oob) {
                 if constexpr (STRICT) gate = gate_event<xf>(before, s, ring, -1.0f);
                 else gate = gate_event<float>(before, s, ring, -1.0f);
-                reward = gate;
-                ep_ret += gate;
-                if (gate > 0.0f) ring_idx += 1;
-                if (gate < 0.0f) {
-                    cause = ACC_COLLISION;
-                } else if (tick == d.max_moves) {
-                    cause = ACC_TIMEOUT;
-                } else if (ring_idx == d.max_rings) {
-                    cause = ACC_SPARE; // course complete
-                } else if (gate > 0.0f) { // the next ring becomes the current one
-                    if (ring_ext) race_load_external_ring(d, i, ring_idx, ring);
-                    else race_next_ring(d, i, episode, ring_idx, ring);
-                    race_store_current_ring(d, i, ring);
-                }
+            }
+            const float reward = oob ? -1.0f : gate;
+            ep_ret += reward;
+            const bool passed = gate > 0.0f;
+            ring_idx += passed ? 1 : 0;
+            cause = oob ? (int)ACC_OOB
+                        : gate < 0.0f ? (int)ACC_COLLISION
+                                      : tick == d.max_moves ? (int)ACC_TIMEOUT : ring_idx == d.max_rings ? (int)ACC_SPARE /* course complete */ : -1;
+#if B2D_EXPERIMENT_NO_RESET
+            cause = -1; // measurement aid: episodes never end (same arithmetic and streaming traffic, no reset path)
+#endif
+            if (passed && cause < 0) { // the next ring becomes the current one
+                if (ring_ext) race_load_external_ring(d, i, ring_idx, ring);
+                else race_next_ring(d, i, episode, ring_idx, ring);
+                race_store_current_ring(d, i, ring);
             }
             d.rew[i] = reward;
             d.term[i] = cause >= 0 ? 1 : 0;
@@ -669,8 +696,14 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
                 const float4 *src = reinterpret_cast<const float4 *>(tile_obs);
                 float4 *dst = reinterpret_cast<float4 *>(gobs);
 #pragma unroll
-                for (int k = 0; k < 7; k++) __stcs(&dst[k * 32 + lane], src[k * 32 + lane]);
-                if (lane < 8) __stcs(&dst[224 + lane], src[224 + lane]);
+#if B2D_EXPERIMENT_NO_OBS_STORE
+                if (src[lane].x == 12345.678f) // measurement aid: the step without its 116 B/env observation store
+#endif
+                {
+#pragma unroll
+                    for (int k = 0; k < 7; k++) __stcs(&dst[k * 32 + lane], src[k * 32 + lane]);
+                    if (lane < 8) __stcs(&dst[224 + lane], src[224 + lane]);
+                }
             } else {
                 for (int k = lane; k < rows * RACE_OBS; k += 32) gobs[k] = tile_obs[k];
             }
