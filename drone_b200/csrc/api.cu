@@ -179,14 +179,12 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
     }
     const size_t ld = d.ld;
     if ((rc = setup_buffers(v, ext)) || (rc = dev_alloc(v, &d.S, RACE_HOT_SLOTS * ld)) ||
-        (rc = dev_alloc(v, &d.N, 3 * ld)) || (rc = dev_alloc(v, &d.NS, ld)) || (rc = dev_alloc(v, &d.NR0, ld)) ||
-        (rc = dev_alloc(v, &d.NR1, ld)) || (rc = dev_alloc(v, &d.carry, (size_t)v->step_ctas * RACE_CARRY)) ||
         (rc = dev_alloc(v, &d.chain, (size_t)v->step_ctas)) || (rc = dev_alloc(v, &d.cta_score, (size_t)v->step_ctas)) ||
         (rc = dev_alloc(v, &d.ctl, 1)) || (rc = finish_create(v))) {
         b2d_vec_close(v);
         return rc;
     }
-    race_ctl_reset_kernel<<<1, 256>>>(d.ctl, d.carry, d.cta_score, 0u, (unsigned int)v->step_ctas, 1);
+    race_ctl_reset_kernel<<<1, 256>>>(d.ctl, d.cta_score, 0u, (unsigned int)v->step_ctas, 1);
     cudaDeviceSynchronize();
 #if B2D_EXPERIMENT_TIMING
     cudaMalloc(&d.trace, (size_t)v->step_ctas * 4 * sizeof(unsigned long long));
@@ -317,7 +315,7 @@ extern "C" int b2d_vec_close(b2d_vec *v) {
         unsigned long long h[12];
         cudaMemcpy(h, v->race.ctl->dbg, sizeof(h), cudaMemcpyDeviceToHost);
         const double it = (double)h[4], w = (double)h[7];
-        fprintf(stderr, "[b2d timing] per tile iteration (cycles): wait_inputs %.0f  compute %.0f  store %.0f  wait_adopt %.0f  install %.0f  refill %.0f | per warp-launch: total %.0f  iterations %.2f\n",
+        fprintf(stderr, "[b2d timing] per tile iteration (cycles): wait_inputs %.0f  compute %.0f  store %.0f  (unused) %.0f  pass %.0f  tail_pass %.0f | per warp-launch: total %.0f  iterations %.2f\n",
                 h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[8] / it, h[5] / it, h[6] / w, it / w);
         if (getenv("B2D_TRACE_FILE")) {
             std::vector<unsigned long long> tr((size_t)v->step_ctas * 4);
@@ -366,7 +364,7 @@ extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
         d.key0 = (uint32_t)seed;
         d.key1 = (uint32_t)(seed >> 32);
         if (d.reset_mode == B2D_RESET_INJECT && !d.payload) return fail(B2D_ESTATE, "inject mode without a payload");
-        race_ctl_reset_kernel<<<1, 256, 0, st>>>(d.ctl, d.carry, d.cta_score, 0u, (unsigned int)v->step_ctas, 0);
+        race_ctl_reset_kernel<<<1, 256, 0, st>>>(d.ctl, d.cta_score, 0u, (unsigned int)v->step_ctas, 0);
         race_reset_kernel<<<(d.n + 127) / 128, 128, 0, st>>>(d);
         v->launches += 2;
         return launch_check("race_reset_kernel");
@@ -662,10 +660,6 @@ extern "C" int b2d_put_state(b2d_vec *v, const int *env_ids, int n, const float 
         CUDA_TRY(cudaMemcpy(v->d_ids_tmp, env_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMemcpy(v->d_blob_tmp, host_blobs, (size_t)n * v->blob_floats * sizeof(float), cudaMemcpyHostToDevice));
-    if (v->kind == KIND_RACE) { // no prepared-slot refill may be in flight once states are edited
-        race_drain_kernel<<<v->step_ctas, 32>>>(v->race);
-        v->launches += 1;
-    }
     if (v->kind == KIND_RACE) race_unpack_kernel<<<(n + 127) / 128, 128>>>(v->race, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
     else swarm_unpack_kernel<<<(n * v->swarm.A + 127) / 128, 128>>>(v->swarm, env_ids ? v->d_ids_tmp : nullptr, n, v->d_blob_tmp);
     v->launches += 1;

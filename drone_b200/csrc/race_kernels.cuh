@@ -63,9 +63,7 @@ constexpr int RACE_MIN_CTAS = B2D_RACE_MIN_CTAS;
 constexpr int RACE_LD_ALIGN = 256; // row padding of the SoA arrays
 constexpr int RACE_OBS = 29;
 constexpr int RESET_MAX_ATTEMPTS = 16;
-constexpr int RACE_QUEUE_CAP = 256;            // refill ring of one CTA (entries, power of two)
-constexpr int RACE_CARRY = 32;                 // refill entries a CTA may carry over to the next launch
-constexpr unsigned int QUEUE_EMPTY = 0xffffffffu;
+constexpr int RACE_LIST_CAP = 64;              // per-warp list of finished envs (a pass starts at 32)
 
 // integer episode-statistics accumulators (all race Log fields are integer valued)
 enum { ACC_N = 0, ACC_RETURN, ACC_LENGTH, ACC_RINGS, ACC_OOB, ACC_COLLISION, ACC_TIMEOUT, ACC_SPARE, ACC_COUNT };
@@ -87,11 +85,6 @@ struct RaceDev {
     float4 *S;           // the hot state, 10 float4 per env: S0..S4, P0..P2, C0, T (see race_at)
     float4 *X0;          // external rings [R][ld] (injected episodes / put_state); allocated on first use
     float2 *X1;
-    float4 *N;           // prepared next episode: params 0..11
-    float4 *NS;          //   (spawn.xyz, j_mot)
-    float4 *NR0;         //   ring 0 (pos.xyz, n.x)
-    float4 *NR1;         //   (n.y, n.z, episode tag as bits, -)
-    uint2 *carry;        // [grid][RACE_CARRY] refill entries a CTA did not get to (env, episode)
     unsigned int *chain; // [grid] sequence number of the last launch CTA c completed
     long long *cta_score; // [grid] sum of score over the episodes CTA c saw end in the LAST step (R/drone_race.h:160)
     int tile_begin, tile_end; // tiles [begin, end) stepped by this launch (host-buffer steps are issued in chunks)
@@ -273,7 +266,7 @@ __device__ __forceinline__ void race_generate_ring(const RaceDev &d, uint32_t en
 }
 
 // ring 0, the 13 drone parameters and the spawn position of episode `episode` of env i
-__device__ __noinline__ void race_generate_episode(const RaceDev &d, int i, uint32_t episode, float params[13],
+__device__ __forceinline__ void race_generate_episode(const RaceDev &d, int i, uint32_t episode, float params[13],
                                                    float spawn[3], float ring0[6]) {
     const uint32_t env = d.env_id_base + (uint32_t)i;
     const float origin[3] = {0.0f, 0.0f, 0.0f};
@@ -340,25 +333,11 @@ __device__ __forceinline__ void race_store_params(const RaceDev &d, int i, const
     reinterpret_cast<float2 *>(race_at(d, SLOT_T, i))[0] = make_float2(p[12], __uint_as_float(episode));
 }
 
-// Generate episode `episode` of env i into the env's PREPARED slot (next params, spawn, ring 0)
-// and publish it by tagging the slot with the episode number.
-__device__ __forceinline__ void race_fill_slot(const RaceDev &d, int i, uint32_t episode) {
-    float p[13], spawn[3], ring0[6];
-    race_generate_episode(d, i, episode, p, spawn, ring0);
-    d.N[0 * (size_t)d.ld + i] = make_float4(p[0], p[1], p[2], p[3]);
-    d.N[1 * (size_t)d.ld + i] = make_float4(p[4], p[5], p[6], p[7]);
-    d.N[2 * (size_t)d.ld + i] = make_float4(p[8], p[9], p[10], p[11]);
-    d.NS[i] = make_float4(spawn[0], spawn[1], spawn[2], p[12]);
-    d.NR0[i] = make_float4(ring0[0], ring0[1], ring0[2], ring0[3]);
-    d.NR1[i] = make_float4(ring0[4], ring0[5], __uint_as_float(episode), 0.0f); // (n.y, n.z, tag, -)
-}
-
 // Generate episode `episode` in place as the LIVE episode of env i (params into P, fresh state,
-// current ring, observation row).  Used when the prepared slot cannot be trusted (see
-// race_adopt_from_smem) and by vec_reset.
+// current ring, observation row): the generation passes of the step kernel and vec_reset.
 template <bool STRICT>
-__device__ __noinline__ void race_begin_generated(const RaceDev &d, int i, uint32_t episode, float *obs_row) {
-    float p[13], spawn[3], ring0[6], s[17];
+__device__ __noinline__ void race_begin_generated(const RaceDev &d, int i, uint32_t episode, float *obs_row_global) {
+    float p[13], spawn[3], ring0[6], s[17], o[RACE_OBS];
     race_generate_episode(d, i, episode, p, spawn, ring0);
 #pragma unroll
     for (int k = 0; k < 17; k++) s[k] = 0.0f;
@@ -367,7 +346,10 @@ __device__ __noinline__ void race_begin_generated(const RaceDev &d, int i, uint3
     race_store_params(d, i, p, episode);
     race_store_state(d, i, s, 0, 0, 0.0f);
     race_store_current_ring(d, i, ring0);
-    race_observe<STRICT>(s, p[10], ring0, obs_row);
+    race_observe<STRICT>(s, p[10], ring0, o);
+    // the row lives in global memory (d.obs): plain global stores, no generic-address decode
+#pragma unroll
+    for (int k = 0; k < RACE_OBS; k++) __stcg(obs_row_global + k, o[k]);
 }
 
 // Parity hook (B2D_RESET_INJECT): the next episode is the oracle's post-reset state from the
@@ -401,13 +383,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // per-warp shared memory:
 //   stage  11 float4 per lane: inputs of the NEXT tile, in flight while the current tile computes
 //   obs    the 32x29 observation tile of the current tile (staging for the coalesced store)
-//   adopt  6 float4 per lane: the prepared episode of a lane whose env just finished, in
-//          flight while the NEXT tile computes
+//   list   up to RACE_LIST_CAP (env, next episode) pairs: envs of this warp's tiles that finished
 constexpr int RACE_STAGE_SLOTS = 11; // act, S0..S4, P0..P2, C0, T
-constexpr int RACE_ADOPT_SLOTS = 6;  // N0..N2, (spawn, j_mot), ring0 (pos,n.x), (n.y, n.z, episode tag, -)
 constexpr int RACE_STAGE_BYTES = RACE_STAGE_SLOTS * 32 * 16;
 constexpr int RACE_TILE_BYTES = 32 * RACE_OBS * 4;
-constexpr int RACE_WARP_SMEM = RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_ADOPT_SLOTS * 32 * 16;
+constexpr int RACE_WARP_SMEM = RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_LIST_CAP * 8;
 constexpr int RACE_SMEM_BYTES = RACE_WARPS * RACE_WARP_SMEM;
 
 __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *stage, int lane, int i) {
@@ -416,46 +396,6 @@ __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *sta
     const size_t st = race_slot_stride(d);
 #pragma unroll
     for (int k = 0; k < RACE_HOT_SLOTS; k++) cp_async16(&stage[(1 + k) * 32 + lane], hot + k * st); // stage order = slot order
-}
-
-// the prepared episode of env i -> this lane's adopt slots
-__device__ __forceinline__ void race_prefetch_slot(const RaceDev &d, float4 *adopt, int lane, int i) {
-    const size_t ld = d.ld;
-#pragma unroll
-    for (int k = 0; k < 3; k++) cp_async16(&adopt[k * 32 + lane], &d.N[k * ld + i]);
-    cp_async16(&adopt[3 * 32 + lane], &d.NS[i]);
-    cp_async16(&adopt[4 * 32 + lane], &d.NR0[i]);
-    cp_async16(&adopt[5 * 32 + lane], &d.NR1[i]);
-}
-
-// A finished env starts episode `want`: ADOPT the prepared slot (already copied into this
-// lane's adopt slots): params / spawn / ring 0 are installed and the first observation row is
-// written.  The slot's episode tag is verified; on a mismatch (slot not restocked yet: an env
-// finishing again within a step or two, a full refill ring, or state edited from outside) or
-// when the caller already knows the slot may be mid-rewrite (`trust` false) the episode is
-// generated in place instead: same pure function of (seed, env, episode number).
-template <bool STRICT>
-__device__ __forceinline__ void race_adopt_from_smem(const RaceDev &d, const float4 *adopt, int lane, int i,
-                                                     uint32_t want, bool trust, float *obs_row) {
-    const float4 a = adopt[0 * 32 + lane], b = adopt[1 * 32 + lane], c = adopt[2 * 32 + lane];
-    const float4 sp = adopt[3 * 32 + lane], r0 = adopt[4 * 32 + lane], r1 = adopt[5 * 32 + lane];
-    if (trust && __float_as_uint(r1.z) == want) {
-        float s[17];
-#pragma unroll
-        for (int k = 0; k < 17; k++) s[k] = 0.0f;
-        s[6] = 1.0f;
-        s[0] = sp.x; s[1] = sp.y; s[2] = sp.z;
-        const float ring0[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
-        *race_at(d, SLOT_P + 0, i) = a;
-        *race_at(d, SLOT_P + 1, i) = b;
-        *race_at(d, SLOT_P + 2, i) = c;
-        reinterpret_cast<float2 *>(race_at(d, SLOT_T, i))[0] = make_float2(sp.w, __uint_as_float(want));
-        race_store_state(d, i, s, 0, 0, 0.0f);
-        race_store_current_ring(d, i, ring0);
-        race_observe<STRICT>(s, c.z, ring0, obs_row);
-    } else {
-        race_begin_generated<STRICT>(d, i, want, obs_row);
-    }
 }
 
 // ---------------------------------------------------------------- the step kernel
@@ -492,11 +432,6 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     __shared__ int s_done;
     __shared__ int s_acc[8];
     __shared__ unsigned int s_ticket;             // tile tickets handed out so far in this CTA
-    __shared__ unsigned int s_q_head, s_q_tail;   // refill ring: entries [tail, head), monotonic
-    __shared__ unsigned int s_q_lock;             // one refill pass at a time
-    __shared__ unsigned int s_npending;           // carried-over entries whose slots are not restocked yet
-    __shared__ unsigned int s_pending[RACE_CARRY];
-    __shared__ uint2 s_queue[RACE_QUEUE_CAP];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -506,7 +441,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     const bool inject = d.reset_mode == 1; // B2D_RESET_INJECT (parity hook)
     float4 *stage = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM);
     float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES);
-    float4 *adopt = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES + RACE_TILE_BYTES);
+    uint2 *ilist = reinterpret_cast<uint2 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES + RACE_TILE_BYTES);
     float *my_row = tile_obs + lane * RACE_OBS;
 
     // Launch overlap (b2d_vec_step_tape): the next launch of this kernel may begin while this one
@@ -537,28 +472,11 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     int next = (RACE_WARPS + warp) * G + first_tile;
     if (tile < ntiles && tile * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, tile * 32 + lane);
     cp_async_commit(); // group: inputs of the first tile
-    cp_async_commit(); // group: (empty) adoption loads "of the tile before the first"
 
     if (tid < 8) s_acc[tid] = 0;
-    for (int k = tid; k < RACE_QUEUE_CAP; k += RACE_BLOCK) s_queue[k] = make_uint2(QUEUE_EMPTY, 0u);
-    __syncthreads();
-    if (warp == 0) { // entries carried over from the previous launch seed the ring
-        const uint2 e = __ldcg(&d.carry[(size_t)blockIdx.x * RACE_CARRY + lane]);
-        const bool have = e.x != QUEUE_EMPTY && !inject;
-        const unsigned int m = __ballot_sync(0xffffffffu, have);
-        if (have) {
-            const int slot = __popc(m & ((1u << lane) - 1u));
-            s_queue[slot] = e;
-            s_pending[slot] = e.x;
-        }
-        if (lane == 0) {
-            s_done = 0;
-            s_ticket = 2 * RACE_WARPS;
-            s_q_head = (unsigned int)__popc(m);
-            s_q_tail = 0u;
-            s_q_lock = 0u;
-            s_npending = (unsigned int)__popc(m);
-        }
+    if (tid == 0) {
+        s_done = 0;
+        s_ticket = 2 * RACE_WARPS;
     }
     __syncthreads();
 
@@ -567,21 +485,34 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     const long long t_begin = clock64();
 #endif
 
-    // state carried from one tile to the next
-    bool pend_adopt = false; // this lane's env finished in the previous tile (Philox mode)
-    bool pend_trust = true;  // ... and its prepared slot cannot be mid-rewrite
-    int pend_i = 0;
-    uint32_t pend_want = 0u; // episode number it starts next
-    unsigned int pend_m = 0u; // ballot of pend_adopt
+    int listed = 0; // entries in this warp's list of finished envs (warp-uniform)
     int claim = 0;            // lane 0: ticket for the tile after `next`
 
     while (true) {
-        const bool have_tile = tile < ntiles;
-        if (!have_tile && pend_m == 0u) break;
+        // One place generates episodes: 32 listed envs at a time while tiles remain, the leftovers after the
+        // warp's last tile (every env that finished in this launch starts its next episode in this launch).
+        if (listed >= 32 || (tile >= ntiles && listed > 0)) {
+            B2D_TICK(t4);
+            if (lane < listed) race_begin_generated<STRICT>(d, (int)ilist[lane].x, ilist[lane].y, d.obs + (size_t)ilist[lane].x * RACE_OBS);
+            __syncwarp();
+            const int rest = max(listed - 32, 0); // < 32
+            uint2 e = make_uint2(0u, 0u);
+            if (lane < rest) e = ilist[32 + lane];
+            __syncwarp();
+            if (lane < rest) ilist[lane] = e;
+            __syncwarp();
+            listed = rest;
+            B2D_TICK(t5);
+#if B2D_EXPERIMENT_TIMING
+            if (tile >= ntiles) tm_refill += t5 - t4; else tm_inst += t5 - t4;
+#endif
+            continue;
+        }
+        if (tile >= ntiles) break;
         const int i = tile * 32 + lane;
-        const bool valid = have_tile && i < d.n;
+        const bool valid = i < d.n;
         B2D_TICK(t0);
-        cp_async_wait<1>(); // this tile's inputs have landed (the newest group, adoption loads, may still fly)
+        cp_async_wait<0>(); // this tile's inputs have landed
         B2D_TICK(t1);
         const float4 a4 = stage[0 * 32 + lane];
         const float4 q0 = stage[1 * 32 + lane], q1 = stage[2 * 32 + lane], q2 = stage[3 * 32 + lane],
@@ -590,9 +521,9 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         const float4 c0 = stage[9 * 32 + lane];
         const float4 tl = stage[10 * 32 + lane]; // (j_mot, episode, ring n.y, ring n.z)
         __syncwarp();
-        if (have_tile && next < ntiles && next * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, next * 32 + lane);
+        if (next < ntiles && next * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, next * 32 + lane);
         cp_async_commit(); // group: inputs of the next tile
-        if (have_tile && lane == 0) claim = (int)atomicAdd(&s_ticket, 1u); // shared memory: lands within the tile
+        if (lane == 0) claim = (int)atomicAdd(&s_ticket, 1u); // shared memory: lands within the tile
 
         float s[17];
         float ring[6];
@@ -667,10 +598,9 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         }
         B2D_TICK(t2);
 
-        // ---- finished lanes book the episode; their next episode is installed one tile later
+        // ---- finished lanes book the episode and list the env for its next one
         const bool finished = cause >= 0;
-        const bool adopt_now = finished && !inject;
-        const unsigned int m = __ballot_sync(0xffffffffu, adopt_now);
+        const unsigned int m = __ballot_sync(0xffffffffu, finished && !inject);
         if (valid && !finished) {
             race_store_state(d, i, s, tick, ring_idx | ring_ext, ep_ret);
             race_observe<STRICT>(s, mrpm, ring, my_row);
@@ -683,19 +613,19 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
             atomicAdd(&s_acc[ACC_RINGS], ring_idx);
             if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
             if (inject) race_inject_episode<STRICT>(d, i, episode + 1u, my_row);
+            else ilist[listed + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)i, episode + 1u);
         }
+        listed += __popc(m);
         __syncwarp();
 
         // ---- observations out: the warp's 3,712-byte tile as 232 lane-consecutive float4.
-        // Rows of lanes that finished hold stale data here; they are rewritten when the episode
-        // is installed one tile later.
-        if (have_tile) {
+        // Rows of lanes that finished hold stale data here; the generation pass rewrites them.
+        {
             const int rows = min(32, d.n - tile * 32);
             float *gobs = d.obs + (size_t)tile * 32 * RACE_OBS;
             if (rows == 32) {
                 const float4 *src = reinterpret_cast<const float4 *>(tile_obs);
                 float4 *dst = reinterpret_cast<float4 *>(gobs);
-#pragma unroll
 #if B2D_EXPERIMENT_NO_OBS_STORE
                 if (src[lane].x == 12345.678f) // measurement aid: the step without its 116 B/env observation store
 #endif
@@ -711,90 +641,13 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         }
         B2D_TICK(t3);
 
-        // ---- install the next episode of the envs that finished in the PREVIOUS tile
-        cp_async_wait<1>(); // their prepared slots have landed (only the next tile's inputs may still fly)
-        B2D_TICK(t4);
-        if (pend_m != 0u) {
-            __syncwarp(); // their stale rows (stored by other lanes one tile ago) are ordered before the rewrite
-            if (pend_adopt) {
-                race_adopt_from_smem<STRICT>(d, adopt, lane, pend_i, pend_want, pend_trust, d.obs + (size_t)pend_i * RACE_OBS);
-                const uint2 e = make_uint2((uint32_t)pend_i, pend_want + 1u); // the slot is consumed
-                // best-effort enqueue of the consumed slot
-                for (;;) {
-                    const unsigned int h = *(volatile unsigned int *)&s_q_head;
-                    if (h - *(volatile unsigned int *)&s_q_tail >= (unsigned int)RACE_QUEUE_CAP) break; // full: drop
-                    if (atomicCAS(&s_q_head, h, h + 1u) == h) {
-                        volatile uint2 *q = &s_queue[h & (RACE_QUEUE_CAP - 1)];
-                        q->y = e.y; // .x (the non-empty marker) last
-                        q->x = e.x;
-                        break;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        B2D_TICK(t5);
-
-        // ---- restock: 32 waiting entries -> one full-occupancy generation pass by this warp
-        if (!inject) {
-            unsigned int take = QUEUE_EMPTY;
-            if (lane == 0) {
-                const unsigned int tl0 = *(volatile unsigned int *)&s_q_tail;
-                if (*(volatile unsigned int *)&s_q_head - tl0 >= 32u && atomicCAS(&s_q_lock, 0u, 1u) == 0u) {
-                    const unsigned int tl1 = *(volatile unsigned int *)&s_q_tail; // re-read under the lock
-                    if (*(volatile unsigned int *)&s_q_head - tl1 >= 32u) take = tl1;
-                    else atomicExch(&s_q_lock, 0u);
-                }
-            }
-            take = __shfl_sync(0xffffffffu, take, 0);
-            if (take != QUEUE_EMPTY) {
-                volatile uint2 *slot = &s_queue[(take + lane) & (RACE_QUEUE_CAP - 1)];
-                uint2 e;
-                do { // the producer writes the entry right after reserving it
-                    e.x = slot->x;
-                    e.y = slot->y;
-                } while (e.x == QUEUE_EMPTY);
-                slot->x = QUEUE_EMPTY;
-                __syncwarp();
-                if (lane == 0) *(volatile unsigned int *)&s_q_tail = take + 32u; // the 32 ring slots may be reused
-                race_fill_slot(d, (int)e.x, e.y);
-                // Slots complete before the pending list is lifted / the lock is released.  The readers
-                // this orders against are warps of THIS CTA (CTA scope: a device-scope fence here was
-                // measured at ~10 us under load); the next launch is ordered by the epilogue's fence.
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) {
-                    if (take == 0u) *(volatile unsigned int *)&s_npending = 0u; // carried entries sit at the ring's front
-                    atomicExch(&s_q_lock, 0u);
-                }
-            }
-        }
-        B2D_TICK(t6);
-
-        // ---- start streaming the prepared slots of the envs that finished in THIS tile
-        bool trust = true;
-        if (adopt_now) {
-            const unsigned int np = *(volatile unsigned int *)&s_npending;
-            for (unsigned int k = 0; k < np; k++) trust = trust && s_pending[k] != (unsigned int)i;
-            race_prefetch_slot(d, adopt, lane, i);
-        }
-        cp_async_commit(); // group: adoption loads of this tile (possibly empty)
-        pend_adopt = adopt_now;
-        pend_trust = trust;
-        pend_i = i;
-        pend_want = episode + 1u;
-        pend_m = m;
 #if B2D_EXPERIMENT_TIMING
-        tm_wait += t1 - t0; tm_math += t2 - t1; tm_store += t3 - t2; tm_adopt += t4 - t3; tm_inst += t5 - t4;
-        tm_refill += t6 - t5; tm_iters += 1;
+        tm_wait += t1 - t0; tm_math += t2 - t1; tm_store += t3 - t2; tm_iters += 1;
 #endif
-        if (have_tile) {
-            tile = next;
-            next = __shfl_sync(0xffffffffu, claim, 0) * G + first_tile;
-        }
+        tile = next;
+        next = __shfl_sync(0xffffffffu, claim, 0) * G + first_tile;
     }
     cp_async_wait<0>();
-
 #if B2D_EXPERIMENT_TIMING
     if (lane == 0) {
         atomicAdd(&d.ctl->dbg[0], (unsigned long long)tm_wait); atomicAdd(&d.ctl->dbg[1], (unsigned long long)tm_math);
@@ -814,20 +667,6 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     last = __shfl_sync(0xffffffffu, last, 0);
     if (last) {
         __threadfence_block();
-        // whole passes still waiting (only when slots were consumed faster than they could be restocked)
-        unsigned int tl0 = *(volatile unsigned int *)&s_q_tail;
-        const unsigned int hd = *(volatile unsigned int *)&s_q_head;
-        while (hd - tl0 >= 32u) {
-            const uint2 e = s_queue[(tl0 + lane) & (RACE_QUEUE_CAP - 1)];
-            race_fill_slot(d, (int)e.x, e.y);
-            tl0 += 32u;
-        }
-        // the rest (< 32 entries) is carried to the next launch
-        {
-            uint2 e = make_uint2(QUEUE_EMPTY, 0u);
-            if ((unsigned int)lane < hd - tl0) e = s_queue[(tl0 + lane) & (RACE_QUEUE_CAP - 1)];
-            d.carry[(size_t)blockIdx.x * RACE_CARRY + lane] = e;
-        }
         if (lane < 7) {
             const int v = s_acc[lane];
             if (v != 0) atomicAdd((unsigned long long *)&d.ctl->acc[lane], (unsigned long long)(long long)v);
@@ -855,7 +694,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
 }
 
 // ---------------------------------------------------------------- vec_reset / observe / blobs
-// vec_reset (EB:500-504): episode 0 becomes the live episode, episode 1 the prepared one.
+// vec_reset (EB:500-504): episode 0 becomes the live episode.
 __global__ void __launch_bounds__(128) race_reset_kernel(const __grid_constant__ RaceDev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.n) return;
@@ -864,23 +703,10 @@ __global__ void __launch_bounds__(128) race_reset_kernel(const __grid_constant__
         return;
     }
     race_begin_generated<true>(d, i, 0u, d.obs + (size_t)i * RACE_OBS);
-    race_fill_slot(d, i, 1u);
 }
 
-// Restock every slot still listed in the carry-over lists now (instead of during the next
-// step) -- used before state is edited from outside (put_state), so that no refill is pending
-// while an edited env may finish again.  One warp per step CTA.
-__global__ void __launch_bounds__(32) race_drain_kernel(const __grid_constant__ RaceDev d) {
-    uint2 *slot = &d.carry[(size_t)blockIdx.x * RACE_CARRY + threadIdx.x];
-    const uint2 e = *slot;
-    if (e.x != QUEUE_EMPTY) race_fill_slot(d, (int)e.x, e.y);
-    *slot = make_uint2(QUEUE_EMPTY, 0u);
-}
-
-// (re)initialise the control block: step counter, carry-over lists, optionally the statistics
-__global__ void race_ctl_reset_kernel(Ctl *ctl, uint2 *carry, long long *cta_score, unsigned int steps, unsigned int grid,
-                                      int clear_acc) {
-    for (unsigned int k = threadIdx.x; k < grid * RACE_CARRY; k += blockDim.x) carry[k] = make_uint2(QUEUE_EMPTY, 0u);
+// (re)initialise the control block: step counter, optionally the statistics
+__global__ void race_ctl_reset_kernel(Ctl *ctl, long long *cta_score, unsigned int steps, unsigned int grid, int clear_acc) {
     for (unsigned int k = threadIdx.x; k < grid; k += blockDim.x) cta_score[k] = 0;
     if (threadIdx.x == 0) {
         ctl->grid = grid;
