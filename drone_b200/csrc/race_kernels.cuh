@@ -6,26 +6,23 @@
 //   race_generate_episode  R/drone_race.h:127-154 c_reset, R/dronelib.h:141-183,250-300,451-460
 //   log accumulation       R/drone_race.h:61-70   add_log, EB:572-591 vec_log
 //
-// Layout in HBM (ld = num_envs rounded up to 256; lane i touches element i of
-// every array, so each warp access is one contiguous 512-byte float4 run; S, P, C0 and T are
-// interleaved per tile of 32 envs, see race_at):
-//   S  float4[5][ld]  (px,py,pz,vx) (vy,vz,qw,qx) (qy,qz,wx,wy) (wz,r0,r1,r2) (r3,tick,ring word,ep_return)
-//                     ring word = ring_idx | (rings are external) << 30
-//   P  float4[3][ld]  (mass,ixx,iyy,izz) (arm,k_thrust,k_ang_damp,k_drag) (b_drag,gravity,max_rpm,k_mot)
-//   C0 float4[ld]     the CURRENT ring (pos.xyz, n.x): no dependent gather per step
-//   T  float4[ld]     (j_mot, live episode number, current ring n.y, n.z)
-//   N float4[3][ld], NS, NR0, NR1 float4[ld]  prepared next episode: params, (spawn, j_mot), ring 0,
-//                     (.., episode tag); rings beyond the current one are generated when reached
+// Layout in HBM.  The ten float4 a step reads per env are interleaved per tile of 32 envs,
+// float4[tile][10][32] (race_at): lane i touches element i of every 512-byte row, and the 5 KB a
+// warp reads for a tile / the 2.5 KB of state it writes back are one contiguous run each.
+//   slots 0-4  S   (px,py,pz,vx) (vy,vz,qw,qx) (qy,qz,wx,wy) (wz,r0,r1,r2) (r3,tick,ring word,ep_return)
+//                  ring word = ring_idx | (rings are external) << 30
+//   slots 5-7  P   (mass,ixx,iyy,izz) (arm,k_thrust,k_ang_damp,k_drag) (b_drag,gravity,max_rpm,k_mot)
+//   slot  8    C0  the CURRENT ring (pos.xyz, n.x): no dependent gather per step
+//   slot  9    T   (j_mot, live episode number, current ring n.y, n.z)
 //   X0 float4[R][ld], X1 float2[R][ld]  rings of episodes that came from outside (reset payload of the
-//                     parity hook, put_state); allocated on first use only
+//                  parity hook, put_state); allocated on first use only
 // Per env-step the kernel reads 172 B (act 16, S 80, P 52, C 24; + 4 B episode number) and writes
 // 201 B (S 80, obs 116, reward 4, terminal 1) = 373 algorithmic bytes.
 //
-// Auto-reset without a reset on the critical path: an env that finishes ADOPTS its
-// prepared episode (13 params + spawn + ring 0: a handful of loads/stores) and queues
-// itself on its CTA's refill ring; whenever 32 entries wait, one warp regenerates the
-// consumed slots (Philox + trig, ~7800 instructions) with every lane busy, in between
-// two of its tiles (see race_step_kernel).
+// Auto-reset.  Episode k of env g is a pure function of (seed, g, k) (counter-based Philox), so
+// nothing about the next episode is stored anywhere: an env that finishes is listed by its warp
+// and the listed envs' next episodes are GENERATED IN PLACE, a different env on every lane (see
+// race_step_kernel).  Rings beyond the current one are generated when they are reached.
 #pragma once
 #include "physics.cuh"
 
@@ -35,7 +32,7 @@ namespace b2d {
 #define B2D_RACE_BLOCK 128
 #endif
 #ifndef B2D_RACE_MIN_CTAS
-#define B2D_RACE_MIN_CTAS 3
+#define B2D_RACE_MIN_CTAS 4
 #endif
 #ifndef B2D_EXPERIMENT_SKIP_MATH
 #define B2D_EXPERIMENT_SKIP_MATH 0 // measurement aid: the memory pipeline without the RK4 arithmetic
@@ -404,26 +401,31 @@ __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *sta
 //
 // Tile order.  CTA c owns tiles c, c+G, c+2G, ... (G = grid size; the same CTA owns the same
 // envs in every launch) and its warps draw them through a SHARED-MEMORY ticket, so a warp that
-// spent time restocking episode slots simply takes fewer tiles.  Across the grid the warps
-// sweep every array as one contiguous frontier, which is what DRAM wants (sharded dynamic
-// claims ran 4% slower with 16 frontiers and 50% slower with 256).
+// spent time generating episodes simply takes fewer tiles.  Across the grid the warps sweep
+// every array as one contiguous frontier, which is what DRAM wants (sharded dynamic claims ran
+// 4% slower with 16 frontiers and 50% slower with 256).
 //
-// Everything with memory latency is software-pipelined one tile deep and costs no registers:
-//   * the inputs of the warp's next tile stream into shared memory (cp.async) while the
-//     current tile computes (~1000 FP32 instructions per lane);
-//   * a lane whose env finished streams the env's prepared next episode into shared memory
-//     and installs it one tile later (no dependent-load stall, no second kernel).
+// The inputs of the warp's next tile stream into shared memory (cp.async) while the current
+// tile computes (~900 FP32 instructions per lane): no register cost, no dependent-load stall.
 // Observation rows ([N,29] row-major, 116 B: not a multiple of 16) are staged per warp in
 // shared memory and leave as lane-consecutive float4 stores, 512 B per instruction.
 //
-// Restocking.  Installing an episode consumes the env's prepared slot; the slot is described
-// by an entry in the CTA's refill ring (shared memory).  Whenever 32 entries are waiting, the
-// next warp that finishes a tile regenerates them in one pass with every lane busy (Philox +
-// trig, ~7800 instructions).  One pass at a time per CTA and FIFO order, so two generations for
-// the same env never interleave.  Fewer than 32 entries left at the end of a launch are carried
-// to the next one (d.carry); an env listed there may have its slot rewritten while the next
-// launch runs, so if it finishes again meanwhile it is generated in place (`s_pending`).
-// Enqueueing is best effort: a full ring drops the entry and the tag check covers it later.
+// Auto-reset costs in proportion to the envs that finish, not to the tiles that contain one, and
+// touches no memory but the env's own state.  About 2.5 % of the envs finish per step, i.e. more
+// than half of all tiles hold one; a finished lane only appends (env, next episode) to its warp's
+// list in shared memory.  When 32 are listed, and after the warp's last tile, the warp runs a
+// GENERATION PASS with a different finished env on every lane: Philox draws, the reference's
+// scale laws and rejection loops (race_generate_episode), then parameters, spawn state, ring 0
+// and the first observation row are written straight over the finished episode.  The list is
+// private to the warp (no atomics), the row an env's tile store left behind is overwritten in
+// program order by the same warp, and every env that finished in a launch has its next episode
+// in place when the launch ends, like the reference's c_step.
+// (Earlier generations of this kernel kept a PREPARED next episode per env -- 96 B in six
+// arrays, restocked through a per-CTA refill ring with carry-over lists between launches -- so
+// that a finish needed only an "adopt".  Measured with the reset path compiled out
+// (B2D_EXPERIMENT_NO_RESET) the step streams at 63 us per 1 M envs; the slot traffic, scattered
+// 16-byte gathers and partial-sector writes for 2.5 % of the envs, cost 15 us on top.  In-place
+// generation has no such traffic: 76 us with 3 CTAs per SM, 74.7 us with 4.)
 //
 // No global atomic in this kernel returns a value (see Ctl).
 template <bool STRICT>

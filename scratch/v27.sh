@@ -1,0 +1,6 @@
+run() { python bench.py --no-e2e --no-cpu-baseline $2 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1', round(d['ms_per_step']*1e3,2), round(d['roofline']['frac'],4), d['clocks']['reasons'], d['episode_stats']['n'])"; }
+for n in b128c4 b128c5 b64c8 b96c5 b256c2 b64c10; do
+B2D_LIBRARY=/root/repo/scratch/libs/lib_$n.so run $n-tape
+B2D_LIBRARY=/root/repo/scratch/libs/lib_$n.so run $n-single "--launch single"
+done
+run base-tape
