@@ -710,9 +710,10 @@ extern "C" int b2d_set_reset_payload(b2d_vec *v, const float *host_payload) {
 }
 
 // Per-kernel timing of the steps issued while profiling is on.  enable=1 starts recording
-// CUDA events around the step kernel and the adopt kernel of every subsequent step (fast math);
-// enable=0 synchronises, returns the mean durations in microseconds (out_us[0] = step kernel,
-// out_us[1] = adopt kernel, out_us[2] = profiled steps) and stops.  Not capturable.
+// CUDA events around the step kernel of every subsequent step; enable=0 synchronises, returns the
+// mean duration in microseconds (out_us[0] = step kernel, out_us[1] = 0: the separate adoption
+// kernel of early builds is gone, the slot is kept for ABI stability, out_us[2] = profiled steps)
+// and stops.  Not capturable.
 extern "C" int b2d_profile_kernels(b2d_vec *v, int enable, float out_us[3]) {
     if (!v) return fail(B2D_EINVAL, "null handle");
     if (enable) {

@@ -184,7 +184,7 @@ int b2d_set_reset_payload(b2d_vec *vec, const float *host_payload);
 int b2d_set_step_count(b2d_vec *vec, uint32_t steps);
 
 /* Per-kernel timing with CUDA events: enable=1 starts timing the kernels of every later step,
- * enable=0 synchronises and returns mean microseconds {step kernel, adopt kernel, steps timed}. */
+ * enable=0 synchronises and returns mean microseconds {step kernel, 0 (reserved), steps timed}. */
 int b2d_profile_kernels(b2d_vec *vec, int enable, float out_us[3]);
 
 /* ---- trainer-side helper -------------------------------------------
