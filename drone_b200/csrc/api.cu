@@ -42,7 +42,8 @@ struct b2d_vec {
     int device;
     int num_envs, num_agents /* rows */, obs_dim, blob_floats, payload_floats;
     int math, write_clamped;
-    int step_ctas;
+    int step_ctas;   // race: CTAs of an overlapped (tape) launch = the largest grid; swarm: unused
+    int single_ctas; // race: CTAs of a launch that runs alone
     RaceDev race;
     SwarmDev swarm;
     // device contract buffers (owned unless external)
@@ -174,8 +175,12 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
         const int warps_per_cta = RACE_BLOCK / 32;
         const int ntiles = (cfg->num_envs + 31) / 32;
         int step_ctas = (ntiles + warps_per_cta - 1) / warps_per_cta;
+        // overlapped launches (b2d_vec_step_tape) run best with every CTA slot taken (finer per-CTA chains:
+        // 68 vs 74 us per 1M envs), a launch that runs alone with one CTA per SM fewer (78 vs 84 us)
+        v->single_ctas = step_ctas < sms * (RACE_MIN_CTAS - 1) ? step_ctas : sms * (RACE_MIN_CTAS - 1);
         if (step_ctas > sms * RACE_MIN_CTAS) step_ctas = sms * RACE_MIN_CTAS;
         v->step_ctas = step_ctas;
+        d.max_grid = step_ctas;
     }
     const size_t ld = d.ld;
     if ((rc = setup_buffers(v, ext)) || (rc = dev_alloc(v, &d.S, RACE_HOT_SLOTS * ld)) ||
@@ -379,7 +384,7 @@ extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
 // previous launch in the stream, which the caller guarantees is the previous step of this handle
 // (b2d_vec_step_tape); every CTA then waits for its own predecessor only (race_step_kernel).
 static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool overlap = false, int tile_begin = 0,
-                     int tile_end = -1, bool first_chunk = true, bool last_chunk = true) {
+                     int tile_end = -1, bool first_chunk = true, bool last_chunk = true, bool series = false) {
     if (v->kind == KIND_RACE) {
         RaceDev d = v->race;
         if (actions) d.act_in = actions;
@@ -399,7 +404,7 @@ static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool ove
         }
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)v->step_ctas);
+        cfg.gridDim = dim3((unsigned)(series ? v->step_ctas : v->single_ctas));
         cfg.blockDim = dim3(RACE_BLOCK);
         cfg.dynamicSmemBytes = RACE_SMEM_BYTES;
         cfg.stream = st;
@@ -445,7 +450,8 @@ extern "C" int b2d_vec_step_tape(b2d_vec *v, const float *device_tape, int tape_
     const size_t stride = (size_t)v->num_agents * 4;
     for (int k = 0; k < steps; k++) {
         const float *a = device_tape + (size_t)((first + k) % tape_len) * stride;
-        int rc = step_impl(v, a, st, k > 0 && cap == cudaStreamCaptureStatusNone && v->kind == KIND_RACE);
+        int rc = step_impl(v, a, st, k > 0 && cap == cudaStreamCaptureStatusNone && v->kind == KIND_RACE, 0, -1, true, true,
+                           steps > 1);
         if (rc) return rc;
     }
     return B2D_OK;
@@ -587,7 +593,7 @@ extern "C" int b2d_step_count(b2d_vec *v, uint32_t *steps, void *stream) {
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     uint32_t w[2] = {0, 1};
     CUDA_TRY(cudaMemcpy(w, &ctl->ctas_done, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    *steps = w[1] ? w[0] / w[1] : 0;
+    *steps = v->kind == KIND_RACE ? w[0] : (w[1] ? w[0] / w[1] : 0);
     return B2D_OK;
 }
 
@@ -595,7 +601,7 @@ extern "C" int b2d_set_step_count(b2d_vec *v, uint32_t steps) {
     if (!v) return fail(B2D_EINVAL, "null handle");
     Ctl *ctl = v->kind == KIND_RACE ? v->race.ctl : v->swarm.ctl;
     CUDA_TRY(cudaDeviceSynchronize());
-    const uint32_t done = steps * (uint32_t)(v->kind == KIND_RACE ? v->step_ctas : 1);
+    const uint32_t done = steps;
     CUDA_TRY(cudaMemcpy(&ctl->ctas_done, &done, sizeof(uint32_t), cudaMemcpyHostToDevice));
     return B2D_OK;
 }

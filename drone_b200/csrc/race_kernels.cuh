@@ -60,7 +60,6 @@ constexpr int RACE_MIN_CTAS = B2D_RACE_MIN_CTAS;
 constexpr int RACE_LD_ALIGN = 256; // row padding of the SoA arrays
 constexpr int RACE_OBS = 29;
 constexpr int RESET_MAX_ATTEMPTS = 16;
-constexpr int RACE_LIST_CAP = 64;              // per-warp list of finished envs (a pass starts at 32)
 
 // integer episode-statistics accumulators (all race Log fields are integer valued)
 enum { ACC_N = 0, ACC_RETURN, ACC_LENGTH, ACC_RINGS, ACC_OOB, ACC_COLLISION, ACC_TIMEOUT, ACC_SPARE, ACC_COUNT };
@@ -69,7 +68,7 @@ enum { ACC_N = 0, ACC_RETURN, ACC_LENGTH, ACC_RINGS, ACC_OOB, ACC_COLLISION, ACC
 // atomic: on B200 a returning ATOMG issued by a busy SM was measured to take 5-10 us (longer
 // than a whole tile of work), so every global update here is a fire-and-forget reduction.
 struct Ctl {
-    unsigned int ctas_done; // step CTAs finished since the last vec_reset; vec steps completed = ctas_done / grid
+    unsigned int ctas_done; // race: vec_steps completed since the last vec_reset (swarm: step CTAs of tile 0, grid = 1)
     unsigned int grid;      // step CTAs per launch (fixed for the life of the handle)
     unsigned int pad0[2];
     long long acc[ACC_COUNT];
@@ -85,6 +84,7 @@ struct RaceDev {
     unsigned int *chain; // [grid] sequence number of the last launch CTA c completed
     long long *cta_score; // [grid] sum of score over the episodes CTA c saw end in the LAST step (R/drone_race.h:160)
     int tile_begin, tile_end; // tiles [begin, end) stepped by this launch (host-buffer steps are issued in chunks)
+    int max_grid;        // the largest grid any launch of this handle uses (size of cta_score / chain)
     int count_step;      // 1: this launch completes a vec_step (the last chunk): bump the step counter
     int score_add;       // 1: add to cta_score instead of overwriting it (chunks after the first)
     uint32_t seq;        // sequence number of this launch (host counter, +1 per launch)
@@ -332,8 +332,10 @@ __device__ __forceinline__ void race_store_params(const RaceDev &d, int i, const
 
 // Generate episode `episode` in place as the LIVE episode of env i (params into P, fresh state,
 // current ring, observation row): the generation passes of the step kernel and vec_reset.
-template <bool STRICT>
-__device__ __noinline__ void race_begin_generated(const RaceDev &d, int i, uint32_t episode, float *obs_row_global) {
+// ROW_SHARED: `obs_row` is the env's row of the warp's shared-memory observation tile (step kernel),
+// else its row of d.obs in global memory (vec_reset).
+template <bool STRICT, bool ROW_SHARED = false>
+__device__ __noinline__ void race_begin_generated(const RaceDev &d, int i, uint32_t episode, float *obs_row) {
     float p[13], spawn[3], ring0[6], s[17], o[RACE_OBS];
     race_generate_episode(d, i, episode, p, spawn, ring0);
 #pragma unroll
@@ -344,9 +346,11 @@ __device__ __noinline__ void race_begin_generated(const RaceDev &d, int i, uint3
     race_store_state(d, i, s, 0, 0, 0.0f);
     race_store_current_ring(d, i, ring0);
     race_observe<STRICT>(s, p[10], ring0, o);
-    // the row lives in global memory (d.obs): plain global stores, no generic-address decode
 #pragma unroll
-    for (int k = 0; k < RACE_OBS; k++) __stcg(obs_row_global + k, o[k]);
+    for (int k = 0; k < RACE_OBS; k++) {
+        if constexpr (ROW_SHARED) obs_row[k] = o[k];
+        else __stcg(obs_row + k, o[k]); // plain global stores, no generic-address decode
+    }
 }
 
 // Parity hook (B2D_RESET_INJECT): the next episode is the oracle's post-reset state from the
@@ -380,11 +384,10 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // per-warp shared memory:
 //   stage  11 float4 per lane: inputs of the NEXT tile, in flight while the current tile computes
 //   obs    the 32x29 observation tile of the current tile (staging for the coalesced store)
-//   list   up to RACE_LIST_CAP (env, next episode) pairs: envs of this warp's tiles that finished
 constexpr int RACE_STAGE_SLOTS = 11; // act, S0..S4, P0..P2, C0, T
 constexpr int RACE_STAGE_BYTES = RACE_STAGE_SLOTS * 32 * 16;
 constexpr int RACE_TILE_BYTES = 32 * RACE_OBS * 4;
-constexpr int RACE_WARP_SMEM = RACE_STAGE_BYTES + RACE_TILE_BYTES + RACE_LIST_CAP * 8;
+constexpr int RACE_WARP_SMEM = RACE_STAGE_BYTES + RACE_TILE_BYTES;
 constexpr int RACE_SMEM_BYTES = RACE_WARPS * RACE_WARP_SMEM;
 
 __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *stage, int lane, int i) {
@@ -443,7 +446,6 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     const bool inject = d.reset_mode == 1; // B2D_RESET_INJECT (parity hook)
     float4 *stage = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM);
     float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES);
-    uint2 *ilist = reinterpret_cast<uint2 *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES + RACE_TILE_BYTES);
     float *my_row = tile_obs + lane * RACE_OBS;
 
     // Launch overlap (b2d_vec_step_tape): the next launch of this kernel may begin while this one
@@ -487,29 +489,9 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     const long long t_begin = clock64();
 #endif
 
-    int listed = 0; // entries in this warp's list of finished envs (warp-uniform)
     int claim = 0;            // lane 0: ticket for the tile after `next`
 
     while (true) {
-        // One place generates episodes: 32 listed envs at a time while tiles remain, the leftovers after the
-        // warp's last tile (every env that finished in this launch starts its next episode in this launch).
-        if (listed >= 32 || (tile >= ntiles && listed > 0)) {
-            B2D_TICK(t4);
-            if (lane < listed) race_begin_generated<STRICT>(d, (int)ilist[lane].x, ilist[lane].y, d.obs + (size_t)ilist[lane].x * RACE_OBS);
-            __syncwarp();
-            const int rest = max(listed - 32, 0); // < 32
-            uint2 e = make_uint2(0u, 0u);
-            if (lane < rest) e = ilist[32 + lane];
-            __syncwarp();
-            if (lane < rest) ilist[lane] = e;
-            __syncwarp();
-            listed = rest;
-            B2D_TICK(t5);
-#if B2D_EXPERIMENT_TIMING
-            if (tile >= ntiles) tm_refill += t5 - t4; else tm_inst += t5 - t4;
-#endif
-            continue;
-        }
         if (tile >= ntiles) break;
         const int i = tile * 32 + lane;
         const bool valid = i < d.n;
@@ -600,9 +582,8 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         }
         B2D_TICK(t2);
 
-        // ---- finished lanes book the episode and list the env for its next one
+        // ---- finished lanes book the episode and start the next one
         const bool finished = cause >= 0;
-        const unsigned int m = __ballot_sync(0xffffffffu, finished && !inject);
         if (valid && !finished) {
             race_store_state(d, i, s, tick, ring_idx | ring_ext, ep_ret);
             race_observe<STRICT>(s, mrpm, ring, my_row);
@@ -614,14 +595,13 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
             atomicAdd(&s_acc[ACC_LENGTH], tick);
             atomicAdd(&s_acc[ACC_RINGS], ring_idx);
             if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
+            // the next episode starts here and now: its first observation goes out with the tile's rows
             if (inject) race_inject_episode<STRICT>(d, i, episode + 1u, my_row);
-            else ilist[listed + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)i, episode + 1u);
+            else race_begin_generated<STRICT, true>(d, i, episode + 1u, my_row);
         }
-        listed += __popc(m);
         __syncwarp();
 
         // ---- observations out: the warp's 3,712-byte tile as 232 lane-consecutive float4.
-        // Rows of lanes that finished hold stale data here; the generation pass rewrites them.
         {
             const int rows = min(32, d.n - tile * 32);
             float *gobs = d.obs + (size_t)tile * 32 * RACE_OBS;
@@ -674,6 +654,9 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
             if (v != 0) atomicAdd((unsigned long long *)&d.ctl->acc[lane], (unsigned long long)(long long)v);
             if (lane == ACC_RINGS) d.cta_score[blockIdx.x] = (long long)v + (d.score_add ? d.cta_score[blockIdx.x] : 0ll);
         }
+        // launches may use fewer CTAs than the handle's largest grid: the unused score slots read zero
+        if (blockIdx.x == 0 && !d.score_add)
+            for (int k = (int)gridDim.x + lane; k < d.max_grid; k += 32) d.cta_score[k] = 0;
 #if B2D_EXPERIMENT_TIMING
         if (lane == 0) {
             atomicAdd(&d.ctl->dbg[10], (unsigned long long)(clock64() - t_begin)); // CTA busy time
@@ -688,7 +671,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
 #endif
         __syncwarp();
         if (lane == 0) {
-            if (d.count_step) atomicAdd(&d.ctl->ctas_done, 1u); // result unused: a reduction, not a returning atomic
+            if (d.count_step && blockIdx.x == 0) atomicAdd(&d.ctl->ctas_done, 1u); // one count per vec_step; result unused
             __threadfence();
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(d.chain + blockIdx.x), "r"(d.seq) : "memory");
         }
@@ -712,7 +695,7 @@ __global__ void race_ctl_reset_kernel(Ctl *ctl, long long *cta_score, unsigned i
     for (unsigned int k = threadIdx.x; k < grid; k += blockDim.x) cta_score[k] = 0;
     if (threadIdx.x == 0) {
         ctl->grid = grid;
-        ctl->ctas_done = steps * grid;
+        ctl->ctas_done = steps;
         if (clear_acc) {
             for (int k = 0; k < ACC_COUNT; k++) ctl->acc[k] = 0;
             for (int k = 0; k < 8; k++) ctl->facc[k] = 0.0;
