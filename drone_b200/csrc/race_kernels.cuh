@@ -20,9 +20,9 @@
 // 201 B (S 80, obs 116, reward 4, terminal 1) = 373 algorithmic bytes.
 //
 // Auto-reset.  Episode k of env g is a pure function of (seed, g, k) (counter-based Philox), so
-// nothing about the next episode is stored anywhere: an env that finishes is listed by its warp
-// and the listed envs' next episodes are GENERATED IN PLACE, a different env on every lane (see
-// race_step_kernel).  Rings beyond the current one are generated when they are reached.
+// nothing about the next episode is stored anywhere: the lane whose env finishes GENERATES the
+// next episode right there, over the finished one (see race_step_kernel).  Rings beyond the
+// current one are generated when they are reached.
 #pragma once
 #include "physics.cuh"
 
@@ -404,7 +404,7 @@ __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *sta
 //
 // Tile order.  CTA c owns tiles c, c+G, c+2G, ... (G = grid size; the same CTA owns the same
 // envs in every launch) and its warps draw them through a SHARED-MEMORY ticket, so a warp that
-// spent time generating episodes simply takes fewer tiles.  Across the grid the warps sweep
+// spent time generating an episode simply takes fewer tiles.  Across the grid the warps sweep
 // every array as one contiguous frontier, which is what DRAM wants (sharded dynamic claims ran
 // 4% slower with 16 frontiers and 50% slower with 256).
 //
@@ -413,22 +413,24 @@ __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *sta
 // Observation rows ([N,29] row-major, 116 B: not a multiple of 16) are staged per warp in
 // shared memory and leave as lane-consecutive float4 stores, 512 B per instruction.
 //
-// Auto-reset costs in proportion to the envs that finish, not to the tiles that contain one, and
-// touches no memory but the env's own state.  About 2.5 % of the envs finish per step, i.e. more
-// than half of all tiles hold one; a finished lane only appends (env, next episode) to its warp's
-// list in shared memory.  When 32 are listed, and after the warp's last tile, the warp runs a
-// GENERATION PASS with a different finished env on every lane: Philox draws, the reference's
-// scale laws and rejection loops (race_generate_episode), then parameters, spawn state, ring 0
-// and the first observation row are written straight over the finished episode.  The list is
-// private to the warp (no atomics), the row an env's tile store left behind is overwritten in
-// program order by the same warp, and every env that finished in a launch has its next episode
-// in place when the launch ends, like the reference's c_step.
-// (Earlier generations of this kernel kept a PREPARED next episode per env -- 96 B in six
-// arrays, restocked through a per-CTA refill ring with carry-over lists between launches -- so
-// that a finish needed only an "adopt".  Measured with the reset path compiled out
-// (B2D_EXPERIMENT_NO_RESET) the step streams at 63 us per 1 M envs; the slot traffic, scattered
-// 16-byte gathers and partial-sector writes for 2.5 % of the envs, cost 15 us on top.  In-place
-// generation has no such traffic: 76 us with 3 CTAs per SM, 74.7 us with 4.)
+// Auto-reset touches no memory but the env's own state.  A lane whose env finished generates the
+// env's next episode on the spot -- Philox draws, the reference's scale laws and rejection loops
+// (race_generate_episode, ~1,100 instructions) -- writes parameters, spawn state and ring 0 over
+// the finished episode and puts the first observation into its row of the warp's tile, which
+// leaves with the other 31 rows.  About 2.5 % of the envs finish per step, so more than half of
+// all tiles pay for one such (divergent) generation; that is affordable because the step is
+// memory-bound with arithmetic to spare (running the RK4 twice per step costs 1 us per 1 M envs)
+// and 16 warps per SM keep the loads and stores flowing meanwhile.
+// How this kernel got here, all measured at 1 M envs (profiles/README.md):
+//   * a PREPARED next episode per env (96 B in six arrays, adopted by scattered 16-byte gathers,
+//     restocked through a per-CTA shared-memory ring with carry-over lists between launches):
+//     78.7 us.  With the reset path compiled out (B2D_EXPERIMENT_NO_RESET) the step streams at
+//     62 us; the slot traffic -- 2.5 % of the envs, but every access a lone sector in its own DRAM
+//     page -- and the adoption latency at the end of each launch cost the rest;
+//   * per-warp LISTS of finished envs, generated in place 32 at a time and after the warp's last
+//     tile: 74.7 us, of which ~5 us was the generation pass every warp ran at the end of a launch;
+//   * generation in the tile (this version): 68.7 us, and no list, queue, pass or tail to reason
+//     about -- every launch is self-contained.
 //
 // No global atomic in this kernel returns a value (see Ctl).
 template <bool STRICT>
