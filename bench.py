@@ -119,6 +119,26 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Multi-rank runs: keep this rank's host threads -- and therefore the first-touch placement of its
+    pinned NumPy buffers -- on the CPUs NVML names as local to its GPU (what `numactl` would do for a
+    launcher).  Only matters for the e2e leg (PCIe traffic from host memory).  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        ideal = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = ideal & allowed
+        if pick and pick != allowed:
+            os.sched_setaffinity(0, pick)
+            return f"nvml-local cpus ({len(pick)} of {len(allowed)})"
+        return "unchanged (all allowed cpus are local)" if pick else "unchanged (no local cpu allowed)"
+    except Exception as e:  # noqa: BLE001
+        return f"unchanged ({type(e).__name__})"
+
+
 def cpu_sample(steps_budget_s=20.0, kind="reference", drones=0):
     """Bounded CPU sample of the same workload shape (rank 0, N=1 only)."""
     from oracle import cpu_worker
@@ -200,7 +220,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = "unchanged (single rank)"
     if world > 1:
+        affinity = bind_to_gpu_numa_node(physical_gpu_index(local_rank))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -289,6 +311,7 @@ def main():
                "d2h_bytes_per_step": total_envs * (116 + 4 + 1), "steps": e2e_steps,
                "ms_per_step": dt / e2e_steps * 1e3,
                "api": "drone_b200.drone_race.DroneRace(buffers='host').step(np.ndarray) -> binding.vec_step_actions -> b2d_vec_step_host_from",
+               "host_cpu_affinity": affinity,
                "checksum": float(np.abs(obs).sum(dtype=np.float64))}
         env.close()
 
