@@ -34,6 +34,12 @@
 
 namespace b2d {
 
+#ifndef B2D_SWARM_EXPERIMENT_DOUBLE_MATH
+#define B2D_SWARM_EXPERIMENT_DOUBLE_MATH 0
+#endif
+#ifndef B2D_SWARM_EXPERIMENT_NO_RESPAWN
+#define B2D_SWARM_EXPERIMENT_NO_RESPAWN 0
+#endif
 constexpr int SWARM_BLOCK = 128;
 constexpr int SWARM_OBS = 41;
 constexpr int SWARM_AGENT_BLOB = 47;
@@ -524,7 +530,19 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             if (d.act_out) reinterpret_cast<float4 *>(d.act_out)[k] = make_float4(act[0], act[1], act[2], act[3]);
             DroneParams p = {g.p[0], g.p[1], g.p[2], g.p[3], g.p[4], g.p[5], g.p[6], g.p[7], g.p[8], g.p[9], g.p[10], g.p[11], g.p[12]};
             advance_body<STRICT>(g.s, p, act);
+#if B2D_SWARM_EXPERIMENT_DOUBLE_MATH
+            {   // measurement aid: the rigid-body arithmetic twice, same memory traffic
+                float s2[17];
+#pragma unroll
+                for (int m = 0; m < 17; m++) s2[m] = g.s[m];
+                advance_body<STRICT>(s2, p, act);
+                g.s[0] = fmaf(s2[0] + s2[6] + s2[12] + s2[16], 1e-30f, g.s[0]);
+            }
+#endif
             oob = g.s[0] < -SW_GX || g.s[0] > SW_GX || g.s[1] < -SW_GY || g.s[1] > SW_GY || g.s[2] < -SW_GZ || g.s[2] > SW_GZ;
+#if B2D_SWARM_EXPERIMENT_NO_RESPAWN
+            oob = false; // measurement aid: nobody leaves the arena (no respawn draws, no episode ends by OOB)
+#endif
             sw_move_target(g.tpos, g.tvel);
             if (oob) {
                 if (inject) {
