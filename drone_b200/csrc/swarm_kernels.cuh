@@ -471,6 +471,35 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
     const int ntiles = (d.n + d.epc - 1) / d.epc;
     const size_t pay_stride = (size_t)A * SWARM_AGENT_PAYLOAD + 2 + 6 * d.R;
 
+    // Everything the phases exchange through shared memory stays inside one env, so the barriers
+    // between the phases only need the env's own threads: a warp when A divides 32 (one or more whole
+    // envs per warp), a named barrier over the env's warps when A is a multiple of 32, the whole CTA
+    // otherwise.  A drone that respawns (Philox draws, a second neighbour scan) then delays its own
+    // env, not the other envs of the CTA: with CTA-wide barriers the respawn path of 2.4 % of the
+    // drones cost a quarter of the step (profiles/r01h_swarm_variants.txt).
+    const int sync_mode = (32 % A == 0) ? 1 : (A % 32 == 0 ? 2 : 0);
+    const int grp_first = sync_mode == 1 ? (t & ~31) : sync_mode == 2 ? le * A : 0;                       // first thread of my group
+    const int grp_size = sync_mode == 1 ? 32 : sync_mode == 2 ? min(A, SWARM_BLOCK - le * A) : SWARM_BLOCK; // threads in it
+    auto env_sync = [&]() {
+        if (sync_mode == 1) __syncwarp();
+        else if (sync_mode == 2) asm volatile("bar.sync %0, %1;" ::"r"(1 + le), "r"(grp_size) : "memory");
+        else __syncthreads();
+    };
+    auto env_any = [&](bool p) -> int {
+        if (sync_mode == 1) return __any_sync(0xffffffffu, p);
+        if (sync_mode == 2) {
+            unsigned int r;
+            asm volatile("{ .reg .pred p, q; setp.ne.u32 p, %1, 0; bar.red.or.pred q, %2, %3, p; selp.u32 %0, 1, 0, q; }"
+                         : "=r"(r)
+                         : "r"((unsigned int)p), "r"(1 + le), "r"(grp_size)
+                         : "memory");
+            return (int)r;
+        }
+        return __syncthreads_or(p ? 1 : 0);
+    };
+    if (t < 8) s_facc[t] = 0.0f; // episode statistics of all this CTA's tiles; flushed once at the end
+    __syncthreads();
+
     if constexpr (!ONLY_RESET) {
         const int e0 = blockIdx.x * d.epc + le;
         if ((int)blockIdx.x < ntiles && le < d.epc && e0 < d.n) sw_prefetch(d, stage, t, e0, e0 * A + a);
@@ -484,7 +513,6 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
     const uint32_t genv = d.env_id_base + (uint32_t)e;
     const float *pay_agent = d.payload ? d.payload + (size_t)e * pay_stride + (size_t)a * SWARM_AGENT_PAYLOAD : nullptr;
     const float *pay_env = d.payload ? d.payload + (size_t)e * pay_stride + (size_t)A * SWARM_AGENT_PAYLOAD : nullptr;
-    if (t < 8) s_facc[t] = 0.0f;
 
     SwarmAgent g;
     int tick = 0, task = 0;
@@ -558,7 +586,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             if (oob) s_trail.put(w0 + A + a, rpos[0], rpos[1], rpos[2]);
             else s_trail.put(w0 + A + a, g.s[0], g.s[1], g.s[2]);
         }
-        __syncthreads();
+        env_sync();
 
         // ---- phase 2: rewards, ring logic, respawn bookkeeping (R/drone_swarm.h:463-491)
         if (active) {
@@ -620,7 +648,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
     }
 
     // ---- phase 3: env-wide reset (R/drone_swarm.h:401-443), every 1023 ticks for all agents of the env at once
-    const int cta_reset = __syncthreads_or(do_reset ? 1 : 0);
+    const int cta_reset = env_any(do_reset);
     if (cta_reset) {
         float first[3] = {0.0f, 0.0f, 0.0f}, np[13];
         if (do_reset) {
@@ -639,7 +667,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             }
             s_trail.put(w0 + 2 * A + a, first[0], first[1], first[2]);
         }
-        __syncthreads();
+        env_sync();
         if (do_reset) {
             // reset_agent: the reward is computed against the STALE target and half-reset neighbours
             sw_respawn_state(g, np, first);
@@ -675,7 +703,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                 g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
             }
         }
-        __syncthreads(); // every agent has read the old ring 0 before the rings are rewritten
+        env_sync(); // every agent has read the old ring 0 before the rings are rewritten
         if (do_reset && a == 0) {
             float prev[3] = {0.0f, 0.0f, 0.0f};
             for (int r = 0; r < d.R; r++) {
@@ -699,7 +727,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                 if (r == 0) { s_ring0[le][0] = ring[0]; s_ring0[le][1] = ring[1]; s_ring0[le][2] = ring[2]; }
             }
         }
-        __syncthreads();
+        env_sync();
         if (do_reset && task == SWARM_TASK_RACE) {
             // start at least 2*radius from the first ring; spawn_pos / prev_pos keep the first draw (R/drone_swarm.h:429-439)
             const float r0[3] = {s_ring0[le][0], s_ring0[le][1], s_ring0[le][2]};
@@ -719,7 +747,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         s_now.put(w0 + a, g.s[0], g.s[1], g.s[2]);
         s_now.put(w0 + A + a, g.s[0], g.s[1], g.s[2]);
     }
-    __syncthreads();
+    env_sync();
 
     // ---- phase 4: state out, observations (R/drone_swarm.h:131-217) staged through shared memory
     if (active) {
@@ -736,27 +764,34 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         if (task == SWARM_TASK_RACE) sw_load_ring(d, e, g.ring_idx, ring);
         sw_observe<STRICT>(g, A, near, task == SWARM_TASK_RACE, ring, s_obs + t * SWARM_OBS, 1);
     }
-    __syncthreads();
-    {
+    env_sync();
+    {   // each group stores its own rows of the tile (contiguous in shared and in global memory)
         const int rows_here = min(d.epc, d.n - tile * d.epc) * A;
-        float *gobs = d.obs + (size_t)tile * d.epc * A * SWARM_OBS;
-        if ((rows_here & 3) == 0 && (((size_t)tile * d.epc * A) & 3) == 0) { // 16-byte aligned tile: float4 stores
-            const float4 *src = reinterpret_cast<const float4 *>(s_obs);
+        const int rows_mine = max(0, min(grp_size, rows_here - grp_first));
+        const size_t row0 = (size_t)tile * d.epc * A + grp_first;
+        float *gobs = d.obs + row0 * SWARM_OBS;
+        const float *sobs = s_obs + (size_t)grp_first * SWARM_OBS;
+        const int tg = t - grp_first;
+        if ((rows_mine & 3) == 0 && (row0 & 3) == 0 && (grp_first & 3) == 0) { // 16-byte aligned: float4 stores
+            const float4 *src = reinterpret_cast<const float4 *>(sobs);
             float4 *dst = reinterpret_cast<float4 *>(gobs);
-            for (int m = t; m < rows_here * SWARM_OBS / 4; m += SWARM_BLOCK) __stcs(&dst[m], src[m]);
+            for (int m = tg; m < rows_mine * SWARM_OBS / 4; m += grp_size) __stcs(&dst[m], src[m]);
         } else {
-            for (int m = t; m < rows_here * SWARM_OBS; m += SWARM_BLOCK) __stcs(&gobs[m], s_obs[m]);
+            for (int m = tg; m < rows_mine * SWARM_OBS; m += grp_size) __stcs(&gobs[m], sobs[m]);
         }
     }
     if constexpr (!ONLY_RESET) {
-        if (t < 8 && s_facc[t] != 0.0f) atomicAdd(&d.ctl->facc[t], (double)s_facc[t]);
         if (t == 0 && tile == 0) atomicAdd(&d.ctl->ctas_done, 1u);
     }
     // the next tile's first barrier (after its phase 1) separates this tile's readers of the
     // shared arrays from their next writers, except the old / fin arrays, which are last read before this
     // tile's final barriers
   }
-  if constexpr (!ONLY_RESET) cp_async_wait<0>();
+  if constexpr (!ONLY_RESET) {
+      cp_async_wait<0>();
+      __syncthreads(); // every warp's statistics are in
+      if (t < 8 && s_facc[t] != 0.0f) atomicAdd(&d.ctl->facc[t], (double)s_facc[t]);
+  }
 }
 
 // snapshot + clear for vec_log: out[0..7] = the float sums in 2^-20 fixed point, so that the
