@@ -2,24 +2,32 @@
 """bench.py -- drone env-steps/sec on B200 (BASELINE.json metric), one JSON line.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload race|race4096|swarm16|swarm32|swarm64|rollout] [--math fast|strict]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], SURVEY 8d "C2"): the single-drone ring-race
-env, 1,048,576 envs per GPU (max_rings=10, max_moves=1000), vec_reset(seed=0),
-actions from a tape of 16 pre-generated [N,4] f32 U(-1,1) tensors (seed 1234)
-cycled t % 16, step-only.  A "step" is one vec_step over all envs of all ranks.
-Envs shard across ranks with no per-step communication (weak scaling: 1M envs per
-GPU); the only collective is the episode-statistics all-reduce of vec_log.
+Headline workload (BASELINE.json configs[1], SURVEY 8d "C2"): the single-drone ring-race env,
+1,048,576 envs per GPU (max_rings=10, max_moves=1000), vec_reset(seed=0), actions from a tape of 16
+pre-generated [N,4] f32 U(-1,1) tensors (seed 1234) cycled t % 16, step-only incl. auto-resets.  A
+"step" is one vec_step over all envs of all ranks.  Envs shard across ranks with no per-step
+communication (weak scaling: 1M envs per GPU); the only collective is the episode-statistics
+all-reduce of vec_log.
 
-value      = env-steps/s, whole job, device-resident buffers (zero-copy path),
-             timed with CUDA events on the launching stream, max over ranks.
+value      = env-steps/s, whole job, device-resident buffers (zero-copy path), timed with CUDA
+             events on the launching stream, max over ranks.
 e2e        = the same metric through the public host-buffer API
-             (DroneRace(buffers="host").step(numpy_actions)): H2D of the actions and
-             D2H of observations/rewards/terminals inside the timed region.
-roofline   = algorithmic bytes (373 B/env-step, SURVEY 8d / DESIGN.md) / kernel time
-             against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
-cpu_baseline = the reference's own C step (oracle/_ref) on this box's host cores,
-             one process per physical core, bounded sample (rank 0, N=1 only).
+             (DroneRace(buffers="host").step(numpy_actions)): H2D of the actions and D2H of
+             observations/rewards/terminals inside the timed region; `pcie_floor_ms` is the same
+             byte counts as bare pinned-memory copies, measured in the same run.
+roofline   = algorithmic bytes (373 B/env-step, SURVEY 8d / DESIGN.md) / kernel time against the
+             measured HBM copy bandwidth in MEASURED_PEAKS.json (strict math: FP32 issue slots).
+cpu_baseline = the reference's own C step (binding.vec_step of oracle/_ref) on this box's host
+             cores, one process per physical core, bounded sample (rank 0, N=1 only).
+parity     = what tests/test_fast_parity_gpu.py measured for the kernels timed here (committed
+             copy: profiles/parity_r02.json).
+extra      = (N=1, default run) the other BASELINE.json configs, each a full sub-result with its own
+             value / ms_per_step / roofline / cpu_baseline / clocks: configs[0] race 4096 envs,
+             configs[2] swarm 65,536 envs x 16 and x 64 drones, configs[3] on-device rollout K=128,
+             plus the headline kernel in strict math and as stand-alone launches.
 --impl reference prints the CPU reference arm in the same format.
 """
 import argparse
@@ -35,7 +43,13 @@ sys.path.insert(0, ROOT)
 ENVS_PER_GPU = 1 << 20
 MAX_RINGS, MAX_MOVES = 10, 1000
 TAPE_LEN, TAPE_SEED = 16, 1234
-ALGO_BYTES_PER_ENV_STEP = 373  # reads 172 + writes 201, SURVEY.md 8(d)
+ALGO_BYTES_PER_ENV_STEP = 373    # reads 172 + writes 201, SURVEY.md 8(d)
+ALGO_BYTES_PER_DRONE_STEP = 521  # swarm, SURVEY.md 8(d)
+ALGO_FLOPS_PER_ENV_STEP = 1330   # as-written FP32 operations of the reference step, SURVEY.md 8(d)
+# rollout (fused policy + env kernel): per env-step only the experience row leaves the SM:
+# obs 116 + action 16 + logprob, value, reward, terminal 4 x 4 = 148 B (DESIGN.md "rollout")
+ALGO_BYTES_PER_ROLLOUT_STEP = 148
+INTERNAL_WARMUP = 64             # steps before the caller's warm-up: past the post-vec_reset transient
 METRIC = "drone_env_steps_per_sec"
 UNIT = "env-steps/s"
 
@@ -50,15 +64,51 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the step kernel from the committed ncu --set full capture."""
+def ncu_traffic(key):
+    """DRAM bytes per launch from the committed ncu --set full capture (not measured in this run)."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("race_step_kernel_fast_bytes_per_launch")
+            return json.load(open(p)).get(key)
         except Exception:  # noqa: BLE001
             pass
     return None
+
+
+def parity_summary():
+    """The committed parity record of the fast kernels (tests/test_fast_parity_gpu.py on a B200)."""
+    p = os.path.join(ROOT, "profiles", "parity_r02.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))
+    except Exception:  # noqa: BLE001
+        return None
+    out = {"source": "profiles/parity_r02.json (written by tests/test_fast_parity_gpu.py on a B200; not re-measured in this run)"}
+    r = d.get("race_fast_per_step")
+    if r:
+        out["race_fast_vs_oracle"] = {
+            "env_steps_compared": r.get("env_steps"), "shape": "slices of the 1,048,576-env vector, per-step resync",
+            "integer_flips": sum(int(r.get(k, 0)) for k in ("terminal_flips", "reward_flips", "tick_flips", "ring_idx_flips", "return_flips")),
+            "worst_obs_abs_err": r.get("worst_obs_abs"), "worst_pos_abs_err_m": r.get("worst_pos_abs"),
+            "worst_err_in_tolerance_units": max(r.get("worst_obs_tol", 0.0), r.get("worst_state_tol", 0.0)),
+            "tolerance": "1e-5 rel + 1e-6 abs per step", "guard_replay_rate": r.get("guard_replay_rate")}
+    for rec in ("bench_uniform", "near_hover"):
+        k = d.get(f"race_fast_drift_{rec}")
+        if k:
+            out[f"race_fast_drift_1000_steps_{rec}"] = {
+                "max_abs_dpos_m": k.get("max_abs_dpos_m"), "mean_abs_dpos_m": k.get("mean_abs_dpos_m"),
+                "max_abs_dquat": k.get("max_abs_dquat"), "mean_abs_dquat": k.get("mean_abs_dquat"),
+                "identical_event_history": k.get("envs_with_identical_event_history_after_1000_steps")}
+    for A in (16, 64):
+        k = d.get(f"swarm_fast_per_step_A{A}")
+        if k:
+            out[f"swarm{A}_fast_vs_oracle"] = {
+                "drone_steps_compared": k.get("drone_steps"),
+                "integer_flips": sum(int(k.get(x, 0)) for x in ("terminal_flips", "ring_idx_flips", "episode_length_flips", "collision_count_flips")),
+                "nearest_neighbour_flips": k.get("nearest_neighbour_flips"),
+                "worst_err_in_tolerance_units": max(k.get("worst_obs_tol", 0.0), k.get("worst_state_tol", 0.0))}
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -139,18 +189,34 @@ def bind_to_gpu_numa_node(gpu_index):
         return f"unchanged ({type(e).__name__})"
 
 
-def cpu_sample(steps_budget_s=20.0, kind="reference", drones=0):
-    """Bounded CPU sample of the same workload shape (rank 0, N=1 only)."""
+# ------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(budget_s=15.0, kind="reference", drones=0, envs=None, policy=False):
+    """Bounded CPU sample of the same workload shape (rank 0, N=1 only): the reference's own
+    binding.vec_step, one process per physical core."""
     from oracle import cpu_worker
     procs = cpu_worker.host_cores()
     per = 2048 if not drones else max(1, 2048 // drones)
-    probe = cpu_worker.run(procs, procs * per, 20, 5, kind, drones=drones)
+    if envs is not None:  # a fixed-size workload (configs[0]: 4096 envs in all)
+        per = max(1, envs // procs)
+    probe = cpu_worker.run(procs, procs * per, 20, 5, kind, drones=drones, policy=policy)
     rate = probe["env_steps_per_s"]
-    envs = procs * per * 2
-    units = envs * max(drones, 1)
-    steps = int(max(50, min(2000, rate * steps_budget_s / units)))
-    res = cpu_worker.run(procs, envs, steps, 20, kind, drones=drones)
-    return res
+    n = procs * per * (1 if envs is not None else 2)
+    units = n * max(drones, 1)
+    steps = int(max(50, min(4000, rate * budget_s / units)))
+    return cpu_worker.run(procs, n, steps, 20, kind, drones=drones, policy=policy)
+
+
+def cpu_baseline_dict(res, unit, what):
+    return {"value": res["env_steps_per_s"], "unit": unit, "cores": res["procs"], "kind": res["kind"],
+            "sample": f"{res['envs']} envs{what} x {res['steps']} steps of the same workload, {res['procs']} processes "
+                      f"(one per physical core), {res['wall_s']:.1f} s; {res.get('api', '')}"}
+
+
+def safe_cpu_baseline(unit, what="", **kw):
+    try:
+        return cpu_baseline_dict(cpu_sample(**kw), unit, what)
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": unit, "cores": 0, "kind": "unavailable", "sample": repr(e)}
 
 
 def run_reference(args, rank, world):
@@ -169,12 +235,13 @@ def run_reference(args, rank, world):
     envs = max(procs * 256, min(ENVS_PER_GPU * world, envs // (procs * 256) * (procs * 256)))
     res = cpu_worker.run(procs, envs, args.steps, args.warmup, kind)
     v = res["env_steps_per_s"]
-    sample = f"{res['envs']} of {ENVS_PER_GPU * world} envs x {args.steps} steps, {procs} processes (one per physical core)"
+    sample = (f"{res['envs']} of {ENVS_PER_GPU * world} envs x {args.steps} steps, {procs} processes (one per physical core); "
+              f"{res.get('api', '')}")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": res["wall_s"] / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(world, "host cores only (reference C c_step via oracle/_ref)"),
+        "config": race_config(ENVS_PER_GPU, world, f"env-sharded x{world}, no per-step collective; vec_log all-reduce over NCCL"),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": res["kind"], "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -182,12 +249,232 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(world, parallelism):
-    return {"workload": "drone_race single-drone gate-race, 1,048,576 envs per GPU, max_rings=10, max_moves=1000, "
-                        "fixed random action tape (16 x U(-1,1), seed 1234), step-only incl. auto-resets "
-                        "(BASELINE.json configs[1])",
-            "envs_per_gpu": ENVS_PER_GPU, "total_envs": ENVS_PER_GPU * world, "parallelism": parallelism,
-            "l2": "working set 391 MB per step per GPU > 126 MB L2 (inputs larger than L2, no flush needed)"}
+def race_config(n, world, parallelism, which="configs[1]"):
+    ws = ALGO_BYTES_PER_ENV_STEP * n / 1e6
+    return {"workload": f"drone_race single-drone gate-race, {n:,} envs per GPU, max_rings=10, max_moves=1000, "
+                        f"fixed random action tape (16 x U(-1,1), seed 1234), step-only incl. auto-resets "
+                        f"(BASELINE.json {which})",
+            "envs_per_gpu": n, "total_envs": n * world, "parallelism": parallelism,
+            "l2": (f"working set {ws:.0f} MB per step per GPU > 126 MB L2 (inputs larger than L2, no flush needed)" if ws > 126 else
+                   f"working set {ws:.1f} MB per step: L2-resident (the reference's own CPU-sized case; timed as is and said so)")}
+
+
+# ------------------------------------------------------------------------------------- GPU workloads
+def roofline_hbm(bytes_per_launch, us, kernel, traffic=None, traffic_src=None):
+    peak, peak_src = measured_peaks()
+    gbs = bytes_per_launch / (us * 1e-6) / 1e9
+    return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic,
+            "traffic_source": traffic_src, "kernel": kernel, "algorithmic_bytes_per_launch": bytes_per_launch,
+            "avg_launch_us": us, "peak_source": peak_src, "per": "GPU"}
+
+
+def roofline_fp32(flops_per_launch, us, kernel, sm_mhz, bytes_per_launch):
+    """Strict math is bound by FP32 issue slots, not by HBM: peak = SMs x 128 lanes x clock (one non-FMA op
+    per lane per cycle; the strict kernel may not contract into FMAs)."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    mhz = sm_mhz or 1965
+    peak = sms * 128 * mhz * 1e6 / 1e12
+    ach = flops_per_launch / (us * 1e-6) / 1e12
+    hbm_peak, _ = measured_peaks()
+    return {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "kernel": kernel, "algorithmic_flops_per_launch": flops_per_launch, "avg_launch_us": us,
+            "peak_source": f"{sms} SMs x 128 FP32 lanes x {mhz} MHz (as-written reference operations, no FMA; IEEE division and "
+                           "square root expand to ~10 issue slots each, so 1.0 is not reachable)",
+            "hbm_frac_for_comparison": bytes_per_launch / (us * 1e-6) / 1e9 / hbm_peak, "per": "GPU"}
+
+
+def time_race(n, math, launch, steps, warmup, dev, rank=0, world=1, dist=None):
+    """CUDA-event time of `steps` vec_steps of the race env (after INTERNAL_WARMUP + warmup untimed ones)."""
+    import torch
+    from drone_b200.vec import RaceVec
+    vec = RaceVec(n, max_rings=MAX_RINGS, max_moves=MAX_MOVES, seed=0, device=dev, math=math, env_id_base=rank * n)
+    g = torch.Generator(device="cpu").manual_seed(TAPE_SEED + rank)
+    tape = (torch.rand((TAPE_LEN, n, 4), generator=g) * 2.0 - 1.0).to(dev)
+    vec.reset(0)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # The timed loop is the reference's own cached-action perf loop (drone_race.py:83-90): one
+    # vec_step per action batch of the tape, issued through b2d_vec_step_tape (one kernel launch
+    # per step; `--launch single` issues them one b2d_vec_step_from call at a time instead).
+    def run_steps(t0, k):
+        if launch == "tape":
+            vec.step_tape(tape, t0 % TAPE_LEN, k)
+        else:
+            for j in range(k):
+                vec.step(tape[(t0 + j) % TAPE_LEN])
+
+    t = 0
+    run_steps(t, INTERNAL_WARMUP + warmup)  # episodes last ~40 steps: the reset rate is steady after 64
+    t += INTERNAL_WARMUP + warmup
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(dev.index))
+    sampler.start()
+    launches0 = vec.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    run_steps(t, steps)
+    t += steps
+    ev1.record(stream)
+    barrier()
+    sampler.stop()
+    launches = vec.kernel_launches - launches0
+    ms = ev0.elapsed_time(ev1)
+    vec.step(tape[t % TAPE_LEN])  # reset fraction of the workload, measured after the timed region
+    reset_frac = float(vec.terminals.sum().item()) / n
+    replays = vec.guard_replays if math == "fast" else 0
+    stats = vec.log(group=True if world > 1 else None)
+    total_steps = INTERNAL_WARMUP + warmup + steps + 1
+    vec.close()
+    del tape
+    torch.cuda.empty_cache()
+    return {"ms": ms, "launches": int(launches), "reset_frac": reset_frac, "stats": stats, "clocks": sampler.summary(),
+            "guard_replay_rate": replays / float(n * total_steps)}
+
+
+def race_line(res, n, math, launch, steps, warmup, world, ms_max, which="configs[1]"):
+    us = ms_max / steps * 1e3
+    kernel = f"race_step_kernel<{'strict' if math == 'strict' else 'fast'}>"
+    if math == "strict":
+        roof = roofline_fp32(ALGO_FLOPS_PER_ENV_STEP * n, us, kernel, res["clocks"].get("sm_mhz"), ALGO_BYTES_PER_ENV_STEP * n)
+    else:
+        roof = roofline_hbm(ALGO_BYTES_PER_ENV_STEP * n, us, kernel,
+                            ncu_traffic("race_step_kernel_fast_bytes_per_launch") if n == ENVS_PER_GPU else None,
+                            "profiles/roofline_traffic.json (ncu --set full capture of this kernel at 1,048,576 envs; not measured in this run)"
+                            if n == ENVS_PER_GPU else None)
+    return {
+        "metric": METRIC, "value": n * world * steps / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "internal_warmup": INTERNAL_WARMUP, "ms_per_step": ms_max / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": race_config(n, world, f"env-sharded x{world}, no per-step collective; vec_log all-reduce over NCCL", which),
+        "math": math, "launch": launch, "reset_fraction_per_step": res["reset_frac"],
+        "guard_replay_rate": res["guard_replay_rate"], "episode_stats": res["stats"], "clocks": res["clocks"],
+        "gpu_launches": res["launches"], "roofline": roof}
+
+
+def bench_swarm(drones, steps, warmup, dev, math="fast", envs=1 << 16, cpu=True):
+    import torch
+    from drone_b200.vec import SwarmVec
+    rows = envs * drones
+    vec = SwarmVec(envs, drones, 10, seed=0, device=dev, math=math)
+    g = torch.Generator(device="cpu").manual_seed(TAPE_SEED)
+    tape = (torch.rand((4, rows, 4), generator=g) * 2.0 - 1.0).to(dev)
+    vec.reset(0)
+    for t in range(max(warmup, 20)):
+        vec.step(tape[t % 4])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(physical_gpu_index(dev.index))
+    sampler.start()
+    l0 = vec.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for t in range(steps):
+        vec.step(tape[t % 4])
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = vec.kernel_launches - l0
+    stats = vec.log()
+    replays = vec.guard_replays if math == "fast" else 0
+    value = rows * steps / (ms * 1e-3)
+    us = ms / steps * 1e3
+    traffic = ncu_traffic(f"swarm_kernel_fast_A{drones}_bytes_per_launch") if (envs == 1 << 16 and math == "fast") else None
+    line = {"metric": "drone_steps_per_sec", "value": value, "unit": "drone-steps/s", "n_gpus": 1, "steps": steps,
+            "warmup": max(warmup, 20), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "math": math,
+            "config": {"workload": f"drone_swarm {envs:,} envs x {drones} drones, max_rings=10, fixed random action tape "
+                                   f"(4 x U(-1,1)), step-only incl. respawns and the 1023-tick env-wide reset "
+                                   f"(BASELINE.json configs[2])",
+                       "rows": rows, "l2": f"working set {rows * ALGO_BYTES_PER_DRONE_STEP / 1e6:.0f} MB per step > 126 MB L2"},
+            "episode_stats": stats, "clocks": sampler.summary(), "gpu_launches": int(launches),
+            "guard_replay_env_rate": replays / float(envs * (steps + max(warmup, 20))),
+            "roofline": roofline_hbm(ALGO_BYTES_PER_DRONE_STEP * rows, us, f"swarm_kernel<{math}>", traffic,
+                                     "profiles/roofline_traffic.json (not measured in this run)" if traffic else None)}
+    vec.close()
+    del tape
+    torch.cuda.empty_cache()
+    if cpu:
+        line["cpu_baseline"] = safe_cpu_baseline("drone-steps/s", f" x {drones} drones", budget_s=8.0, drones=drones)
+    return line
+
+
+def bench_rollout(replays, dev, envs=1 << 20, horizon=128, impl="auto", cpu=True):
+    """BASELINE.json configs[3]: policy forward + sampling + experience stores + env step, K=128 per launch/graph."""
+    import torch
+    from drone_b200.rollout import DeviceRollout, DronePolicy
+    from drone_b200.vec import RaceVec
+    torch.manual_seed(0)
+    vec = RaceVec(envs, seed=0, device=dev)
+    vec.reset(0)
+    policy = DronePolicy().to(dev)
+    ro = DeviceRollout(vec, policy, horizon=horizon, policy_impl=impl)
+    ro.collect()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(physical_gpu_index(dev.index))
+    sampler.start()
+    l0 = ro.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(replays):
+        ro.collect()
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    steps = replays * horizon
+    us = ms / steps * 1e3
+    launches = ro.kernel_launches - l0
+    fused = ro.policy_impl == "rollout_kernel"
+    algo = ALGO_BYTES_PER_ROLLOUT_STEP if fused else (ALGO_BYTES_PER_ENV_STEP + 285)
+    line = {"metric": "rollout_env_steps_per_sec", "value": envs * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+            "steps": steps, "warmup": horizon, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 env / tf32 policy GEMMs (the reference's matmul precision, pufferl.py:55)",
+            "data": "synthetic", "policy_impl": ro.policy_impl, "gpu_launches": int(launches),
+            "config": {"workload": f"on-device rollout: Default policy (29 -> 128 GELU -> 4 means + value, Normal sampling) + race env step, "
+                                   f"{envs:,} envs, K={horizon} steps per collect() (BASELINE.json configs[3])",
+                       "l2": f"experience written per step {envs * 148 / 1e6:.0f} MB > 126 MB L2"},
+            "episode_stats": vec.log(), "clocks": sampler.summary(),
+            "roofline": roofline_hbm(algo * envs, us, ro.kernel_name)}
+    line["roofline"]["note"] = ("bytes that must move per env-step: " +
+                                ("the experience row only (state stays on chip for the K steps)" if fused else
+                                 "env step 373 B + policy step 285 B (two kernels per step)") +
+                                "; the kernel is FP32-issue bound (exact GELU x 128 per env-step), see DESIGN.md")
+    vec.close()
+    del ro
+    torch.cuda.empty_cache()
+    if cpu:
+        line["cpu_baseline"] = safe_cpu_baseline(UNIT, budget_s=8.0, policy=True)
+    return line
+
+
+def pcie_floor_ms(n, dev, iters=5):
+    """The bytes of one host-buffer step (16 B/env up, 121 B/env down) as bare pinned-memory copies on two
+    streams, nothing else: the floor the e2e figure sits on."""
+    import torch
+    up_h = torch.zeros(n * 16, dtype=torch.uint8, pin_memory=True)
+    dn_h = torch.zeros(n * 121, dtype=torch.uint8, pin_memory=True)
+    up_d = torch.zeros(n * 16, dtype=torch.uint8, device=dev)
+    dn_d = torch.zeros(n * 121, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    best = None
+    for _ in range(iters + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            up_d.copy_(up_h, non_blocking=True)
+        with torch.cuda.stream(s2):
+            dn_h.copy_(dn_d, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        best = dt if best is None else min(best, dt)
+    return best
 
 
 def main():
@@ -196,11 +483,14 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="race", choices=["race", "race4096", "swarm16", "swarm32", "swarm64", "rollout"])
     ap.add_argument("--math", default="fast", choices=["fast", "strict"])
     ap.add_argument("--launch", default="tape", choices=["tape", "single"])
+    ap.add_argument("--rollout-impl", default="auto", choices=["auto", "rollout_kernel", "fused", "torch"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the sub-results for the other BASELINE configs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -220,22 +510,40 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu = not args.no_cpu_baseline
+
+    # ---- secondary workloads as the main line (single GPU)
+    if args.workload != "race":
+        if world > 1:
+            raise SystemExit("--workload other than race runs on one GPU")
+        if args.workload == "race4096":
+            res = time_race(4096, args.math, args.launch, args.steps, args.warmup, dev)
+            line = race_line(res, 4096, args.math, args.launch, args.steps, args.warmup, 1, res["ms"], "configs[0]")
+            if cpu:
+                line["cpu_baseline"] = safe_cpu_baseline(UNIT, budget_s=8.0, envs=4096)
+        elif args.workload.startswith("swarm"):
+            line = bench_swarm(int(args.workload[5:]), min(args.steps, 1100) if args.steps != 2000 else 1100, args.warmup, dev,
+                               math=args.math, cpu=cpu)
+        else:
+            line = bench_rollout(max(1, min(8, args.steps // 128)) if args.steps != 2000 else 4, dev, impl=args.rollout_impl, cpu=cpu)
+        print(json.dumps(line), flush=True)
+        return
+
     affinity = "unchanged (single rank)"
     if world > 1:
         affinity = bind_to_gpu_numa_node(physical_gpu_index(local_rank))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from drone_b200.vec import RaceVec
     from drone_b200.drone_race import DroneRace
 
     n = args.envs_per_gpu
-    vec = RaceVec(n, max_rings=MAX_RINGS, max_moves=MAX_MOVES, seed=0, device=dev, math=args.math,
-                  env_id_base=rank * n)
-    g = torch.Generator(device="cpu").manual_seed(TAPE_SEED + rank)
-    tape = (torch.rand((TAPE_LEN, n, 4), generator=g) * 2.0 - 1.0).to(dev)
-    vec.reset(0)
-    stream = torch.cuda.current_stream()
+    res = time_race(n, args.math, args.launch, args.steps, args.warmup, dev, rank, world, dist)
+    tms = torch.tensor([res["ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    total_envs = n * world
 
     def barrier():
         torch.cuda.synchronize()
@@ -243,52 +551,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # The timed loop is the reference's own cached-action perf loop (drone_race.py:83-90): one
-    # vec_step per action batch of the tape, issued through b2d_vec_step_tape (one kernel launch
-    # per step; `--launch single` issues them one b2d_vec_step_from call at a time instead).
-    def run_steps(t0, k):
-        if args.launch == "tape":
-            vec.step_tape(tape, t0 % TAPE_LEN, k)
-        else:
-            for j in range(k):
-                vec.step(tape[(t0 + j) % TAPE_LEN])
-
-    t = 0
-    run_steps(t, args.warmup)
-    t += args.warmup
-    barrier()
-    sampler = ClockSampler(physical_gpu_index(local_rank))
-    sampler.start()
-    launches0 = vec.kernel_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    term_count = torch.zeros((), dtype=torch.int64, device=dev)
-    ev0.record(stream)
-    run_steps(t, args.steps)
-    t += args.steps
-    ev1.record(stream)
-    barrier()
-    sampler.stop()
-    launches = vec.kernel_launches - launches0
-    ms = ev0.elapsed_time(ev1)
-    # reset fraction of the workload, measured after the timed region (one extra step)
-    vec.step(tape[t % TAPE_LEN])
-    term_count = vec.terminals.sum()
-    reset_frac = float(term_count.item()) / n
-    stats = vec.log(group=True if world > 1 else None)
-
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
-    total_envs = n * world
-    value = total_envs * args.steps / (ms_max * 1e-3)
-
     # ---- e2e: public host-buffer API (numpy in / numpy out), PCIe inside the timed region
     e2e = None
     if not args.no_e2e:
-        vec.close()
-        del tape
-        torch.cuda.empty_cache()
         env = DroneRace(num_envs=n, report_interval=1 << 30, seed=0, buffers="host", device=local_rank,
                         math=args.math, env_id_base=rank * n)
         env.reset(0)
@@ -307,43 +572,60 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dt = float(te.item())
+        checksum = float(np.abs(obs).sum(dtype=np.float64))
+        env.close()
+        barrier()
+        floor = pcie_floor_ms(n, dev)  # all ranks copy at once, like the step does
+        tf = torch.tensor([floor], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        floor = float(tf.item())
         e2e = {"value": total_envs * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": total_envs * 16,
                "d2h_bytes_per_step": total_envs * (116 + 4 + 1), "steps": e2e_steps,
                "ms_per_step": dt / e2e_steps * 1e3,
+               "pcie_floor_ms": floor, "ms_per_step_over_pcie_floor": dt / e2e_steps * 1e3 / floor,
+               "pcie_floor_note": f"bare pinned copies of the same bytes per rank ({n * 16 / 1e6:.1f} MB up beside {n * 121 / 1e6:.1f} MB down), "
+                                  f"all {world} rank(s) copying at once, best of 5, measured in this run"
+                                  + ("; with several ranks the box's host DMA is the limiter, not the GPUs" if world > 1 else ""),
                "api": "drone_b200.drone_race.DroneRace(buffers='host').step(np.ndarray) -> binding.vec_step_actions -> b2d_vec_step_host_from",
-               "host_cpu_affinity": affinity,
-               "checksum": float(np.abs(obs).sum(dtype=np.float64))}
-        env.close()
+               "host_cpu_affinity": affinity, "checksum": checksum}
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        per_gpu_gbs = ALGO_BYTES_PER_ENV_STEP * n * args.steps / (ms_max * 1e-3) / 1e9
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world, f"env-sharded x{world}, no per-step collective; vec_log all-reduce over NCCL"),
-            "math": args.math, "launch": args.launch, "reset_fraction_per_step": reset_frac,
-            "episode_stats": stats,
-            "clocks": sampler.summary(),
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": per_gpu_gbs / peak, "traffic": ncu_traffic(),
-                         "kernel": f"race_step_kernel<{'strict' if args.math == 'strict' else 'fast'}>",
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
-                         "avg_launch_us": ms_max / args.steps * 1e3, "peak_source": peak_src, "per": "GPU"},
-        }
+        line = race_line(res, n, args.math, args.launch, args.steps, args.warmup, world, ms_max)
         if e2e is not None:
             line["e2e"] = e2e
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                res = cpu_sample()
-                line["cpu_baseline"] = {
-                    "value": res["env_steps_per_s"], "unit": UNIT, "cores": res["procs"], "kind": res["kind"],
-                    "sample": f"{res['envs']} envs x {res['steps']} steps of the same workload, "
-                              f"{res['procs']} processes (one per physical core), {res['wall_s']:.1f} s"}
-            except Exception as e:  # noqa: BLE001
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        par = parity_summary()
+        if par:
+            line["parity"] = par
+        if world == 1 and cpu:
+            line["cpu_baseline"] = safe_cpu_baseline(UNIT, budget_s=15.0)
+        if world == 1 and not args.no_extra:
+            extra = {}
+
+            def sub(name, fn):
+                try:
+                    extra[name] = fn()
+                except Exception as e:  # noqa: BLE001 - a failing sub-result must not cost the headline line
+                    extra[name] = {"error": repr(e)}
+
+            def race_variant(nn, math, launch, which, steps):
+                r = time_race(nn, math, launch, steps, 20, dev)
+                ln = race_line(r, nn, math, launch, steps, 20, 1, r["ms"], which)
+                return ln
+
+            def c0():
+                ln = race_variant(4096, "fast", "tape", "configs[0]", 2000)
+                if cpu:
+                    ln["cpu_baseline"] = safe_cpu_baseline(UNIT, budget_s=6.0, envs=4096)
+                return ln
+
+            sub("race4096_configs0", c0)
+            sub("swarm16_configs2", lambda: bench_swarm(16, 1100, 20, dev, cpu=cpu))
+            sub("swarm64_configs2", lambda: bench_swarm(64, 1100, 20, dev, cpu=cpu))
+            sub("rollout_configs3", lambda: bench_rollout(4, dev, impl=args.rollout_impl, cpu=cpu))
+            sub("race_strict_math", lambda: race_variant(n, "strict", "tape", "configs[1]", 500))
+            sub("race_single_launches", lambda: race_variant(n, "fast", "single", "configs[1]", 1000))
+            line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

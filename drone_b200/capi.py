@@ -72,6 +72,7 @@ SYMBOLS = {
     "b2d_state_blob_floats": (C.c_int, [_P]),
     "b2d_kernel_launches": (C.c_longlong, [_P]),
     "b2d_step_count": (C.c_int, [_P, C.POINTER(C.c_uint32), _P]),
+    "b2d_guard_replays": (C.c_int, [_P, C.POINTER(C.c_ulonglong), _P]),
     "b2d_get_state": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_float)]),
     "b2d_put_state": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_float)]),
     "b2d_observe": (C.c_int, [_P, _P]),

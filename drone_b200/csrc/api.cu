@@ -37,11 +37,33 @@ static int fail(int code, const char *fmt, ...) {
 
 enum { KIND_RACE = 0, KIND_SWARM = 1 };
 
+// Every entry point that touches the device runs with the handle's device current and restores the
+// caller's device on the way out (a handle on cuda:1 may be stepped while cuda:0 is current).
+struct DeviceScope {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceScope(int dev) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+        if (cur != dev) {
+            ok = cudaSetDevice(dev) == cudaSuccess;
+            prev = cur;
+        }
+    }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define DEVICE_SCOPE(v)                                                                      \
+    DeviceScope dev_scope_((v)->device);                                                     \
+    if (!dev_scope_.ok) return fail(B2D_ECUDA, "cudaSetDevice(%d) failed", (v)->device)
+
 struct b2d_vec {
     int kind;
     int device;
     int num_envs, num_agents /* rows */, obs_dim, blob_floats, payload_floats;
     int math, write_clamped;
+    bool host_clamp; // host buffers: leave clamp(action, -1, 1) in the caller's action array like DR/dronelib.h:437
     int step_ctas;   // race: CTAs of an overlapped (tape) launch = the largest grid; swarm: unused
     int single_ctas; // race: CTAs of a launch that runs alone
     RaceDev race;
@@ -62,6 +84,7 @@ struct b2d_vec {
     long long h_log_out[16];
     double h_flog_out[8];
     long long launches;
+    int swarm_grid[2]; // swarm: persistent step grid per math mode (resident CTA slots of the handle's device)
     uint32_t seq; // step-kernel launches so far (RaceDev::seq)
     cudaStream_t copy_streams[2];
     cudaEvent_t ev_step, ev_copy[2];
@@ -148,7 +171,8 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
     if (cfg->math != B2D_MATH_FAST && cfg->math != B2D_MATH_STRICT) return fail(B2D_EINVAL, "unknown math mode");
     int rc = check_ext(ext);
     if (rc) return rc;
-    CUDA_TRY(cudaSetDevice(cfg->device));
+    DeviceScope scope(cfg->device);
+    if (!scope.ok) return fail(B2D_ECUDA, "cudaSetDevice(%d) failed", cfg->device);
     b2d_vec *v = new (std::nothrow) b2d_vec();
     if (!v) return fail(B2D_ENOMEM, "out of host memory");
     v->kind = KIND_RACE;
@@ -158,7 +182,8 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
     v->blob_floats = B2D_RACE_BLOB + 6 * cfg->max_rings;
     v->payload_floats = v->blob_floats;
     v->math = cfg->math;
-    v->write_clamped = cfg->write_clamped_actions;
+    v->write_clamped = cfg->write_clamped_actions == 1;
+    v->host_clamp = cfg->write_clamped_actions < 0;
     RaceDev &d = v->race;
     memset(&d, 0, sizeof(d));
     d.n = cfg->num_envs;
@@ -170,15 +195,28 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
     d.env_id_base = cfg->env_id_base;
     d.reset_mode = B2D_RESET_PHILOX;
     {   // persistent grid: one resident set of step CTAs per SM (or fewer for small N)
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        int sms = 0, per_sm = 0, per_sm_strict = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(race_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RACE_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(race_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RACE_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(race_step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(race_step_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, race_step_kernel<false>, RACE_BLOCK, RACE_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_strict, race_step_kernel<true>, RACE_BLOCK, RACE_SMEM_BYTES);
+        if (e != cudaSuccess || sms < 1 || per_sm < 1 || per_sm_strict < 1) {
+            delete v;
+            return fail(B2D_ECUDA, "race_step_kernel setup on device %d: %s", cfg->device,
+                        e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit on an SM");
+        }
+        if (per_sm > RACE_MIN_CTAS) per_sm = RACE_MIN_CTAS; // what the kernel is tuned for (__launch_bounds__)
         const int warps_per_cta = RACE_BLOCK / 32;
         const int ntiles = (cfg->num_envs + 31) / 32;
         int step_ctas = (ntiles + warps_per_cta - 1) / warps_per_cta;
         // overlapped launches (b2d_vec_step_tape) run best with every CTA slot taken (finer per-CTA chains:
         // 68 vs 74 us per 1M envs), a launch that runs alone with one CTA per SM fewer (78 vs 84 us)
-        v->single_ctas = step_ctas < sms * (RACE_MIN_CTAS - 1) ? step_ctas : sms * (RACE_MIN_CTAS - 1);
-        if (step_ctas > sms * RACE_MIN_CTAS) step_ctas = sms * RACE_MIN_CTAS;
+        const int alone = sms * (per_sm > 1 ? per_sm - 1 : 1);
+        v->single_ctas = step_ctas < alone ? step_ctas : alone;
+        if (step_ctas > sms * per_sm) step_ctas = sms * per_sm;
         v->step_ctas = step_ctas;
         d.max_grid = step_ctas;
     }
@@ -190,7 +228,14 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
         return rc;
     }
     race_ctl_reset_kernel<<<1, 256>>>(d.ctl, d.cta_score, 0u, (unsigned int)v->step_ctas, 1);
-    cudaDeviceSynchronize();
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            b2d_vec_close(v);
+            return fail(B2D_ECUDA, "race_ctl_reset_kernel: %s", cudaGetErrorString(e));
+        }
+    }
 #if B2D_EXPERIMENT_TIMING
     cudaMalloc(&d.trace, (size_t)v->step_ctas * 4 * sizeof(unsigned long long));
 #endif
@@ -199,10 +244,6 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
     d.act_out = v->write_clamped ? v->dev.actions : nullptr;
     d.rew = v->dev.rewards;
     d.term = v->dev.terminals;
-    cudaFuncSetAttribute(race_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RACE_SMEM_BYTES);
-    cudaFuncSetAttribute(race_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RACE_SMEM_BYTES);
-    cudaFuncSetAttribute(race_step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(race_step_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     *out = v;
     return B2D_OK;
 }
@@ -256,7 +297,8 @@ extern "C" int b2d_swarm_create(b2d_vec **out, const b2d_swarm_cfg *cfg, const b
     if ((long long)cfg->num_envs * cfg->num_agents > 0x7fffffffLL / 64) return fail(B2D_EINVAL, "too many agents");
     int rc = check_ext(ext);
     if (rc) return rc;
-    CUDA_TRY(cudaSetDevice(cfg->device));
+    DeviceScope scope(cfg->device);
+    if (!scope.ok) return fail(B2D_ECUDA, "cudaSetDevice(%d) failed", cfg->device);
     b2d_vec *v = new (std::nothrow) b2d_vec();
     if (!v) return fail(B2D_ENOMEM, "out of host memory");
     v->kind = KIND_SWARM;
@@ -267,7 +309,8 @@ extern "C" int b2d_swarm_create(b2d_vec **out, const b2d_swarm_cfg *cfg, const b
     v->blob_floats = cfg->num_agents * B2D_SWARM_AGENT_BLOB + 2 + 6 * cfg->max_rings;
     v->payload_floats = cfg->num_agents * B2D_SWARM_AGENT_PAYLOAD + 2 + 6 * cfg->max_rings;
     v->math = cfg->math;
-    v->write_clamped = cfg->write_clamped_actions;
+    v->write_clamped = cfg->write_clamped_actions == 1;
+    v->host_clamp = cfg->write_clamped_actions < 0;
     v->step_ctas = 1;
     memset(&v->race, 0, sizeof(v->race));
     SwarmDev &d = v->swarm;
@@ -301,6 +344,10 @@ extern "C" int b2d_swarm_create(b2d_vec **out, const b2d_swarm_cfg *cfg, const b
         return fail(B2D_ECUDA, "swarm table upload failed");
     }
     d.form = form;
+    if ((rc = swarm_step_setup(d, cfg->device, v->swarm_grid))) { // per handle: its device's SM count and kernel attributes
+        b2d_vec_close(v);
+        return fail(B2D_ECUDA, "swarm_kernel setup on device %d failed", cfg->device);
+    }
     d.obs = v->dev.observations;
     d.act_in = v->dev.actions;
     d.act_out = v->write_clamped ? v->dev.actions : nullptr;
@@ -313,7 +360,7 @@ extern "C" int b2d_swarm_create(b2d_vec **out, const b2d_swarm_cfg *cfg, const b
 
 extern "C" int b2d_vec_close(b2d_vec *v) {
     if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
-    cudaSetDevice(v->device);
+    DeviceScope scope(v->device);
     cudaDeviceSynchronize();
 #if B2D_EXPERIMENT_TIMING
     if (v->kind == KIND_RACE && v->race.ctl) {
@@ -363,6 +410,7 @@ static int launch_check(const char *what) {
 
 extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
     if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    DEVICE_SCOPE(v);
     cudaStream_t st = (cudaStream_t)stream;
     if (v->kind == KIND_RACE) {
         RaceDev &d = v->race;
@@ -385,6 +433,8 @@ extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
 // (b2d_vec_step_tape); every CTA then waits for its own predecessor only (race_step_kernel).
 static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool overlap = false, int tile_begin = 0,
                      int tile_end = -1, bool first_chunk = true, bool last_chunk = true, bool series = false) {
+    if ((v->kind == KIND_RACE ? v->race.reset_mode : v->swarm.reset_mode) == B2D_RESET_INJECT && !v->d_payload)
+        return fail(B2D_ESTATE, "inject mode without a payload (b2d_set_reset_payload)");
     if (v->kind == KIND_RACE) {
         RaceDev d = v->race;
         if (actions) d.act_in = actions;
@@ -420,18 +470,20 @@ static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool ove
         v->launches += 1;
         return launch_check("race_step_kernel");
     }
-    swarm_vec_step(v->swarm, actions, v->math, st, &v->launches);
+    swarm_vec_step(v->swarm, actions, v->math, v->swarm_grid[v->math == B2D_MATH_STRICT ? 1 : 0], st, &v->launches);
     return launch_check("swarm_step_kernel");
 }
 
 extern "C" int b2d_vec_step(b2d_vec *v, void *stream) {
     if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    DEVICE_SCOPE(v);
     return step_impl(v, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int b2d_vec_step_from(b2d_vec *v, const float *device_actions, void *stream) {
     if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
     if (!device_actions || ((uintptr_t)device_actions & 15u)) return fail(B2D_EINVAL, "actions must be a 16-byte aligned device pointer");
+    DEVICE_SCOPE(v);
     return step_impl(v, device_actions, (cudaStream_t)stream);
 }
 
@@ -444,6 +496,7 @@ extern "C" int b2d_vec_step_tape(b2d_vec *v, const float *device_tape, int tape_
     if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
     if (!device_tape || ((uintptr_t)device_tape & 15u) || tape_len <= 0 || first < 0 || steps < 0)
         return fail(B2D_EINVAL, "b2d_vec_step_tape: bad argument");
+    DEVICE_SCOPE(v);
     cudaStream_t st = (cudaStream_t)stream;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
@@ -463,6 +516,14 @@ extern "C" int b2d_vec_step_tape(b2d_vec *v, const float *device_tape, int tape_
 // the copy streams.  `host_actions` (optional) are copied into the caller-visible action buffer
 // like the reference's wrapper does (`self.actions[:] = actions`), chunk by chunk, so that the
 // 1 ms CPU copy of 16 MB hides behind the transfers as well.
+// dst = clamp(src, -1, 1) with the reference's branch order (a NaN stays a NaN), DR/dronelib.h:73-79,437
+static void clamp_copy(float *dst, const float *src, size_t count) {
+    for (size_t k = 0; k < count; k++) {
+        const float a = src[k];
+        dst[k] = a < -1.0f ? -1.0f : (a > 1.0f ? 1.0f : a);
+    }
+}
+
 static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st) {
     const size_t rows = (size_t)v->num_agents;
     const bool copy_in = host_actions && host_actions != v->host.actions;
@@ -483,7 +544,9 @@ static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st
         const size_t nr = r1 - r0;
         cudaStream_t cs = v->copy_streams[j & 1];
         // the CPU copy of this chunk's actions overlaps the transfers of the chunks already in flight
-        if (copy_in) memcpy(v->host.actions + r0 * 4, host_actions + r0 * 4, nr * 4 * sizeof(float));
+        // (with host_clamp the caller-visible buffer receives the clamped values, as the reference leaves them)
+        if (v->host_clamp) clamp_copy(v->host.actions + r0 * 4, (copy_in ? host_actions : v->host.actions) + r0 * 4, nr * 4);
+        else if (copy_in) memcpy(v->host.actions + r0 * 4, host_actions + r0 * 4, nr * 4 * sizeof(float));
         CUDA_TRY(cudaMemcpyAsync(v->dev.actions + r0 * 4, v->host.actions + r0 * 4, nr * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
         int rc = step_impl(v, nullptr, st, false, (int)bnd[j], (int)bnd[j + 1], j == 0, j == nchunks - 1);
         if (rc) return rc;
@@ -507,18 +570,21 @@ static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st
 extern "C" int b2d_vec_step_host(b2d_vec *v, void *stream) {
     if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
     if (!v->has_host) return fail(B2D_ESTATE, "handle was not created with host buffers");
+    DEVICE_SCOPE(v);
     return step_host_impl(v, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int b2d_vec_step_host_from(b2d_vec *v, const float *host_actions, void *stream) {
     if (!v || !host_actions) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
     if (!v->has_host) return fail(B2D_ESTATE, "handle was not created with host buffers");
+    DEVICE_SCOPE(v);
     return step_host_impl(v, host_actions, (cudaStream_t)stream);
 }
 
 extern "C" int b2d_vec_reset_host(b2d_vec *v, uint64_t seed, void *stream) {
     if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
     if (!v->has_host) return fail(B2D_ESTATE, "handle was not created with host buffers");
+    DEVICE_SCOPE(v);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = b2d_vec_reset(v, seed, stream);
     if (rc) return rc;
@@ -530,6 +596,7 @@ extern "C" int b2d_vec_reset_host(b2d_vec *v, uint64_t seed, void *stream) {
 // ---------------------------------------------------------------- vec_log
 extern "C" int b2d_vec_log_begin(b2d_vec *v, void *stream, long long **device_sums, int *count) {
     if (!v) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    DEVICE_SCOPE(v);
     cudaStream_t st = (cudaStream_t)stream;
     Ctl *ctl = v->kind == KIND_RACE ? v->race.ctl : v->swarm.ctl;
     if (v->kind == KIND_RACE) race_log_snapshot_kernel<<<1, 32, 0, st>>>(ctl, v->race.cta_score, v->d_log_out);
@@ -542,6 +609,7 @@ extern "C" int b2d_vec_log_begin(b2d_vec *v, void *stream, long long **device_su
 
 extern "C" int b2d_vec_log_end(b2d_vec *v, float out[B2D_LOG_FIELDS], void *stream) {
     if (!v || !out) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    DEVICE_SCOPE(v);
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpyAsync(v->h_log_out, v->d_log_out, 16 * sizeof(long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -589,6 +657,7 @@ extern "C" long long b2d_kernel_launches(const b2d_vec *v) { return v ? v->launc
 
 extern "C" int b2d_step_count(b2d_vec *v, uint32_t *steps, void *stream) {
     if (!v || !steps) return fail(B2D_EINVAL, "null argument");
+    DEVICE_SCOPE(v);
     Ctl *ctl = v->kind == KIND_RACE ? v->race.ctl : v->swarm.ctl;
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     uint32_t w[2] = {0, 1};
@@ -597,8 +666,18 @@ extern "C" int b2d_step_count(b2d_vec *v, uint32_t *steps, void *stream) {
     return B2D_OK;
 }
 
+extern "C" int b2d_guard_replays(b2d_vec *v, unsigned long long *count, void *stream) {
+    if (!v || !count) return fail(B2D_EINVAL, "null argument");
+    DEVICE_SCOPE(v);
+    Ctl *ctl = v->kind == KIND_RACE ? v->race.ctl : v->swarm.ctl;
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    CUDA_TRY(cudaMemcpy(count, &ctl->guard_replays, sizeof(*count), cudaMemcpyDeviceToHost));
+    return B2D_OK;
+}
+
 extern "C" int b2d_set_step_count(b2d_vec *v, uint32_t steps) {
     if (!v) return fail(B2D_EINVAL, "null handle");
+    DEVICE_SCOPE(v);
     Ctl *ctl = v->kind == KIND_RACE ? v->race.ctl : v->swarm.ctl;
     CUDA_TRY(cudaDeviceSynchronize());
     const uint32_t done = steps;
@@ -638,6 +717,7 @@ static int ensure_tmp(b2d_vec *v, int n) {
 
 extern "C" int b2d_get_state(b2d_vec *v, const int *env_ids, int n, float *host_blobs) {
     if (!v || !host_blobs || n <= 0 || n > v->num_envs) return fail(B2D_EINVAL, "b2d_get_state: bad argument");
+    DEVICE_SCOPE(v);
     int rc = ensure_tmp(v, n);
     if (rc) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
@@ -656,6 +736,7 @@ extern "C" int b2d_get_state(b2d_vec *v, const int *env_ids, int n, float *host_
 
 extern "C" int b2d_put_state(b2d_vec *v, const int *env_ids, int n, const float *host_blobs) {
     if (!v || !host_blobs || n <= 0 || n > v->num_envs) return fail(B2D_EINVAL, "b2d_put_state: bad argument");
+    DEVICE_SCOPE(v);
     int rc = ensure_tmp(v, n);
     if (rc) return rc;
     if ((rc = ensure_external_rings(v))) return rc;
@@ -676,6 +757,7 @@ extern "C" int b2d_put_state(b2d_vec *v, const int *env_ids, int n, const float 
 
 extern "C" int b2d_observe(b2d_vec *v, void *stream) {
     if (!v) return fail(B2D_EINVAL, "null handle");
+    DEVICE_SCOPE(v);
     cudaStream_t st = (cudaStream_t)stream;
     if (v->kind == KIND_RACE) race_observe_kernel<<<(v->race.n + 127) / 128, 128, 0, st>>>(v->race);
     else swarm_observe_launch(v->swarm, st);
@@ -692,6 +774,7 @@ extern "C" int b2d_set_math(b2d_vec *v, int math) {
 
 extern "C" int b2d_set_reset_mode(b2d_vec *v, int mode) {
     if (!v || (mode != B2D_RESET_PHILOX && mode != B2D_RESET_INJECT)) return fail(B2D_EINVAL, "unknown reset mode");
+    DEVICE_SCOPE(v);
     if (mode == B2D_RESET_INJECT) {
         CUDA_TRY(cudaDeviceSynchronize());
         int rc = ensure_external_rings(v);
@@ -704,6 +787,7 @@ extern "C" int b2d_set_reset_mode(b2d_vec *v, int mode) {
 
 extern "C" int b2d_set_reset_payload(b2d_vec *v, const float *host_payload) {
     if (!v || !host_payload) return fail(B2D_EINVAL, "null argument");
+    DEVICE_SCOPE(v);
     const size_t bytes = (size_t)v->num_envs * v->payload_floats * sizeof(float);
     if (!v->d_payload) {
         if (cudaMalloc(&v->d_payload, bytes) != cudaSuccess) return fail(B2D_ENOMEM, "cudaMalloc payload");
@@ -726,6 +810,7 @@ extern "C" int b2d_profile_kernels(b2d_vec *v, int enable, float out_us[3]) {
         v->profile = true;
         return B2D_OK;
     }
+    DEVICE_SCOPE(v);
     v->profile = false;
     CUDA_TRY(cudaDeviceSynchronize());
     double a = 0, b = 0;

@@ -73,7 +73,7 @@ static int set_b2d_error(int rc) {
 /* One contract buffer: NumPy array or __cuda_array_interface__ object.
  * Error strings and exception types follow EB:62-135. */
 static int parse_buffer(PyObject *o, const char *name, int want_1d, int reject_f64, int min_2d, void **ptr,
-                        int *location, Py_ssize_t *rows, Py_ssize_t *stride0) {
+                        int *location, Py_ssize_t *rows, Py_ssize_t *stride0, Py_ssize_t *itemsize, Py_ssize_t *inner_out) {
     char msg[128];
     if (PyObject_TypeCheck(o, &PyArray_Type)) {
         PyArrayObject *a = (PyArrayObject *)o;
@@ -99,6 +99,9 @@ static int parse_buffer(PyObject *o, const char *name, int want_1d, int reject_f
         *location = B2D_MEM_HOST;
         *rows = PyArray_NDIM(a) > 0 ? PyArray_DIM(a, 0) : 1;
         *stride0 = PyArray_NDIM(a) > 0 ? PyArray_STRIDE(a, 0) : 0;
+        *itemsize = PyArray_ITEMSIZE(a);
+        *inner_out = 1;
+        for (int k = 1; k < PyArray_NDIM(a); k++) *inner_out *= PyArray_DIM(a, k);
         return 0;
     }
     PyObject *cai = PyObject_GetAttrString(o, "__cuda_array_interface__");
@@ -153,7 +156,9 @@ static int parse_buffer(PyObject *o, const char *name, int want_1d, int reject_f
         Py_ssize_t inner = 1;
         for (Py_ssize_t k = 1; k < nd; k++) inner *= PyLong_AsSsize_t(PyTuple_GetItem(shape, k));
         const char *ts = typestr ? PyUnicode_AsUTF8(typestr) : NULL;
-        *stride0 = inner * (ts ? atoi(ts + 2) : 4);
+        *itemsize = ts ? atoi(ts + 2) : 4;
+        *inner_out = inner;
+        *stride0 = inner * *itemsize;
     }
     *ptr = PyLong_AsVoidPtr(PyTuple_GetItem(data, 0));
     *location = B2D_MEM_DEVICE;
@@ -165,7 +170,7 @@ done:
 
 typedef struct {
     void *ptr[5];
-    Py_ssize_t rows[5], stride[5];
+    Py_ssize_t rows[5], stride[5], itemsize[5], inner[5];
     int location;
 } FiveBufs;
 
@@ -176,8 +181,29 @@ static int parse_five(PyObject *args, int batched, FiveBufs *f) {
     for (int k = 0; k < 5; k++) {
         int want_1d = k >= 2;
         if (parse_buffer(PyTuple_GetItem(args, k), BUF_NAMES[k], want_1d, k == 1, batched && k == 0, &f->ptr[k], &loc[k],
-                         &f->rows[k], &f->stride[k]) < 0)
+                         &f->rows[k], &f->stride[k], &f->itemsize[k], &f->inner[k]) < 0)
             return -1;
+    }
+    /* The library DMA-writes rows * OBS_DIM * 4, rows * 4 and rows bytes into these arrays: element size and
+     * row width must be what the kernels assume (the reference touches one env's slice at a time and can
+     * afford to be looser, EB:62-135). */
+    {
+        static const Py_ssize_t want_item[5] = {4, 4, 4, 1, 1};
+        const Py_ssize_t want_inner[5] = {OBS_DIM, B2D_ACT, 1, 1, 1};
+        char msg[160];
+        for (int k = 0; k < 5; k++) {
+            if (f->itemsize[k] != want_item[k]) {
+                snprintf(msg, sizeof msg, "%s must have %d-byte elements (%s), got %d-byte elements", BUF_NAMES[k], (int)want_item[k],
+                         k < 3 ? "float32" : "bool / uint8", (int)f->itemsize[k]);
+                PyErr_SetString(PyExc_ValueError, msg);
+                return -1;
+            }
+            if (f->inner[k] != want_inner[k]) {
+                snprintf(msg, sizeof msg, "%s must have %d values per row, got %d", BUF_NAMES[k], (int)want_inner[k], (int)f->inner[k]);
+                PyErr_SetString(PyExc_ValueError, msg);
+                return -1;
+            }
+        }
     }
     for (int k = 1; k < 5; k++) {
         if (loc[k] != loc[0]) {
@@ -252,15 +278,18 @@ typedef struct {
 } Extra;
 
 /* placement / arithmetic kwargs that have no counterpart in the reference: device=0, env_id_base=0,
- * math="fast"|"strict", write_clamped_actions=0.  The reference clamps the shared action buffer in
- * place (DR/dronelib.h:437); the step uses the clamped values either way, but storing them back
- * (16 B/env, plus a D2H copy for NumPy callers) is opt-in. */
+ * math="fast"|"strict", write_clamped_actions.  The reference clamps the shared action buffer in
+ * place (DR/dronelib.h:437), so after a step the caller's `actions` array holds clamp(action, -1, 1).
+ * write_clamped_actions=-1 (default) means "like the reference where the caller can see it": NumPy
+ * buffers get the clamped values back (host-side clamp of the caller-visible array, no extra PCIe
+ * traffic); device buffers are left untouched unless write_clamped_actions=1 (a policy's output
+ * tensor is usually not the env's to modify, and the store costs 16 B/env of HBM traffic). */
 static Extra parse_extra(PyObject *kwargs) {
     Extra x;
     x.device = opt_int(kwargs, "device", 0);
     x.env_id_base = opt_int(kwargs, "env_id_base", 0);
     x.math = opt_int(kwargs, "math", B2D_MATH_FAST);
-    x.write_clamped = opt_int(kwargs, "write_clamped_actions", 0);
+    x.write_clamped = opt_int(kwargs, "write_clamped_actions", -1);
     return x;
 }
 
@@ -556,9 +585,11 @@ static PyObject *vec_init(PyObject *self, PyObject *args, PyObject *kwargs) {
     if (parse_five(args, 1, &f) < 0) return NULL;
     int max_rings, max_moves, num_agents;
     if (parse_env_kwargs(kwargs, &max_rings, &max_moves, &num_agents) < 0) return NULL;
-    if (f.rows[0] < (Py_ssize_t)num_envs * num_agents || f.rows[1] < (Py_ssize_t)num_envs * num_agents) {
-        PyErr_SetString(PyExc_ValueError, "buffers are smaller than num_envs rows");
-        return NULL;
+    for (int k = 0; k < 5; k++) {
+        if (f.rows[k] < (Py_ssize_t)num_envs * num_agents) {
+            PyErr_SetString(PyExc_ValueError, "buffers are smaller than num_envs rows");
+            return NULL;
+        }
     }
     VecH *vh = make_vec(&f, num_envs, seed, max_rings, max_moves, num_agents, parse_extra(kwargs));
     if (!vh) return NULL;

@@ -46,6 +46,9 @@ namespace b2d {
 #ifndef B2D_EXPERIMENT_NO_RESET
 #define B2D_EXPERIMENT_NO_RESET 0 // measurement aid: episodes never end
 #endif
+#ifndef B2D_EXPERIMENT_NO_GUARD
+#define B2D_EXPERIMENT_NO_GUARD 0 // measurement aid: the fast step without its near-threshold guard
+#endif
 #ifndef B2D_EXPERIMENT_TIMING
 #define B2D_EXPERIMENT_TIMING 0 // measurement aid: clock64 sums per phase, printed by b2d_vec_close
 #endif
@@ -70,7 +73,7 @@ enum { ACC_N = 0, ACC_RETURN, ACC_LENGTH, ACC_RINGS, ACC_OOB, ACC_COLLISION, ACC
 struct Ctl {
     unsigned int ctas_done; // race: vec_steps completed since the last vec_reset (swarm: step CTAs of tile 0, grid = 1)
     unsigned int grid;      // step CTAs per launch (fixed for the life of the handle)
-    unsigned int pad0[2];
+    unsigned long long guard_replays; // env-steps the fast kernels re-did in reference arithmetic (race_strict_replay)
     long long acc[ACC_COUNT];
     double facc[8];          // float-valued sums (swarm)
     unsigned long long dbg[12]; // B2D_EXPERIMENT_TIMING
@@ -374,6 +377,43 @@ __device__ __noinline__ void race_inject_episode(const RaceDev &d, int i, uint32
     race_observe<STRICT>(s, b[27], g, obs_row);
 }
 
+// ---------------------------------------------------------------- near-threshold guard of the fast step
+// The fast arithmetic (FMA contraction, approximate reciprocals) moves the drone to within ~1e-5 m of
+// where the reference's arithmetic moves it.  That is inside the tolerance for every continuous output,
+// but the step also takes DECISIONS on the position -- out of bounds (|coordinate| > 10,
+// DR/drone_race.h:165-172), ring plane crossed, hit point inside radius -/+ 0.5 (DR/dronelib.h:462-489) --
+// and a decision taken within rounding distance of its threshold could come out differently: a terminal,
+// a reward of +-1 or a ring index that differs from the reference's.  So a lane whose fast result lies
+// within a guard band of any threshold re-does the step in the reference's arithmetic, from the env's
+// pre-step state, which is still in global memory at that point.  The bands (2e-4 m at the walls and the
+// ring plane, 0.1 m around the rim) are 20x the worst fast-vs-reference position error, so every integer
+// output of the fast kernel equals the strict kernel's; about 1 env-step in 10^4 is replayed.
+constexpr float RACE_GUARD_WALL = 2e-4f;
+constexpr float RACE_GUARD_PLANE = 2e-4f;
+constexpr float RACE_GUARD_RADIUS = 2.6f;
+
+// out[0:17] = state after the step, out[17] = out of bounds (0/1), out[18] = gate event; `out` is shared memory
+__device__ __noinline__ void race_strict_replay(const RaceDev &d, int i, float4 a4, float *out) {
+    const float4 *hot = race_hot(d, i);
+    const size_t st = race_slot_stride(d);
+    const float4 q0 = __ldcg(hot + 0 * st), q1 = __ldcg(hot + 1 * st), q2 = __ldcg(hot + 2 * st), q3 = __ldcg(hot + 3 * st),
+                 q4 = __ldcg(hot + 4 * st);
+    const float4 p0 = __ldcg(hot + 5 * st), p1 = __ldcg(hot + 6 * st), p2 = __ldcg(hot + 7 * st);
+    const float4 c0 = __ldcg(hot + 8 * st), tl = __ldcg(hot + 9 * st);
+    float s[17] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x};
+    const DroneParams p = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, tl.x};
+    const float ring[6] = {c0.x, c0.y, c0.z, c0.w, tl.z, tl.w};
+    const float act[4] = {xclamp(xf(a4.x), -1.0f, 1.0f).v, xclamp(xf(a4.y), -1.0f, 1.0f).v, xclamp(xf(a4.z), -1.0f, 1.0f).v,
+                          xclamp(xf(a4.w), -1.0f, 1.0f).v};
+    const float before[3] = {s[0], s[1], s[2]};
+    advance_body_strict(s, p, act);
+    const bool oob = s[0] < -10.0f || s[0] > 10.0f || s[1] < -10.0f || s[1] > 10.0f || s[2] < -10.0f || s[2] > 10.0f;
+#pragma unroll
+    for (int k = 0; k < 17; k++) out[k] = s[k];
+    out[17] = oob ? 1.0f : 0.0f;
+    out[18] = oob ? 0.0f : gate_event<xf>(before, s, ring, -1.0f);
+}
+
 // ---------------------------------------------------------------- async copy helpers
 __device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
@@ -558,11 +598,25 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
 
             // ---- episode logic: R/drone_race.h:165-203, as selects (the only branches left are the
             // rare ones: a plane crossing inside gate_event, a ring pass that needs the next ring)
-            const bool oob = s[0] < -10.0f || s[0] > 10.0f || s[1] < -10.0f || s[1] > 10.0f || s[2] < -10.0f || s[2] > 10.0f;
+            bool oob = s[0] < -10.0f || s[0] > 10.0f || s[1] < -10.0f || s[1] > 10.0f || s[2] < -10.0f || s[2] > 10.0f;
             float gate = 0.0f;
-            if (!oob) {
-                if constexpr (STRICT) gate = gate_event<xf>(before, s, ring, -1.0f);
-                else gate = gate_event<float>(before, s, ring, -1.0f);
+            if constexpr (STRICT) {
+                if (!oob) gate = gate_event<xf>(before, s, ring, -1.0f);
+            } else {
+                // decisions within a guard band of their threshold are re-taken in the reference's arithmetic
+                const float wall = fminf(fminf(fabsf(fabsf(s[0]) - 10.0f), fabsf(fabsf(s[1]) - 10.0f)), fabsf(fabsf(s[2]) - 10.0f));
+                bool suspect = false;
+                if (!oob) gate = gate_event_guarded(before, s, ring, -1.0f, RACE_GUARD_PLANE, RACE_GUARD_RADIUS, suspect);
+#if !B2D_EXPERIMENT_SKIP_MATH && !B2D_EXPERIMENT_NO_GUARD
+                if (wall < RACE_GUARD_WALL || suspect) {
+                    race_strict_replay(d, i, a4, my_row);
+#pragma unroll
+                    for (int k = 0; k < 17; k++) s[k] = my_row[k];
+                    oob = my_row[17] != 0.0f;
+                    gate = my_row[18];
+                    atomicAdd(&s_acc[ACC_SPARE], 1);
+                }
+#endif
             }
             const float reward = oob ? -1.0f : gate;
             ep_ret += reward;
@@ -654,6 +708,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         if (lane < 7) {
             const int v = s_acc[lane];
             if (v != 0) atomicAdd((unsigned long long *)&d.ctl->acc[lane], (unsigned long long)(long long)v);
+            if (lane == 0 && s_acc[ACC_SPARE] != 0) atomicAdd(&d.ctl->guard_replays, (unsigned long long)s_acc[ACC_SPARE]);
             if (lane == ACC_RINGS) d.cta_score[blockIdx.x] = (long long)v + (d.score_add ? d.cta_score[blockIdx.x] : 0ll);
         }
         // launches may use fewer CTAs than the handle's largest grid: the unused score slots read zero
@@ -702,6 +757,7 @@ __global__ void race_ctl_reset_kernel(Ctl *ctl, long long *cta_score, unsigned i
             for (int k = 0; k < ACC_COUNT; k++) ctl->acc[k] = 0;
             for (int k = 0; k < 8; k++) ctl->facc[k] = 0.0;
             for (int k = 0; k < 12; k++) ctl->dbg[k] = 0;
+            ctl->guard_replays = 0;
         }
     }
 }

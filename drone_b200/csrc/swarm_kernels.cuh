@@ -889,29 +889,31 @@ static inline void swarm_vec_reset(SwarmDev &d, uint64_t seed, cudaStream_t st, 
     *launches += 1;
 }
 
-// persistent step grid: every resident CTA slot of the device, or one CTA per tile when there are fewer tiles
-static inline int swarm_step_grid(const SwarmDev &d, int math) {
-    static int per_sm[2] = {0, 0}, sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(swarm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM);
-        cudaFuncSetAttribute(swarm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM);
-        cudaFuncSetAttribute(swarm_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(swarm_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], swarm_kernel<false, false>, SWARM_BLOCK, SW_DYN_SMEM);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], swarm_kernel<true, false>, SWARM_BLOCK, SW_DYN_SMEM);
-        for (int m = 0; m < 2; m++) if (per_sm[m] < 1) per_sm[m] = 1;
+// persistent step grid: every resident CTA slot of the handle's device, or one CTA per tile when there
+// are fewer tiles.  Called once per handle at create time with the handle's device current: the
+// dynamic shared memory opt-in is per device, and so are the SM count and the occupancy.
+static inline int swarm_step_setup(const SwarmDev &d, int device, int grid_out[2]) {
+    int sms = 0, per_sm[2] = {0, 0};
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(swarm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(swarm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(swarm_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
+        cudaFuncSetAttribute(swarm_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], swarm_kernel<false, false>, SWARM_BLOCK, SW_DYN_SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], swarm_kernel<true, false>, SWARM_BLOCK, SW_DYN_SMEM) != cudaSuccess)
+        return -1;
+    const int tiles = swarm_grid(d);
+    for (int m = 0; m < 2; m++) {
+        if (per_sm[m] < 1) return -1;
+        const int slots = sms * per_sm[m];
+        grid_out[m] = tiles < slots ? tiles : slots;
     }
-    const int tiles = swarm_grid(d), slots = sms * per_sm[math == 1 ? 1 : 0];
-    return tiles < slots ? tiles : slots;
+    return 0;
 }
 
-static inline void swarm_vec_step(SwarmDev &dev, const float *actions, int math, cudaStream_t st, long long *launches) {
+static inline void swarm_vec_step(SwarmDev &dev, const float *actions, int math, int grid, cudaStream_t st, long long *launches) {
     SwarmDev d = dev;
     if (actions) d.act_in = actions;
-    const int grid = swarm_step_grid(d, math);
     if (math == 1) swarm_kernel<true, false><<<grid, SWARM_BLOCK, SW_DYN_SMEM, st>>>(d);
     else swarm_kernel<false, false><<<grid, SWARM_BLOCK, SW_DYN_SMEM, st>>>(d);
     *launches += 1;

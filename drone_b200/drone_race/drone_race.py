@@ -24,16 +24,20 @@ def _pinned(shape, dtype):
         import torch
         if torch.cuda.is_available():
             tdt = {np.dtype(np.float32): torch.float32, np.dtype(bool): torch.bool}[np.dtype(dtype)]
-            t = torch.zeros(shape, dtype=tdt, pin_memory=True)
-            a = t.numpy()
-            a_base_keepalive.append(t)
-            return a
+            # the ndarray's base is the tensor (torch sets it in .numpy()), so the pinned allocation lives
+            # exactly as long as the array: nothing to keep alive on the side, nothing leaks per env
+            return torch.zeros(shape, dtype=tdt, pin_memory=True).numpy()
     except Exception:  # noqa: BLE001 - pinning is an optimisation only
         pass
     return np.zeros(shape, dtype=dtype)
 
 
-a_base_keepalive = []
+def _bind_stream(env):
+    """Device buffers: the kernels run on torch's CURRENT stream of the env's device, the stream the
+    caller's action writes and observation reads are ordered on (side streams and graph capture included)."""
+    import torch
+    binding_mod = env._binding
+    binding_mod.vec_set_stream(env.c_envs, torch.cuda.current_stream(env.device).cuda_stream)
 
 
 class DroneRace(PufferEnv):
@@ -47,6 +51,7 @@ class DroneRace(PufferEnv):
         self.report_interval = report_interval
         self.tick = 0
         self.buffers = buffers
+        self._binding = binding
 
         if buffers == "device":
             import torch
@@ -106,11 +111,14 @@ class DroneRace(PufferEnv):
 
     def reset(self, seed=None):
         self.tick = 0
+        if self.buffers == "device":
+            _bind_stream(self)
         binding.vec_reset(self.c_envs, seed)
         return self.observations, []
 
     def step(self, actions):
         if self.buffers == "device":
+            _bind_stream(self)
             if actions is not self.actions:
                 self.actions.copy_(actions)
         self.tick += 1

@@ -7,7 +7,7 @@ torch CUDA tensors).
 """
 import numpy as np
 
-from ..drone_race.drone_race import _pinned
+from ..drone_race.drone_race import _bind_stream, _pinned
 from ..pufferenv import Box, PufferEnv
 from . import binding
 
@@ -22,6 +22,7 @@ class DroneSwarm(PufferEnv):
         self.report_interval = report_interval
         self.tick = 0
         self.buffers = buffers
+        self._binding = binding
         n = self.num_agents
 
         if buffers == "device":
@@ -67,11 +68,14 @@ class DroneSwarm(PufferEnv):
 
     def reset(self, seed=None):
         self.tick = 0
+        if self.buffers == "device":
+            _bind_stream(self)
         binding.vec_reset(self.c_envs, seed)
         return self.observations, []
 
     def step(self, actions):
         if self.buffers == "device":
+            _bind_stream(self)
             if actions is not self.actions:
                 self.actions.copy_(actions)
         self.tick += 1

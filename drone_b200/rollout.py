@@ -72,6 +72,20 @@ class DeviceRollout:
         self.graph = None
         self.use_graph = use_graph
         self.env_steps = 0
+        self._graph_launches_per_replay = 0
+        self._replays = 0
+
+    @property
+    def kernel_name(self):
+        if self.policy_impl == "fused":
+            return f"policy_act_{self.fused.precision}_kernel + race_step_kernel (two launches per step)"
+        return "torch policy ops + race_step_kernel"
+
+    @property
+    def kernel_launches(self):
+        """Kernels of this package launched for the rollout so far (graph replays re-launch the captured ones)."""
+        eager = self.vec.kernel_launches + (self.fused.launches if self.fused is not None else 0)
+        return eager + self._graph_launches_per_replay * max(0, self._replays - 1)
 
     @torch.no_grad()
     def _one_step(self, k):
@@ -124,9 +138,13 @@ class DeviceRollout:
                 torch.cuda.synchronize()
                 self.env_steps += 2
                 self.graph = torch.cuda.CUDAGraph()
+                before = self.vec.kernel_launches + (self.fused.launches if self.fused is not None else 0)
                 with torch.cuda.graph(self.graph):
                     self._collect_eager()
+                self._graph_launches_per_replay = (self.vec.kernel_launches +
+                                                   (self.fused.launches if self.fused is not None else 0)) - before
             self.graph.replay()
+            self._replays += 1
         self.env_steps += self.horizon
         return self
 

@@ -14,9 +14,9 @@ import torch
 from . import capi
 
 
-def _stream_ptr(stream=None):
+def _stream_ptr(stream=None, device=None):
     if stream is None:
-        stream = torch.cuda.current_stream()
+        stream = torch.cuda.current_stream(device)
     return C.c_void_p(stream.cuda_stream)
 
 
@@ -33,20 +33,20 @@ class _Vec:
 
     # ---- the hot path -----------------------------------------------------
     def reset(self, seed=0, stream=None):
-        capi.check(capi.lib().b2d_vec_reset(self.h, int(seed) & (2**64 - 1), _stream_ptr(stream)))
+        capi.check(capi.lib().b2d_vec_reset(self.h, int(seed) & (2**64 - 1), _stream_ptr(stream, self.device)))
 
     def step(self, actions=None, stream=None):
         """One env step on the current stream (async).  `actions`: optional CUDA float32
         tensor [num_agents, 4] to read instead of `self.actions` (no copy)."""
         L = capi.lib()
         if actions is None:
-            capi.check(L.b2d_vec_step(self.h, _stream_ptr(stream)))
+            capi.check(L.b2d_vec_step(self.h, _stream_ptr(stream, self.device)))
         else:
             if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous():
                 raise ValueError("actions must be a contiguous float32 CUDA tensor")
             if actions.numel() != self.num_agents * 4:
                 raise ValueError("actions must have shape [num_agents, 4]")
-            capi.check(L.b2d_vec_step_from(self.h, C.c_void_p(actions.data_ptr()), _stream_ptr(stream)))
+            capi.check(L.b2d_vec_step_from(self.h, C.c_void_p(actions.data_ptr()), _stream_ptr(stream, self.device)))
 
     def step_tape(self, tape, first, steps, stream=None):
         """`steps` consecutive steps reading actions from a CUDA tape [T, num_agents, 4]
@@ -56,13 +56,13 @@ class _Vec:
         if tape.shape[1] * tape.shape[2] != self.num_agents * 4:
             raise ValueError("tape slices must have shape [num_agents, 4]")
         capi.check(capi.lib().b2d_vec_step_tape(self.h, C.c_void_p(tape.data_ptr()), int(tape.shape[0]), int(first),
-                                                int(steps), _stream_ptr(stream)))
+                                                int(steps), _stream_ptr(stream, self.device)))
 
     def step_host(self, stream=None):
-        capi.check(capi.lib().b2d_vec_step_host(self.h, _stream_ptr(stream)))
+        capi.check(capi.lib().b2d_vec_step_host(self.h, _stream_ptr(stream, self.device)))
 
     def reset_host(self, seed=0, stream=None):
-        capi.check(capi.lib().b2d_vec_reset_host(self.h, int(seed) & (2**64 - 1), _stream_ptr(stream)))
+        capi.check(capi.lib().b2d_vec_reset_host(self.h, int(seed) & (2**64 - 1), _stream_ptr(stream, self.device)))
 
     # ---- statistics -------------------------------------------------------------
     def log(self, stream=None, group=None):
@@ -72,14 +72,14 @@ class _Vec:
         L = capi.lib()
         out = (C.c_float * 9)()
         if group is None:
-            capi.check(L.b2d_vec_log(self.h, out, _stream_ptr(stream)))
+            capi.check(L.b2d_vec_log(self.h, out, _stream_ptr(stream, self.device)))
         else:
             from .shard import reduce_log_sums
             ptr, cnt = C.c_void_p(), C.c_int()
-            capi.check(L.b2d_vec_log_begin(self.h, _stream_ptr(stream), C.byref(ptr), C.byref(cnt)))
+            capi.check(L.b2d_vec_log_begin(self.h, _stream_ptr(stream, self.device), C.byref(ptr), C.byref(cnt)))
             sums = _alias(ptr.value, (cnt.value,), torch.int64, self.device, self)
             reduce_log_sums(sums, None if group is True else group)
-            capi.check(L.b2d_vec_log_end(self.h, out, _stream_ptr(stream)))
+            capi.check(L.b2d_vec_log_end(self.h, out, _stream_ptr(stream, self.device)))
         vals = [float(x) for x in out]
         if vals[8] == 0.0:
             return {}
@@ -100,7 +100,7 @@ class _Vec:
         capi.check(capi.lib().b2d_put_state(self.h, ids, n, blobs.ctypes.data_as(C.POINTER(C.c_float))))
 
     def observe(self, stream=None):
-        capi.check(capi.lib().b2d_observe(self.h, _stream_ptr(stream)))
+        capi.check(capi.lib().b2d_observe(self.h, _stream_ptr(stream, self.device)))
 
     def set_math(self, math):
         capi.check(capi.lib().b2d_set_math(self.h, _math(math)))
@@ -116,12 +116,19 @@ class _Vec:
     @property
     def step_count(self):
         v = C.c_uint32()
-        capi.check(capi.lib().b2d_step_count(self.h, C.byref(v), _stream_ptr()))
+        capi.check(capi.lib().b2d_step_count(self.h, C.byref(v), _stream_ptr(None, self.device)))
         return int(v.value)
 
     @step_count.setter
     def step_count(self, v):
         capi.check(capi.lib().b2d_set_step_count(self.h, int(v)))
+
+    @property
+    def guard_replays(self):
+        """Steps the fast kernel re-did in the reference's arithmetic (near-threshold guard)."""
+        v = C.c_ulonglong()
+        capi.check(capi.lib().b2d_guard_replays(self.h, C.byref(v), _stream_ptr(None, self.device)))
+        return int(v.value)
 
     def profile_kernels(self, enable):
         """Start (True) or stop (False) per-kernel CUDA-event timing; stopping returns

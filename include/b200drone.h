@@ -79,7 +79,10 @@ typedef struct b2d_race_cfg {
     uint64_t seed;           /* Philox key until the first b2d_vec_reset */
     uint32_t env_id_base;    /* global id of env 0 (multi-GPU shards keep results invariant to the split) */
     int math;                /* b2d_math */
-    int write_clamped_actions; /* 1: store clamp(action,-1,1) back like DR/dronelib.h:437 */
+    int write_clamped_actions; /* DR/dronelib.h:437 clamps the shared action buffer in place.  1: the kernel stores
+                                  clamp(action,-1,1) back into the device action buffer (and the host-buffer step copies
+                                  it down); -1: host-buffer steps clamp the caller's host array on the host (what the
+                                  reference's caller observes, no PCIe traffic), device buffers untouched; 0: never */
 } b2d_race_cfg;
 
 /* kwargs of DS/binding.c:6-11 + placement */
@@ -156,6 +159,12 @@ int b2d_obs_dim(const b2d_vec *vec);
 int b2d_state_blob_floats(const b2d_vec *vec); /* floats per env in get/put_state blobs */
 long long b2d_kernel_launches(const b2d_vec *vec); /* kernels launched by this handle so far */
 int b2d_step_count(b2d_vec *vec, uint32_t *steps, void *cuda_stream); /* steps since the last reset (sync) */
+/* B2D_MATH_FAST only: agent-steps (race) / env-steps (swarm) the step kernel re-did in the reference's
+ * arithmetic since creation because a decision (out of bounds DR/drone_race.h:165-172, ring test
+ * DR/dronelib.h:462-489, swarm collision / nearest neighbour DS/drone_swarm.h:107-129,347-352) fell within
+ * rounding distance of its threshold; this guard is what makes the integer outputs of the fast kernels
+ * identical to the strict ones.  Synchronises the stream. */
+int b2d_guard_replays(b2d_vec *vec, unsigned long long *count, void *cuda_stream);
 
 /* ---- state hooks (env_get / env_put, EB:228-260; also the env checkpoint) ---
  * Race blob per env, float32[33 + 6*max_rings], ints stored as exact floats:
