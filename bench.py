@@ -491,6 +491,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the sub-results for the other BASELINE configs")
+    ap.add_argument("--e2e-clamp", type=int, default=-1, help=argparse.SUPPRESS)  # A/B aid: write_clamped_actions of the e2e env
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -555,7 +556,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         env = DroneRace(num_envs=n, report_interval=1 << 30, seed=0, buffers="host", device=local_rank,
-                        math=args.math, env_id_base=rank * n)
+                        math=args.math, env_id_base=rank * n, write_clamped_actions=args.e2e_clamp)
         env.reset(0)
         rng = np.random.default_rng(TAPE_SEED + rank)
         htape = rng.uniform(-1, 1, size=(4, n, 4)).astype(np.float32)

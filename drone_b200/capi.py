@@ -49,6 +49,11 @@ class PolicyIO(C.Structure):
                 ("store_values", C.c_void_p), ("rows", C.c_int), ("obs_dim", C.c_int), ("row_id_base", C.c_uint32)]
 
 
+class RolloutStore(C.Structure):
+    _fields_ = [("observations", C.c_void_p), ("actions", C.c_void_p), ("logprobs", C.c_void_p), ("rewards", C.c_void_p),
+                ("terminals", C.c_void_p), ("values", C.c_void_p)]
+
+
 # every symbol include/b200drone.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -84,6 +89,7 @@ SYMBOLS = {
     "b2d_puff_advantage": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_longlong, C.c_longlong,
                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _P]),
     "b2d_policy_act": (C.c_int, [C.POINTER(PolicyWeights), C.POINTER(PolicyIO), C.c_uint64, _P, C.c_int, _P]),
+    "b2d_race_rollout": (C.c_int, [_P, C.POINTER(PolicyWeights), C.POINTER(RolloutStore), C.c_int, C.c_uint64, _P, C.c_int, _P]),
     "b2d_last_error": (C.c_char_p, []),
     "b2d_version": (C.c_int, []),
 }

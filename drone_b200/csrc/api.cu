@@ -9,6 +9,7 @@
 #include "swarm_kernels.cuh"
 #include "advantage_kernels.cuh"
 #include "policy_kernels.cuh"
+#include "rollout_kernels.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -929,6 +930,61 @@ extern "C" int b2d_policy_act(const b2d_policy_weights *w, const b2d_policy_io *
     if (io->obs_dim == B2D_RACE_OBS)
         return policy_launch(policy_act_kernel<B2D_RACE_OBS>, 0, POL_THREADS, POL_WARPS, policy_smem_fp32(B2D_RACE_OBS, H), a, st);
     return policy_launch(policy_act_kernel<B2D_SWARM_OBS>, 1, POL_THREADS, POL_WARPS, policy_smem_fp32(B2D_SWARM_OBS, H), a, st);
+}
+
+// ---------------------------------------------------------------- the rollout as one kernel
+extern "C" int b2d_race_rollout(b2d_vec *v, const b2d_policy_weights *w, const b2d_rollout_store *store, int horizon,
+                                uint64_t noise_seed, unsigned int *device_counter, int deterministic, void *stream) {
+    if (!v || !w || !store) return fail(B2D_EINVAL, "b2d_race_rollout: null argument");
+    if (v->kind != KIND_RACE) return fail(B2D_EINVAL, "b2d_race_rollout: race handles only");
+    if (!w->encoder_weight || !w->encoder_bias || !w->decoder_mean_weight || !w->decoder_mean_bias || !w->decoder_logstd ||
+        !w->value_weight || !w->value_bias)
+        return fail(B2D_EINVAL, "b2d_race_rollout: null weight tensor");
+    if (w->hidden != RO_HIDDEN) return fail(B2D_EINVAL, "b2d_race_rollout: hidden must be 128");
+    if (horizon <= 0) return fail(B2D_EINVAL, "b2d_race_rollout: horizon must be positive");
+    if (!device_counter) return fail(B2D_EINVAL, "b2d_race_rollout: null call counter");
+    if (((uintptr_t)store->actions & 15)) return fail(B2D_EINVAL, "b2d_race_rollout: the action store must be 16-byte aligned");
+    if (v->race.reset_mode != B2D_RESET_PHILOX) return fail(B2D_ESTATE, "b2d_race_rollout: not available in inject mode");
+    DEVICE_SCOPE(v);
+    static int grid_for[2][64] = {{0}};
+    const int dev = v->device, m = v->math == B2D_MATH_STRICT ? 1 : 0;
+    if (dev < 0 || dev >= 64) return fail(B2D_EINVAL, "device ordinal out of range");
+    if (grid_for[m][dev] == 0) {
+        int per_sm = 0, sms = 0;
+        if (m) {
+            CUDA_TRY(cudaFuncSetAttribute(race_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RO_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(race_rollout_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, race_rollout_kernel<true>, RO_THREADS, RO_SMEM_BYTES));
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(race_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RO_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(race_rollout_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, race_rollout_kernel<false>, RO_THREADS, RO_SMEM_BYTES));
+        }
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (per_sm < 1) return fail(B2D_ECUDA, "race_rollout_kernel does not fit on an SM");
+        if (per_sm > RO_CTAS_PER_SM) per_sm = RO_CTAS_PER_SM; // TMEM: 160 of the SM's 512 columns per CTA
+        grid_for[m][dev] = per_sm * sms;
+    }
+    RolloutArgs a;
+    a.d = v->race;
+    a.enc_w = w->encoder_weight; a.enc_b = w->encoder_bias; a.mean_w = w->decoder_mean_weight; a.mean_b = w->decoder_mean_bias;
+    a.logstd = w->decoder_logstd; a.value_w = w->value_weight; a.value_b = w->value_bias;
+    a.st_obs = store->observations; a.st_act = store->actions; a.st_logp = store->logprobs; a.st_rew = store->rewards;
+    a.st_term = store->terminals; a.st_val = store->values;
+    a.env_act = v->dev.actions;
+    a.horizon = horizon;
+    a.row_id_base = v->race.env_id_base;
+    a.seed_lo = (uint32_t)noise_seed;
+    a.seed_hi = (uint32_t)(noise_seed >> 32);
+    a.counter = device_counter;
+    a.deterministic = deterministic ? 1 : 0;
+    const int chunks = (v->race.n + RO_THREADS - 1) / RO_THREADS;
+    const int grid = chunks < grid_for[m][dev] ? chunks : grid_for[m][dev];
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m) race_rollout_kernel<true><<<grid, RO_THREADS, RO_SMEM_BYTES, st>>>(a);
+    else race_rollout_kernel<false><<<grid, RO_THREADS, RO_SMEM_BYTES, st>>>(a);
+    v->launches += 1;
+    return launch_check("race_rollout_kernel");
 }
 
 extern "C" const char *b2d_last_error(void) { return g_err; }

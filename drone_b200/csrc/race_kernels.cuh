@@ -385,12 +385,12 @@ __device__ __noinline__ void race_inject_episode(const RaceDev &d, int i, uint32
 // and a decision taken within rounding distance of its threshold could come out differently: a terminal,
 // a reward of +-1 or a ring index that differs from the reference's.  So a lane whose fast result lies
 // within a guard band of any threshold re-does the step in the reference's arithmetic, from the env's
-// pre-step state, which is still in global memory at that point.  The bands (2e-4 m at the walls and the
-// ring plane, 0.1 m around the rim) are 20x the worst fast-vs-reference position error, so every integer
-// output of the fast kernel equals the strict kernel's; about 1 env-step in 10^4 is replayed.
-constexpr float RACE_GUARD_WALL = 2e-4f;
-constexpr float RACE_GUARD_PLANE = 2e-4f;
-constexpr float RACE_GUARD_RADIUS = 2.6f;
+// pre-step state, which is still in global memory at that point.  The bands (5e-5 m at the walls and the
+// ring plane, a conditioning-scaled band around the two radii, see gate_event_guarded) are 50x the worst
+// fast-vs-reference position error measured (1 ulp at 10 m, profiles/parity_r02.json), so every integer
+// output of the fast kernel equals the strict kernel's; a few env-steps in 10^5 are replayed.
+constexpr float RACE_GUARD_WALL = 5e-5f;
+constexpr float RACE_GUARD_PLANE = 5e-5f;
 
 // out[0:17] = state after the step, out[17] = out of bounds (0/1), out[18] = gate event; `out` is shared memory
 __device__ __noinline__ void race_strict_replay(const RaceDev &d, int i, float4 a4, float *out) {
@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
                 // decisions within a guard band of their threshold are re-taken in the reference's arithmetic
                 const float wall = fminf(fminf(fabsf(fabsf(s[0]) - 10.0f), fabsf(fabsf(s[1]) - 10.0f)), fabsf(fabsf(s[2]) - 10.0f));
                 bool suspect = false;
-                if (!oob) gate = gate_event_guarded(before, s, ring, -1.0f, RACE_GUARD_PLANE, RACE_GUARD_RADIUS, suspect);
+                if (!oob) gate = gate_event_guarded(before, s, ring, -1.0f, RACE_GUARD_PLANE, suspect);
 #if !B2D_EXPERIMENT_SKIP_MATH && !B2D_EXPERIMENT_NO_GUARD
                 if (wall < RACE_GUARD_WALL || suspect) {
                     race_strict_replay(d, i, a4, my_row);

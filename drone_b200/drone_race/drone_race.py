@@ -43,7 +43,7 @@ def _bind_stream(env):
 class DroneRace(PufferEnv):
     def __init__(self, num_envs=16, render_mode=None, report_interval=1, buf=None, seed=0,
                  max_rings=10, max_moves=1000, buffers="host", device=0, math="fast",
-                 env_id_base=0, per_env_init=False):
+                 env_id_base=0, per_env_init=False, write_clamped_actions=-1):
         self.single_observation_space = Box(low=-1, high=1, shape=(29,), dtype=np.float32)
         self.single_action_space = Box(low=-1, high=1, shape=(4,), dtype=np.float32)
         self.num_agents = num_envs
@@ -74,7 +74,9 @@ class DroneRace(PufferEnv):
         else:
             raise ValueError("buffers must be 'host' or 'device'")
 
-        kwargs = dict(max_rings=max_rings, max_moves=max_moves)
+        # -1: the caller-visible NumPy action buffer holds clamp(action, -1, 1) after a step like the
+        # reference's (dronelib.h:437); device buffers are left alone unless write_clamped_actions=1
+        kwargs = dict(max_rings=max_rings, max_moves=max_moves, write_clamped_actions=write_clamped_actions)
         if per_env_init:
             # the reference's own construction path (drone_race.py:37-51): one env_init per env
             c_envs = []

@@ -6,19 +6,28 @@ envs whose buffers already live on the GPU: what that loop does per step -- recv
 done), `policy.forward_eval`, `sample_logits` on a Normal (pufferlib/pytorch.py:189-199), store
 (obs, action, logprob, reward clamped to [-1, 1], done, value), clip the action to the action
 space, send -- happens here without the per-step `.to(device)` / `.cpu().numpy()` round trips
-(pufferl.py:240-243,292) that cap any GPU env at ~1e6 steps/s.  Per step there are two kernels:
-the fused policy step (`policy_impl="fused"`, drone_b200.policy / csrc/policy_kernels.cuh: MLP,
-sampling, log-prob, experience stores and action clip in one launch) and the env step behind
-`vec.step()`.  `policy_impl="torch"` keeps the same loop on plain torch ops (library GEMMs) -- the
-form any other policy class uses, and the fused kernel's cross-check in the tests.
+(pufferl.py:240-243,292) that cap any GPU env at ~1e6 steps/s.  Three forms:
+
+  policy_impl="rollout_kernel"  the WHOLE K-step loop as one kernel (b2d_race_rollout,
+      csrc/rollout_kernels.cuh): 128 envs per CTA stay in registers for all K steps, both Linear
+      layers run as tcgen05 tensor-core GEMMs with TMEM accumulators, only the experience row is
+      written per step.  Race envs + DronePolicy(hidden 128); what "auto" picks when it applies.
+  policy_impl="fused"  two kernels per step: the fused policy step (drone_b200.policy /
+      csrc/policy_kernels.cuh: MLP, sampling, log-prob, experience stores and action clip in one
+      launch) and the env step behind `vec.step()`; K steps captured in one CUDA graph.
+  policy_impl="torch"  the same loop on plain torch ops (library GEMMs) -- the form any other
+      policy class uses, and the cross-check of the other two in the tests.
 
 Experience is stored time-major, [horizon, num_agents, ...], so every store is one contiguous
 write; `segments()` returns the reference's [num_agents, horizon, ...] views.
 """
+import ctypes as C
 import math
 
 import torch
 from torch import nn
+
+from . import capi
 
 
 class DronePolicy(nn.Module):
@@ -50,12 +59,26 @@ class DeviceRollout:
                  policy_impl="auto", noise_seed=0, precision="tf32"):
         self.vec, self.policy, self.horizon = vec, policy, int(horizon)
         self.deterministic, self.autocast = deterministic, autocast
+        kernel_ok = (isinstance(policy, DronePolicy) and autocast is None and getattr(vec, "obs_dim", 0) == 29 and
+                     policy.encoder[0].weight.shape == (128, 29) and precision == "tf32")
         if policy_impl == "auto":
-            policy_impl = "fused" if (isinstance(policy, DronePolicy) and autocast is None) else "torch"
-        if policy_impl not in ("fused", "torch"):
-            raise ValueError("policy_impl must be 'auto', 'fused' or 'torch'")
+            policy_impl = "rollout_kernel" if kernel_ok else ("fused" if (isinstance(policy, DronePolicy) and autocast is None) else "torch")
+        if policy_impl not in ("rollout_kernel", "fused", "torch"):
+            raise ValueError("policy_impl must be 'auto', 'rollout_kernel', 'fused' or 'torch'")
+        if policy_impl == "rollout_kernel" and not kernel_ok:
+            raise ValueError("policy_impl='rollout_kernel' needs a race vec, a DronePolicy with hidden_size=128, precision='tf32' and no autocast")
         self.policy_impl = policy_impl
+        self.noise_seed = int(noise_seed)
         self.fused = None
+        self._kernel_launches = 0
+        if policy_impl == "rollout_kernel":
+            enc, mean, value = policy.encoder[0], policy.decoder_mean, policy.value
+            params = (enc.weight, enc.bias, mean.weight, mean.bias, policy.decoder_logstd, value.weight, value.bias)
+            for p in params:
+                if p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous() or p.device != vec.device:
+                    raise ValueError("policy parameters must be contiguous float32 CUDA tensors on the env's device")
+            self._weights = capi.PolicyWeights(*[p.data_ptr() for p in params], 128, capi.POLICY_TF32)
+            self.counter = torch.zeros(2, dtype=torch.int32, device=vec.device)  # [policy calls completed, CTA arrivals]
         if policy_impl == "fused":
             from .policy import FusedPolicyStep
             self.fused = FusedPolicyStep(policy, vec.observations, vec.rewards, vec.terminals, vec.actions,
@@ -77,6 +100,8 @@ class DeviceRollout:
 
     @property
     def kernel_name(self):
+        if self.policy_impl == "rollout_kernel":
+            return "race_rollout_kernel (tcgen05 policy GEMMs + env step, K steps per launch)"
         if self.policy_impl == "fused":
             return f"policy_act_{self.fused.precision}_kernel + race_step_kernel (two launches per step)"
         return "torch policy ops + race_step_kernel"
@@ -86,6 +111,16 @@ class DeviceRollout:
         """Kernels of this package launched for the rollout so far (graph replays re-launch the captured ones)."""
         eager = self.vec.kernel_launches + (self.fused.launches if self.fused is not None else 0)
         return eager + self._graph_launches_per_replay * max(0, self._replays - 1)
+
+    def _launch_rollout_kernel(self):
+        vec = self.vec
+        store = capi.RolloutStore(self.observations.data_ptr(), self.actions.data_ptr(), self.logprobs.data_ptr(),
+                                  self.rewards.data_ptr(), self.terminals.data_ptr(), self.values.data_ptr())
+        with torch.cuda.device(vec.device):
+            st = torch.cuda.current_stream(vec.device)
+            capi.check(capi.lib().b2d_race_rollout(vec.h, C.byref(self._weights), C.byref(store), self.horizon,
+                                                   C.c_uint64(self.noise_seed), C.c_void_p(self.counter.data_ptr()),
+                                                   int(self.deterministic), C.c_void_p(st.cuda_stream)))
 
     @torch.no_grad()
     def _one_step(self, k):
@@ -125,6 +160,12 @@ class DeviceRollout:
     @torch.no_grad()
     def collect(self):
         """One horizon of experience.  Asynchronous: returns after enqueueing (graph replay)."""
+        if self.policy_impl == "rollout_kernel":
+            # one launch is the whole K-step loop: nothing for a graph to save; state that must advance between
+            # collections (noise call counter, step counter, episode numbers) lives on the device
+            self._launch_rollout_kernel()
+            self.env_steps += self.horizon
+            return self
         if not self.use_graph:
             self._collect_eager()
         else:

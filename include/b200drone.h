@@ -259,6 +259,29 @@ typedef struct b2d_policy_io {
 int b2d_policy_act(const b2d_policy_weights *weights, const b2d_policy_io *io, uint64_t noise_seed,
                    unsigned int *device_counter, int deterministic, void *cuda_stream);
 
+/* ---- the whole rollout as one kernel (BASELINE.json configs[3]) -------------------
+ * replaces PuffeRL.evaluate's per-step loop (pufferl.py:214-314) for a race vec: `horizon` consecutive
+ * (policy step, vec_step) pairs.  Each CTA keeps 128 envs in registers for all steps; both Linear layers of
+ * the Default policy (hidden must be 128, precision is TF32 as under torch.set_float32_matmul_precision('high'),
+ * pufferl.py:55) run as tcgen05 tensor-core GEMMs with TMEM accumulators; per env-step only the experience row
+ * is written.  Step k stores, time-major: observations[k] = the observation the policy saw, rewards[k] /
+ * terminals[k] = what the env returned for step k-1 (the contract buffers at entry for k = 0; reward clamped to
+ * [-1, 1]), actions[k] (unclipped sample), logprobs[k], values[k]; the env receives clip(action, -1, 1).
+ * On return (stream-ordered) the contract buffers hold the results of the last step, exactly as after
+ * `horizon` calls of b2d_policy_act + b2d_vec_step, and the step counter has advanced by `horizon`.
+ * Noise as in b2d_policy_act: call number = device_counter[0] + k, advanced by `horizon` by the kernel.
+ * Race handles in B2D_RESET_PHILOX mode only.  Capturable. */
+typedef struct b2d_rollout_store { /* device pointers, float32, [horizon][num_agents][...]; each may be NULL */
+    float *observations; /* [horizon, num_agents, 29] */
+    float *actions;      /* [horizon, num_agents, 4] */
+    float *logprobs;     /* [horizon, num_agents] */
+    float *rewards;      /* [horizon, num_agents] */
+    float *terminals;    /* [horizon, num_agents] */
+    float *values;       /* [horizon, num_agents] */
+} b2d_rollout_store;
+int b2d_race_rollout(b2d_vec *vec, const b2d_policy_weights *weights, const b2d_rollout_store *store, int horizon,
+                     uint64_t noise_seed, unsigned int *device_counter, int deterministic, void *cuda_stream);
+
 const char *b2d_last_error(void);
 int b2d_version(void);
 

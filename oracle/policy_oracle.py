@@ -54,23 +54,32 @@ def tf32(x):
     return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
 
 
-def forward_eval(w, obs, tf32_gemm=False):
+def tf32_truncate(x):
+    """float32 -> TF32 by dropping the low 13 mantissa bits: what a tensor core does with a 32-bit operand that was
+    not rounded first (the second GEMM of csrc/rollout_kernels.cuh reads the GELU activations this way)."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return (b & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def forward_eval(w, obs, tf32_gemm=False, hidden="round"):
     """models.Default.forward_eval for a Box action space; w = dict of numpy arrays in nn.Linear layouts.
-    tf32_gemm: round the operands of both Linear layers to TF32 first (products and sums stay exact/float64)."""
+    tf32_gemm: round the operands of both Linear layers to TF32 first (products and sums stay exact/float64);
+    hidden = "round" | "truncate": how the activations become TF32 operands of the second layer."""
     rnd = tf32 if tf32_gemm else (lambda z: np.asarray(z, dtype=np.float32))
     x = rnd(obs).astype(np.float64) @ rnd(w["encoder_weight"]).astype(np.float64).T + w["encoder_bias"].astype(np.float64)
-    hidden = 0.5 * x * (1.0 + special.erf(x / np.sqrt(2.0)))
+    hidden_act = 0.5 * x * (1.0 + special.erf(x / np.sqrt(2.0)))
     if tf32_gemm:
-        hidden = tf32(hidden.astype(np.float32)).astype(np.float64)
+        hidden_act = (tf32 if hidden == "round" else tf32_truncate)(hidden_act.astype(np.float32)).astype(np.float64)
+    hidden = hidden_act
     mean = hidden @ rnd(w["decoder_mean_weight"]).astype(np.float64).T + w["decoder_mean_bias"].astype(np.float64)
     value = hidden @ rnd(w["value_weight"]).astype(np.float64).T + w["value_bias"].astype(np.float64)
     logstd = np.broadcast_to(w["decoder_logstd"].astype(np.float64).reshape(1, -1), mean.shape)
     return mean, logstd, value[:, 0]
 
 
-def policy_act(w, obs, rewards, terminals, call, seed, row_id_base=0, deterministic=False, tf32_gemm=False):
+def policy_act(w, obs, rewards, terminals, call, seed, row_id_base=0, deterministic=False, tf32_gemm=False, hidden="round"):
     """One policy step: returns dict(actions, logprobs, values, rewards, terminals, env_actions)."""
-    mean, logstd, value = forward_eval(w, obs, tf32_gemm)
+    mean, logstd, value = forward_eval(w, obs, tf32_gemm, hidden)
     std = np.exp(logstd)
     eps = np.zeros_like(mean) if deterministic else noise(obs.shape[0], call, seed, row_id_base)
     action = mean + std * eps
