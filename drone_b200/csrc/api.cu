@@ -330,7 +330,7 @@ extern "C" int b2d_swarm_create(b2d_vec **out, const b2d_swarm_cfg *cfg, const b
     float *form = nullptr;
     if ((rc = setup_buffers(v, ext)) || (rc = dev_alloc(v, &d.S, 5 * ld)) || (rc = dev_alloc(v, &d.P, 3 * ld)) ||
         (rc = dev_alloc(v, &d.T, ld)) || (rc = dev_alloc(v, &d.U, ld)) || (rc = dev_alloc(v, &d.V, ld)) ||
-        (rc = dev_alloc(v, &d.W, ld)) || (rc = dev_alloc(v, &d.E, (size_t)d.n)) ||
+        (rc = dev_alloc(v, &d.W, ld)) || (rc = dev_alloc(v, &d.RS, 4 * ld)) || (rc = dev_alloc(v, &d.E, (size_t)d.n)) ||
         (rc = dev_alloc(v, &d.G0, (size_t)d.R * d.n)) || (rc = dev_alloc(v, &d.G1, (size_t)d.R * d.n)) ||
         (rc = dev_alloc(v, &form, (size_t)9 * d.A)) || (rc = dev_alloc(v, &d.ctl, 1)) || (rc = finish_create(v))) {
         b2d_vec_close(v);
@@ -354,7 +354,12 @@ extern "C" int b2d_swarm_create(b2d_vec **out, const b2d_swarm_cfg *cfg, const b
     d.act_out = v->write_clamped ? v->dev.actions : nullptr;
     d.rew = v->dev.rewards;
     d.term = v->dev.terminals;
-    // quaternion identity for every drone so that a put_state-free first step is well defined
+    // every drone's first respawn is prepared from the start (vec_reset re-keys and regenerates)
+    swarm_fill_slots_kernel<<<(d.rows + 127) / 128, 128>>>(d);
+    if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+        b2d_vec_close(v);
+        return fail(B2D_ECUDA, "swarm_fill_slots_kernel failed");
+    }
     *out = v;
     return B2D_OK;
 }
@@ -383,6 +388,20 @@ extern "C" int b2d_vec_close(b2d_vec *v) {
         }
         fprintf(stderr, "[b2d timing] slowest warp loop %.0f cycles; CTA busy: mean %.0f, slowest %.0f cycles (any launch)\n", (double)h[9],
                 (double)h[10] / (w / RACE_WARPS), (double)h[11]);
+    }
+#endif
+#if B2D_RO_TIMING
+    if (v->kind == KIND_RACE && v->race.ctl) {
+        unsigned long long h[12];
+        cudaMemcpy(h, v->race.ctl->dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        if (h[8]) {
+            const char *names[8] = {"obs->smem", "barrier1", "stores+noise", "wait GEMM1", "GELU", "barrier2", "GEMM2 trip", "sample+env"};
+            double tot = 0;
+            for (int m = 0; m < 8; m++) tot += (double)h[m];
+            fprintf(stderr, "[b2d rollout timing] share of a warp's step loop:");
+            for (int m = 0; m < 8; m++) fprintf(stderr, " %s %.1f%%", names[m], 100.0 * h[m] / tot);
+            fprintf(stderr, " | cycles per warp launch %.0f\n", tot / (double)h[8]);
+        }
     }
 #endif
     if (v->has_host) {
@@ -962,7 +981,12 @@ extern "C" int b2d_race_rollout(b2d_vec *v, const b2d_policy_weights *w, const b
         }
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (per_sm < 1) return fail(B2D_ECUDA, "race_rollout_kernel does not fit on an SM");
-        if (per_sm > RO_CTAS_PER_SM) per_sm = RO_CTAS_PER_SM; // TMEM: 160 of the SM's 512 columns per CTA
+        // The occupancy calculator answers 1 for a kernel that allocates tensor memory (it cannot know how many of
+        // the SM's 512 TMEM columns a CTA will ask for); the kernel takes 160, registers (168 x 128) and shared
+        // memory (72 KB) are sized for RO_CTAS_PER_SM = 3, and three CTAs per SM is what runs (measured: 346 / 206 /
+        // 161 us per step with 1 / 2 / 3 CTAs per SM; a fourth waits in tcgen05.alloc).
+        per_sm = RO_CTAS_PER_SM;
+        if (getenv("B2D_RO_CTAS")) per_sm = atoi(getenv("B2D_RO_CTAS")); // measurement aid
         grid_for[m][dev] = per_sm * sms;
     }
     RolloutArgs a;

@@ -33,8 +33,20 @@
 
 namespace b2d {
 
+#ifndef B2D_RO_TIMING
+#define B2D_RO_TIMING 0 // measurement aid: clock64 sums per phase of the step loop, printed by b2d_vec_close
+#endif
+#if B2D_RO_TIMING
+#define RO_TICK(n) { const long long now_ = clock64(); tm[n] += now_ - tprev; tprev = now_; }
+#else
+#define RO_TICK(n)
+#endif
+
 constexpr int RO_THREADS = 128;     // = envs per CTA = rows of the MMA tile = TMEM lanes
-constexpr int RO_CTAS_PER_SM = 3;   // 3 x (128 + 32) TMEM columns of the SM's 512
+#ifndef B2D_RO_CTAS_PER_SM
+#define B2D_RO_CTAS_PER_SM 3
+#endif
+constexpr int RO_CTAS_PER_SM = B2D_RO_CTAS_PER_SM;   // 3 x (128 + 32) TMEM columns of the SM's 512
 constexpr int RO_HIDDEN = 128;
 constexpr int RO_K1 = 32;           // encoder K: 29 observations + bias hi + bias lo + 0
 constexpr int RO_N2 = 16;           // head outputs padded to the smallest N of an M = 128 MMA
@@ -45,7 +57,7 @@ constexpr int RO_TILE_BYTES = 32 * RACE_OBS * 4;            // per-warp staging 
 constexpr int RO_SMEM_USED = RO_B1_BYTES + RO_B2_BYTES + RO_A1_BYTES + 4 * RO_TILE_BYTES;
 // request enough shared memory that exactly RO_CTAS_PER_SM CTAs fit on an SM: a fourth CTA would find no TMEM
 // columns left and sit in tcgen05.alloc until another CTA exits
-constexpr int RO_SMEM_BYTES = 72 * 1024;
+constexpr int RO_SMEM_BYTES = RO_CTAS_PER_SM >= 4 ? 56 * 1024 : 72 * 1024;
 static_assert(RO_SMEM_USED <= RO_SMEM_BYTES, "rollout kernel shared memory");
 
 struct RolloutArgs {
@@ -252,9 +264,12 @@ __device__ __forceinline__ void ro_env_step(const RaceDev &d, int i, RaceRegs &e
     e.ep_ret += reward;
     const bool passed = gate > 0.0f;
     e.ring_idx += passed ? 1 : 0;
-    const int cause = oob ? (int)ACC_OOB
-                          : gate < 0.0f ? (int)ACC_COLLISION
-                                        : e.tick == d.max_moves ? (int)ACC_TIMEOUT : e.ring_idx == d.max_rings ? (int)ACC_SPARE : -1;
+    int cause = oob ? (int)ACC_OOB
+                    : gate < 0.0f ? (int)ACC_COLLISION
+                                  : e.tick == d.max_moves ? (int)ACC_TIMEOUT : e.ring_idx == d.max_rings ? (int)ACC_SPARE : -1;
+#if B2D_EXPERIMENT_NO_RESET
+    cause = -1; // measurement aid: episodes never end
+#endif
     terminal = cause >= 0 ? 1 : 0;
     if (passed && cause < 0) { // the next ring becomes the current one
         float ring[6];
@@ -374,6 +389,9 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
     const int nchunks = (d.n + RO_THREADS - 1) / RO_THREADS;
     uint32_t phase = 0;
     int score_last = 0;
+#if B2D_RO_TIMING
+    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
 
     for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const int i = chunk * RO_THREADS + tid;
@@ -416,6 +434,9 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
             __syncwarp();
         }
 
+#if B2D_RO_TIMING
+        tprev = clock64();
+#endif
         for (int k = 0; k < K; k++) {
             __syncwarp(); // lanes reconverge after the divergent episode logic before the warp-collective tcgen05 ops
             // ---- 1. observation row -> A operand of the encoder GEMM (TF32, rounded) and -> the warp's staging tile
@@ -429,9 +450,11 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
 #pragma unroll
                 for (int m = 0; m < RACE_OBS; m++) my_row[m] = o[m];
             }
+            RO_TICK(0) // observation row to shared memory
             ro_fence_proxy_async();
             ro_tc_fence_before();
             __syncthreads();
+            RO_TICK(1) // barrier: wait for the slowest warp of the CTA
             if (tid == 0) {
                 ro_tc_fence_after();
 #pragma unroll
@@ -464,9 +487,11 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
             float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (!a.deterministic) policy_noise(a.row_id_base + (uint32_t)i, call0 + (unsigned int)k, a.seed_lo, a.seed_hi, z);
 
+            RO_TICK(2) // experience stores + noise (overlaps the encoder GEMM)
             // ---- 2. hidden = GELU(encoder(obs)): accumulator row -> registers -> activations back into the same columns
             ro_mbar_wait(&s_mbar[0], phase);
             ro_tc_fence_after();
+            RO_TICK(3) // wait for the encoder GEMM
 #pragma unroll 1
             for (int c = 0; c < RO_HIDDEN / 32; c++) {
                 uint32_t r[32];
@@ -480,9 +505,11 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
                 }
                 ro_tmem_st32(tm_h + lane_base + c * 32, r);
             }
+            RO_TICK(4) // GELU
             ro_tc_wait_st();
             ro_tc_fence_before();
             __syncthreads();
+            RO_TICK(5) // barrier
             // ---- 3. heads: [means | value] = hidden . W2^T, A from TMEM
             if (tid == 0) {
                 ro_tc_fence_after();
@@ -498,6 +525,7 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
             ro_tmem_ld8(tm_o + lane_base, hd);
             ro_tc_wait_ld();
             ro_tc_fence_before(); // the next step's MMAs overwrite these columns after the next barrier
+            RO_TICK(6) // head GEMM round trip
 
             // ---- 4. sample, log-prob, experience stores, clip (pufferl.py:258-294)
             float act[4], lp = lp0;
@@ -523,6 +551,7 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
             if (valid) ro_env_step<STRICT>(d, i, e, a4, reward, terminal, o, s_acc, k == K - 1, score_last);
             prev_rew = reward;
             prev_term = (float)terminal;
+            RO_TICK(7) // sampling, stores, env step
             if (k == K - 1 && valid) reinterpret_cast<float4 *>(a.env_act)[i] = a4;
         }
 
@@ -546,6 +575,12 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
         __syncwarp();
     }
 
+#if B2D_RO_TIMING
+    if (lane == 0) {
+        for (int m = 0; m < 8; m++) atomicAdd(&d.ctl->dbg[m], (unsigned long long)tm[m]);
+        atomicAdd(&d.ctl->dbg[8], 1ull);
+    }
+#endif
     // ---- teardown: TMEM back, statistics out, call counter advanced by K
     ro_tc_fence_before();
     __syncthreads();

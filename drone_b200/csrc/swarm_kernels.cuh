@@ -67,6 +67,7 @@ struct SwarmDev {
     unsigned char *term;
     Ctl *ctl;
     const float *payload; // [n][A*41 + 2 + 6R] draw results (inject mode)
+    float4 *RS;           // [4][ld] the PREPARED next respawn of every drone: 13 params + position (see sw_refill_pass)
     uint32_t key0, key1, env_id_base;
     int reset_mode;
 };
@@ -222,86 +223,174 @@ struct SwarmWin {
 // STRICT: ascending index, strict '<' on the reference's sqrtf values (lowest index wins ties);
 // the root is taken only for a candidate whose SQUARED distance beats the best so far (sqrtf is
 // monotonic, nothing else can win): a handful of roots per sweep instead of A - 1.
-// Fast: the window sweep above, two candidates per iteration; the winner is the minimum of
-// (squared distance with its 7 low mantissa bits replaced by the window offset) taken with one
-// 3-input integer min per pair.  Candidates closer than 1.5e-5 relative in squared distance may
-// therefore swap (the tests count such flips); the returned distance is recomputed exactly.
-template <bool STRICT>
-__device__ __forceinline__ float sw_nearest(const float *w, int A, int a, const float self[3], float other[3]) {
+__device__ __forceinline__ float sw_nearest_strict(const float *w, int A, int a, const float self[3], float other[3]) {
     other[0] = other[1] = other[2] = 0.0f;
-    if constexpr (STRICT) {
-        float best2 = __int_as_float(0x7f800000), bestd = 999999.0f;
-        int idx = -1;
-        auto consider = [&](int j, float v) {
-            if (j != a && v < best2) {
-                const float r = xsqrt(xf(v)).v;
-                if (r < bestd) { bestd = r; best2 = v; idx = j; }
-            }
-        };
-        if ((A & 1) == 0) {
+    float best2 = __int_as_float(0x7f800000), bestd = 999999.0f;
+    int idx = -1;
+    auto consider = [&](int j, float v) {
+        if (j != a && v < best2) {
+            const float r = xsqrt(xf(v)).v;
+            if (r < bestd) { bestd = r; best2 = v; idx = j; }
+        }
+    };
+    if ((A & 1) == 0) {
 #pragma unroll 2
-            for (int j = 0; j < A; j += 2) {
-                const float *src = w + (j < a ? A : 0) + j; // a pair never straddles a: the element at a is skipped
-                const float2 ox = *reinterpret_cast<const float2 *>(src);
-                const float2 oy = *reinterpret_cast<const float2 *>(src + SW_WIN);
-                const float2 oz = *reinterpret_cast<const float2 *>(src + 2 * SW_WIN);
-                const float2 dx = __fadd2_rn(ox, make_float2(-self[0], -self[0])), dy = __fadd2_rn(oy, make_float2(-self[1], -self[1])),
-                             dz = __fadd2_rn(oz, make_float2(-self[2], -self[2]));
-                const float2 d2 = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
-                consider(j, d2.x);
-                consider(j + 1, d2.y);
-            }
-        } else {
-            for (int j = 0; j < A; j++) {
-                const float *src = w + (j < a ? A : 0) + j;
-                const float dx = __fsub_rn(src[0], self[0]), dy = __fsub_rn(src[SW_WIN], self[1]), dz = __fsub_rn(src[2 * SW_WIN], self[2]);
-                consider(j, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-            }
+        for (int j = 0; j < A; j += 2) {
+            const float *src = w + (j < a ? A : 0) + j; // a pair never straddles a: the element at a is skipped
+            const float2 ox = *reinterpret_cast<const float2 *>(src);
+            const float2 oy = *reinterpret_cast<const float2 *>(src + SW_WIN);
+            const float2 oz = *reinterpret_cast<const float2 *>(src + 2 * SW_WIN);
+            const float2 dx = __fadd2_rn(ox, make_float2(-self[0], -self[0])), dy = __fadd2_rn(oy, make_float2(-self[1], -self[1])),
+                         dz = __fadd2_rn(oz, make_float2(-self[2], -self[2]));
+            const float2 d2 = __fadd2_rn(__fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy)), __fmul2_rn(dz, dz));
+            consider(j, d2.x);
+            consider(j + 1, d2.y);
         }
-        if (idx >= 0) {
-            const float *src = w + (idx < a ? A : 0) + idx;
-            other[0] = src[0]; other[1] = src[SW_WIN]; other[2] = src[2 * SW_WIN];
-        }
-        return bestd;
     } else {
-        constexpr unsigned int KEY_NONE = 0x7f800000u, CODE_MASK = 127u;
-        unsigned int best = KEY_NONE;
-        int a2 = a;
-        if ((A & 1) == 0) {
-            a2 = a & ~1;
-            {   // the other agent of a's own pair: code 1
-                const float *src = w + ((a & 1) ? A + a - 1 : a + 1);
-                const float dx = src[0] - self[0], dy = src[SW_WIN] - self[1], dz = src[2 * SW_WIN] - self[2];
-                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                best = min(best, (__float_as_uint(d2) & ~CODE_MASK) | 1u);
-            }
-            const float2 nx = make_float2(-self[0], -self[0]), ny = make_float2(-self[1], -self[1]), nz = make_float2(-self[2], -self[2]);
-            const float *src = w + a2;
-#pragma unroll 4
-            for (int c = 2; c < A; c += 2) { // window offsets c, c + 1 from a's pair
-                const float2 ox = *reinterpret_cast<const float2 *>(src + c);
-                const float2 oy = *reinterpret_cast<const float2 *>(src + c + SW_WIN);
-                const float2 oz = *reinterpret_cast<const float2 *>(src + c + 2 * SW_WIN);
-                const float2 dx = __fadd2_rn(ox, nx), dy = __fadd2_rn(oy, ny), dz = __fadd2_rn(oz, nz);
-                const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-                const unsigned int k0 = (__float_as_uint(d2.x) & ~CODE_MASK) | (unsigned int)c;
-                const unsigned int k1 = (__float_as_uint(d2.y) & ~CODE_MASK) | (unsigned int)(c + 1);
-                best = __vimin3_u32(best, k0, k1);
-            }
-        } else {
-            for (int c = 1; c < A; c++) { // odd A: one candidate at a time, window offsets from a itself
-                const float *src = w + a + c;
-                const float dx = src[0] - self[0], dy = src[SW_WIN] - self[1], dz = src[2 * SW_WIN] - self[2];
-                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                best = min(best, (__float_as_uint(d2) & ~CODE_MASK) | (unsigned int)c);
-            }
+        for (int j = 0; j < A; j++) {
+            const float *src = w + (j < a ? A : 0) + j;
+            const float dx = __fsub_rn(src[0], self[0]), dy = __fsub_rn(src[SW_WIN], self[1]), dz = __fsub_rn(src[2 * SW_WIN], self[2]);
+            consider(j, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
         }
-        if (best >= KEY_NONE) return 999999.0f;
-        const int code = (int)(best & CODE_MASK);
-        const float *src = ((A & 1) == 0 && code == 1) ? w + ((a & 1) ? A + a - 1 : a + 1) : w + a2 + code;
+    }
+    if (idx >= 0) {
+        const float *src = w + (idx < a ? A : 0) + idx;
         other[0] = src[0]; other[1] = src[SW_WIN]; other[2] = src[2 * SW_WIN];
-        const float dx = other[0] - self[0], dy = other[1] - self[1], dz = other[2] - self[2];
-        return sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    }
+    return bestd;
+}
+// out of line for the fast kernel's guard (a decision within rounding distance of its threshold is re-taken
+// in the reference's arithmetic): rare, and it must not cost the hot loop registers
+__device__ __noinline__ float sw_nearest_strict_call(const float *w, int A, int a, float sx, float sy, float sz, float *other) {
+    const float self[3] = {sx, sy, sz};
+    float o[3];
+    const float r = sw_nearest_strict(w, A, a, self, o);
+    other[0] = o[0]; other[1] = o[1]; other[2] = o[2];
+    return r;
+}
+
+// Fast, distance only (the reward needs no identity, R/drone_swarm.h:347-352): the window sweep above,
+// two candidates per iteration on packed FP32x2, the minimum of the squared distances as one 3-input
+// integer min per pair (non-negative floats order like their bit patterns).  Exact minimum of the
+// squared distances as computed; the collision decision `distance < 1` is guarded by the caller.
+__device__ __forceinline__ float sw_nearest_dist_fast(const float *w, int A, int a, const float self[3]) {
+    unsigned int best = 0x7f800000u;
+    if ((A & 1) == 0) {
+        const int a2 = a & ~1;
+        {   // the other agent of a's own pair
+            const float *src = w + ((a & 1) ? A + a - 1 : a + 1);
+            const float dx = src[0] - self[0], dy = src[SW_WIN] - self[1], dz = src[2 * SW_WIN] - self[2];
+            best = min(best, __float_as_uint(fmaf(dz, dz, fmaf(dy, dy, dx * dx))));
+        }
+        const float2 nx = make_float2(-self[0], -self[0]), ny = make_float2(-self[1], -self[1]), nz = make_float2(-self[2], -self[2]);
+        const float *src = w + a2;
+#pragma unroll 4
+        for (int c = 2; c < A; c += 2) {
+            const float2 ox = *reinterpret_cast<const float2 *>(src + c);
+            const float2 oy = *reinterpret_cast<const float2 *>(src + c + SW_WIN);
+            const float2 oz = *reinterpret_cast<const float2 *>(src + c + 2 * SW_WIN);
+            const float2 dx = __fadd2_rn(ox, nx), dy = __fadd2_rn(oy, ny), dz = __fadd2_rn(oz, nz);
+            const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+            best = __vimin3_u32(best, __float_as_uint(d2.x), __float_as_uint(d2.y));
+        }
+    } else {
+        for (int c = 1; c < A; c++) {
+            const float *src = w + a + c;
+            const float dx = src[0] - self[0], dy = src[SW_WIN] - self[1], dz = src[2 * SW_WIN] - self[2];
+            best = min(best, __float_as_uint(fmaf(dz, dz, fmaf(dy, dy, dx * dx))));
+        }
+    }
+    return best >= 0x7f800000u ? 999999.0f : sqrtf(__uint_as_float(best));
+}
+
+// Fast, with the neighbour's identity (the observation needs its position, R/drone_swarm.h:187-196).  Keys =
+// squared distance with its 7 low mantissa bits replaced by the window offset; the sweep keeps the smallest
+// AND the second smallest key.  When the two lie within two key buckets (3e-5 relative) the order of the
+// candidates is not safe against rounding -- `ambiguous` -- and the caller re-takes the decision with
+// sw_nearest_strict_call; otherwise the winner is the reference's.
+__device__ __forceinline__ void sw_nearest_fast(const float *w, int A, int a, const float self[3], float other[3], bool &ambiguous) {
+    constexpr unsigned int KEY_NONE = 0x7f800000u, CODE_MASK = 127u;
+    other[0] = other[1] = other[2] = 0.0f;
+    unsigned int best = KEY_NONE, second = KEY_NONE;
+    int a2 = a;
+    if ((A & 1) == 0) {
+        a2 = a & ~1;
+        {   // the other agent of a's own pair: code 1
+            const float *src = w + ((a & 1) ? A + a - 1 : a + 1);
+            const float dx = src[0] - self[0], dy = src[SW_WIN] - self[1], dz = src[2 * SW_WIN] - self[2];
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            best = (__float_as_uint(d2) & ~CODE_MASK) | 1u;
+        }
+        const float2 nx = make_float2(-self[0], -self[0]), ny = make_float2(-self[1], -self[1]), nz = make_float2(-self[2], -self[2]);
+        const float *src = w + a2;
+#pragma unroll 4
+        for (int c = 2; c < A; c += 2) { // window offsets c, c + 1 from a's pair
+            const float2 ox = *reinterpret_cast<const float2 *>(src + c);
+            const float2 oy = *reinterpret_cast<const float2 *>(src + c + SW_WIN);
+            const float2 oz = *reinterpret_cast<const float2 *>(src + c + 2 * SW_WIN);
+            const float2 dx = __fadd2_rn(ox, nx), dy = __fadd2_rn(oy, ny), dz = __fadd2_rn(oz, nz);
+            const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+            const unsigned int k0 = (__float_as_uint(d2.x) & ~CODE_MASK) | (unsigned int)c;
+            const unsigned int k1 = (__float_as_uint(d2.y) & ~CODE_MASK) | (unsigned int)(c + 1);
+            const unsigned int lo = min(k0, k1), hi = max(k0, k1);
+            second = __vimin3_u32(second, hi, max(best, lo)); // second smallest of {best, second, k0, k1}
+            best = min(best, lo);
+        }
+    } else {
+        for (int c = 1; c < A; c++) { // odd A: one candidate at a time, window offsets from a itself
+            const float *src = w + a + c;
+            const float dx = src[0] - self[0], dy = src[SW_WIN] - self[1], dz = src[2 * SW_WIN] - self[2];
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const unsigned int k0 = (__float_as_uint(d2) & ~CODE_MASK) | (unsigned int)c;
+            second = min(second, max(best, k0));
+            best = min(best, k0);
+        }
+    }
+    ambiguous = second < KEY_NONE && (second & ~CODE_MASK) - (best & ~CODE_MASK) <= 2u * (CODE_MASK + 1u);
+    if (best >= KEY_NONE) return;
+    const int code = (int)(best & CODE_MASK);
+    const float *src = ((A & 1) == 0 && code == 1) ? w + ((a & 1) ? A + a - 1 : a + 1) : w + a2 + code;
+    other[0] = src[0]; other[1] = src[SW_WIN]; other[2] = src[2 * SW_WIN];
+}
+
+// Guard bands of the fast kernel (see race_strict_replay for the idea): decisions within these distances of
+// their threshold are re-taken in the reference's arithmetic.  Arena half-widths are 30 / 30 / 10 m (1 ulp =
+// 2e-6 m), the largest fast-vs-reference position error measured is 1 ulp (profiles/parity_r02.json).
+constexpr float SW_GUARD_WALL = 1e-4f;   // out of bounds: | |coordinate| - half width |
+constexpr float SW_GUARD_PLANE = 1e-4f;  // ring plane crossing
+constexpr float SW_GUARD_DIST = 1e-4f;   // collision: | nearest distance - 1 |
+
+// nearest-neighbour DISTANCE for compute_reward (R/drone_swarm.h:347-352)
+template <bool STRICT>
+__device__ __forceinline__ float sw_reward_distance(const float *w, int A, int a, const float self[3], int &guard_hits) {
+    if constexpr (STRICT) {
+        float other[3];
+        return sw_nearest_strict(w, A, a, self, other);
+    } else {
+        float nd = sw_nearest_dist_fast(w, A, a, self);
+        if (fabsf(nd - 1.0f) < SW_GUARD_DIST) {
+            float other[3];
+            nd = sw_nearest_strict_call(w, A, a, self[0], self[1], self[2], other);
+            guard_hits += 1;
+        }
+        return nd;
+    }
+}
+
+// nearest neighbour's POSITION for compute_observations (R/drone_swarm.h:187-196)
+template <bool STRICT>
+__device__ __forceinline__ void sw_obs_neighbour(const float *w, int A, int a, const float self[3], float near[3], int &guard_hits) {
+    if constexpr (STRICT) {
+        sw_nearest_strict(w, A, a, self, near);
+    } else {
+        bool ambiguous;
+        sw_nearest_fast(w, A, a, self, near, ambiguous);
+        if (ambiguous) {
+            float other[3];
+            sw_nearest_strict_call(w, A, a, self[0], self[1], self[2], other);
+            near[0] = other[0]; near[1] = other[1]; near[2] = other[2];
+            guard_hits += 1;
+        }
     }
 }
 
@@ -443,6 +532,59 @@ __device__ __forceinline__ void sw_respawn_state(SwarmAgent &g, const float p[13
     g.spawn[0] = pos[0]; g.spawn[1] = pos[1]; g.spawn[2] = pos[2];
 }
 
+// The fast kernel's guard for the move itself: the drone's step re-done in the reference's arithmetic from its
+// pre-step state (still in global memory: the step stores state in its last phase), plus the ring test.
+// out[0:17] = state, out[17] = gate event
+__device__ __noinline__ void sw_strict_move(const SwarmDev &d, int k, float4 a4, const float *ring /* nullptr: no ring test */, float *out) {
+    const size_t ld = d.ld;
+    const float4 q0 = __ldcg(&d.S[0 * ld + k]), q1 = __ldcg(&d.S[1 * ld + k]), q2 = __ldcg(&d.S[2 * ld + k]), q3 = __ldcg(&d.S[3 * ld + k]),
+                 q4 = __ldcg(&d.S[4 * ld + k]);
+    const float4 p0 = __ldcg(&d.P[0 * ld + k]), p1 = __ldcg(&d.P[1 * ld + k]), p2 = __ldcg(&d.P[2 * ld + k]), tt = __ldcg(&d.T[k]);
+    float s[17] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x};
+    const DroneParams p = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, tt.x};
+    const float act[4] = {xclamp(xf(a4.x), -1.0f, 1.0f).v, xclamp(xf(a4.y), -1.0f, 1.0f).v, xclamp(xf(a4.z), -1.0f, 1.0f).v,
+                          xclamp(xf(a4.w), -1.0f, 1.0f).v};
+    const float before[3] = {s[0], s[1], s[2]};
+    advance_body_strict(s, p, act);
+#pragma unroll
+    for (int m = 0; m < 17; m++) out[m] = s[m];
+    float gate = 0.0f;
+    if (ring) {
+        const float rg[6] = {ring[0], ring[1], ring[2], ring[3], ring[4], ring[5]};
+        gate = gate_event<xf>(before, s, rg, -0.0f);
+    }
+    out[17] = gate;
+}
+
+// ---- prepared respawns.  The respawn of agent a of env g after r earlier respawns is a pure function of
+// (seed, g, a, r + 1) (sw_draw_params / sw_draw_box).  Drawing it where it is needed puts ~700 instructions
+// behind a branch 2.4 % of the drones take per step: more than half of all warps ran them with one lane
+// active, a quarter of the whole step (profiles/r01h_swarm_variants.txt).  So every drone's NEXT respawn
+// sits ready in d.RS (64 B per drone); a drone that leaves the arena reads it and leaves its row id in its
+// warp's list; a warp regenerates slots 32 at a time -- all lanes busy -- once its list holds 32 rows, and
+// flushes the rest at the end of the launch.  A slot is read at most once per launch, by the warp that
+// later rewrites it, so every launch is self-contained.
+__device__ __forceinline__ void sw_generate_slot(const SwarmDev &d, int k, uint32_t ordinal) {
+    const int env = k / d.A, a = k - env * d.A;
+    const uint32_t genv = d.env_id_base + (uint32_t)env;
+    float rp[13], rpos[3];
+    sw_draw_params(d, genv, (uint32_t)a | 0x10000u, ordinal, rp);
+    sw_draw_box(d, genv, (uint32_t)a | 0x10000u, ordinal, 4u, 0u, 29.0f, 29.0f, 9.0f, rpos);
+    const size_t ld = d.ld;
+    d.RS[0 * ld + k] = make_float4(rp[0], rp[1], rp[2], rp[3]);
+    d.RS[1 * ld + k] = make_float4(rp[4], rp[5], rp[6], rp[7]);
+    d.RS[2 * ld + k] = make_float4(rp[8], rp[9], rp[10], rp[11]);
+    d.RS[3 * ld + k] = make_float4(rp[12], rpos[0], rpos[1], rpos[2]);
+}
+__device__ __noinline__ void sw_refill_pass(const SwarmDev &d, const int2 *list, int count, int lane) {
+    if (lane < count) sw_generate_slot(d, list[lane].x, (uint32_t)list[lane].y);
+}
+// every drone's slot from its current respawn count (create, vec_reset)
+__global__ void __launch_bounds__(128) swarm_fill_slots_kernel(const __grid_constant__ SwarmDev d) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < d.rows) sw_generate_slot(d, k, __float_as_uint(d.T[k].y) + 1u);
+}
+
 // ---------------------------------------------------------------- the kernel
 // ONLY_RESET = false: one vec_step.  ONLY_RESET = true: vec_reset (every env runs c_reset).
 //
@@ -458,11 +600,15 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
     __shared__ __align__(16) SwarmWin s_now; // per env [pos | pos]: final positions of the tick (what the observations see)
     __shared__ float s_ring0[SWARM_BLOCK][3];
     __shared__ float s_facc[8];
+    __shared__ int2 s_rlist[SWARM_BLOCK / 32][64]; // per warp: (row, ordinal) of the respawn slots to regenerate
+    __shared__ int s_rcnt[SWARM_BLOCK / 32];
+    __shared__ int s_guard;
     extern __shared__ __align__(128) unsigned char s_dyn[];
     float4 *stage = reinterpret_cast<float4 *>(s_dyn);                       // step launches only
     float *s_obs = reinterpret_cast<float *>(s_dyn + (ONLY_RESET ? 0 : SW_STAGE_BYTES));
 
     const int t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
     const int A = d.A;
     const int le = t / A;
     const int a = t - le * A;
@@ -498,6 +644,9 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         return __syncthreads_or(p ? 1 : 0);
     };
     if (t < 8) s_facc[t] = 0.0f; // episode statistics of all this CTA's tiles; flushed once at the end
+    if (t < SWARM_BLOCK / 32) s_rcnt[t] = 0;
+    if (t == 0) s_guard = 0;
+    int guard_hits = 0;
     __syncthreads();
 
     if constexpr (!ONLY_RESET) {
@@ -542,9 +691,10 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
     if (active) s_trail.put(w0 + a, g.s[0], g.s[1], g.s[2]);
 
     if constexpr (!ONLY_RESET) {
-        // ---- phase 1: every drone moves (R/drone_swarm.h:452-461); agents that leave the arena draw their respawn
+        // ---- phase 1: every drone moves (R/drone_swarm.h:452-461); agents that leave the arena take their prepared respawn
         bool oob = false;
-        float rp[13], rpos[3] = {0.0f, 0.0f, 0.0f};
+        float rpos[3] = {0.0f, 0.0f, 0.0f};
+        float passed = 0.0f; // ring test of this move (race task), R/drone_swarm.h:465
         if (active) {
             tick = (tick + 1) % SWARM_HORIZON;
             float act[4];
@@ -557,6 +707,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             }
             if (d.act_out) reinterpret_cast<float4 *>(d.act_out)[k] = make_float4(act[0], act[1], act[2], act[3]);
             DroneParams p = {g.p[0], g.p[1], g.p[2], g.p[3], g.p[4], g.p[5], g.p[6], g.p[7], g.p[8], g.p[9], g.p[10], g.p[11], g.p[12]};
+            const float before[3] = {g.s[0], g.s[1], g.s[2]};
             advance_body<STRICT>(g.s, p, act);
 #if B2D_SWARM_EXPERIMENT_DOUBLE_MATH
             {   // measurement aid: the rigid-body arithmetic twice, same memory traffic
@@ -567,6 +718,25 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                 g.s[0] = fmaf(s2[0] + s2[6] + s2[12] + s2[16], 1e-30f, g.s[0]);
             }
 #endif
+            const bool race = task == SWARM_TASK_RACE;
+            float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (race) sw_load_ring(d, e, g.ring_idx, ring);
+            if constexpr (STRICT) {
+                if (race) passed = gate_event<xf>(before, g.s, ring, -0.0f);
+            } else {
+                // decisions within a guard band of their threshold are re-taken in the reference's arithmetic
+                const float wall = fminf(fminf(fabsf(fabsf(g.s[0]) - SW_GX), fabsf(fabsf(g.s[1]) - SW_GY)), fabsf(fabsf(g.s[2]) - SW_GZ));
+                bool suspect = false;
+                if (race) passed = gate_event_guarded(before, g.s, ring, -0.0f, SW_GUARD_PLANE, suspect);
+                if (wall < SW_GUARD_WALL || suspect) {
+                    float out[18];
+                    sw_strict_move(d, k, a4, race ? ring : nullptr, out);
+#pragma unroll
+                    for (int m = 0; m < 17; m++) g.s[m] = out[m];
+                    passed = out[17];
+                    guard_hits += 1;
+                }
+            }
             oob = g.s[0] < -SW_GX || g.s[0] > SW_GX || g.s[1] < -SW_GY || g.s[1] > SW_GY || g.s[2] < -SW_GZ || g.s[2] > SW_GZ;
 #if B2D_SWARM_EXPERIMENT_NO_RESPAWN
             oob = false; // measurement aid: nobody leaves the arena (no respawn draws, no episode ends by OOB)
@@ -574,35 +744,38 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             sw_move_target(g.tpos, g.tvel);
             if (oob) {
                 if (inject) {
-#pragma unroll
-                    for (int m = 0; m < 13; m++) rp[m] = pay_agent[m];
                     rpos[0] = pay_agent[13]; rpos[1] = pay_agent[14]; rpos[2] = pay_agent[15];
                 } else {
                     g.respawns += 1u;
-                    sw_draw_params(d, genv, (uint32_t)a | 0x10000u, g.respawns, rp);
-                    sw_draw_box(d, genv, (uint32_t)a | 0x10000u, g.respawns, 4u, 0u, 29.0f, 29.0f, 9.0f, rpos);
+                    const float4 r3 = __ldcg(&d.RS[3 * (size_t)d.ld + k]);
+                    rpos[0] = r3.y; rpos[1] = r3.z; rpos[2] = r3.w;
                 }
             }
             if (oob) s_trail.put(w0 + A + a, rpos[0], rpos[1], rpos[2]);
             else s_trail.put(w0 + A + a, g.s[0], g.s[1], g.s[2]);
         }
+        {   // drones that consumed their prepared respawn queue its regeneration (warp-uniform code)
+            const bool want = active && oob && !inject;
+            const unsigned int m = __ballot_sync(0xffffffffu, want);
+            if (m) {
+                const int base = s_rcnt[warp];
+                if (want) s_rlist[warp][base + __popc(m & ((1u << lane) - 1u))] = make_int2(k, (int)(g.respawns + 1u));
+                __syncwarp();
+                if (lane == 0) s_rcnt[warp] = base + __popc(m);
+                __syncwarp();
+            }
+        }
         env_sync();
 
         // ---- phase 2: rewards, ring logic, respawn bookkeeping (R/drone_swarm.h:463-491)
         if (active) {
-            const float before[3] = {s_trail.x[w0 + a], s_trail.y[w0 + a], s_trail.z[w0 + a]};
             const float self[3] = {g.s[0], g.s[1], g.s[2]};
-            float other[3];
             float nd = 0.0f;
-            if (A > 1) nd = sw_nearest<STRICT>(&s_trail.x[w0], A, a, self, other);
+            if (A > 1) nd = sw_reward_distance<STRICT>(&s_trail.x[w0], A, a, self, guard_hits);
             if (task == SWARM_TASK_RACE) {
-                float ring[6];
-                sw_load_ring(d, e, g.ring_idx, ring);
                 reward = sw_reward<STRICT>(g, self, true, A, nd);
-                float passed;
-                if constexpr (STRICT) passed = gate_event<xf>(before, self, ring, -0.0f);
-                else passed = gate_event<float>(before, self, ring, -0.0f);
                 if (passed > 0.0f) {
+                    float ring[6];
                     g.ring_idx = (g.ring_idx + 1) % d.R;
                     atomicAdd(&s_facc[FACC_RINGS], 1.0f);
                     sw_load_ring(d, e, g.ring_idx, ring);
@@ -631,10 +804,21 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             }
             if (oob) {
                 reward = __fsub_rn(reward, 1.0f);
+                float rp[13];
+                if (inject) {
+#pragma unroll
+                    for (int m = 0; m < 13; m++) rp[m] = pay_agent[m];
+                } else {
+                    const size_t ld = d.ld;
+                    const float4 r0 = __ldcg(&d.RS[0 * ld + k]), r1 = __ldcg(&d.RS[1 * ld + k]), r2 = __ldcg(&d.RS[2 * ld + k]);
+                    rp[0] = r0.x; rp[1] = r0.y; rp[2] = r0.z; rp[3] = r0.w; rp[4] = r1.x; rp[5] = r1.y; rp[6] = r1.z; rp[7] = r1.w;
+                    rp[8] = r2.x; rp[9] = r2.y; rp[10] = r2.z; rp[11] = r2.w;
+                    rp[12] = __ldcg(&d.RS[3 * ld + k]).x;
+                }
                 sw_respawn_state(g, rp, rpos);
                 params_dirty = true;
                 float nd2 = 0.0f;
-                if (A > 1 && task != SWARM_TASK_RACE) nd2 = sw_nearest<STRICT>(&s_trail.x[w0], A, a, rpos, other);
+                if (A > 1 && task != SWARM_TASK_RACE) nd2 = sw_reward_distance<STRICT>(&s_trail.x[w0], A, a, rpos, guard_hits);
                 sw_reward<STRICT>(g, rpos, task != SWARM_TASK_RACE, A, nd2);
             }
             do_reset = horizon;
@@ -672,8 +856,8 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             // reset_agent: the reward is computed against the STALE target and half-reset neighbours
             sw_respawn_state(g, np, first);
             params_dirty = true;
-            float other[3], nd = 0.0f;
-            if (A > 1 && task != SWARM_TASK_RACE) nd = sw_nearest<STRICT>(&s_trail.x[w0 + A], A, a, first, other);
+            float nd = 0.0f;
+            if (A > 1 && task != SWARM_TASK_RACE) nd = sw_reward_distance<STRICT>(&s_trail.x[w0 + A], A, a, first, guard_hits);
             sw_reward<STRICT>(g, first, task != SWARM_TASK_RACE, A, nd);
             // set_target: R/drone_swarm.h:234-333
             if (inject) {
@@ -759,7 +943,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         }
         const float self[3] = {g.s[0], g.s[1], g.s[2]};
         float near[3] = {0.0f, 0.0f, 0.0f};
-        if (A > 1) sw_nearest<STRICT>(&s_now.x[w0], A, a, self, near);
+        if (A > 1) sw_obs_neighbour<STRICT>(&s_now.x[w0], A, a, self, near, guard_hits);
         float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
         if (task == SWARM_TASK_RACE) sw_load_ring(d, e, g.ring_idx, ring);
         sw_observe<STRICT>(g, A, near, task == SWARM_TASK_RACE, ring, s_obs + t * SWARM_OBS, 1);
@@ -782,6 +966,18 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
     }
     if constexpr (!ONLY_RESET) {
         if (t == 0 && tile == 0) atomicAdd(&d.ctl->ctas_done, 1u);
+        // a full warp's worth of consumed respawn slots: regenerate them with every lane busy
+        __syncwarp();
+        const int cnt = s_rcnt[warp];
+        if (cnt >= 32) {
+            sw_refill_pass(d, s_rlist[warp], 32, lane);
+            __syncwarp();
+            const int2 keep = lane + 32 < cnt ? s_rlist[warp][lane + 32] : make_int2(0, 0);
+            __syncwarp();
+            s_rlist[warp][lane] = keep;
+            if (lane == 0) s_rcnt[warp] = cnt - 32;
+            __syncwarp();
+        }
     }
     // the next tile's first barrier (after its phase 1) separates this tile's readers of the
     // shared arrays from their next writers, except the old / fin arrays, which are last read before this
@@ -789,8 +985,12 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
   }
   if constexpr (!ONLY_RESET) {
       cp_async_wait<0>();
+      __syncwarp();
+      sw_refill_pass(d, s_rlist[warp], s_rcnt[warp], lane); // the rest of this warp's list
+      if (guard_hits) atomicAdd(&s_guard, guard_hits);
       __syncthreads(); // every warp's statistics are in
       if (t < 8 && s_facc[t] != 0.0f) atomicAdd(&d.ctl->facc[t], (double)s_facc[t]);
+      if (t == 0 && s_guard != 0) atomicAdd(&d.ctl->guard_replays, (unsigned long long)s_guard);
   }
 }
 
@@ -873,7 +1073,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_observe_kernel(const __grid
     const int task = d.E[e].y;
     const float self[3] = {g.s[0], g.s[1], g.s[2]};
     float near[3] = {0.0f, 0.0f, 0.0f};
-    if (A > 1) sw_nearest<STRICT>(&s_now.x[w0], A, a, self, near);
+    if (A > 1) sw_nearest_strict(&s_now.x[w0], A, a, self, near);
     float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     if (task == SWARM_TASK_RACE) sw_load_ring(d, e, g.ring_idx, ring);
     sw_observe<STRICT>(g, A, near, task == SWARM_TASK_RACE, ring, d.obs + (size_t)(e * A + a) * SWARM_OBS, 1);
@@ -886,7 +1086,8 @@ static inline void swarm_vec_reset(SwarmDev &d, uint64_t seed, cudaStream_t st, 
     d.key0 = (uint32_t)seed;
     d.key1 = (uint32_t)(seed >> 32);
     swarm_kernel<true, true><<<swarm_grid(d), SWARM_BLOCK, SWARM_BLOCK * SWARM_OBS * 4, st>>>(d);
-    *launches += 1;
+    swarm_fill_slots_kernel<<<(d.rows + 127) / 128, 128, 0, st>>>(d); // respawn counts are zero again: slot = first respawn
+    *launches += 2;
 }
 
 // persistent step grid: every resident CTA slot of the handle's device, or one CTA per tile when there
