@@ -70,6 +70,7 @@ SYMBOLS = {
     "b2d_vec_log": (C.c_int, [_P, C.POINTER(C.c_float), _P]),
     "b2d_vec_log_begin": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(C.c_int)]),
     "b2d_vec_log_end": (C.c_int, [_P, C.POINTER(C.c_float), _P]),
+    "b2d_vec_log_reduce": (C.c_int, [_P, C.POINTER(C.c_float), _P, _P]),
     "b2d_log_average": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_float)]),
     "b2d_get_buffers": (C.c_int, [_P, C.POINTER(Buffers)]),
     "b2d_num_agents": (C.c_int, [_P]),

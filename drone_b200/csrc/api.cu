@@ -12,6 +12,7 @@
 #include "rollout_kernels.cuh"
 
 #include <cstdarg>
+#include <dlfcn.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -636,6 +637,40 @@ extern "C" int b2d_vec_log_end(b2d_vec *v, float out[B2D_LOG_FIELDS], void *stre
     return b2d_log_average(v->kind, v->kind == KIND_RACE ? v->race.max_rings : v->swarm.max_rings, v->h_log_out, 16, out);
 }
 
+// ncclAllReduce of the process's own NCCL, resolved lazily (no link-time dependency; nccl.h: ncclInt64 = 4, ncclSum = 0)
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+static nccl_allreduce_fn resolve_nccl_allreduce() {
+    static nccl_allreduce_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+        if (!sym) {
+            void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (h) sym = dlsym(h, "ncclAllReduce");
+        }
+        fn = (nccl_allreduce_fn)sym;
+    }
+    return fn;
+}
+
+extern "C" int b2d_vec_log_reduce(b2d_vec *v, float out[B2D_LOG_FIELDS], void *nccl_comm, void *stream) {
+    if (!v || !out) return fail(B2D_EINVAL, "Missing or invalid vec env handle");
+    long long *sums = nullptr;
+    int count = 0;
+    int rc = b2d_vec_log_begin(v, stream, &sums, &count);
+    if (rc) return rc;
+    if (nccl_comm) {
+        nccl_allreduce_fn all_reduce = resolve_nccl_allreduce();
+        if (!all_reduce) return fail(B2D_ESTATE, "b2d_vec_log_reduce: no NCCL in this process (ncclAllReduce not found)");
+        DEVICE_SCOPE(v);
+        const int nrc = all_reduce(sums, sums, (size_t)count, 4 /* ncclInt64 */, 0 /* ncclSum */, nccl_comm, (cudaStream_t)stream);
+        if (nrc != 0) return fail(B2D_ECUDA, "ncclAllReduce failed with ncclResult_t %d", nrc);
+    }
+    return b2d_vec_log_end(v, out, stream);
+}
+
 extern "C" int b2d_log_average(int kind, int max_rings, const long long *a, int count, float out[B2D_LOG_FIELDS]) {
     if (!a || !out || count < 16 || max_rings <= 0) return fail(B2D_EINVAL, "b2d_log_average: bad argument");
     for (int k = 0; k < B2D_LOG_FIELDS; k++) out[k] = 0.0f;
@@ -989,6 +1024,18 @@ extern "C" int b2d_race_rollout(b2d_vec *v, const b2d_policy_weights *w, const b
         if (getenv("B2D_RO_CTAS")) per_sm = atoi(getenv("B2D_RO_CTAS")); // measurement aid
         grid_for[m][dev] = per_sm * sms;
     }
+    // the episode bank: allocated on first use (not inside a stream capture), topped up before every launch
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!v->race.bank) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        if (cap != cudaStreamCaptureStatusNone)
+            return fail(B2D_ESTATE, "b2d_race_rollout: call once outside stream capture first (allocates the episode bank)");
+        int rc = dev_alloc(v, &v->race.bank, (size_t)v->race.n * RACE_BANK_SLOTS * 6);
+        if (rc) return rc;
+    }
+    race_bank_fill_kernel<<<(v->race.n * RACE_BANK_SLOTS + 127) / 128, 128, 0, st>>>(v->race);
+    v->launches += 1;
     RolloutArgs a;
     a.d = v->race;
     a.enc_w = w->encoder_weight; a.enc_b = w->encoder_bias; a.mean_w = w->decoder_mean_weight; a.mean_b = w->decoder_mean_bias;
@@ -1004,7 +1051,6 @@ extern "C" int b2d_race_rollout(b2d_vec *v, const b2d_policy_weights *w, const b
     a.deterministic = deterministic ? 1 : 0;
     const int chunks = (v->race.n + RO_THREADS - 1) / RO_THREADS;
     const int grid = chunks < grid_for[m][dev] ? chunks : grid_for[m][dev];
-    cudaStream_t st = (cudaStream_t)stream;
     if (m) race_rollout_kernel<true><<<grid, RO_THREADS, RO_SMEM_BYTES, st>>>(a);
     else race_rollout_kernel<false><<<grid, RO_THREADS, RO_SMEM_BYTES, st>>>(a);
     v->launches += 1;

@@ -100,6 +100,7 @@ struct RaceDev {
     unsigned char *term; // [n]
     Ctl *ctl;
     const float *payload; // [n][33+6R] next-episode blobs (inject mode)
+    float4 *bank;         // [n][RACE_BANK_SLOTS][6] prepared episodes for the rollout kernel (race_bank_fill_kernel); or nullptr
     uint32_t key0, key1, env_id_base;
     int reset_mode; // b2d_reset_mode
 #if B2D_EXPERIMENT_TIMING
@@ -375,6 +376,35 @@ __device__ __noinline__ void race_inject_episode(const RaceDev &d, int i, uint32
     race_store_state(d, i, s, tick, ring_idx | RING_EXTERNAL, b[32]);
     race_store_current_ring(d, i, g);
     race_observe<STRICT>(s, b[27], g, obs_row);
+}
+
+// ---------------------------------------------------------------- episode bank (rollout kernel)
+// Episode k of env g is a pure function of (seed, g, k), so it can be generated at any time.  The one-kernel
+// rollout (rollout_kernels.cuh) steps a block of 128 envs in lock-step through CTA-wide barriers; generating
+// an episode where it is needed (~1,100 instructions on one lane) would put that latency on the critical path
+// of all 128 envs at almost every step (P(no reset among 128 envs) = 4 %).  Instead the next RACE_BANK_SLOTS
+// episodes of every env are generated up front, all lanes busy, by this kernel (launched before every rollout
+// launch; entries that are still valid are skipped), and a reset inside the rollout is six 16-byte loads.
+// Entry of episode k: slot k % RACE_BANK_SLOTS of the env, 24 floats = 13 params, spawn position, ring 0
+// (position + normal), k itself as the tag.  An env that finishes more than RACE_BANK_SLOTS episodes within
+// one launch (0.6 % of the envs at K = 128) falls back to in-place generation for the excess.
+constexpr int RACE_BANK_SLOTS = 8;
+__global__ void __launch_bounds__(128) race_bank_fill_kernel(const __grid_constant__ RaceDev d) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d.n * RACE_BANK_SLOTS) return;
+    const int i = j / RACE_BANK_SLOTS, s = j - i * RACE_BANK_SLOTS;
+    const uint32_t live = __float_as_uint(race_at(d, SLOT_T, i)->y);
+    const uint32_t episode = live + 1u + (uint32_t)s;
+    float4 *b = d.bank + ((size_t)i * RACE_BANK_SLOTS + (episode % RACE_BANK_SLOTS)) * 6;
+    if (__float_as_uint(b[5].z) == episode && __float_as_uint(b[5].w) == (d.key0 ^ (d.key1 * 0x9E3779B9u) ^ 0xB2D0u)) return; // still valid
+    float p[13], spawn[3], ring0[6];
+    race_generate_episode(d, i, episode, p, spawn, ring0);
+    b[0] = make_float4(p[0], p[1], p[2], p[3]);
+    b[1] = make_float4(p[4], p[5], p[6], p[7]);
+    b[2] = make_float4(p[8], p[9], p[10], p[11]);
+    b[3] = make_float4(p[12], spawn[0], spawn[1], spawn[2]);
+    b[4] = make_float4(ring0[0], ring0[1], ring0[2], ring0[3]);
+    b[5] = make_float4(ring0[4], ring0[5], __uint_as_float(episode), __uint_as_float(d.key0 ^ (d.key1 * 0x9E3779B9u) ^ 0xB2D0u));
 }
 
 // ---------------------------------------------------------------- near-threshold guard of the fast step

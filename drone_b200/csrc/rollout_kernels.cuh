@@ -288,10 +288,23 @@ __device__ __forceinline__ void ro_env_step(const RaceDev &d, int i, RaceRegs &e
         atomicAdd(&s_acc[ACC_RINGS], e.ring_idx);
         if (cause != ACC_SPARE) atomicAdd(&s_acc[cause], 1);
         if (last_step) score_last += e.ring_idx;
-        // c_reset: the next episode of this env, generated in place (Philox stream of the step kernel)
+        // c_reset: the next episode of this env (Philox stream of the step kernel): from the episode bank when its
+        // entry is there (race_bank_fill_kernel), generated in place otherwise
         float g[22];
         e.episode += 1u;
-        ro_generate_episode(d, i, e.episode, g);
+        bool banked = false;
+        if (d.bank) {
+            const float4 *b = d.bank + ((size_t)i * RACE_BANK_SLOTS + (e.episode % RACE_BANK_SLOTS)) * 6;
+            const float4 b5 = __ldcg(b + 5);
+            if (__float_as_uint(b5.z) == e.episode && __float_as_uint(b5.w) == (d.key0 ^ (d.key1 * 0x9E3779B9u) ^ 0xB2D0u)) {
+                const float4 b0 = __ldcg(b + 0), b1 = __ldcg(b + 1), b2 = __ldcg(b + 2), b3 = __ldcg(b + 3), b4 = __ldcg(b + 4);
+                g[0] = b0.x; g[1] = b0.y; g[2] = b0.z; g[3] = b0.w; g[4] = b1.x; g[5] = b1.y; g[6] = b1.z; g[7] = b1.w;
+                g[8] = b2.x; g[9] = b2.y; g[10] = b2.z; g[11] = b2.w; g[12] = b3.x; g[13] = b3.y; g[14] = b3.z; g[15] = b3.w;
+                g[16] = b4.x; g[17] = b4.y; g[18] = b4.z; g[19] = b4.w; g[20] = b5.x; g[21] = b5.y;
+                banked = true;
+            }
+        }
+        if (!banked) ro_generate_episode(d, i, e.episode, g);
         e.p = {g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7], g[8], g[9], g[10], g[11], g[12]};
 #pragma unroll
         for (int k = 0; k < 17; k++) e.s[k] = 0.0f;

@@ -100,9 +100,20 @@ __device__ __forceinline__ void sw_load(const SwarmDev &d, int k, SwarmAgent &g)
 
 // Inputs of one agent for one step, staged in shared memory by cp.async one tile ahead of their
 // use (slot s of thread t at stage[s * SWARM_BLOCK + t]: conflict-free, thread-private).
-constexpr int SW_STAGE_SLOTS = 14; // act, S0..S4, P0..P2, T, U, V, W, E
+constexpr int SW_STAGE_SLOTS = 15; // act, S0..S4, P0..P2, T, U, V, W, E, RS3 (the prepared respawn position)
 constexpr int SW_STAGE_BYTES = SW_STAGE_SLOTS * SWARM_BLOCK * 16;
 constexpr int SW_DYN_SMEM = SW_STAGE_BYTES + SWARM_BLOCK * SWARM_OBS * 4;
+// The rings of a tile's envs ride along with the prefetch (two buffers of [epc][R][8 floats]) when they fit in
+// SW_RING_STAGE_MAX bytes, so that the ring test, the race target and the observation never wait on a dependent
+// global load; larger configurations (tiny A or hundreds of rings) read rings from global memory as before.
+constexpr int SW_RING_STAGE_MAX = 8192;
+__host__ __device__ inline int sw_ring_stage_bytes(int epc, int R) {
+    const int b = 2 * epc * R * 32;
+    return b <= SW_RING_STAGE_MAX ? b : 0;
+}
+__device__ __forceinline__ void cp_async8(void *sdst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
 
 __device__ __forceinline__ void sw_prefetch(const SwarmDev &d, float4 *stage, int t, int e, int k) {
     const size_t ld = d.ld;
@@ -116,6 +127,15 @@ __device__ __forceinline__ void sw_prefetch(const SwarmDev &d, float4 *stage, in
     cp_async16(&stage[11 * SWARM_BLOCK + t], &d.V[k]);
     cp_async16(&stage[12 * SWARM_BLOCK + t], &d.W[k]);
     cp_async16(&stage[13 * SWARM_BLOCK + t], &d.E[e]);
+    cp_async16(&stage[14 * SWARM_BLOCK + t], &d.RS[3 * ld + k]);
+}
+// the env's rings into ring-stage buffer `buf` (threads a = 0..A-1 of env slot le share the R rings)
+__device__ __forceinline__ void sw_prefetch_rings(const SwarmDev &d, float *rstage, int buf, int le, int a, int e) {
+    float *dst = rstage + ((size_t)(buf * d.epc + le) * d.R) * 8;
+    for (int r = a; r < d.R; r += d.A) {
+        cp_async16(dst + r * 8, &d.G0[(size_t)r * d.n + e]);
+        cp_async8(dst + r * 8 + 4, &d.G1[(size_t)r * d.n + e]);
+    }
 }
 
 __device__ __forceinline__ void sw_load_staged(const float4 *stage, int t, SwarmAgent &g, float4 &a4, int4 &ev) {
@@ -599,13 +619,16 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
     __shared__ __align__(16) SwarmWin s_trail;
     __shared__ __align__(16) SwarmWin s_now; // per env [pos | pos]: final positions of the tick (what the observations see)
     __shared__ float s_ring0[SWARM_BLOCK][3];
-    __shared__ float s_facc[8];
+    __shared__ unsigned long long s_iacc[8]; // episode statistics in 2^-20 fixed point (native shared-memory integer atomics)
     __shared__ int2 s_rlist[SWARM_BLOCK / 32][64]; // per warp: (row, ordinal) of the respawn slots to regenerate
     __shared__ int s_rcnt[SWARM_BLOCK / 32];
     __shared__ int s_guard;
     extern __shared__ __align__(128) unsigned char s_dyn[];
     float4 *stage = reinterpret_cast<float4 *>(s_dyn);                       // step launches only
     float *s_obs = reinterpret_cast<float *>(s_dyn + (ONLY_RESET ? 0 : SW_STAGE_BYTES));
+    float *rstage = reinterpret_cast<float *>(s_dyn + SW_DYN_SMEM); // step launches only, when ring_staged
+    const bool ring_staged = !ONLY_RESET && sw_ring_stage_bytes(d.epc, d.R) > 0;
+    int rbuf = 0; // ring-stage buffer of the current tile
 
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
@@ -643,7 +666,20 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         }
         return __syncthreads_or(p ? 1 : 0);
     };
-    if (t < 8) s_facc[t] = 0.0f; // episode statistics of all this CTA's tiles; flushed once at the end
+    if (t < 8) s_iacc[t] = 0ull; // episode statistics of all this CTA's tiles; flushed once at the end
+    auto stat_add = [&](int which, float x) { // sums arrive at vec_log as 2^-20 fixed point anyway (swarm_log_snapshot_kernel)
+        atomicAdd(&s_iacc[which], (unsigned long long)__float2ll_rn(x * 1048576.0f));
+    };
+    auto load_ring = [&](int e_, int r, float ring[6]) {
+        if (ring_staged) {
+            const float *src = rstage + ((size_t)(rbuf * d.epc + le) * d.R + r) * 8;
+            const float4 q = *reinterpret_cast<const float4 *>(src);
+            const float2 h = *reinterpret_cast<const float2 *>(src + 4);
+            ring[0] = q.x; ring[1] = q.y; ring[2] = q.z; ring[3] = q.w; ring[4] = h.x; ring[5] = h.y;
+        } else {
+            sw_load_ring(d, e_, r, ring);
+        }
+    };
     if (t < SWARM_BLOCK / 32) s_rcnt[t] = 0;
     if (t == 0) s_guard = 0;
     int guard_hits = 0;
@@ -651,7 +687,10 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
 
     if constexpr (!ONLY_RESET) {
         const int e0 = blockIdx.x * d.epc + le;
-        if ((int)blockIdx.x < ntiles && le < d.epc && e0 < d.n) sw_prefetch(d, stage, t, e0, e0 * A + a);
+        if ((int)blockIdx.x < ntiles && le < d.epc && e0 < d.n) {
+            sw_prefetch(d, stage, t, e0, e0 * A + a);
+            if (ring_staged) sw_prefetch_rings(d, rstage, 0, le, a, e0);
+        }
         cp_async_commit();
     }
 
@@ -679,14 +718,13 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         }
     } else {
         cp_async_wait<0>(); // this thread's staged inputs of this tile have landed
+        if (ring_staged) env_sync(); // ... and the env's rings, which its threads fetched together
         if (active) {
             int4 ev;
             sw_load_staged(stage, t, g, a4, ev);
             tick = ev.x; task = ev.y; env_episode = (uint32_t)ev.z;
         }
-        const int tn = tile + gridDim.x, en = tn * d.epc + le;
-        if (tn < ntiles && le < d.epc && en < d.n) sw_prefetch(d, stage, t, en, en * A + a); // slots are thread-private
-        cp_async_commit();
+        // (the next tile's prefetch is issued after phase 1: until then the stage still holds this tile's inputs)
     }
     if (active) s_trail.put(w0 + a, g.s[0], g.s[1], g.s[2]);
 
@@ -720,7 +758,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
 #endif
             const bool race = task == SWARM_TASK_RACE;
             float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-            if (race) sw_load_ring(d, e, g.ring_idx, ring);
+            if (race) load_ring(e, g.ring_idx, ring);
             if constexpr (STRICT) {
                 if (race) passed = gate_event<xf>(before, g.s, ring, -0.0f);
             } else {
@@ -728,9 +766,11 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                 const float wall = fminf(fminf(fabsf(fabsf(g.s[0]) - SW_GX), fabsf(fabsf(g.s[1]) - SW_GY)), fabsf(fabsf(g.s[2]) - SW_GZ));
                 bool suspect = false;
                 if (race) passed = gate_event_guarded(before, g.s, ring, -0.0f, SW_GUARD_PLANE, suspect);
-                if (wall < SW_GUARD_WALL || suspect) {
-                    float out[18];
-                    sw_strict_move(d, k, a4, race ? ring : nullptr, out);
+                if (__builtin_expect(wall < SW_GUARD_WALL || suspect, 0)) {
+                    float out[18], rg[6]; // (copies: the hot path's ring[] must not have its address taken)
+#pragma unroll
+                    for (int m = 0; m < 6; m++) rg[m] = ring[m];
+                    sw_strict_move(d, k, a4, race ? rg : nullptr, out);
 #pragma unroll
                     for (int m = 0; m < 17; m++) g.s[m] = out[m];
                     passed = out[17];
@@ -742,12 +782,12 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             oob = false; // measurement aid: nobody leaves the arena (no respawn draws, no episode ends by OOB)
 #endif
             sw_move_target(g.tpos, g.tvel);
-            if (oob) {
+            if (__builtin_expect(oob, 0)) {
                 if (inject) {
                     rpos[0] = pay_agent[13]; rpos[1] = pay_agent[14]; rpos[2] = pay_agent[15];
                 } else {
                     g.respawns += 1u;
-                    const float4 r3 = __ldcg(&d.RS[3 * (size_t)d.ld + k]);
+                    const float4 r3 = stage[14 * SWARM_BLOCK + t]; // prefetched with the state
                     rpos[0] = r3.y; rpos[1] = r3.z; rpos[2] = r3.w;
                 }
             }
@@ -765,6 +805,14 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                 __syncwarp();
             }
         }
+        {   // the next tile's inputs stream in while phases 2-4 of this tile run (stage slots are thread-private)
+            const int tn = tile + gridDim.x, en = tn * d.epc + le;
+            if (tn < ntiles && le < d.epc && en < d.n) {
+                sw_prefetch(d, stage, t, en, en * A + a);
+                if (ring_staged) sw_prefetch_rings(d, rstage, rbuf ^ 1, le, a, en);
+            }
+            cp_async_commit();
+        }
         env_sync();
 
         // ---- phase 2: rewards, ring logic, respawn bookkeeping (R/drone_swarm.h:463-491)
@@ -777,8 +825,8 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                 if (passed > 0.0f) {
                     float ring[6];
                     g.ring_idx = (g.ring_idx + 1) % d.R;
-                    atomicAdd(&s_facc[FACC_RINGS], 1.0f);
-                    sw_load_ring(d, e, g.ring_idx, ring);
+                    stat_add(FACC_RINGS, 1.0f);
+                    load_ring(e, g.ring_idx, ring);
                     g.tpos[0] = ring[0]; g.tpos[1] = ring[1]; g.tpos[2] = ring[2];
                     g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
                     sw_reward<STRICT>(g, self, true, A, nd);
@@ -789,20 +837,20 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             }
             g.ep_ret = __fadd_rn(g.ep_ret, reward);
             const bool horizon = tick >= SWARM_HORIZON - 1;
-            if (oob || horizon) { // add_log: R/drone_swarm.h:91-105
+            if (__builtin_expect(oob || horizon, 0)) { // add_log: R/drone_swarm.h:91-105
                 terminal = 1;
                 const float len = (float)g.ep_len;
-                atomicAdd(&s_facc[FACC_SCORE], g.score);
-                atomicAdd(&s_facc[FACC_RETURN], g.ep_ret);
-                atomicAdd(&s_facc[FACC_LENGTH], len);
-                atomicAdd(&s_facc[FACC_COLLISION], g.collisions / len);
-                atomicAdd(&s_facc[FACC_PERF], g.score / len);
-                if (oob) atomicAdd(&s_facc[FACC_OOB], 1.0f);
-                atomicAdd(&s_facc[FACC_N], 1.0f);
+                stat_add(FACC_SCORE, g.score);
+                stat_add(FACC_RETURN, g.ep_ret);
+                stat_add(FACC_LENGTH, len);
+                stat_add(FACC_COLLISION, g.collisions / len);
+                stat_add(FACC_PERF, g.score / len);
+                if (oob) stat_add(FACC_OOB, 1.0f);
+                stat_add(FACC_N, 1.0f);
                 g.ep_len = 0;
                 g.ep_ret = 0.0f;
             }
-            if (oob) {
+            if (__builtin_expect(oob, 0)) {
                 reward = __fsub_rn(reward, 1.0f);
                 float rp[13];
                 if (inject) {
@@ -833,7 +881,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
 
     // ---- phase 3: env-wide reset (R/drone_swarm.h:401-443), every 1023 ticks for all agents of the env at once
     const int cta_reset = env_any(do_reset);
-    if (cta_reset) {
+    if (__builtin_expect(cta_reset, 0)) {
         float first[3] = {0.0f, 0.0f, 0.0f}, np[13];
         if (do_reset) {
             tick = 0;
@@ -878,7 +926,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             } else if (task == SWARM_TASK_RACE) {
                 // rings are regenerated AFTER the targets are set: the target is the previous episode's ring 0
                 float ring[6];
-                sw_load_ring(d, e, 0, ring);
+                load_ring(e, 0, ring);
                 g.tpos[0] = ring[0]; g.tpos[1] = ring[1]; g.tpos[2] = ring[2];
                 g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
             } else {
@@ -908,6 +956,11 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                 prev[0] = ring[0]; prev[1] = ring[1]; prev[2] = ring[2];
                 d.G0[(size_t)r * d.n + e] = make_float4(ring[0], ring[1], ring[2], ring[3]);
                 d.G1[(size_t)r * d.n + e] = make_float2(ring[4], ring[5]);
+                if (ring_staged) { // the staged copy of this tile follows (the observation below reads ring 0)
+                    float *dst = rstage + ((size_t)(rbuf * d.epc + le) * d.R + r) * 8;
+#pragma unroll
+                    for (int m = 0; m < 6; m++) dst[m] = ring[m];
+                }
                 if (r == 0) { s_ring0[le][0] = ring[0]; s_ring0[le][1] = ring[1]; s_ring0[le][2] = ring[2]; }
             }
         }
@@ -945,7 +998,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         float near[3] = {0.0f, 0.0f, 0.0f};
         if (A > 1) sw_obs_neighbour<STRICT>(&s_now.x[w0], A, a, self, near, guard_hits);
         float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-        if (task == SWARM_TASK_RACE) sw_load_ring(d, e, g.ring_idx, ring);
+        if (task == SWARM_TASK_RACE) load_ring(e, g.ring_idx, ring);
         sw_observe<STRICT>(g, A, near, task == SWARM_TASK_RACE, ring, s_obs + t * SWARM_OBS, 1);
     }
     env_sync();
@@ -966,6 +1019,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
     }
     if constexpr (!ONLY_RESET) {
         if (t == 0 && tile == 0) atomicAdd(&d.ctl->ctas_done, 1u);
+        rbuf ^= 1;
         // a full warp's worth of consumed respawn slots: regenerate them with every lane busy
         __syncwarp();
         const int cnt = s_rcnt[warp];
@@ -989,7 +1043,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
       sw_refill_pass(d, s_rlist[warp], s_rcnt[warp], lane); // the rest of this warp's list
       if (guard_hits) atomicAdd(&s_guard, guard_hits);
       __syncthreads(); // every warp's statistics are in
-      if (t < 8 && s_facc[t] != 0.0f) atomicAdd(&d.ctl->facc[t], (double)s_facc[t]);
+      if (t < 8 && s_iacc[t] != 0ull) atomicAdd(&d.ctl->facc[t], (double)(long long)s_iacc[t] * (1.0 / 1048576.0));
       if (t == 0 && s_guard != 0) atomicAdd(&d.ctl->guard_replays, (unsigned long long)s_guard);
   }
 }
@@ -1093,15 +1147,18 @@ static inline void swarm_vec_reset(SwarmDev &d, uint64_t seed, cudaStream_t st, 
 // persistent step grid: every resident CTA slot of the handle's device, or one CTA per tile when there
 // are fewer tiles.  Called once per handle at create time with the handle's device current: the
 // dynamic shared memory opt-in is per device, and so are the SM count and the occupancy.
+static inline int swarm_step_smem(const SwarmDev &d) { return SW_DYN_SMEM + sw_ring_stage_bytes(d.epc, d.R); }
+
 static inline int swarm_step_setup(const SwarmDev &d, int device, int grid_out[2]) {
     int sms = 0, per_sm[2] = {0, 0};
+    const int smem = swarm_step_smem(d);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(swarm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(swarm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM) != cudaSuccess ||
+    if (cudaFuncSetAttribute(swarm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM + SW_RING_STAGE_MAX) != cudaSuccess ||
+        cudaFuncSetAttribute(swarm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM + SW_RING_STAGE_MAX) != cudaSuccess ||
         cudaFuncSetAttribute(swarm_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
         cudaFuncSetAttribute(swarm_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], swarm_kernel<false, false>, SWARM_BLOCK, SW_DYN_SMEM) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], swarm_kernel<true, false>, SWARM_BLOCK, SW_DYN_SMEM) != cudaSuccess)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], swarm_kernel<false, false>, SWARM_BLOCK, smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], swarm_kernel<true, false>, SWARM_BLOCK, smem) != cudaSuccess)
         return -1;
     const int tiles = swarm_grid(d);
     for (int m = 0; m < 2; m++) {
@@ -1115,8 +1172,9 @@ static inline int swarm_step_setup(const SwarmDev &d, int device, int grid_out[2
 static inline void swarm_vec_step(SwarmDev &dev, const float *actions, int math, int grid, cudaStream_t st, long long *launches) {
     SwarmDev d = dev;
     if (actions) d.act_in = actions;
-    if (math == 1) swarm_kernel<true, false><<<grid, SWARM_BLOCK, SW_DYN_SMEM, st>>>(d);
-    else swarm_kernel<false, false><<<grid, SWARM_BLOCK, SW_DYN_SMEM, st>>>(d);
+    const int smem = swarm_step_smem(d);
+    if (math == 1) swarm_kernel<true, false><<<grid, SWARM_BLOCK, smem, st>>>(d);
+    else swarm_kernel<false, false><<<grid, SWARM_BLOCK, smem, st>>>(d);
     *launches += 1;
 }
 

@@ -148,6 +148,14 @@ int b2d_vec_log(b2d_vec *vec, float out[B2D_LOG_FIELDS], void *cuda_stream);
  * caller may all-reduce (NCCL sum) in place; end synchronises and averages. */
 int b2d_vec_log_begin(b2d_vec *vec, void *cuda_stream, long long **device_sums, int *count);
 int b2d_vec_log_end(b2d_vec *vec, float out[B2D_LOG_FIELDS], void *cuda_stream);
+/* vec_log across the ranks of a multi-GPU job in one call, for hosts without torch.distributed: snapshot, NCCL
+ * all-reduce (sum, int64, in place, on `cuda_stream`) over `nccl_comm` -- an ncclComm_t of the caller's NCCL,
+ * passed as void* so that this header needs no nccl.h -- then the averaging of EB:588-591 on the global sums:
+ * every rank receives the same averages and the global episode count in out[8] (the semantics of EB:564-598
+ * over all shards).  The library does not link NCCL: ncclAllReduce is resolved at run time from the NCCL the
+ * process has loaded (dlsym, falling back to dlopen of libnccl.so.2); B2D_ESTATE when none is found.
+ * nccl_comm == NULL reduces nothing (single rank).  Synchronises the stream. */
+int b2d_vec_log_reduce(b2d_vec *vec, float out[B2D_LOG_FIELDS], void *nccl_comm, void *cuda_stream);
 /* the averaging step of vec_log_end on host sums (kind 0 = race, 1 = swarm): pure host
  * arithmetic, EB:588-591 + my_log; used after a cross-rank reduction of the sums */
 int b2d_log_average(int kind, int max_rings, const long long *sums, int count, float out[B2D_LOG_FIELDS]);

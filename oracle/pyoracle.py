@@ -16,6 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_RACE_SO = os.path.join(HERE, "_ref", "libref_race.so")
 REF_SWARM_SO = os.path.join(HERE, "_ref", "libref_swarm.so")
+REF_ADVANTAGE_SO = os.path.join(HERE, "_ref", "libref_advantage.so")
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 
 RESET_LIBC, RESET_PHILOX, RESET_INJECT = 0, 1, 2
@@ -416,3 +417,27 @@ def puff_advantage(values, rewards, dones, importance, gamma, lam, rho_clip, c_c
     L.orc_puff_advantage(_f(a[0]), _f(a[1]), _f(a[2]), _f(a[3]), _f(adv), _f(prio), rows, horizon, rs, ts,
                          gamma, lam, rho_clip, c_clip)
     return adv, prio
+
+
+def have_ref_advantage():
+    return os.path.exists(REF_ADVANTAGE_SO)
+
+
+_REF_ADV = None
+
+
+def ref_puff_advantage(values, rewards, dones, importance, gamma, lam, rho_clip, c_clip):
+    """The UNMODIFIED reference implementation (pufferlib/extensions/pufferlib.cpp puff_advantage, compiled into
+    oracle/_ref/libref_advantage.so by oracle/Makefile) on row-major [num_steps, horizon] float32 arrays."""
+    global _REF_ADV
+    if _REF_ADV is None:
+        import torch  # noqa: F401  (the reference source registers a torch op: its libraries must be loaded first)
+        L = C.CDLL(REF_ADVANTAGE_SO)
+        L.ref_puff_advantage.restype = None
+        L.ref_puff_advantage.argtypes = [_fp, _fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
+        _REF_ADV = L
+    a = [np.ascontiguousarray(x, np.float32).copy() for x in (values, rewards, dones, importance)]
+    rows, horizon = a[0].shape
+    adv = np.zeros_like(a[0])
+    _REF_ADV.ref_puff_advantage(_f(a[0]), _f(a[1]), _f(a[2]), _f(a[3]), _f(adv), gamma, lam, rho_clip, c_clip, rows, horizon)
+    return adv

@@ -1,9 +1,45 @@
-"""The advantage oracle (oracle/drone_oracle.c orc_puff_advantage = pufferlib.cpp:28-41,63-72) against
-an independent float64 statement of the same recurrence and a literal float32 Python transcription.
-The reference's own test for this op (tests/test_c_advantage.cu) is stale and does not build
-(SURVEY.md section 4): parity for this row is pinned by these two checks only."""
+"""The advantage oracle (oracle/drone_oracle.c orc_puff_advantage = pufferlib.cpp:28-41,63-72).
+
+PINNED against the reference itself: tests/golden/advantage_*.npz hold outputs of the UNMODIFIED
+pufferlib/extensions/pufferlib.cpp (compiled into oracle/_ref/libref_advantage.so by oracle/Makefile, vectors
+written by tests/golden/make_golden_advantage.py); the restatement must reproduce them bit for bit, and where
+oracle/_ref is present the reference is also run live on fresh inputs.  (The reference's own test for this op,
+tests/test_c_advantage.cu, is stale and does not build)  An independent float64 statement
+of the recurrence and a literal float32 transcription stay as cross-checks."""
+import glob
+import os
+
 import numpy as np
 import pytest
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "advantage_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_restatement_reproduces_the_reference_golden_vectors(oracle, path):
+    g = np.load(path)
+    gamma, lam, rho, c = (float(x) for x in g["hyper"])
+    adv, prio = oracle.puff_advantage(g["values"], g["rewards"], g["dones"], g["importance"], gamma, lam, rho, c)
+    assert np.array_equal(adv.view(np.uint32), g["advantages"].view(np.uint32))
+    tm, _ = oracle.puff_advantage(g["values"].T.copy(), g["rewards"].T.copy(), g["dones"].T.copy(), g["importance"].T.copy(),
+                                  gamma, lam, rho, c, time_major=True)
+    assert np.array_equal(tm.T.copy().view(np.uint32), g["advantages"].view(np.uint32))
+
+
+def test_golden_files_exist():
+    assert len(GOLDEN) >= 4
+
+
+def test_restatement_equals_the_live_reference(oracle):
+    """Fresh inputs through the compiled reference source (build container / any box that carries oracle/_ref)."""
+    if not oracle.have_ref_advantage():
+        pytest.skip("oracle/_ref/libref_advantage.so not present")
+    for seed, (rows, horizon) in enumerate([(1, 2), (257, 64), (33, 1), (1000, 128)]):
+        v, r, d, imp = _inputs(rows, horizon, seed=100 + seed)
+        for rho, c in ((1.0, 1.0), (0.8, 1.2)):
+            want = oracle.ref_puff_advantage(v, r, d, imp, 0.99, 0.95, rho, c)
+            adv, _ = oracle.puff_advantage(v, r, d, imp, 0.99, 0.95, rho, c)
+            assert np.array_equal(adv.view(np.uint32), want.view(np.uint32)), (rows, horizon, rho, c)
 
 
 def _inputs(rows, horizon, seed=0):

@@ -1,8 +1,11 @@
-"""b2d_puff_advantage on the GPU against the oracle (the reference's CPU twin restated)."""
+"""b2d_puff_advantage on the GPU against the reference's golden vectors (tests/golden/advantage_*.npz, outputs of
+the unmodified pufferlib/extensions/pufferlib.cpp) and the oracle restatement pinned to them."""
+import os
+
 import numpy as np
 import pytest
 
-from test_advantage_cpu import _inputs
+from test_advantage_cpu import GOLDEN, _inputs
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -23,6 +26,24 @@ def test_strict_bit_exact_both_layouts(oracle, rows, horizon, time_major):
     assert out is adv
     assert np.array_equal(adv.cpu().numpy().view(np.uint32), want.view(np.uint32))
     assert np.array_equal(pr.cpu().numpy().view(np.uint32), prio.view(np.uint32))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+@pytest.mark.parametrize("time_major", [False, True])
+def test_strict_kernel_reproduces_the_reference_golden_vectors(path, time_major):
+    from drone_b200.advantage import compute_puff_advantage
+    g = np.load(path)
+    gamma, lam, rho, c = (float(x) for x in g["hyper"])
+    arrs = [g[k] for k in ("values", "rewards", "dones", "importance")]
+    if time_major:
+        arrs = [np.ascontiguousarray(x.T) for x in arrs]
+    tv, tr, td, ti = (torch.from_numpy(x).cuda() for x in arrs)
+    adv = torch.zeros_like(tv)
+    compute_puff_advantage(tv, tr, td, ti, adv, gamma, lam, rho, c, time_major=time_major, math="strict")
+    got = adv.cpu().numpy()
+    if time_major:
+        got = np.ascontiguousarray(got.T)
+    assert np.array_equal(got.view(np.uint32), g["advantages"].view(np.uint32))
 
 
 def test_fast_math_within_tolerance_and_errors(oracle):

@@ -1,4 +1,5 @@
-"""On-device rollout (BASELINE.json configs[3]): torch MLP policy + env step in a CUDA graph."""
+"""On-device rollout (BASELINE.json configs[3]), two-kernel form: fused policy step + env step, K steps in one CUDA
+graph (policy_impl="fused"; the one-kernel form is covered by tests/test_rollout_kernel_gpu.py)."""
 import numpy as np
 import pytest
 
@@ -16,7 +17,7 @@ def test_graph_rollout_equals_eager_rollout_deterministic_policy():
     for graph in (False, True):
         vec = RaceVec(n, seed=5, math="strict", max_moves=30)
         vec.reset(5)
-        ro = DeviceRollout(vec, policy, horizon=K, use_graph=graph, deterministic=True)
+        ro = DeviceRollout(vec, policy, horizon=K, use_graph=graph, deterministic=True, policy_impl="fused")
         if not graph:
             for _ in range(2):  # the graph path runs two warm-up steps before capture
                 ro._one_step(0)
@@ -43,7 +44,7 @@ def test_stochastic_rollout_statistics_and_contract():
         policy.decoder_logstd.fill_(-0.5)
     vec = RaceVec(n, seed=2)
     vec.reset(2)
-    ro = DeviceRollout(vec, policy, horizon=K, use_graph=True)
+    ro = DeviceRollout(vec, policy, horizon=K, use_graph=True, policy_impl="fused")
     ro.collect()
     first = ro.actions.clone()
     ro.collect()
