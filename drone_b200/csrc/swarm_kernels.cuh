@@ -202,7 +202,7 @@ __device__ __noinline__ void sw_draw_params(const SwarmDev &d, uint32_t env, uin
     drone_params_from_draws(u, 0.1f, 0.4f, p); // size ~ U(0.1, 0.4): R/drone_swarm.h:387
 }
 
-__device__ __forceinline__ void sw_draw_box(const SwarmDev &d, uint32_t env, uint32_t who, uint32_t ordinal, uint32_t item,
+__device__ __noinline__ void sw_draw_box(const SwarmDev &d, uint32_t env, uint32_t who, uint32_t ordinal, uint32_t item,
                                             uint32_t attempt, float bx, float by, float bz, float out[3]) {
     const uint4 w = sw_words(d, env, who, ordinal, item, attempt);
     out[0] = lerp_u(-bx, bx, unit_from_word(w.x)).v;
@@ -289,6 +289,22 @@ __device__ __noinline__ float sw_nearest_strict_call(const float *w, int A, int 
     return r;
 }
 
+// odd A (not a performance target): one candidate at a time, window offsets from a itself; out of line to keep
+// the step kernel's hot loop short.  keys = false: x = smallest squared-distance bits; keys = true: (smallest,
+// second smallest) key = squared distance with the window offset in its 7 low mantissa bits.
+__device__ __noinline__ uint2 sw_scan_odd(const float *w, int A, int a, float sx, float sy, float sz, bool keys) {
+    unsigned int best = 0x7f800000u, second = 0x7f800000u;
+    for (int c = 1; c < A; c++) {
+        const float *src = w + a + c;
+        const float dx = src[0] - sx, dy = src[SW_WIN] - sy, dz = src[2 * SW_WIN] - sz;
+        const unsigned int bits = __float_as_uint(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        const unsigned int k0 = keys ? ((bits & ~127u) | (unsigned int)c) : bits;
+        second = min(second, max(best, k0));
+        best = min(best, k0);
+    }
+    return make_uint2(best, second);
+}
+
 // Fast, distance only (the reward needs no identity, R/drone_swarm.h:347-352): the window sweep above,
 // two candidates per iteration on packed FP32x2, the minimum of the squared distances as one 3-input
 // integer min per pair (non-negative floats order like their bit patterns).  Exact minimum of the
@@ -314,11 +330,7 @@ __device__ __forceinline__ float sw_nearest_dist_fast(const float *w, int A, int
             best = __vimin3_u32(best, __float_as_uint(d2.x), __float_as_uint(d2.y));
         }
     } else {
-        for (int c = 1; c < A; c++) {
-            const float *src = w + a + c;
-            const float dx = src[0] - self[0], dy = src[SW_WIN] - self[1], dz = src[2 * SW_WIN] - self[2];
-            best = min(best, __float_as_uint(fmaf(dz, dz, fmaf(dy, dy, dx * dx))));
-        }
+        best = sw_scan_odd(w, A, a, self[0], self[1], self[2], false).x;
     }
     return best >= 0x7f800000u ? 999999.0f : sqrtf(__uint_as_float(best));
 }
@@ -357,14 +369,9 @@ __device__ __forceinline__ void sw_nearest_fast(const float *w, int A, int a, co
             best = min(best, lo);
         }
     } else {
-        for (int c = 1; c < A; c++) { // odd A: one candidate at a time, window offsets from a itself
-            const float *src = w + a + c;
-            const float dx = src[0] - self[0], dy = src[SW_WIN] - self[1], dz = src[2 * SW_WIN] - self[2];
-            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            const unsigned int k0 = (__float_as_uint(d2) & ~CODE_MASK) | (unsigned int)c;
-            second = min(second, max(best, k0));
-            best = min(best, k0);
-        }
+        const uint2 bs = sw_scan_odd(w, A, a, self[0], self[1], self[2], true);
+        best = bs.x;
+        second = bs.y;
     }
     ambiguous = second < KEY_NONE && (second & ~CODE_MASK) - (best & ~CODE_MASK) <= 2u * (CODE_MASK + 1u);
     if (best >= KEY_NONE) return;
@@ -395,6 +402,16 @@ __device__ __forceinline__ float sw_reward_distance(const float *w, int A, int a
         }
         return nd;
     }
+}
+
+// the same, out of line: the scans of the rare paths (respawn, env-wide reset)
+template <bool STRICT>
+__device__ __noinline__ float sw_reward_distance_cold(const float *w, int A, int a, float sx, float sy, float sz, int *guard_hits) {
+    const float self[3] = {sx, sy, sz};
+    int hits = 0;
+    const float nd = sw_reward_distance<STRICT>(w, A, a, self, hits);
+    *guard_hits += hits;
+    return nd;
 }
 
 // nearest neighbour's POSITION for compute_observations (R/drone_swarm.h:187-196)
@@ -603,6 +620,136 @@ __device__ __noinline__ void sw_refill_pass(const SwarmDev &d, const int2 *list,
 __global__ void __launch_bounds__(128) swarm_fill_slots_kernel(const __grid_constant__ SwarmDev d) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < d.rows) sw_generate_slot(d, k, __float_as_uint(d.T[k].y) + 1u);
+}
+
+// barrier over the threads of one env (see swarm_kernel): warp / named barrier / CTA
+__device__ __forceinline__ void sw_env_sync(int sync_mode, int le, int grp_size) {
+    if (sync_mode == 1) __syncwarp();
+    else if (sync_mode == 2) asm volatile("bar.sync %0, %1;" ::"r"(1 + le), "r"(grp_size) : "memory");
+    else __syncthreads();
+}
+
+struct SwResetCtx {
+    SwarmAgent g;
+    int tick, task;
+    uint32_t env_episode;
+    bool do_reset, params_dirty;
+    int guard_hits;
+};
+
+// c_reset of the swarm env (R/drone_swarm.h:401-443) for the envs of this barrier group whose horizon is up
+// (do_reset); called by every thread of the group.  rings_le: the env's staged rings in shared memory, or nullptr.
+template <bool STRICT, bool ONLY_RESET>
+__device__ __noinline__ void sw_reset_phase(const SwarmDev &d, SwResetCtx *c, SwarmWin *s_trail, float (*s_ring0)[3], float *rings_le,
+                                            int le, int a, int w0, int e, const float *pay_agent, const float *pay_env,
+                                            int sync_mode, int grp_size) {
+    const int A = d.A;
+    const bool inject = d.reset_mode == 1;
+    const uint32_t genv = d.env_id_base + (uint32_t)e;
+    SwarmAgent g = c->g;
+    int tick = c->tick, task = c->task, guard_hits = 0;
+    uint32_t env_episode = c->env_episode;
+    const bool do_reset = c->do_reset;
+    bool params_dirty = c->params_dirty;
+    float first[3] = {0.0f, 0.0f, 0.0f}, np[13];
+    if (do_reset) {
+        tick = 0;
+        env_episode = ONLY_RESET ? 0u : env_episode + 1u;
+        if (inject) {
+            task = (int)pay_env[1];
+#pragma unroll
+            for (int m = 0; m < 13; m++) np[m] = pay_agent[16 + m];
+            first[0] = pay_agent[29]; first[1] = pay_agent[30]; first[2] = pay_agent[31];
+        } else {
+            const uint4 w = sw_words(d, genv, 0xFFFF0000u, env_episode, 0u, 0u);
+            task = ((w.x >> 1) % 4u) ? SWARM_TASK_RACE : (int)((w.y >> 1) % 7u);
+            sw_draw_params(d, genv, (uint32_t)a, env_episode, np);
+            sw_draw_box(d, genv, (uint32_t)a, env_episode, 4u, 0u, 29.0f, 29.0f, 9.0f, first);
+        }
+        s_trail->put(w0 + 2 * A + a, first[0], first[1], first[2]);
+    }
+    sw_env_sync(sync_mode, le, grp_size);
+    if (do_reset) {
+        // reset_agent: the reward is computed against the STALE target and half-reset neighbours
+        sw_respawn_state(g, np, first);
+        params_dirty = true;
+        float nd = 0.0f;
+        if (A > 1 && task != SWARM_TASK_RACE) nd = sw_reward_distance<STRICT>(&s_trail->x[w0 + A], A, a, first, guard_hits);
+        sw_reward<STRICT>(g, first, task != SWARM_TASK_RACE, A, nd);
+        // set_target: R/drone_swarm.h:234-333
+        if (inject) {
+#pragma unroll
+            for (int m = 0; m < 3; m++) { g.tpos[m] = pay_agent[32 + m]; g.tvel[m] = pay_agent[35 + m]; }
+        } else if (task == 0 || ((task == 3 || task == 5) && a == 0)) {
+            sw_draw_box(d, genv, (uint32_t)a, env_episode, 5u, 0u, 29.0f, 29.0f, 9.0f, g.tpos);
+            sw_draw_box(d, genv, (uint32_t)a, env_episode, 6u, 0u, 0.05f, 0.05f, 0.05f, g.tvel);
+        } else if (task == 3 || task == 5) {
+            // follow: agent 0's idle target; congo: the same target advanced 40 moves per link of the chain
+            sw_draw_box(d, genv, 0u, env_episode, 5u, 0u, 29.0f, 29.0f, 9.0f, g.tpos);
+            sw_draw_box(d, genv, 0u, env_episode, 6u, 0u, 0.05f, 0.05f, 0.05f, g.tvel);
+            if (task == 5)
+                for (int m = 0; m < 40 * a; m++) sw_move_target(g.tpos, g.tvel);
+        } else if (task == 1) {
+            g.tpos[0] = first[0]; g.tpos[1] = first[1]; g.tpos[2] = first[2];
+            g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
+        } else if (task == SWARM_TASK_RACE) {
+            // rings are regenerated AFTER the targets are set: the target is the previous episode's ring 0
+            float ring[6];
+            if (rings_le) { for (int m = 0; m < 6; m++) ring[m] = rings_le[m]; } else sw_load_ring(d, e, 0, ring);
+            g.tpos[0] = ring[0]; g.tpos[1] = ring[1]; g.tpos[2] = ring[2];
+            g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
+        } else {
+            const float *f = d.form + ((size_t)(task == 2 ? 0 : (task == 4 ? 1 : 2)) * A + a) * 3;
+            g.tpos[0] = f[0]; g.tpos[1] = f[1]; g.tpos[2] = f[2];
+            g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
+        }
+    }
+    sw_env_sync(sync_mode, le, grp_size); // every agent has read the old ring 0 before the rings are rewritten
+    if (do_reset && a == 0) {
+        float prev[3] = {0.0f, 0.0f, 0.0f};
+        for (int r = 0; r < d.R; r++) {
+            float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (task == SWARM_TASK_RACE) {
+                if (inject) {
+#pragma unroll
+                    for (int m = 0; m < 6; m++) ring[m] = pay_env[2 + 6 * r + m];
+                } else {
+                    for (uint32_t at = 0; at < RESET_MAX_ATTEMPTS; at++) {
+                        const uint4 wa = sw_words(d, genv, 0xFFFF0000u, env_episode, 0x10u + 2u * r, at);
+                        const uint4 wb = sw_words(d, genv, 0xFFFF0000u, env_episode, 0x11u + 2u * r, at);
+                        ring_from_words(wa, wb, 26.0f, 26.0f, 6.0f, ring);
+                        if (r == 0 || !(dist3_exact(ring, prev) < 4.0f)) break;
+                    }
+                }
+            }
+            prev[0] = ring[0]; prev[1] = ring[1]; prev[2] = ring[2];
+            d.G0[(size_t)r * d.n + e] = make_float4(ring[0], ring[1], ring[2], ring[3]);
+            d.G1[(size_t)r * d.n + e] = make_float2(ring[4], ring[5]);
+            if (rings_le) { // the staged copy of this tile follows (the observation below reads ring 0)
+                float *dst = rings_le + r * 8;
+#pragma unroll
+                for (int m = 0; m < 6; m++) dst[m] = ring[m];
+            }
+            if (r == 0) { s_ring0[le][0] = ring[0]; s_ring0[le][1] = ring[1]; s_ring0[le][2] = ring[2]; }
+        }
+    }
+    sw_env_sync(sync_mode, le, grp_size);
+    if (do_reset && task == SWARM_TASK_RACE) {
+        // start at least 2*radius from the first ring; spawn_pos / prev_pos keep the first draw (R/drone_swarm.h:429-439)
+        const float r0[3] = {s_ring0[le][0], s_ring0[le][1], s_ring0[le][2]};
+        float c[3];
+        if (inject) {
+            c[0] = pay_agent[38]; c[1] = pay_agent[39]; c[2] = pay_agent[40];
+        } else {
+            for (uint32_t at = 0; at < RESET_MAX_ATTEMPTS; at++) {
+                sw_draw_box(d, genv, (uint32_t)a, env_episode, 7u, at, 29.0f, 29.0f, 9.0f, c);
+                if (!(dist3_exact(c, r0) < 4.0f)) break;
+            }
+        }
+        g.s[0] = c[0]; g.s[1] = c[1]; g.s[2] = c[2];
+    }
+
+    c->g = g; c->tick = tick; c->task = task; c->env_episode = env_episode; c->params_dirty = params_dirty; c->guard_hits = guard_hits;
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -866,7 +1013,11 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                 sw_respawn_state(g, rp, rpos);
                 params_dirty = true;
                 float nd2 = 0.0f;
-                if (A > 1 && task != SWARM_TASK_RACE) nd2 = sw_reward_distance<STRICT>(&s_trail.x[w0], A, a, rpos, guard_hits);
+                if (A > 1 && task != SWARM_TASK_RACE) {
+                    int hits = 0;
+                    nd2 = sw_reward_distance_cold<STRICT>(&s_trail.x[w0], A, a, rpos[0], rpos[1], rpos[2], &hits);
+                    guard_hits += hits;
+                }
                 sw_reward<STRICT>(g, rpos, task != SWARM_TASK_RACE, A, nd2);
             }
             do_reset = horizon;
@@ -879,106 +1030,18 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         }
     }
 
-    // ---- phase 3: env-wide reset (R/drone_swarm.h:401-443), every 1023 ticks for all agents of the env at once
+    // ---- phase 3: env-wide reset (R/drone_swarm.h:401-443), every 1023 ticks for all agents of the env at once.
+    // Out of line (sw_reset_phase): it is a third of the kernel's code and runs once per 1023 steps; the agent
+    // travels through a local copy so that the hot path's registers never have their address taken.
     const int cta_reset = env_any(do_reset);
     if (__builtin_expect(cta_reset, 0)) {
-        float first[3] = {0.0f, 0.0f, 0.0f}, np[13];
-        if (do_reset) {
-            tick = 0;
-            env_episode = ONLY_RESET ? 0u : env_episode + 1u;
-            if (inject) {
-                task = (int)pay_env[1];
-#pragma unroll
-                for (int m = 0; m < 13; m++) np[m] = pay_agent[16 + m];
-                first[0] = pay_agent[29]; first[1] = pay_agent[30]; first[2] = pay_agent[31];
-            } else {
-                const uint4 w = sw_words(d, genv, 0xFFFF0000u, env_episode, 0u, 0u);
-                task = ((w.x >> 1) % 4u) ? SWARM_TASK_RACE : (int)((w.y >> 1) % 7u);
-                sw_draw_params(d, genv, (uint32_t)a, env_episode, np);
-                sw_draw_box(d, genv, (uint32_t)a, env_episode, 4u, 0u, 29.0f, 29.0f, 9.0f, first);
-            }
-            s_trail.put(w0 + 2 * A + a, first[0], first[1], first[2]);
-        }
-        env_sync();
-        if (do_reset) {
-            // reset_agent: the reward is computed against the STALE target and half-reset neighbours
-            sw_respawn_state(g, np, first);
-            params_dirty = true;
-            float nd = 0.0f;
-            if (A > 1 && task != SWARM_TASK_RACE) nd = sw_reward_distance<STRICT>(&s_trail.x[w0 + A], A, a, first, guard_hits);
-            sw_reward<STRICT>(g, first, task != SWARM_TASK_RACE, A, nd);
-            // set_target: R/drone_swarm.h:234-333
-            if (inject) {
-#pragma unroll
-                for (int m = 0; m < 3; m++) { g.tpos[m] = pay_agent[32 + m]; g.tvel[m] = pay_agent[35 + m]; }
-            } else if (task == 0 || ((task == 3 || task == 5) && a == 0)) {
-                sw_draw_box(d, genv, (uint32_t)a, env_episode, 5u, 0u, 29.0f, 29.0f, 9.0f, g.tpos);
-                sw_draw_box(d, genv, (uint32_t)a, env_episode, 6u, 0u, 0.05f, 0.05f, 0.05f, g.tvel);
-            } else if (task == 3 || task == 5) {
-                // follow: agent 0's idle target; congo: the same target advanced 40 moves per link of the chain
-                sw_draw_box(d, genv, 0u, env_episode, 5u, 0u, 29.0f, 29.0f, 9.0f, g.tpos);
-                sw_draw_box(d, genv, 0u, env_episode, 6u, 0u, 0.05f, 0.05f, 0.05f, g.tvel);
-                if (task == 5)
-                    for (int m = 0; m < 40 * a; m++) sw_move_target(g.tpos, g.tvel);
-            } else if (task == 1) {
-                g.tpos[0] = first[0]; g.tpos[1] = first[1]; g.tpos[2] = first[2];
-                g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
-            } else if (task == SWARM_TASK_RACE) {
-                // rings are regenerated AFTER the targets are set: the target is the previous episode's ring 0
-                float ring[6];
-                load_ring(e, 0, ring);
-                g.tpos[0] = ring[0]; g.tpos[1] = ring[1]; g.tpos[2] = ring[2];
-                g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
-            } else {
-                const float *f = d.form + ((size_t)(task == 2 ? 0 : (task == 4 ? 1 : 2)) * A + a) * 3;
-                g.tpos[0] = f[0]; g.tpos[1] = f[1]; g.tpos[2] = f[2];
-                g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
-            }
-        }
-        env_sync(); // every agent has read the old ring 0 before the rings are rewritten
-        if (do_reset && a == 0) {
-            float prev[3] = {0.0f, 0.0f, 0.0f};
-            for (int r = 0; r < d.R; r++) {
-                float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-                if (task == SWARM_TASK_RACE) {
-                    if (inject) {
-#pragma unroll
-                        for (int m = 0; m < 6; m++) ring[m] = pay_env[2 + 6 * r + m];
-                    } else {
-                        for (uint32_t at = 0; at < RESET_MAX_ATTEMPTS; at++) {
-                            const uint4 wa = sw_words(d, genv, 0xFFFF0000u, env_episode, 0x10u + 2u * r, at);
-                            const uint4 wb = sw_words(d, genv, 0xFFFF0000u, env_episode, 0x11u + 2u * r, at);
-                            ring_from_words(wa, wb, 26.0f, 26.0f, 6.0f, ring);
-                            if (r == 0 || !(dist3_exact(ring, prev) < 4.0f)) break;
-                        }
-                    }
-                }
-                prev[0] = ring[0]; prev[1] = ring[1]; prev[2] = ring[2];
-                d.G0[(size_t)r * d.n + e] = make_float4(ring[0], ring[1], ring[2], ring[3]);
-                d.G1[(size_t)r * d.n + e] = make_float2(ring[4], ring[5]);
-                if (ring_staged) { // the staged copy of this tile follows (the observation below reads ring 0)
-                    float *dst = rstage + ((size_t)(rbuf * d.epc + le) * d.R + r) * 8;
-#pragma unroll
-                    for (int m = 0; m < 6; m++) dst[m] = ring[m];
-                }
-                if (r == 0) { s_ring0[le][0] = ring[0]; s_ring0[le][1] = ring[1]; s_ring0[le][2] = ring[2]; }
-            }
-        }
-        env_sync();
-        if (do_reset && task == SWARM_TASK_RACE) {
-            // start at least 2*radius from the first ring; spawn_pos / prev_pos keep the first draw (R/drone_swarm.h:429-439)
-            const float r0[3] = {s_ring0[le][0], s_ring0[le][1], s_ring0[le][2]};
-            float c[3];
-            if (inject) {
-                c[0] = pay_agent[38]; c[1] = pay_agent[39]; c[2] = pay_agent[40];
-            } else {
-                for (uint32_t at = 0; at < RESET_MAX_ATTEMPTS; at++) {
-                    sw_draw_box(d, genv, (uint32_t)a, env_episode, 7u, at, 29.0f, 29.0f, 9.0f, c);
-                    if (!(dist3_exact(c, r0) < 4.0f)) break;
-                }
-            }
-            g.s[0] = c[0]; g.s[1] = c[1]; g.s[2] = c[2];
-        }
+        SwResetCtx c;
+        c.g = g; c.tick = tick; c.task = task; c.env_episode = env_episode; c.do_reset = do_reset; c.params_dirty = params_dirty;
+        c.guard_hits = 0;
+        sw_reset_phase<STRICT, ONLY_RESET>(d, &c, &s_trail, s_ring0, ring_staged ? rstage + ((size_t)(rbuf * d.epc + le) * d.R) * 8 : nullptr,
+                                           le, a, w0, e, pay_agent, pay_env, sync_mode, grp_size);
+        g = c.g; tick = c.tick; task = c.task; env_episode = c.env_episode; params_dirty = c.params_dirty;
+        guard_hits += c.guard_hits;
     }
     if (active) {
         s_now.put(w0 + a, g.s[0], g.s[1], g.s[2]);
