@@ -49,6 +49,26 @@ class PolicyIO(C.Structure):
                 ("store_values", C.c_void_p), ("rows", C.c_int), ("obs_dim", C.c_int), ("row_id_base", C.c_uint32)]
 
 
+class RefDrone(C.Structure):
+    """Memory layout of the reference's `Drone` (dronelib.h:191-247), 208 bytes."""
+    _fields_ = [("pos", C.c_float * 3), ("vel", C.c_float * 3), ("quat", C.c_float * 4), ("omega", C.c_float * 3),
+                ("rpms", C.c_float * 4),
+                ("mass", C.c_float), ("ixx", C.c_float), ("iyy", C.c_float), ("izz", C.c_float), ("arm_len", C.c_float),
+                ("k_thrust", C.c_float), ("k_ang_damp", C.c_float), ("k_drag", C.c_float), ("b_drag", C.c_float),
+                ("gravity", C.c_float), ("max_rpm", C.c_float), ("max_vel", C.c_float), ("max_omega", C.c_float),
+                ("k_mot", C.c_float), ("j_mot", C.c_float),
+                ("spawn_pos", C.c_float * 3), ("prev_pos", C.c_float * 3), ("target_pos", C.c_float * 3),
+                ("target_vel", C.c_float * 3),
+                ("last_abs_reward", C.c_float), ("last_target_reward", C.c_float), ("last_collision_reward", C.c_float),
+                ("episode_return", C.c_float), ("collisions", C.c_float), ("episode_length", C.c_int),
+                ("score", C.c_float), ("ring_idx", C.c_int)]
+
+
+class RefRing(C.Structure):
+    """Memory layout of the reference's `Ring` (dronelib.h:161-166), 44 bytes."""
+    _fields_ = [("pos", C.c_float * 3), ("orientation", C.c_float * 4), ("normal", C.c_float * 3), ("radius", C.c_float)]
+
+
 class RolloutStore(C.Structure):
     _fields_ = [("observations", C.c_void_p), ("actions", C.c_void_p), ("logprobs", C.c_void_p), ("rewards", C.c_void_p),
                 ("terminals", C.c_void_p), ("values", C.c_void_p)]
@@ -82,6 +102,12 @@ SYMBOLS = {
     "b2d_get_state": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_float)]),
     "b2d_put_state": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_float)]),
     "b2d_observe": (C.c_int, [_P, _P]),
+    "b2d_race_blob_to_ref": (C.c_int, [C.POINTER(C.c_float), C.c_int, C.POINTER(RefDrone), C.POINTER(RefRing), C.POINTER(C.c_int),
+                                       C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    "b2d_swarm_blob_to_ref": (C.c_int, [C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(RefDrone), C.POINTER(RefRing),
+                                        C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b2d_export_ref": (C.c_int, [_P, C.c_int, C.POINTER(RefDrone), C.POINTER(RefRing), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_float)]),
     "b2d_set_math": (C.c_int, [_P, C.c_int]),
     "b2d_set_reset_mode": (C.c_int, [_P, C.c_int]),
     "b2d_set_reset_payload": (C.c_int, [_P, C.POINTER(C.c_float)]),

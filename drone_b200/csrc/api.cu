@@ -16,7 +16,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 using namespace b2d;
@@ -38,6 +42,85 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 enum { KIND_RACE = 0, KIND_SWARM = 1 };
+
+// dst = clamp(src, -1, 1) with the reference's branch order (a NaN stays a NaN), DR/dronelib.h:73-79,437
+static void clamp_copy(float *dst, const float *src, size_t count) {
+    for (size_t k = 0; k < count; k++) {
+        const float a = src[k];
+        dst[k] = a < -1.0f ? -1.0f : (a > 1.0f ? 1.0f : a);
+    }
+}
+
+// Host-side copy of the action batch into the caller-visible (pinned) action buffer, optionally clamping.
+// One core moves 16 MB in 1.3 ms (2.7 ms with the clamp) on the bench box -- as long as the whole PCIe step --
+// so the copy of each chunk is shared by a few threads that live as long as the handle.
+class CopyPool {
+public:
+    explicit CopyPool(int workers) {
+        for (int w = 0; w < workers; w++) threads_.emplace_back([this, w] { loop(w); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+            gen_++;
+        }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    void copy(float *dst, const float *src, size_t count, bool clamp) {
+        const size_t parts = threads_.size() + 1;
+        if (threads_.empty() || count < (1u << 16)) { // small: not worth a wake-up
+            part(dst, src, count, clamp);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> g(m_);
+            dst_ = dst; src_ = src; count_ = count; clamp_ = clamp;
+            pending_.store((int)threads_.size());
+            gen_++;
+        }
+        cv_.notify_all();
+        const size_t per = (count / parts + 15) & ~(size_t)15;
+        const size_t lo = per * threads_.size();
+        if (lo < count) part(dst + lo, src + lo, count - lo, clamp); // the caller's own share: the tail
+        while (pending_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+    }
+
+private:
+    static void part(float *dst, const float *src, size_t n, bool clamp) {
+        if (clamp) clamp_copy(dst, src, n);
+        else if (dst != src) memcpy(dst, src, n * sizeof(float));
+    }
+    void loop(int w) {
+        unsigned long long seen = 0;
+        for (;;) {
+            float *dst; const float *src; size_t count; bool clamp;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                dst = dst_; src = src_; count = count_; clamp = clamp_;
+            }
+            const size_t parts = threads_.size() + 1;
+            const size_t per = (count / parts + 15) & ~(size_t)15;
+            const size_t lo = per * (size_t)w, hi = lo + per < count ? lo + per : count;
+            if (lo < hi) part(dst + lo, src + lo, hi - lo, clamp);
+            pending_.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+    float *dst_ = nullptr;
+    const float *src_ = nullptr;
+    size_t count_ = 0;
+    bool clamp_ = false;
+    std::atomic<int> pending_{0};
+};
 
 // Every entry point that touches the device runs with the handle's device current and restores the
 // caller's device on the way out (a handle on cuda:1 may be stepped while cuda:0 is current).
@@ -66,6 +149,7 @@ struct b2d_vec {
     int num_envs, num_agents /* rows */, obs_dim, blob_floats, payload_floats;
     int math, write_clamped;
     bool host_clamp; // host buffers: leave clamp(action, -1, 1) in the caller's action array like DR/dronelib.h:437
+    CopyPool *pool;  // host buffers: threads that share the action copy
     int step_ctas;   // race: CTAs of an overlapped (tape) launch = the largest grid; swarm: unused
     int single_ctas; // race: CTAs of a launch that runs alone
     RaceDev race;
@@ -138,6 +222,11 @@ static int setup_buffers(b2d_vec *v, const b2d_buffers *ext) {
     v->has_host = ext && ext->location == B2D_MEM_HOST;
     if (v->has_host) {
         v->host = *ext;
+        unsigned int hw = std::thread::hardware_concurrency();
+        int workers = rows >= (1u << 18) ? (hw >= 8 ? 3 : (hw >= 4 ? 1 : 0)) : 0; // small vectors copy inline
+        if (const char *env = getenv("B2D_COPY_THREADS")) workers = atoi(env) > 0 ? atoi(env) - 1 : 0;
+        v->pool = new (std::nothrow) CopyPool(workers);
+        if (!v->pool) return fail(B2D_ENOMEM, "out of host memory");
         // page-lock the caller's buffers for the life of the handle (they must outlive it anyway:
         // ownership as in the reference).  Already-pinned memory reports an error that is ignored.
         void *ptrs[5] = {ext->observations, ext->actions, ext->rewards, ext->terminals, ext->truncations};
@@ -410,6 +499,8 @@ extern "C" int b2d_vec_close(b2d_vec *v) {
         for (int k = 0; k < 5; k++)
             if (v->registered[k] && ptrs[k]) cudaHostUnregister(ptrs[k]);
     }
+    delete v->pool;
+    v->pool = nullptr;
     for (void *p : v->allocs) cudaFree(p);
     if (v->d_payload) cudaFree(v->d_payload);
     if (v->d_blob_tmp) cudaFree(v->d_blob_tmp);
@@ -537,14 +628,6 @@ extern "C" int b2d_vec_step_tape(b2d_vec *v, const float *device_tape, int tape_
 // the copy streams.  `host_actions` (optional) are copied into the caller-visible action buffer
 // like the reference's wrapper does (`self.actions[:] = actions`), chunk by chunk, so that the
 // 1 ms CPU copy of 16 MB hides behind the transfers as well.
-// dst = clamp(src, -1, 1) with the reference's branch order (a NaN stays a NaN), DR/dronelib.h:73-79,437
-static void clamp_copy(float *dst, const float *src, size_t count) {
-    for (size_t k = 0; k < count; k++) {
-        const float a = src[k];
-        dst[k] = a < -1.0f ? -1.0f : (a > 1.0f ? 1.0f : a);
-    }
-}
-
 static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st) {
     const size_t rows = (size_t)v->num_agents;
     const bool copy_in = host_actions && host_actions != v->host.actions;
@@ -566,8 +649,8 @@ static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st
         cudaStream_t cs = v->copy_streams[j & 1];
         // the CPU copy of this chunk's actions overlaps the transfers of the chunks already in flight
         // (with host_clamp the caller-visible buffer receives the clamped values, as the reference leaves them)
-        if (v->host_clamp) clamp_copy(v->host.actions + r0 * 4, (copy_in ? host_actions : v->host.actions) + r0 * 4, nr * 4);
-        else if (copy_in) memcpy(v->host.actions + r0 * 4, host_actions + r0 * 4, nr * 4 * sizeof(float));
+        if (v->host_clamp || copy_in)
+            v->pool->copy(v->host.actions + r0 * 4, (copy_in ? host_actions : v->host.actions) + r0 * 4, nr * 4, v->host_clamp);
         CUDA_TRY(cudaMemcpyAsync(v->dev.actions + r0 * 4, v->host.actions + r0 * 4, nr * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
         int rc = step_impl(v, nullptr, st, false, (int)bnd[j], (int)bnd[j + 1], j == 0, j == nchunks - 1);
         if (rc) return rc;
@@ -808,6 +891,76 @@ extern "C" int b2d_put_state(b2d_vec *v, const int *env_ids, int n, const float 
     if ((rc = launch_check("unpack_kernel"))) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
     return B2D_OK;
+}
+
+// ---------------------------------------------------------------- render / checkpoint bridge
+static_assert(sizeof(b2d_ref_drone) == 208, "b2d_ref_drone must match the reference's Drone (dronelib.h:191-247)");
+static_assert(sizeof(b2d_ref_ring) == 44, "b2d_ref_ring must match the reference's Ring (dronelib.h:161-166)");
+
+static void ref_ring_from(const float *g, b2d_ref_ring *r) {
+    r->pos[0] = g[0]; r->pos[1] = g[1]; r->pos[2] = g[2];
+    r->normal[0] = g[3]; r->normal[1] = g[4]; r->normal[2] = g[5];
+    const bool none = g[3] == 0.0f && g[4] == 0.0f && g[5] == 0.0f; // a zeroed ring of a non-race swarm task
+    r->radius = none ? 0.0f : 2.0f;
+    // shortest rotation taking +z to the normal: q = (1 + n.z, z x n) normalised
+    float w = 1.0f + g[5], x = -g[4], y = g[3], z = 0.0f;
+    const float n2 = w * w + x * x + y * y;
+    if (none || n2 < 1e-12f) { w = none ? 1.0f : 0.0f; x = none ? 0.0f : 1.0f; y = 0.0f; }
+    else { const float inv = 1.0f / sqrtf(n2); w *= inv; x *= inv; y *= inv; }
+    r->orientation[0] = w; r->orientation[1] = x; r->orientation[2] = y; r->orientation[3] = z;
+}
+
+// b[0:17] state, b[17:30] the 13 randomised params (blob order)
+static void ref_drone_core(const float *b, b2d_ref_drone *d) {
+    memset(d, 0, sizeof(*d));
+    for (int k = 0; k < 3; k++) { d->pos[k] = b[k]; d->vel[k] = b[3 + k]; d->omega[k] = b[10 + k]; d->prev_pos[k] = b[k]; }
+    for (int k = 0; k < 4; k++) { d->quat[k] = b[6 + k]; d->rpms[k] = b[13 + k]; }
+    d->mass = b[17]; d->ixx = b[18]; d->iyy = b[19]; d->izz = b[20]; d->arm_len = b[21]; d->k_thrust = b[22];
+    d->k_ang_damp = b[23]; d->k_drag = b[24]; d->b_drag = b[25]; d->gravity = b[26]; d->max_rpm = b[27];
+    d->max_vel = 50.0f; d->max_omega = 50.0f; // BASE_MAX_VEL / BASE_MAX_OMEGA, DR/dronelib.h:286-287
+    d->k_mot = b[28]; d->j_mot = b[29];
+}
+
+extern "C" int b2d_race_blob_to_ref(const float *blob, int max_rings, b2d_ref_drone *drone, b2d_ref_ring *rings, int *tick,
+                                    int *ring_idx, float *episodic_return) {
+    if (!blob || !drone || !rings || max_rings <= 0) return fail(B2D_EINVAL, "b2d_race_blob_to_ref: bad argument");
+    ref_drone_core(blob, drone);
+    drone->ring_idx = 0; // the race env keeps ring_idx / score on DroneRace, not on the Drone
+    if (tick) *tick = (int)blob[30];
+    if (ring_idx) *ring_idx = (int)blob[31];
+    if (episodic_return) *episodic_return = blob[32];
+    for (int r = 0; r < max_rings; r++) ref_ring_from(blob + B2D_RACE_BLOB + 6 * r, &rings[r]);
+    return B2D_OK;
+}
+
+extern "C" int b2d_swarm_blob_to_ref(const float *blob, int num_agents, int max_rings, b2d_ref_drone *drones, b2d_ref_ring *rings,
+                                     int *tick, int *task) {
+    if (!blob || !drones || !rings || num_agents <= 0 || max_rings <= 0) return fail(B2D_EINVAL, "b2d_swarm_blob_to_ref: bad argument");
+    for (int a = 0; a < num_agents; a++) {
+        const float *b = blob + (size_t)a * B2D_SWARM_AGENT_BLOB;
+        b2d_ref_drone *d = &drones[a];
+        ref_drone_core(b, d);
+        for (int k = 0; k < 3; k++) { d->spawn_pos[k] = b[30 + k]; d->target_pos[k] = b[33 + k]; d->target_vel[k] = b[36 + k]; }
+        d->last_abs_reward = b[39]; d->last_target_reward = b[40]; d->last_collision_reward = b[41];
+        d->episode_return = b[42]; d->collisions = b[43]; d->episode_length = (int)b[44]; d->score = b[45]; d->ring_idx = (int)b[46];
+    }
+    const float *eb = blob + (size_t)num_agents * B2D_SWARM_AGENT_BLOB;
+    if (tick) *tick = (int)eb[0];
+    if (task) *task = (int)eb[1];
+    for (int r = 0; r < max_rings; r++) ref_ring_from(eb + 2 + 6 * r, &rings[r]);
+    return B2D_OK;
+}
+
+extern "C" int b2d_export_ref(b2d_vec *v, int env_id, b2d_ref_drone *drones, b2d_ref_ring *rings, int *tick, int *aux,
+                              float *episodic_return) {
+    if (!v || !drones || !rings) return fail(B2D_EINVAL, "b2d_export_ref: null argument");
+    if (env_id < 0 || env_id >= v->num_envs) return fail(B2D_EINVAL, "env id out of range");
+    std::vector<float> blob((size_t)v->blob_floats);
+    int rc = b2d_get_state(v, &env_id, 1, blob.data());
+    if (rc) return rc;
+    if (v->kind == KIND_RACE) return b2d_race_blob_to_ref(blob.data(), v->race.max_rings, drones, rings, tick, aux, episodic_return);
+    if (episodic_return) *episodic_return = 0.0f;
+    return b2d_swarm_blob_to_ref(blob.data(), v->swarm.A, v->swarm.max_rings, drones, rings, tick, aux);
 }
 
 extern "C" int b2d_observe(b2d_vec *v, void *stream) {

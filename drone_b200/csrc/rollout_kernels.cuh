@@ -169,6 +169,31 @@ __device__ __forceinline__ void ro_tmem_st32(uint32_t taddr, const uint32_t (&r)
         "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ void ro_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void ro_tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void ro_gelu16(uint32_t (&r)[16]) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const float2 g = gelu2(make_float2(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1])));
+        r[2 * q] = __float_as_uint(g.x);
+        r[2 * q + 1] = __float_as_uint(g.y);
+    }
+}
 __device__ __forceinline__ void ro_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -496,27 +521,26 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
                     if (a.st_term) __stcs(&a.st_term[(size_t)k * d.n + i], prev_term);
                 }
             }
-            // noise of this (row, call): independent of the GEMMs, computed while they run
-            float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (!a.deterministic) policy_noise(a.row_id_base + (uint32_t)i, call0 + (unsigned int)k, a.seed_lo, a.seed_hi, z);
-
-            RO_TICK(2) // experience stores + noise (overlaps the encoder GEMM)
+            RO_TICK(2) // experience stores (overlap the encoder GEMM)
             // ---- 2. hidden = GELU(encoder(obs)): accumulator row -> registers -> activations back into the same columns
             ro_mbar_wait(&s_mbar[0], phase);
             ro_tc_fence_after();
             RO_TICK(3) // wait for the encoder GEMM
-#pragma unroll 1
-            for (int c = 0; c < RO_HIDDEN / 32; c++) {
-                uint32_t r[32];
-                ro_tmem_ld32(tm_h + lane_base + c * 32, r);
+            {   // 16 columns at a time, the next chunk's tcgen05.ld in flight while this one is computed
+                uint32_t ra[16], rb[16];
+                ro_tmem_ld16(tm_h + lane_base, ra);
                 ro_tc_wait_ld();
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    const float2 g = gelu2(make_float2(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1])));
-                    r[2 * q] = __float_as_uint(g.x);
-                    r[2 * q + 1] = __float_as_uint(g.y);
+#pragma unroll 1
+                for (int c = 0; c < RO_HIDDEN / 32; c++) {
+                    ro_tmem_ld16(tm_h + lane_base + c * 32 + 16, rb);
+                    ro_gelu16(ra);
+                    ro_tmem_st16(tm_h + lane_base + c * 32, ra);
+                    ro_tc_wait_ld();
+                    if (c + 1 < RO_HIDDEN / 32) ro_tmem_ld16(tm_h + lane_base + c * 32 + 32, ra);
+                    ro_gelu16(rb);
+                    ro_tmem_st16(tm_h + lane_base + c * 32 + 16, rb);
+                    ro_tc_wait_ld();
                 }
-                ro_tmem_st32(tm_h + lane_base + c * 32, r);
             }
             RO_TICK(4) // GELU
             ro_tc_wait_st();
@@ -531,6 +555,9 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
                     ro_mma_ts(tm_o, tm_h + j * 8, ro_umma_desc(sB2 + j * 2 * (RO_N2 * 16), RO_N2 * 16, 128), IDESC2, j > 0 ? 1u : 0u);
                 ro_tc_commit(&s_mbar[1]);
             }
+            // noise of this (row, call): independent of the GEMMs, computed while the head GEMM runs
+            float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (!a.deterministic) policy_noise(a.row_id_base + (uint32_t)i, call0 + (unsigned int)k, a.seed_lo, a.seed_hi, z);
             ro_mbar_wait(&s_mbar[1], phase);
             ro_tc_fence_after();
             phase ^= 1u;

@@ -845,7 +845,6 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
     const int e = tile * d.epc + le;
     const bool active = le < d.epc && e < d.n;
     const int k = e * A + a;
-    const uint32_t genv = d.env_id_base + (uint32_t)e;
     const float *pay_agent = d.payload ? d.payload + (size_t)e * pay_stride + (size_t)a * SWARM_AGENT_PAYLOAD : nullptr;
     const float *pay_env = d.payload ? d.payload + (size_t)e * pay_stride + (size_t)A * SWARM_AGENT_PAYLOAD : nullptr;
 

@@ -185,6 +185,41 @@ int b2d_put_state(b2d_vec *vec, const int *env_ids, int n, const float *host_blo
 /* recompute observation rows from the current state (after put_state) */
 int b2d_observe(b2d_vec *vec, void *cuda_stream);
 
+/* ---- render / checkpoint bridge ----------------------------------------
+ * Host structs with the memory layout of the reference's `Drone` (DR/dronelib.h:191-247: State, Params,
+ * spawn/prev/target vectors, reward bookkeeping; 208 bytes) and `Ring` (DR/dronelib.h:161-166; 44 bytes), so
+ * that a device env can be handed to code written against the reference's structs -- its viewer
+ * (c_render, DR/drone_race.h:331-462; the raylib client is outside this library), compute_observations, a
+ * debugger.  Fields the device does not keep are filled consistently: prev_pos = pos, max_vel = max_omega =
+ * 50 (DR/dronelib.h:286-287), ring radius = 2 (DR/drone_race.h:135), ring orientation = the shortest rotation
+ * that turns +z into the ring normal (the reference's is a uniformly random quaternion with the same normal;
+ * it only matters to the viewer).  race spawn_pos / target_pos / target_vel are unused by the reference: zero. */
+typedef struct b2d_ref_drone {
+    float pos[3], vel[3], quat[4] /* w,x,y,z */, omega[3], rpms[4];                             /* State  */
+    float mass, ixx, iyy, izz, arm_len, k_thrust, k_ang_damp, k_drag, b_drag, gravity, max_rpm,
+          max_vel, max_omega, k_mot, j_mot;                                                    /* Params */
+    float spawn_pos[3], prev_pos[3], target_pos[3], target_vel[3];
+    float last_abs_reward, last_target_reward, last_collision_reward, episode_return, collisions;
+    int episode_length;
+    float score;
+    int ring_idx;
+} b2d_ref_drone;
+typedef struct b2d_ref_ring {
+    float pos[3], orientation[4] /* w,x,y,z */, normal[3], radius;
+} b2d_ref_ring;
+/* state blob (b2d_get_state layout) -> reference structs; pure host arithmetic, no device needed.
+ * race: one drone, `max_rings` rings, *tick / *ring_idx / *episodic_return = the DroneRace scalars
+ * (score == ring_idx, moves_left == max_moves - tick, DR/drone_race.h:31-53).
+ * swarm: `num_agents` drones, `max_rings` rings (radius 0 for a zeroed ring of a non-race task), *tick, *task. */
+int b2d_race_blob_to_ref(const float *blob, int max_rings, b2d_ref_drone *drone, b2d_ref_ring *rings, int *tick,
+                         int *ring_idx, float *episodic_return);
+int b2d_swarm_blob_to_ref(const float *blob, int num_agents, int max_rings, b2d_ref_drone *drones, b2d_ref_ring *rings,
+                          int *tick, int *task);
+/* b2d_get_state of one env + the conversion above (synchronous).  aux = ring_idx (race) / task (swarm);
+ * episodic_return may be NULL. */
+int b2d_export_ref(b2d_vec *vec, int env_id, b2d_ref_drone *drones, b2d_ref_ring *rings, int *tick, int *aux,
+                   float *episodic_return);
+
 /* ---- parity / configuration hooks --------------------------------------------- */
 int b2d_set_math(b2d_vec *vec, int math);
 int b2d_set_reset_mode(b2d_vec *vec, int reset_mode);

@@ -137,3 +137,18 @@ void refrace_close(void *vp) {
 }
 
 int refrace_sizeof_env(void) { return (int)sizeof(DroneRace); }
+int refrace_sizeof_drone(void) { return (int)sizeof(Drone); }
+int refrace_sizeof_ring(void) { return (int)sizeof(Ring); }
+
+/* the reference's compute_observations on caller-provided reference structs (the render / checkpoint bridge of
+ * include/b200drone.h hands out exactly these): a DroneRace is assembled around them, nothing else is touched */
+void refrace_observe_structs(const Drone *drone, Ring *rings, int max_rings, int ring_idx, float *obs29) {
+    DroneRace env;
+    memset(&env, 0, sizeof(env));
+    env.observations = obs29;
+    env.max_rings = max_rings;
+    env.ring_idx = ring_idx;
+    env.ring_buffer = rings;
+    env.drone = *drone;
+    compute_observations(&env);
+}

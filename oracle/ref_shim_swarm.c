@@ -152,3 +152,18 @@ void refswarm_close(void *vp) {
 }
 
 int refswarm_sizeof_env(void) { return (int)sizeof(DroneSwarm); }
+int refswarm_sizeof_drone(void) { return (int)sizeof(Drone); }
+int refswarm_sizeof_ring(void) { return (int)sizeof(Ring); }
+
+/* the reference's compute_observations on caller-provided reference structs (see ref_shim_race.c) */
+void refswarm_observe_structs(Drone *agents, int num_agents, Ring *rings, int max_rings, int task, float *obs) {
+    DroneSwarm env;
+    memset(&env, 0, sizeof(env));
+    env.observations = obs;
+    env.num_agents = num_agents;
+    env.agents = agents;
+    env.max_rings = max_rings;
+    env.ring_buffer = rings;
+    env.task = task;
+    compute_observations(&env);
+}

@@ -124,8 +124,8 @@ def test_noise_stream_bits_calls_and_graph_replay(precision):
 
 
 def test_gelu_accuracy_over_the_whole_range():
-    """value = GELU(x) through a one-hot encoder row: |error| <= 2e-7 * max(1, |x|) (the erf
-    approximation is within 1e-7 absolute of erf, the float32 rounding floor)."""
+    """value = GELU(x) through a one-hot encoder row: |error| <= 3e-7 * max(1, |x|): 2.5 float32 ulps of 1 (the
+    approximation itself is within 8e-8 of GELU in exact arithmetic; the rest is float32 rounding)."""
     from math import erf, sqrt
     rows = 200001
     p, obs, rew, term, env_act, fused = _setup(rows, precision="fp32")
@@ -142,7 +142,7 @@ def test_gelu_accuracy_over_the_whole_range():
     x = obs[:, 2].cpu().numpy().astype(np.float64)
     exact = np.array([0.5 * v * (1.0 + erf(v / sqrt(2.0))) for v in x])
     err = np.abs(vals.cpu().numpy() - exact)
-    assert (err <= 2e-7 * np.maximum(1.0, np.abs(x))).all(), err.max()
+    assert (err <= 3e-7 * np.maximum(1.0, np.abs(x))).all(), err.max()
     tg = torch.nn.functional.gelu(obs[:, 2]).cpu().numpy()  # torch's own float32 GELU is not closer
     assert err.max() <= 4 * np.abs(tg - exact).max() + 2e-7
 
