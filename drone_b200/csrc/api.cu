@@ -43,21 +43,22 @@ static int fail(int code, const char *fmt, ...) {
 
 enum { KIND_RACE = 0, KIND_SWARM = 1 };
 
-// dst = clamp(src, -1, 1) with the reference's branch order (a NaN stays a NaN), DR/dronelib.h:73-79,437
-static void clamp_copy(float *dst, const float *src, size_t count) {
-    for (size_t k = 0; k < count; k++) {
-        const float a = src[k];
-        dst[k] = a < -1.0f ? -1.0f : (a > 1.0f ? 1.0f : a);
-    }
-}
+// dst = clamp(src, -1, 1), a NaN stays a NaN (DR/dronelib.h:73-79,437): host_copy.c (SIMD, memcpy speed)
+extern "C" void b2d_clamp_copy(float *dst, const float *src, size_t n);
+static void clamp_copy(float *dst, const float *src, size_t count) { b2d_clamp_copy(dst, src, count); }
 
 // Host-side copy of the action batch into the caller-visible (pinned) action buffer, optionally clamping.
-// One core moves 16 MB in 1.3 ms (2.7 ms with the clamp) on the bench box -- as long as the whole PCIe step --
-// so the copy of each chunk is shared by a few threads that live as long as the handle.
+// The step hands over all its chunks at once; chunks are claimed in order from an atomic counter and published
+// with a release store; the issuing thread waits for chunk j (claiming chunks itself meanwhile) before it
+// enqueues chunk j's transfers.  Helper threads are OFF by default: measured on the bench box (16 vCPUs, one
+// B200, 1 M envs) the step takes 2.62 / 2.77 / 3.10 / 3.48 ms with 1 / 2 / 4 / 6 copying threads -- the copy
+// competes with the step's own DMA traffic for host memory bandwidth, so one core copying at SIMD speed is the
+// optimum there; B2D_COPY_THREADS=n enables n - 1 helpers for hosts where it is not.
 class CopyPool {
 public:
+    static constexpr int MAX_CHUNKS = 64;
     explicit CopyPool(int workers) {
-        for (int w = 0; w < workers; w++) threads_.emplace_back([this, w] { loop(w); });
+        for (int w = 0; w < workers; w++) threads_.emplace_back([this] { loop(); });
     }
     ~CopyPool() {
         {
@@ -68,58 +69,69 @@ public:
         cv_.notify_all();
         for (auto &t : threads_) t.join();
     }
-    void copy(float *dst, const float *src, size_t count, bool clamp) {
-        const size_t parts = threads_.size() + 1;
-        if (threads_.empty() || count < (1u << 16)) { // small: not worth a wake-up
-            part(dst, src, count, clamp);
-            return;
-        }
+    // chunk j covers floats [bounds[j], bounds[j + 1]) of dst / src
+    void begin(float *dst, const float *src, const size_t *bounds, int nchunks, bool clamp) {
         {
-            std::lock_guard<std::mutex> g(m_);
-            dst_ = dst; src_ = src; count_ = count; clamp_ = clamp;
-            pending_.store((int)threads_.size());
+            std::unique_lock<std::mutex> g(m_);
+            idle_cv_.wait(g, [&] { return busy_ == 0; }); // stragglers of the previous step have left their claim loops
+            dst_ = dst; src_ = src; clamp_ = clamp; nchunks_ = nchunks;
+            for (int j = 0; j <= nchunks; j++) bounds_[j] = bounds[j];
+            for (int j = 0; j < nchunks; j++) done_[j].store(0, std::memory_order_relaxed);
+            next_.store(0, std::memory_order_relaxed);
             gen_++;
         }
-        cv_.notify_all();
-        const size_t per = (count / parts + 15) & ~(size_t)15;
-        const size_t lo = per * threads_.size();
-        if (lo < count) part(dst + lo, src + lo, count - lo, clamp); // the caller's own share: the tail
-        while (pending_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+        if (!threads_.empty()) cv_.notify_all();
+    }
+    void wait(int j) { // chunk j is in place when this returns
+        while (done_[j].load(std::memory_order_acquire) == 0) {
+            if (!claim_one()) std::this_thread::yield();
+        }
     }
 
 private:
-    static void part(float *dst, const float *src, size_t n, bool clamp) {
-        if (clamp) clamp_copy(dst, src, n);
-        else if (dst != src) memcpy(dst, src, n * sizeof(float));
+    bool claim_one() {
+        const int c = next_.fetch_add(1, std::memory_order_relaxed);
+        if (c >= nchunks_) return false;
+        float *d = dst_ + bounds_[c];
+        const float *s = src_ + bounds_[c];
+        const size_t n = bounds_[c + 1] - bounds_[c];
+        if (clamp_) clamp_copy(d, s, n);
+        else if (d != s) memcpy(d, s, n * sizeof(float));
+        done_[c].store(1, std::memory_order_release);
+        return true;
     }
-    void loop(int w) {
+    void loop() {
         unsigned long long seen = 0;
         for (;;) {
-            float *dst; const float *src; size_t count; bool clamp;
             {
                 std::unique_lock<std::mutex> g(m_);
                 cv_.wait(g, [&] { return gen_ != seen; });
                 seen = gen_;
                 if (stop_) return;
-                dst = dst_; src = src_; count = count_; clamp = clamp_;
+                busy_++;
             }
-            const size_t parts = threads_.size() + 1;
-            const size_t per = (count / parts + 15) & ~(size_t)15;
-            const size_t lo = per * (size_t)w, hi = lo + per < count ? lo + per : count;
-            if (lo < hi) part(dst + lo, src + lo, hi - lo, clamp);
-            pending_.fetch_sub(1, std::memory_order_release);
+            while (claim_one()) {
+            }
+            {
+                std::lock_guard<std::mutex> g(m_);
+                busy_--;
+            }
+            idle_cv_.notify_one();
         }
     }
     std::vector<std::thread> threads_;
     std::mutex m_;
-    std::condition_variable cv_;
+    std::condition_variable cv_, idle_cv_;
     unsigned long long gen_ = 0;
+    int busy_ = 0;
     bool stop_ = false;
     float *dst_ = nullptr;
     const float *src_ = nullptr;
-    size_t count_ = 0;
     bool clamp_ = false;
-    std::atomic<int> pending_{0};
+    int nchunks_ = 0;
+    size_t bounds_[MAX_CHUNKS + 1];
+    std::atomic<int> done_[MAX_CHUNKS];
+    std::atomic<int> next_{0};
 };
 
 // Every entry point that touches the device runs with the handle's device current and restores the
@@ -172,6 +184,8 @@ struct b2d_vec {
     long long launches;
     int swarm_grid[2]; // swarm: persistent step grid per math mode (resident CTA slots of the handle's device)
     uint32_t seq; // step-kernel launches so far (RaceDev::seq)
+    uint32_t last_full_seq;  // race: seq of the last launch that covered all tiles with the full grid (0: none)
+    cudaStream_t last_stream; // ... and the stream it went to
     cudaStream_t copy_streams[2];
     cudaEvent_t ev_step, ev_copy[2];
     // optional per-kernel timing (b2d_profile_kernels): event triples of the profiled steps
@@ -222,8 +236,7 @@ static int setup_buffers(b2d_vec *v, const b2d_buffers *ext) {
     v->has_host = ext && ext->location == B2D_MEM_HOST;
     if (v->has_host) {
         v->host = *ext;
-        unsigned int hw = std::thread::hardware_concurrency();
-        int workers = rows >= (1u << 18) ? (hw >= 8 ? 3 : (hw >= 4 ? 1 : 0)) : 0; // small vectors copy inline
+        int workers = 0; // see CopyPool: helpers lose on the measured host
         if (const char *env = getenv("B2D_COPY_THREADS")) workers = atoi(env) > 0 ? atoi(env) - 1 : 0;
         v->pool = new (std::nothrow) CopyPool(workers);
         if (!v->pool) return fail(B2D_ENOMEM, "out of host memory");
@@ -328,7 +341,8 @@ extern "C" int b2d_race_create(b2d_vec **out, const b2d_race_cfg *cfg, const b2d
         }
     }
 #if B2D_EXPERIMENT_TIMING
-    cudaMalloc(&d.trace, (size_t)v->step_ctas * 4 * sizeof(unsigned long long));
+    cudaMalloc(&d.trace, (size_t)2 * v->step_ctas * 4 * sizeof(unsigned long long));
+    cudaMemset(d.trace, 0, (size_t)2 * v->step_ctas * 4 * sizeof(unsigned long long));
 #endif
     d.obs = v->dev.observations;
     d.act_in = v->dev.actions;
@@ -465,14 +479,19 @@ extern "C" int b2d_vec_close(b2d_vec *v) {
         const double it = (double)h[4], w = (double)h[7];
         fprintf(stderr, "[b2d timing] per tile iteration (cycles): wait_inputs %.0f  compute %.0f  store %.0f  (unused) %.0f  pass %.0f  tail_pass %.0f | per warp-launch: total %.0f  iterations %.2f\n",
                 h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[8] / it, h[5] / it, h[6] / w, it / w);
-        if (getenv("B2D_TRACE_FILE")) {
-            std::vector<unsigned long long> tr((size_t)v->step_ctas * 4);
+        if (getenv("B2D_TRACE_FILE")) { // the last two launches, CTA by CTA: shows launch t+1 starting inside launch t
+            std::vector<unsigned long long> tr((size_t)2 * v->step_ctas * 4);
             cudaMemcpy(tr.data(), v->race.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
             FILE *f = fopen(getenv("B2D_TRACE_FILE"), "w");
             if (f) {
-                fprintf(f, "cta,smid,entry_ns,go_ns,done_ns\n");
-                for (int c = 0; c < v->step_ctas; c++)
-                    fprintf(f, "%d,%llu,%llu,%llu,%llu\n", c, tr[c * 4], tr[c * 4 + 1], tr[c * 4 + 2], tr[c * 4 + 3]);
+                fprintf(f, "launch_seq,cta,smid,entry_ns,go_ns,done_ns\n");
+                for (int which = 0; which < 2; which++) {
+                    const uint32_t seq = v->seq - (uint32_t)(1 - which); // older launch first
+                    const size_t base = (size_t)(seq & 1u) * v->step_ctas * 4;
+                    for (int c = 0; c < v->step_ctas; c++)
+                        fprintf(f, "%u,%d,%llu,%llu,%llu,%llu\n", seq, c, tr[base + c * 4], tr[base + c * 4 + 1], tr[base + c * 4 + 2],
+                                tr[base + c * 4 + 3]);
+                }
                 fclose(f);
             }
         }
@@ -540,16 +559,26 @@ extern "C" int b2d_vec_reset(b2d_vec *v, uint64_t seed, void *stream) {
     return launch_check("swarm_reset_kernel");
 }
 
-// One launch of the step kernel.  `overlap`: the launch is made programmatically dependent on the
-// previous launch in the stream, which the caller guarantees is the previous step of this handle
-// (b2d_vec_step_tape); every CTA then waits for its own predecessor only (race_step_kernel).
-static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool overlap = false, int tile_begin = 0,
-                     int tile_end = -1, bool first_chunk = true, bool last_chunk = true, bool series = false) {
+// One launch of the step kernel.  Launch overlap: a launch that covers all tiles with the full grid, outside
+// stream capture, and directly follows such a launch of the SAME handle on the SAME stream is made
+// programmatically dependent on it (PDL): it may begin while its predecessor drains, and every CTA then waits
+// for exactly its own predecessor's completion flag (race_step_kernel, chain_wait).  Whatever else sits between
+// two steps in the stream (a policy kernel, a copy) is an ordinary full dependency, so the flags are already
+// set when the next step arrives; `allow_overlap` = false forces a plain launch.
+static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool allow_overlap = true, int tile_begin = 0,
+                     int tile_end = -1, bool first_chunk = true, bool last_chunk = true) {
     if ((v->kind == KIND_RACE ? v->race.reset_mode : v->swarm.reset_mode) == B2D_RESET_INJECT && !v->d_payload)
         return fail(B2D_ESTATE, "inject mode without a payload (b2d_set_reset_payload)");
     if (v->kind == KIND_RACE) {
         RaceDev d = v->race;
         if (actions) d.act_in = actions;
+        const bool full = tile_begin == 0 && tile_end < 0;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        const bool capturing = cap != cudaStreamCaptureStatusNone;
+        // inside a capture the sequence numbers the flags carry would be frozen into the graph: plain launches there
+        const bool full_grid = full && !capturing;
+        const bool overlap = allow_overlap && full_grid && v->last_full_seq != 0 && v->last_full_seq == v->seq && v->last_stream == st;
         d.seq = ++v->seq;
         d.chain_wait = overlap ? 1 : 0;
         {   // tiles of this launch: the whole vector, or one chunk of it (host-buffer pipeline)
@@ -566,7 +595,9 @@ static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool ove
         }
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)(series ? v->step_ctas : v->single_ctas));
+        // every CTA slot for launches that can overlap their neighbours (finer per-CTA chains: 68 vs 74 us per 1M
+        // envs), one CTA per SM fewer for launches that run alone (chunks of a host step, captured launches)
+        cfg.gridDim = dim3((unsigned)(full_grid ? v->step_ctas : v->single_ctas));
         cfg.blockDim = dim3(RACE_BLOCK);
         cfg.dynamicSmemBytes = RACE_SMEM_BYTES;
         cfg.stream = st;
@@ -580,6 +611,8 @@ static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool ove
         if (e != cudaSuccess) return fail(B2D_ECUDA, "race_step_kernel launch: %s", cudaGetErrorString(e));
         if (v->profile) cudaEventRecord(pe[1], st);
         v->launches += 1;
+        v->last_full_seq = full_grid ? d.seq : 0;
+        v->last_stream = st;
         return launch_check("race_step_kernel");
     }
     swarm_vec_step(v->swarm, actions, v->math, v->swarm_grid[v->math == B2D_MATH_STRICT ? 1 : 0], st, &v->launches);
@@ -610,13 +643,10 @@ extern "C" int b2d_vec_step_tape(b2d_vec *v, const float *device_tape, int tape_
         return fail(B2D_EINVAL, "b2d_vec_step_tape: bad argument");
     DEVICE_SCOPE(v);
     cudaStream_t st = (cudaStream_t)stream;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(st, &cap);
     const size_t stride = (size_t)v->num_agents * 4;
     for (int k = 0; k < steps; k++) {
         const float *a = device_tape + (size_t)((first + k) % tape_len) * stride;
-        int rc = step_impl(v, a, st, k > 0 && cap == cudaStreamCaptureStatusNone && v->kind == KIND_RACE, 0, -1, true, true,
-                           steps > 1);
+        int rc = step_impl(v, a, st);
         if (rc) return rc;
     }
     return B2D_OK;
@@ -642,15 +672,20 @@ static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st
     for (int j = 1; j < chunks && (size_t)j * per_tiles < tiles; j++) bnd.push_back((size_t)j * per_tiles);
     bnd.push_back(tiles);
     const int nchunks = (int)bnd.size() - 1;
+    const bool host_copy = v->host_clamp || copy_in;
+    if (host_copy) { // all chunks of the action copy go to the pool at once; chunk j is awaited right before its H2D
+        size_t fb[CopyPool::MAX_CHUNKS + 1];
+        for (int j = 0; j <= nchunks; j++) fb[j] = (bnd[j] * 32 < rows ? bnd[j] * 32 : rows) * 4;
+        v->pool->begin(v->host.actions, copy_in ? host_actions : v->host.actions, fb, nchunks, v->host_clamp);
+    }
     for (int j = 0; j < nchunks; j++) {
         const size_t r0 = bnd[j] * 32;
         const size_t r1 = bnd[j + 1] * 32 < rows ? bnd[j + 1] * 32 : rows;
         const size_t nr = r1 - r0;
         cudaStream_t cs = v->copy_streams[j & 1];
-        // the CPU copy of this chunk's actions overlaps the transfers of the chunks already in flight
+        // the copy of later chunks overlaps the transfers of the chunks already in flight
         // (with host_clamp the caller-visible buffer receives the clamped values, as the reference leaves them)
-        if (v->host_clamp || copy_in)
-            v->pool->copy(v->host.actions + r0 * 4, (copy_in ? host_actions : v->host.actions) + r0 * 4, nr * 4, v->host_clamp);
+        if (host_copy) v->pool->wait(j);
         CUDA_TRY(cudaMemcpyAsync(v->dev.actions + r0 * 4, v->host.actions + r0 * 4, nr * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
         int rc = step_impl(v, nullptr, st, false, (int)bnd[j], (int)bnd[j + 1], j == 0, j == nchunks - 1);
         if (rc) return rc;

@@ -101,42 +101,35 @@ __device__ __forceinline__ xf unit_from_word(uint32_t w) {
 }
 __device__ __forceinline__ xf lerp_u(float a, float b, xf u) { return xf(a) + u * (xf(b) - xf(a)); }
 
-// Deterministic sin/cos for theta in [0, 2*pi], one IEEE double op at a time; must stay in
-// lock-step with oracle/drone_oracle.c:orc_sincos_det.
+// Deterministic sin/cos for theta in [0, 2*pi], one IEEE binary32 operation at a time; must stay in
+// lock-step with oracle/drone_oracle.c:orc_sincos_det (same constants, same order): quadrant
+// k = floor(theta * 2/pi + 1/2) <= 4, three-term Cody-Waite reduction (k * DP1 and k * DP2 are exact),
+// Cephes sinf / cosf minimax polynomials on [-pi/4, pi/4]; |error| < 1e-7.  (The round-1 version did this in
+// double precision: 84 DMUL + 84 DADD per ring on the reset path of the step kernel.)
 __device__ __forceinline__ void sincos_det(float theta, float &s, float &c) {
-    const double TWO_OVER_PI = 0.63661977236758134308;
-    const double PIO2 = 1.57079632679489661923;
-    double t = (double)theta;
-    int k = __double2int_rz(__dadd_rn(__dmul_rn(t, TWO_OVER_PI), 0.5));
-    double r = __dsub_rn(t, __dmul_rn((double)k, PIO2));
-    double z = __dmul_rn(r, r);
-    double ps = -1.0 / 1307674368000.0;
-    ps = __dadd_rn(__dmul_rn(ps, z), 1.0 / 6227020800.0);
-    ps = __dadd_rn(__dmul_rn(ps, z), -1.0 / 39916800.0);
-    ps = __dadd_rn(__dmul_rn(ps, z), 1.0 / 362880.0);
-    ps = __dadd_rn(__dmul_rn(ps, z), -1.0 / 5040.0);
-    ps = __dadd_rn(__dmul_rn(ps, z), 1.0 / 120.0);
-    ps = __dadd_rn(__dmul_rn(ps, z), -1.0 / 6.0);
-    ps = __dadd_rn(__dmul_rn(ps, z), 1.0);
-    double sr = __dmul_rn(ps, r);
-    double pc = 1.0 / 20922789888000.0;
-    pc = __dadd_rn(__dmul_rn(pc, z), -1.0 / 87178291200.0);
-    pc = __dadd_rn(__dmul_rn(pc, z), 1.0 / 479001600.0);
-    pc = __dadd_rn(__dmul_rn(pc, z), -1.0 / 3628800.0);
-    pc = __dadd_rn(__dmul_rn(pc, z), 1.0 / 40320.0);
-    pc = __dadd_rn(__dmul_rn(pc, z), -1.0 / 720.0);
-    pc = __dadd_rn(__dmul_rn(pc, z), 1.0 / 24.0);
-    pc = __dadd_rn(__dmul_rn(pc, z), -0.5);
-    double cr = __dadd_rn(__dmul_rn(pc, z), 1.0);
-    double sv, cv;
+    const xf DP1(1.5703125f), DP2(4.837512969970703125e-4f), DP3(7.54978995489188216e-8f);
+    const xf t(theta);
+    const int k = __float2int_rz((t * xf(0.636619746685028076171875f) + xf(0.5f)).v);
+    const xf kf((float)k);
+    const xf r = ((t - kf * DP1) - kf * DP2) - kf * DP3;
+    const xf z = r * r;
+    xf ps(-1.9515295891e-4f);
+    ps = ps * z + xf(8.3321608736e-3f);
+    ps = ps * z + xf(-1.6666654611e-1f);
+    const xf sr = ps * z * r + r;
+    xf pc(2.443315711809948e-5f);
+    pc = pc * z + xf(-1.388731625493765e-3f);
+    pc = pc * z + xf(4.166664568298827e-2f);
+    const xf cr = pc * z * z + (xf(1.0f) - xf(0.5f) * z);
+    float sv, cv;
     switch (k & 3) {
-    case 0: sv = sr; cv = cr; break;
-    case 1: sv = cr; cv = -sr; break;
-    case 2: sv = -sr; cv = -cr; break;
-    default: sv = -cr; cv = sr; break;
+    case 0: sv = sr.v; cv = cr.v; break;
+    case 1: sv = cr.v; cv = -sr.v; break;
+    case 2: sv = -sr.v; cv = -cr.v; break;
+    default: sv = -cr.v; cv = sr.v; break;
     }
-    s = __double2float_rn(sv);
-    c = __double2float_rn(cv);
+    s = sv;
+    c = cv;
 }
 
 // x^3 rounded once from a double product (stands in for the reference's powf(x, 3.0f))

@@ -104,7 +104,7 @@ struct RaceDev {
     uint32_t key0, key1, env_id_base;
     int reset_mode; // b2d_reset_mode
 #if B2D_EXPERIMENT_TIMING
-    unsigned long long *trace; // [grid][4] (smid, CTA entry ns, first tile ns, CTA done ns) of the last launch
+    unsigned long long *trace; // [2][max_grid][4] (smid, CTA entry ns, first tile ns, CTA done ns) of the last two launches (slot = seq & 1)
 #endif
 };
 
@@ -752,8 +752,8 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
             unsigned int smid;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_done));
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            d.trace[blockIdx.x * 4 + 0] = smid; d.trace[blockIdx.x * 4 + 1] = tr_entry;
-            d.trace[blockIdx.x * 4 + 2] = tr_go; d.trace[blockIdx.x * 4 + 3] = tr_done;
+            unsigned long long *tr = d.trace + ((size_t)(d.seq & 1u) * d.max_grid + blockIdx.x) * 4;
+            tr[0] = smid; tr[1] = tr_entry; tr[2] = tr_go; tr[3] = tr_done;
         }
 #endif
         __syncwarp();

@@ -106,41 +106,33 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  * __dmul_rn/__dadd_rn.  Quadrant reduction + Taylor polynomials on |r|<=pi/4
  * (truncation error < 5e-17), result rounded once to float. */
 void orc_sincos_det(float theta, float *s, float *c) {
-    const double TWO_OVER_PI = 0.63661977236758134308;
-    const double PIO2 = 1.57079632679489661923;
-    double t = (double)theta;
-    int k = (int)(t * TWO_OVER_PI + 0.5);
-    double r = t - (double)k * PIO2;
-    double z = r * r;
-    /* sin r = r (1 + z(-1/3! + z(1/5! + z(-1/7! + z(1/9! + z(-1/11! + z(1/13! + z(-1/15!)))))))) */
-    double ps = -1.0 / 1307674368000.0;
-    ps = ps * z + 1.0 / 6227020800.0;
-    ps = ps * z + -1.0 / 39916800.0;
-    ps = ps * z + 1.0 / 362880.0;
-    ps = ps * z + -1.0 / 5040.0;
-    ps = ps * z + 1.0 / 120.0;
-    ps = ps * z + -1.0 / 6.0;
-    ps = ps * z + 1.0;
-    double sr = ps * r;
-    /* cos r = 1 + z(-1/2! + z(1/4! + ... + z(1/16!))) */
-    double pc = 1.0 / 20922789888000.0;
-    pc = pc * z + -1.0 / 87178291200.0;
-    pc = pc * z + 1.0 / 479001600.0;
-    pc = pc * z + -1.0 / 3628800.0;
-    pc = pc * z + 1.0 / 40320.0;
-    pc = pc * z + -1.0 / 720.0;
-    pc = pc * z + 1.0 / 24.0;
-    pc = pc * z + -0.5;
-    double cr = pc * z + 1.0;
-    double sv, cv;
+    /* theta in [0, 2 pi].  Single-precision throughout, one IEEE operation at a time (this file is built with
+     * -ffp-contract=off; the device twin b2d_math.cuh:sincos_det uses __fadd_rn / __fmul_rn): quadrant
+     * k = floor(theta * 2/pi + 1/2) <= 4, three-term Cody-Waite reduction r = theta - k pi/2 (the products
+     * k * DP1 and k * DP2 are exact), minimax polynomials on [-pi/4, pi/4] (Cephes sinf / cosf). */
+    const float DP1 = 1.5703125f, DP2 = 4.837512969970703125e-4f, DP3 = 7.54978995489188216e-8f;
+    float t = theta;
+    int k = (int)(t * 0.636619746685028076171875f + 0.5f);
+    float kf = (float)k;
+    float r = ((t - kf * DP1) - kf * DP2) - kf * DP3;
+    float z = r * r;
+    float ps = -1.9515295891e-4f;
+    ps = ps * z + 8.3321608736e-3f;
+    ps = ps * z + -1.6666654611e-1f;
+    float sr = ps * z * r + r;
+    float pc = 2.443315711809948e-5f;
+    pc = pc * z + -1.388731625493765e-3f;
+    pc = pc * z + 4.166664568298827e-2f;
+    float cr = pc * z * z + (1.0f - 0.5f * z);
+    float sv, cv;
     switch (k & 3) {
     case 0: sv = sr; cv = cr; break;
     case 1: sv = cr; cv = -sr; break;
     case 2: sv = -sr; cv = -cr; break;
     default: sv = -cr; cv = sr; break;
     }
-    *s = (float)sv;
-    *c = (float)cv;
+    *s = sv;
+    *c = cv;
 }
 
 /* ------------------------------------------------------------------ random sources */
