@@ -451,13 +451,61 @@ __device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---------------------------------------------------------------- bulk async copies (TMA engine, no tensor map)
+// A tile's inputs are two contiguous runs in global memory (5,120 B of hot state thanks to the tile-interleaved
+// layout, 512 B of actions) and its observation rows one contiguous run of 3,712 B, so one lane moves each
+// with a single cp.async.bulk instruction -- completion of the loads on a per-warp mbarrier, of the store
+// through the bulk async-group -- instead of 11 LDGSTS per lane in and 7 LDS.128 + 7 STG.128 per lane out.
+// MEASURED AND NOT THE DEFAULT (profiles/README.md, r02): same box, 4,000 steps at 1 M envs, bit-exact either way:
+// bulk 69.39 / 69.34 us per step, per-lane cp.async 68.74 / 69.00 us.  The ~30 issue slots per lane-tile it saves
+// are not what limits a kernel that waits on HBM; the extra mbarrier wait, proxy fences and the second
+// observation buffer cost as much.  -DB2D_RACE_BULK=1 builds it (needs the tile-interleaved layout).
+#ifndef B2D_RACE_BULK
+#define B2D_RACE_BULK 0
+#endif
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "B2D_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra B2D_DONE;\n\t"
+        "bra B2D_WAIT;\n\t"
+        "B2D_DONE:\n\t"
+        "}" ::"r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+}
+// generic-proxy accesses to shared memory ordered against the async proxy (bulk copies) and back
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all but the newest `N` bulk stores of this thread have finished READING shared memory
+template <int N> __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // per-warp shared memory:
 //   stage  11 float4 per lane: inputs of the NEXT tile, in flight while the current tile computes
-//   obs    the 32x29 observation tile of the current tile (staging for the coalesced store)
+//   obs    the 32x29 observation tile of the current tile (staging for the coalesced store); two of them when
+//          the tile leaves by bulk store, so that a tile's rows can be written while the previous store drains
 constexpr int RACE_STAGE_SLOTS = 11; // act, S0..S4, P0..P2, C0, T
 constexpr int RACE_STAGE_BYTES = RACE_STAGE_SLOTS * 32 * 16;
 constexpr int RACE_TILE_BYTES = 32 * RACE_OBS * 4;
-constexpr int RACE_WARP_SMEM = RACE_STAGE_BYTES + RACE_TILE_BYTES;
+constexpr int RACE_OBS_BUFFERS = B2D_RACE_BULK ? 2 : 1;
+constexpr int RACE_WARP_SMEM = RACE_STAGE_BYTES + RACE_OBS_BUFFERS * RACE_TILE_BYTES;
 constexpr int RACE_SMEM_BYTES = RACE_WARPS * RACE_WARP_SMEM;
 
 __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *stage, int lane, int i) {
@@ -467,6 +515,15 @@ __device__ __forceinline__ void race_prefetch_tile(const RaceDev &d, float4 *sta
 #pragma unroll
     for (int k = 0; k < RACE_HOT_SLOTS; k++) cp_async16(&stage[(1 + k) * 32 + lane], hot + k * st); // stage order = slot order
 }
+#if B2D_RACE_BULK
+// lane 0: the tile's actions (rows * 16 B) and hot-state block (5,120 B) land in `stage`, completion on `bar`
+__device__ __forceinline__ void race_prefetch_tile_bulk(const RaceDev &d, float4 *stage, int tile, unsigned long long *bar) {
+    const uint32_t act_bytes = (uint32_t)min(32, d.n - tile * 32) * 16u;
+    mbar_expect_tx(bar, act_bytes + RACE_HOT_SLOTS * 32 * 16);
+    bulk_load(stage, reinterpret_cast<const float4 *>(d.act_in) + (size_t)tile * 32, act_bytes, bar);
+    bulk_load(stage + 32, d.S + (size_t)tile * (RACE_HOT_SLOTS * 32), RACE_HOT_SLOTS * 32 * 16, bar);
+}
+#endif
 
 // ---------------------------------------------------------------- the step kernel
 // ONE launch per vec_step.  Persistent grid (RACE_MIN_CTAS resident CTAs per SM), RACE_WARPS
@@ -519,6 +576,16 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     float4 *stage = reinterpret_cast<float4 *>(s_dyn + warp * RACE_WARP_SMEM);
     float *tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES);
     float *my_row = tile_obs + lane * RACE_OBS;
+#if B2D_RACE_BULK
+    __shared__ __align__(8) unsigned long long s_mbar[RACE_WARPS]; // one per warp: the tile inputs have landed
+    uint32_t in_phase = 0;
+    int obs_buf = 0;
+    if (lane == 0) {
+        mbar_init(&s_mbar[warp], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+#endif
 
     // Launch overlap (b2d_vec_step_tape): the next launch of this kernel may begin while this one
     // drains; its CTA c owns the same envs as this CTA c and waits for exactly this CTA's flag.
@@ -546,8 +613,12 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
     const int first_tile = d.tile_begin + (int)((blockIdx.x + G - d.tile_begin % G) % G);
     int tile = warp * G + first_tile;
     int next = (RACE_WARPS + warp) * G + first_tile;
+#if B2D_RACE_BULK
+    if (tile < ntiles && lane == 0) race_prefetch_tile_bulk(d, stage, tile, &s_mbar[warp]);
+#else
     if (tile < ntiles && tile * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, tile * 32 + lane);
     cp_async_commit(); // group: inputs of the first tile
+#endif
 
     if (tid < 8) s_acc[tid] = 0;
     if (tid == 0) {
@@ -568,7 +639,12 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         const int i = tile * 32 + lane;
         const bool valid = i < d.n;
         B2D_TICK(t0);
+#if B2D_RACE_BULK
+        mbar_wait(&s_mbar[warp], in_phase); // this tile's inputs have landed
+        in_phase ^= 1u;
+#else
         cp_async_wait<0>(); // this tile's inputs have landed
+#endif
         B2D_TICK(t1);
         const float4 a4 = stage[0 * 32 + lane];
         const float4 q0 = stage[1 * 32 + lane], q1 = stage[2 * 32 + lane], q2 = stage[3 * 32 + lane],
@@ -577,8 +653,22 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         const float4 c0 = stage[9 * 32 + lane];
         const float4 tl = stage[10 * 32 + lane]; // (j_mot, episode, ring n.y, ring n.z)
         __syncwarp();
+#if B2D_RACE_BULK
+        if (lane == 0) {
+            if (next < ntiles) {
+                fence_proxy_async_smem(); // the warp's reads of the stage (above) before the async proxy rewrites it
+                race_prefetch_tile_bulk(d, stage, next, &s_mbar[warp]);
+            }
+            bulk_store_wait_read<1>(); // the observation buffer of two tiles ago has been read out: it is written below
+        }
+        tile_obs = reinterpret_cast<float *>(s_dyn + warp * RACE_WARP_SMEM + RACE_STAGE_BYTES + obs_buf * RACE_TILE_BYTES);
+        my_row = tile_obs + lane * RACE_OBS;
+        obs_buf ^= 1;
+        __syncwarp();
+#else
         if (next < ntiles && next * 32 + lane < d.n) race_prefetch_tile(d, stage, lane, next * 32 + lane);
         cp_async_commit(); // group: inputs of the next tile
+#endif
         if (lane == 0) claim = (int)atomicAdd(&s_ticket, 1u); // shared memory: lands within the tile
 
         float s[17];
@@ -692,15 +782,22 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
             const int rows = min(32, d.n - tile * 32);
             float *gobs = d.obs + (size_t)tile * 32 * RACE_OBS;
             if (rows == 32) {
-                const float4 *src = reinterpret_cast<const float4 *>(tile_obs);
-                float4 *dst = reinterpret_cast<float4 *>(gobs);
 #if B2D_EXPERIMENT_NO_OBS_STORE
-                if (src[lane].x == 12345.678f) // measurement aid: the step without its 116 B/env observation store
+                if (tile_obs[lane] == 12345.678f) // measurement aid: the step without its 116 B/env observation store
 #endif
                 {
+#if B2D_RACE_BULK
+                    // one 3,712-byte run: generic-proxy writes of all lanes -> fence -> one bulk store by lane 0
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) bulk_store(gobs, tile_obs, RACE_TILE_BYTES);
+#else
+                    const float4 *src = reinterpret_cast<const float4 *>(tile_obs);
+                    float4 *dst = reinterpret_cast<float4 *>(gobs);
 #pragma unroll
                     for (int k = 0; k < 7; k++) __stcs(&dst[k * 32 + lane], src[k * 32 + lane]);
                     if (lane < 8) __stcs(&dst[224 + lane], src[224 + lane]);
+#endif
                 }
             } else {
                 for (int k = lane; k < rows * RACE_OBS; k += 32) gobs[k] = tile_obs[k];
@@ -715,7 +812,11 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
         tile = next;
         next = __shfl_sync(0xffffffffu, claim, 0) * G + first_tile;
     }
+#if B2D_RACE_BULK
+    if (lane == 0) bulk_store_wait_all(); // this warp's observation rows are in global memory before the CTA's completion flag
+#else
     cp_async_wait<0>();
+#endif
 #if B2D_EXPERIMENT_TIMING
     if (lane == 0) {
         atomicAdd(&d.ctl->dbg[0], (unsigned long long)tm_wait); atomicAdd(&d.ctl->dbg[1], (unsigned long long)tm_math);
