@@ -453,6 +453,10 @@ extern "C" int b2d_swarm_create(b2d_vec **out, const b2d_swarm_cfg *cfg, const b
         b2d_vec_close(v);
         return fail(B2D_ECUDA, "swarm_kernel setup on device %d failed", cfg->device);
     }
+    if ((rc = dev_alloc(v, &d.chain, (size_t)(v->swarm_grid[0] > v->swarm_grid[1] ? v->swarm_grid[0] : v->swarm_grid[1])))) {
+        b2d_vec_close(v);
+        return rc;
+    }
     d.obs = v->dev.observations;
     d.act_in = v->dev.actions;
     d.act_out = v->write_clamped ? v->dev.actions : nullptr;
@@ -615,7 +619,19 @@ static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool all
         v->last_stream = st;
         return launch_check("race_step_kernel");
     }
-    swarm_vec_step(v->swarm, actions, v->math, v->swarm_grid[v->math == B2D_MATH_STRICT ? 1 : 0], st, &v->launches);
+    {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        const bool capturing = cap != cudaStreamCaptureStatusNone; // sequence numbers would be frozen into the graph
+        const bool overlap = B2D_SW_OVERLAP && allow_overlap && !capturing && v->last_full_seq != 0 && v->last_full_seq == v->seq &&
+                             v->last_stream == st;
+        const unsigned int seq = ++v->seq;
+        cudaError_t e = swarm_vec_step(v->swarm, actions, v->math, v->swarm_grid[v->math == B2D_MATH_STRICT ? 1 : 0], st, &v->launches,
+                                       seq, overlap);
+        if (e != cudaSuccess) return fail(B2D_ECUDA, "swarm_kernel launch: %s", cudaGetErrorString(e));
+        v->last_full_seq = capturing ? 0 : seq;
+        v->last_stream = st;
+    }
     return launch_check("swarm_step_kernel");
 }
 

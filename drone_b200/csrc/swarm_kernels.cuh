@@ -40,6 +40,18 @@ namespace b2d {
 #ifndef B2D_SWARM_EXPERIMENT_NO_RESPAWN
 #define B2D_SWARM_EXPERIMENT_NO_RESPAWN 0
 #endif
+#ifndef B2D_SW_OVERLAP
+#define B2D_SW_OVERLAP 1 // consecutive step launches overlap at their edges (PDL + per-CTA completion flags)
+#endif
+#ifndef B2D_SW_RS_POOL
+#define B2D_SW_RS_POOL 8 // per warp: prepared respawn parameters fetched by cp.async a phase ahead (0: plain loads)
+#endif
+#ifndef B2D_SW_OBS_UNROLL
+#define B2D_SW_OBS_UNROLL 0 // measured: 8 % slower (145 -> 157 us at A = 16)
+#endif
+#ifndef B2D_SW_RK4_LOOP
+#define B2D_SW_RK4_LOOP 1 // RK4 stages as a loop: the hot path shrinks by ~4.5 KB of code
+#endif
 constexpr int SWARM_BLOCK = 128;
 constexpr int SWARM_OBS = 41;
 constexpr int SWARM_AGENT_BLOB = 47;
@@ -70,6 +82,11 @@ struct SwarmDev {
     float4 *RS;           // [4][ld] the PREPARED next respawn of every drone: 13 params + position (see sw_refill_pass)
     uint32_t key0, key1, env_id_base;
     int reset_mode;
+    // launch overlap (see race_step_kernel): CTA c of step launch `seq` may start while launch seq - 1 drains and
+    // waits for chain[c] == seq - 1 only; CTA c owns the same tiles in every launch
+    unsigned int *chain; // [grid]
+    unsigned int seq;
+    int chain_wait;
 };
 
 struct SwarmAgent {
@@ -760,7 +777,7 @@ __device__ __noinline__ void sw_reset_phase(const SwarmDev &d, SwResetCtx *c, Sw
 // instructions per agent) the 14 input words of the CTA's next tile stream into shared memory
 // with cp.async, so no warp ever waits on a global load at the top of a tile.
 template <bool STRICT, bool ONLY_RESET>
-__global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constant__ SwarmDev d) {
+__global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_constant__ SwarmDev d) {
     // per env (3A floats apart): [old | fin | rst] = before this tick's move | after the move, or the respawn
     // position of an agent that left the arena | first position drawn by an env-wide reset
     __shared__ __align__(16) SwarmWin s_trail;
@@ -769,6 +786,11 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
     __shared__ unsigned long long s_iacc[8]; // episode statistics in 2^-20 fixed point (native shared-memory integer atomics)
     __shared__ int2 s_rlist[SWARM_BLOCK / 32][64]; // per warp: (row, ordinal) of the respawn slots to regenerate
     __shared__ int s_rcnt[SWARM_BLOCK / 32];
+#if B2D_SW_RS_POOL
+    // per warp: the prepared respawn parameters (3 float4) of the first few drones that leave the arena in this
+    // tile, fetched by cp.async in phase 1 and read in phase 2 (a dependent DRAM load there cost 8 % of the step)
+    __shared__ __align__(16) float4 s_rspool[SWARM_BLOCK / 32][B2D_SW_RS_POOL][3];
+#endif
     __shared__ int s_guard;
     extern __shared__ __align__(128) unsigned char s_dyn[];
     float4 *stage = reinterpret_cast<float4 *>(s_dyn);                       // step launches only
@@ -830,6 +852,19 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
     if (t < SWARM_BLOCK / 32) s_rcnt[t] = 0;
     if (t == 0) s_guard = 0;
     int guard_hits = 0;
+    if constexpr (!ONLY_RESET) {
+#if B2D_SW_OVERLAP
+        // the next step launch may take CTA slots as this launch's CTAs leave; its CTA c waits for this CTA c only
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (d.chain_wait && t == 0) {
+            unsigned int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(d.chain + blockIdx.x) : "memory");
+                if (seen != d.seq - 1u) __nanosleep(64);
+            } while (seen != d.seq - 1u);
+        }
+#endif
+    }
     __syncthreads();
 
     if constexpr (!ONLY_RESET) {
@@ -879,6 +914,8 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         bool oob = false;
         float rpos[3] = {0.0f, 0.0f, 0.0f};
         float passed = 0.0f; // ring test of this move (race task), R/drone_swarm.h:465
+        float rs3x = 0.0f;   // 13th prepared respawn parameter (rides with the prepared position)
+        int rs_rank = -1;    // this drone's slot in the warp's respawn-parameter pool
         if (active) {
             tick = (tick + 1) % SWARM_HORIZON;
             float act[4];
@@ -892,7 +929,12 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             if (d.act_out) reinterpret_cast<float4 *>(d.act_out)[k] = make_float4(act[0], act[1], act[2], act[3]);
             DroneParams p = {g.p[0], g.p[1], g.p[2], g.p[3], g.p[4], g.p[5], g.p[6], g.p[7], g.p[8], g.p[9], g.p[10], g.p[11], g.p[12]};
             const float before[3] = {g.s[0], g.s[1], g.s[2]};
+#if B2D_SW_RK4_LOOP
+            if constexpr (STRICT) advance_body_strict(g.s, p, act);
+            else advance_body_fast_loop(g.s, p, act);
+#else
             advance_body<STRICT>(g.s, p, act);
+#endif
 #if B2D_SWARM_EXPERIMENT_DOUBLE_MATH
             {   // measurement aid: the rigid-body arithmetic twice, same memory traffic
                 float s2[17];
@@ -935,6 +977,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                     g.respawns += 1u;
                     const float4 r3 = stage[14 * SWARM_BLOCK + t]; // prefetched with the state
                     rpos[0] = r3.y; rpos[1] = r3.z; rpos[2] = r3.w;
+                    rs3x = r3.x;
                 }
             }
             if (oob) s_trail.put(w0 + A + a, rpos[0], rpos[1], rpos[2]);
@@ -945,12 +988,26 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
             const unsigned int m = __ballot_sync(0xffffffffu, want);
             if (m) {
                 const int base = s_rcnt[warp];
-                if (want) s_rlist[warp][base + __popc(m & ((1u << lane) - 1u))] = make_int2(k, (int)(g.respawns + 1u));
+                const int rank = __popc(m & ((1u << lane) - 1u));
+                if (want) {
+                    s_rlist[warp][base + rank] = make_int2(k, (int)(g.respawns + 1u));
+#if B2D_SW_RS_POOL
+                    if (rank < B2D_SW_RS_POOL) {
+                        rs_rank = rank;
+                        const size_t ld = d.ld;
+#pragma unroll
+                        for (int q = 0; q < 3; q++) cp_async16(&s_rspool[warp][rank][q], &d.RS[q * ld + k]);
+                    }
+#endif
+                }
                 __syncwarp();
                 if (lane == 0) s_rcnt[warp] = base + __popc(m);
                 __syncwarp();
             }
         }
+#if B2D_SW_RS_POOL
+        cp_async_commit(); // group: this tile's respawn parameters (awaited in phase 2 by the drones that need them)
+#endif
         {   // the next tile's inputs stream in while phases 2-4 of this tile run (stage slots are thread-private)
             const int tn = tile + gridDim.x, en = tn * d.epc + le;
             if (tn < ntiles && le < d.epc && en < d.n) {
@@ -1004,10 +1061,19 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
                     for (int m = 0; m < 13; m++) rp[m] = pay_agent[m];
                 } else {
                     const size_t ld = d.ld;
-                    const float4 r0 = __ldcg(&d.RS[0 * ld + k]), r1 = __ldcg(&d.RS[1 * ld + k]), r2 = __ldcg(&d.RS[2 * ld + k]);
+                    float4 r0, r1, r2;
+#if B2D_SW_RS_POOL
+                    if (rs_rank >= 0) {
+                        cp_async_wait<1>(); // all but the next tile's inputs: this drone's three pool words have landed
+                        r0 = s_rspool[warp][rs_rank][0]; r1 = s_rspool[warp][rs_rank][1]; r2 = s_rspool[warp][rs_rank][2];
+                    } else
+#endif
+                    {
+                        r0 = __ldcg(&d.RS[0 * ld + k]); r1 = __ldcg(&d.RS[1 * ld + k]); r2 = __ldcg(&d.RS[2 * ld + k]);
+                    }
                     rp[0] = r0.x; rp[1] = r0.y; rp[2] = r0.z; rp[3] = r0.w; rp[4] = r1.x; rp[5] = r1.y; rp[6] = r1.z; rp[7] = r1.w;
                     rp[8] = r2.x; rp[9] = r2.y; rp[10] = r2.z; rp[11] = r2.w;
-                    rp[12] = __ldcg(&d.RS[3 * ld + k]).x;
+                    rp[12] = rs3x;
                 }
                 sw_respawn_state(g, rp, rpos);
                 params_dirty = true;
@@ -1074,7 +1140,26 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
         if ((rows_mine & 3) == 0 && (row0 & 3) == 0 && (grp_first & 3) == 0) { // 16-byte aligned: float4 stores
             const float4 *src = reinterpret_cast<const float4 *>(sobs);
             float4 *dst = reinterpret_cast<float4 *>(gobs);
-            for (int m = tg; m < rows_mine * SWARM_OBS / 4; m += grp_size) __stcs(&dst[m], src[m]);
+            const int n4 = rows_mine * SWARM_OBS / 4; // <= 10.25 * grp_size
+#if B2D_SW_OBS_UNROLL
+            // loads first, stores after: the loop form exposed the shared-memory latency once per iteration
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                float4 v[6];
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    const int m = tg + (h * 6 + i) * grp_size;
+                    if (m < n4) v[i] = src[m];
+                }
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    const int m = tg + (h * 6 + i) * grp_size;
+                    if (m < n4) __stcs(&dst[m], v[i]);
+                }
+            }
+#else
+            for (int m = tg; m < n4; m += grp_size) __stcs(&dst[m], src[m]);
+#endif
         } else {
             for (int m = tg; m < rows_mine * SWARM_OBS; m += grp_size) __stcs(&gobs[m], sobs[m]);
         }
@@ -1107,6 +1192,12 @@ __global__ void __launch_bounds__(SWARM_BLOCK) swarm_kernel(const __grid_constan
       __syncthreads(); // every warp's statistics are in
       if (t < 8 && s_iacc[t] != 0ull) atomicAdd(&d.ctl->facc[t], (double)(long long)s_iacc[t] * (1.0 / 1048576.0));
       if (t == 0 && s_guard != 0) atomicAdd(&d.ctl->guard_replays, (unsigned long long)s_guard);
+#if B2D_SW_OVERLAP
+      if (t == 0 && d.chain) { // everything this CTA wrote (the barrier above) is visible before the flag
+          __threadfence();
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(d.chain + blockIdx.x), "r"(d.seq) : "memory");
+      }
+#endif
   }
 }
 
@@ -1231,13 +1322,26 @@ static inline int swarm_step_setup(const SwarmDev &d, int device, int grid_out[2
     return 0;
 }
 
-static inline void swarm_vec_step(SwarmDev &dev, const float *actions, int math, int grid, cudaStream_t st, long long *launches) {
+// overlap: this launch directly follows step launch seq - 1 of the same handle on the same stream (api.cu step_impl)
+static inline cudaError_t swarm_vec_step(SwarmDev &dev, const float *actions, int math, int grid, cudaStream_t st, long long *launches,
+                                         unsigned int seq, bool overlap) {
     SwarmDev d = dev;
     if (actions) d.act_in = actions;
-    const int smem = swarm_step_smem(d);
-    if (math == 1) swarm_kernel<true, false><<<grid, SWARM_BLOCK, smem, st>>>(d);
-    else swarm_kernel<false, false><<<grid, SWARM_BLOCK, smem, st>>>(d);
+    d.seq = seq;
+    d.chain_wait = overlap ? 1 : 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(SWARM_BLOCK);
+    cfg.dynamicSmemBytes = (size_t)swarm_step_smem(d);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap ? 1 : 0;
     *launches += 1;
+    return math == 1 ? cudaLaunchKernelEx(&cfg, swarm_kernel<true, false>, d) : cudaLaunchKernelEx(&cfg, swarm_kernel<false, false>, d);
 }
 
 static inline void swarm_observe_launch(SwarmDev &d, cudaStream_t st) {

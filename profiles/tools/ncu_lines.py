@@ -5,10 +5,10 @@ usage: ncu_lines.py report.ncu-rep mangled_kernel_name [top]"""
 import csv, io, os, re, subprocess, sys, tempfile, collections
 rep, fun = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-lib = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'drone_b200', 'lib', 'libb200drone.so')
+lib = os.environ.get('B2D_LIBRARY') or os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..', 'drone_b200', 'lib', 'libb200drone.so')
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
+cubin = max((f for f in os.listdir(tmp) if f.endswith('.cubin')), key=lambda f: os.path.getsize(os.path.join(tmp, f)))
 dis = subprocess.run(['nvdisasm', '-gi', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
 start = next(i for i, l in enumerate(dis) if l.startswith('.text.' + fun + ':'))
 ins = []  # (offset, outer_line, inner (file,line))
@@ -44,3 +44,7 @@ for k, v in by_outer.most_common(top):
 print('--- by innermost frame')
 for k, v in by_inner.most_common(top):
     print(f'{k[0]}:{k[1]:<5d} {100.0 * v / tot:6.2f}%  {100.0 * s_inner[k] / sum(s_inner.values()):6.2f}%')
+print('--- by kernel line, sorted by samples: samples%, instr%')
+ts = sum(s_outer.values())
+for k, v in s_outer.most_common(top):
+    print(f'{k[0]}:{k[1]:<5d} {100.0 * v / ts:6.2f}%  {100.0 * by_outer[k] / tot:6.2f}%')
