@@ -37,6 +37,9 @@ namespace b2d {
 #ifndef B2D_SWARM_EXPERIMENT_DOUBLE_MATH
 #define B2D_SWARM_EXPERIMENT_DOUBLE_MATH 0
 #endif
+#ifndef B2D_SWARM_EXPERIMENT_NO_STATS
+#define B2D_SWARM_EXPERIMENT_NO_STATS 0
+#endif
 #ifndef B2D_SWARM_EXPERIMENT_NO_RESPAWN
 #define B2D_SWARM_EXPERIMENT_NO_RESPAWN 0
 #endif
@@ -783,7 +786,10 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
     __shared__ __align__(16) SwarmWin s_trail;
     __shared__ __align__(16) SwarmWin s_now; // per env [pos | pos]: final positions of the tick (what the observations see)
     __shared__ float s_ring0[SWARM_BLOCK][3];
-    __shared__ unsigned long long s_iacc[8]; // episode statistics in 2^-20 fixed point (native shared-memory integer atomics)
+    // episode statistics in 2^-20 fixed point, one set per warp, updated by the warp's lane 0 with plain loads and
+    // stores (64-bit shared-memory atomics are compare-and-swap loops: seven of them per finished episode on seven
+    // words shared by the whole CTA cost 15 % of the step at A = 16)
+    __shared__ long long s_wacc[SWARM_BLOCK / 32][8];
     __shared__ int2 s_rlist[SWARM_BLOCK / 32][64]; // per warp: (row, ordinal) of the respawn slots to regenerate
     __shared__ int s_rcnt[SWARM_BLOCK / 32];
 #if B2D_SW_RS_POOL
@@ -835,10 +841,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
         }
         return __syncthreads_or(p ? 1 : 0);
     };
-    if (t < 8) s_iacc[t] = 0ull; // episode statistics of all this CTA's tiles; flushed once at the end
-    auto stat_add = [&](int which, float x) { // sums arrive at vec_log as 2^-20 fixed point anyway (swarm_log_snapshot_kernel)
-        atomicAdd(&s_iacc[which], (unsigned long long)__float2ll_rn(x * 1048576.0f));
-    };
+    if (t < (SWARM_BLOCK / 32) * 8) s_wacc[t >> 3][t & 7] = 0ll; // all this CTA's tiles; flushed once at the end
     auto load_ring = [&](int e_, int r, float ring[6]) {
         if (ring_staged) {
             const float *src = rstage + ((size_t)(rbuf * d.epc + le) * d.R + r) * 8;
@@ -1019,6 +1022,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
         env_sync();
 
         // ---- phase 2: rewards, ring logic, respawn bookkeeping (R/drone_swarm.h:463-491)
+        bool ended = false, horizon = false;
         if (active) {
             const float self[3] = {g.s[0], g.s[1], g.s[2]};
             float nd = 0.0f;
@@ -1028,7 +1032,6 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
                 if (passed > 0.0f) {
                     float ring[6];
                     g.ring_idx = (g.ring_idx + 1) % d.R;
-                    stat_add(FACC_RINGS, 1.0f);
                     load_ring(e, g.ring_idx, ring);
                     g.tpos[0] = ring[0]; g.tpos[1] = ring[1]; g.tpos[2] = ring[2];
                     g.tvel[0] = g.tvel[1] = g.tvel[2] = 0.0f;
@@ -1039,17 +1042,57 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
                 reward = sw_reward<STRICT>(g, self, true, A, nd);
             }
             g.ep_ret = __fadd_rn(g.ep_ret, reward);
-            const bool horizon = tick >= SWARM_HORIZON - 1;
-            if (__builtin_expect(oob || horizon, 0)) { // add_log: R/drone_swarm.h:91-105
+            horizon = tick >= SWARM_HORIZON - 1;
+            ended = oob || horizon;
+        }
+#if !B2D_SWARM_EXPERIMENT_NO_STATS
+        {   // add_log (R/drone_swarm.h:91-105) for the warp's finished episodes, as warp-uniform code: every sum is an
+            // exact integer sum of __float2ll_rn(x * 2^20) terms, so neither the order nor the grouping matters
+            const unsigned int m_end = __ballot_sync(0xffffffffu, ended);
+            const unsigned int m_ring = __ballot_sync(0xffffffffu, active && task == SWARM_TASK_RACE && passed > 0.0f);
+            if ((m_end | m_ring) != 0u) { // every other warp-tile at A = 16
+                const unsigned int m_oob = __ballot_sync(0xffffffffu, ended && oob);
+                long long f[4] = {0ll, 0ll, 0ll, 0ll};
+                int ilen = 0;
+                if (ended) {
+                    const float len = (float)g.ep_len;
+                    ilen = g.ep_len;
+                    f[0] = __float2ll_rn(g.score * 1048576.0f);
+                    f[1] = __float2ll_rn(g.ep_ret * 1048576.0f);
+#if B2D_SWARM_EXPERIMENT_NO_DIV
+                    f[2] = __float2ll_rn((g.collisions * len) * 1048576.0f);
+                    f[3] = __float2ll_rn((g.score * len) * 1048576.0f);
+#else
+                    // (a zero numerator sends the IEEE division down its slow path: most episodes have no collision)
+                    f[2] = g.collisions == 0.0f ? 0ll : __float2ll_rn((g.collisions / len) * 1048576.0f);
+                    f[3] = g.score == 0.0f ? 0ll : __float2ll_rn((g.score / len) * 1048576.0f);
+#endif
+                }
+                long long sum[4] = {0ll, 0ll, 0ll, 0ll};
+                int slen = 0;
+                for (unsigned int m = m_end; m; m &= m - 1u) { // one finished episode at a time: there are rarely more than two
+                    const int src = __ffs((int)m) - 1;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) sum[q] += __shfl_sync(0xffffffffu, f[q], src);
+                    slen += __shfl_sync(0xffffffffu, ilen, src);
+                }
+                if (lane == 0) {
+                    long long *acc = s_wacc[warp];
+                    acc[FACC_SCORE] += sum[0];
+                    acc[FACC_RETURN] += sum[1];
+                    acc[FACC_COLLISION] += sum[2];
+                    acc[FACC_PERF] += sum[3];
+                    acc[FACC_LENGTH] += (long long)slen << 20;
+                    acc[FACC_N] += (long long)__popc(m_end) << 20;
+                    acc[FACC_OOB] += (long long)__popc(m_oob) << 20;
+                    acc[FACC_RINGS] += (long long)__popc(m_ring) << 20;
+                }
+            }
+        }
+#endif
+        if (active) {
+            if (__builtin_expect(ended, 0)) {
                 terminal = 1;
-                const float len = (float)g.ep_len;
-                stat_add(FACC_SCORE, g.score);
-                stat_add(FACC_RETURN, g.ep_ret);
-                stat_add(FACC_LENGTH, len);
-                stat_add(FACC_COLLISION, g.collisions / len);
-                stat_add(FACC_PERF, g.score / len);
-                if (oob) stat_add(FACC_OOB, 1.0f);
-                stat_add(FACC_N, 1.0f);
                 g.ep_len = 0;
                 g.ep_ret = 0.0f;
             }
@@ -1190,7 +1233,14 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
       sw_refill_pass(d, s_rlist[warp], s_rcnt[warp], lane); // the rest of this warp's list
       if (guard_hits) atomicAdd(&s_guard, guard_hits);
       __syncthreads(); // every warp's statistics are in
-      if (t < 8 && s_iacc[t] != 0ull) atomicAdd(&d.ctl->facc[t], (double)(long long)s_iacc[t] * (1.0 / 1048576.0));
+      if (t < 8) {
+          long long sum = 0ll;
+#pragma unroll
+          for (int w = 0; w < SWARM_BLOCK / 32; w++) sum += s_wacc[w][t];
+#if !B2D_SWARM_EXPERIMENT_NO_FLUSH
+          if (sum != 0ll) atomicAdd(&d.ctl->facc[t], (double)sum * (1.0 / 1048576.0));
+#endif
+      }
       if (t == 0 && s_guard != 0) atomicAdd(&d.ctl->guard_replays, (unsigned long long)s_guard);
 #if B2D_SW_OVERLAP
       if (t == 0 && d.chain) { // everything this CTA wrote (the barrier above) is visible before the flag
