@@ -52,10 +52,14 @@ namespace b2d {
 #ifndef B2D_SW_OBS_UNROLL
 #define B2D_SW_OBS_UNROLL 0 // measured: 8 % slower (145 -> 157 us at A = 16)
 #endif
+#ifndef B2D_SW_OBS_LOOP_UNROLL
+#define B2D_SW_OBS_LOOP_UNROLL 1
+#endif
 #ifndef B2D_SW_RK4_LOOP
 #define B2D_SW_RK4_LOOP 1 // RK4 stages as a loop: the hot path shrinks by ~4.5 KB of code
 #endif
 constexpr int SWARM_BLOCK = 128;
+constexpr int SW_OBS_LOOP_UNROLL = B2D_SW_OBS_LOOP_UNROLL;
 constexpr int SWARM_OBS = 41;
 constexpr int SWARM_AGENT_BLOB = 47;
 constexpr int SWARM_AGENT_PAYLOAD = 41; // oracle/drone_oracle.c "swarm env": respawn [0:16], env reset [16:41]
@@ -1201,6 +1205,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
                 }
             }
 #else
+#pragma unroll SW_OBS_LOOP_UNROLL
             for (int m = tg; m < n4; m += grp_size) __stcs(&dst[m], src[m]);
 #endif
         } else {
