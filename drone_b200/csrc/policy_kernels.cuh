@@ -83,6 +83,9 @@ __device__ __forceinline__ float2 gelu2(float2 v) {
     return __ffma2_rn(hu, e, make_float2(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f)));
 }
 
+#ifndef B2D_POLICY_FAST_SINCOS
+#define B2D_POLICY_FAST_SINCOS 1
+#endif
 // four standard normals for (row, call): Philox4x32-10 + Box-Muller
 __device__ __forceinline__ void policy_noise(uint32_t row, uint32_t call, uint32_t k0, uint32_t k1, float z[4]) {
     const uint4 w = philox4x32_10(make_uint4(row, call, 0x504f4c49u, 0u), k0, k1);
@@ -90,6 +93,17 @@ __device__ __forceinline__ void policy_noise(uint32_t row, uint32_t call, uint32
     const float u0 = ((float)(w.x >> 9) + 0.5f) * S, u1 = ((float)(w.y >> 9) + 0.5f) * S;
     const float u2 = ((float)(w.z >> 9) + 0.5f) * S, u3 = ((float)(w.w >> 9) + 0.5f) * S;
     const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+#if B2D_POLICY_FAST_SINCOS
+    // sin / cos of the uniform angle on the special-function unit: the angle 2 pi u is taken as theta + pi with
+    // theta = 2 pi (u - 0.5) in (-pi, pi), where sin.approx / cos.approx are good to 2^-21.4 absolute
+    // (|z| error < 3e-6, inside the 2e-6 max(1, |z|) of tests/test_policy_gpu.py); sin(theta + pi) = -sin theta.
+    const float t0 = 6.283185307179586f * (u1 - 0.5f), t1 = 6.283185307179586f * (u3 - 0.5f);
+    const float nr0 = -r0, nr1 = -r1;
+    z[0] = nr0 * __cosf(t0);
+    z[1] = nr0 * __sinf(t0);
+    z[2] = nr1 * __cosf(t1);
+    z[3] = nr1 * __sinf(t1);
+#else
     float s0, c0, s1, c1;
     sincospif(2.0f * u1, &s0, &c0);
     sincospif(2.0f * u3, &s1, &c1);
@@ -97,6 +111,7 @@ __device__ __forceinline__ void policy_noise(uint32_t row, uint32_t call, uint32
     z[1] = r0 * s0;
     z[2] = r1 * c1;
     z[3] = r1 * s1;
+#endif
 }
 
 // sample, log-prob, experience stores and the clipped env action of one row (pufferl.py:258-294)

@@ -54,7 +54,14 @@ constexpr int RO_B1_BYTES = (RO_K1 / 4) * RO_HIDDEN * 16;   // [8 chunks][128 n]
 constexpr int RO_B2_BYTES = (RO_HIDDEN / 4) * RO_N2 * 16;   // [32 chunks][16 n] float4
 constexpr int RO_A1_BYTES = (RO_K1 / 4) * RO_THREADS * 16;  // [8 chunks][128 rows] float4
 constexpr int RO_TILE_BYTES = 32 * RACE_OBS * 4;            // per-warp staging of observation rows
-constexpr int RO_SMEM_USED = RO_B1_BYTES + RO_B2_BYTES + RO_A1_BYTES + 4 * RO_TILE_BYTES;
+#ifndef B2D_RO_BANK_PREFETCH
+#define B2D_RO_BANK_PREFETCH 1
+#endif
+// per lane: the bank entry of the env's NEXT episode (6 x 16 B), fetched by cp.async when the current episode
+// begins, so that an episode end -- some lane of the CTA has one in 96 % of the steps, and the whole CTA waits for
+// it at the step's next barrier -- never waits for DRAM (it was 6 % long-scoreboard + 12 % barrier stall samples)
+constexpr int RO_NEXT_BYTES = B2D_RO_BANK_PREFETCH ? 6 * RO_THREADS * 16 : 0;
+constexpr int RO_SMEM_USED = RO_B1_BYTES + RO_B2_BYTES + RO_A1_BYTES + 4 * RO_TILE_BYTES + RO_NEXT_BYTES;
 // request enough shared memory that exactly RO_CTAS_PER_SM CTAs fit on an SM: a fourth CTA would find no TMEM
 // columns left and sit in tcgen05.alloc until another CTA exits
 constexpr int RO_SMEM_BYTES = RO_CTAS_PER_SM >= 4 ? 56 * 1024 : 72 * 1024;
@@ -244,9 +251,17 @@ __device__ __noinline__ void ro_strict_replay(const float *in, float *out) {
 
 // One c_step (DR/drone_race.h:156-208) of the env in `e` on the raw action `a4`; leaves the observation of the
 // (possibly new) episode in o[29].  Same decisions, same arithmetic as race_step_kernel.
+// the bank entry of episode `episode` of env i -> this lane's six staging words (slot q at nxt[q * RO_THREADS])
+__device__ __forceinline__ void ro_prefetch_bank(const RaceDev &d, int i, uint32_t episode, float4 *nxt) {
+    const float4 *b = d.bank + ((size_t)i * RACE_BANK_SLOTS + (episode % RACE_BANK_SLOTS)) * 6;
+#pragma unroll
+    for (int q = 0; q < 6; q++) cp_async16(&nxt[q * RO_THREADS], b + q);
+    cp_async_commit();
+}
+
 template <bool STRICT>
 __device__ __forceinline__ void ro_env_step(const RaceDev &d, int i, RaceRegs &e, float4 a4, float &reward, int &terminal,
-                                            float (&o)[RACE_OBS], int *s_acc, bool last_step, int &score_last) {
+                                            float (&o)[RACE_OBS], int *s_acc, bool last_step, int &score_last, float4 *nxt) {
     float act[4];
     if constexpr (STRICT) {
         act[0] = xclamp(xf(a4.x), -1.0f, 1.0f).v; act[1] = xclamp(xf(a4.y), -1.0f, 1.0f).v;
@@ -319,10 +334,19 @@ __device__ __forceinline__ void ro_env_step(const RaceDev &d, int i, RaceRegs &e
         e.episode += 1u;
         bool banked = false;
         if (d.bank) {
+#if B2D_RO_BANK_PREFETCH
+            cp_async_wait<0>(); // this lane's staged entry (fetched when the episode that just ended began)
+            const float4 b5 = nxt[5 * RO_THREADS];
+            const float4 b0 = nxt[0 * RO_THREADS], b1 = nxt[1 * RO_THREADS], b2 = nxt[2 * RO_THREADS], b3 = nxt[3 * RO_THREADS],
+                         b4 = nxt[4 * RO_THREADS];
+#else
             const float4 *b = d.bank + ((size_t)i * RACE_BANK_SLOTS + (e.episode % RACE_BANK_SLOTS)) * 6;
+            // all six words at once: the tag check must not put a second DRAM round trip behind the first (the whole
+            // CTA waits for this lane at the step's next barrier)
             const float4 b5 = __ldcg(b + 5);
+            const float4 b0 = __ldcg(b + 0), b1 = __ldcg(b + 1), b2 = __ldcg(b + 2), b3 = __ldcg(b + 3), b4 = __ldcg(b + 4);
+#endif
             if (__float_as_uint(b5.z) == e.episode && __float_as_uint(b5.w) == (d.key0 ^ (d.key1 * 0x9E3779B9u) ^ 0xB2D0u)) {
-                const float4 b0 = __ldcg(b + 0), b1 = __ldcg(b + 1), b2 = __ldcg(b + 2), b3 = __ldcg(b + 3), b4 = __ldcg(b + 4);
                 g[0] = b0.x; g[1] = b0.y; g[2] = b0.z; g[3] = b0.w; g[4] = b1.x; g[5] = b1.y; g[6] = b1.z; g[7] = b1.w;
                 g[8] = b2.x; g[9] = b2.y; g[10] = b2.z; g[11] = b2.w; g[12] = b3.x; g[13] = b3.y; g[14] = b3.z; g[15] = b3.w;
                 g[16] = b4.x; g[17] = b4.y; g[18] = b4.z; g[19] = b4.w; g[20] = b5.x; g[21] = b5.y;
@@ -330,6 +354,9 @@ __device__ __forceinline__ void ro_env_step(const RaceDev &d, int i, RaceRegs &e
             }
         }
         if (!banked) ro_generate_episode(d, i, e.episode, g);
+#if B2D_RO_BANK_PREFETCH
+        if (d.bank) ro_prefetch_bank(d, i, e.episode + 1u, nxt); // the staged words have been consumed into g[]
+#endif
         e.p = {g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7], g[8], g[9], g[10], g[11], g[12]};
 #pragma unroll
         for (int k = 0; k < 17; k++) e.s[k] = 0.0f;
@@ -360,6 +387,7 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *tile = reinterpret_cast<float *>(ro_smem + RO_B1_BYTES + RO_B2_BYTES + RO_A1_BYTES + warp * RO_TILE_BYTES);
     float *my_row = tile + lane * RACE_OBS;
+    float4 *nxt = reinterpret_cast<float4 *>(ro_smem + RO_B1_BYTES + RO_B2_BYTES + RO_A1_BYTES + 4 * RO_TILE_BYTES) + tid;
     const RaceDev &d = a.d;
 
     // ---- weights -> shared memory, canonical K-major layout, TF32 (round to nearest, ties away)
@@ -462,6 +490,9 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
             e.p = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w, tl.x};
             e.episode = __float_as_uint(tl.y);
             e.ring[0] = c0.x; e.ring[1] = c0.y; e.ring[2] = c0.z; e.ring[3] = c0.w; e.ring[4] = tl.z; e.ring[5] = tl.w;
+#if B2D_RO_BANK_PREFETCH
+            if (valid && d.bank) ro_prefetch_bank(d, i, e.episode + 1u, nxt);
+#endif
             // current observation rows of the warp's 32 envs: coalesced into the tile, then one row per lane
             const float *gobs = d.obs + (size_t)(chunk * RO_THREADS + warp * 32) * RACE_OBS;
             __syncwarp();
@@ -588,7 +619,7 @@ __global__ void __launch_bounds__(RO_THREADS, RO_CTAS_PER_SM) race_rollout_kerne
             // ---- 5. the env step, in registers
             float reward = 0.0f;
             int terminal = 0;
-            if (valid) ro_env_step<STRICT>(d, i, e, a4, reward, terminal, o, s_acc, k == K - 1, score_last);
+            if (valid) ro_env_step<STRICT>(d, i, e, a4, reward, terminal, o, s_acc, k == K - 1, score_last, nxt);
             prev_rew = reward;
             prev_term = (float)terminal;
             RO_TICK(7) // sampling, stores, env step
