@@ -54,6 +54,9 @@ constexpr int RO_B1_BYTES = (RO_K1 / 4) * RO_HIDDEN * 16;   // [8 chunks][128 n]
 constexpr int RO_B2_BYTES = (RO_HIDDEN / 4) * RO_N2 * 16;   // [32 chunks][16 n] float4
 constexpr int RO_A1_BYTES = (RO_K1 / 4) * RO_THREADS * 16;  // [8 chunks][128 rows] float4
 constexpr int RO_TILE_BYTES = 32 * RACE_OBS * 4;            // per-warp staging of observation rows
+#ifndef B2D_RO_GELU_DEG4
+#define B2D_RO_GELU_DEG4 1
+#endif
 #ifndef B2D_RO_BANK_PREFETCH
 #define B2D_RO_BANK_PREFETCH 1
 #endif
@@ -196,7 +199,11 @@ __device__ __forceinline__ void ro_tmem_st16(uint32_t taddr, const uint32_t (&r)
 __device__ __forceinline__ void ro_gelu16(uint32_t (&r)[16]) {
 #pragma unroll
     for (int q = 0; q < 8; q++) {
+        #if B2D_RO_GELU_DEG4
+        const float2 g = gelu2_tf32(make_float2(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1])));
+#else
         const float2 g = gelu2(make_float2(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1])));
+#endif
         r[2 * q] = __float_as_uint(g.x);
         r[2 * q + 1] = __float_as_uint(g.y);
     }
