@@ -481,9 +481,11 @@ __device__ __forceinline__ void advance_body_fast_loop(float s[17], const DroneP
     s[13] = b.r01.x; s[14] = b.r01.y; s[15] = b.r23.x; s[16] = b.r23.y;
 }
 
-template <bool STRICT>
+// LOOP: the fast form with its four stages as a loop (bit-identical results; for kernels short of instruction cache)
+template <bool STRICT, bool LOOP = false>
 __device__ __forceinline__ void advance_body(float s[17], const DroneParams &p, const float act[4]) {
     if constexpr (STRICT) advance_body_strict(s, p, act);
+    else if constexpr (LOOP) advance_body_fast_loop(s, p, act);
 #if B2D_PACKED_RK4
     else advance_body_fast_packed(s, p, act);
 #else

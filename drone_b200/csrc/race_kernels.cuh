@@ -26,6 +26,12 @@
 #pragma once
 #include "physics.cuh"
 
+#ifndef B2D_RACE_RK4_LOOP
+#define B2D_RACE_RK4_LOOP 0
+#endif
+#ifndef B2D_RO_RK4_LOOP
+#define B2D_RO_RK4_LOOP 0
+#endif
 namespace b2d {
 
 #ifndef B2D_RACE_BLOCK
@@ -704,7 +710,7 @@ __global__ void __launch_bounds__(RACE_BLOCK, RACE_MIN_CTAS) race_step_kernel(co
 #if B2D_EXPERIMENT_SKIP_MATH
             s[0] = fmaf(act[0], 1e-6f, s[0]); s[4] += p.mass * 1e-9f; s[13] += act[3];
 #else
-            advance_body<STRICT>(s, p, act);
+            advance_body<STRICT, B2D_RACE_RK4_LOOP>(s, p, act);
 #if B2D_EXPERIMENT_DOUBLE_MATH
             {   // measurement aid: the arithmetic twice, same memory traffic (the second result is folded in at 1e-30)
                 float s2[17];

@@ -281,7 +281,7 @@ __device__ __forceinline__ void ro_env_step(const RaceDev &d, int i, RaceRegs &e
     float s0[17];
 #pragma unroll
     for (int k = 0; k < 17; k++) s0[k] = e.s[k];
-    advance_body<STRICT>(e.s, e.p, act);
+    advance_body<STRICT, B2D_RO_RK4_LOOP>(e.s, e.p, act);
     bool oob = e.s[0] < -10.0f || e.s[0] > 10.0f || e.s[1] < -10.0f || e.s[1] > 10.0f || e.s[2] < -10.0f || e.s[2] > 10.0f;
     float gate = 0.0f;
     if constexpr (STRICT) {
