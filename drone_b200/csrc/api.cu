@@ -688,6 +688,7 @@ static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st
     for (int j = 1; j < chunks && (size_t)j * per_tiles < tiles; j++) bnd.push_back((size_t)j * per_tiles);
     bnd.push_back(tiles);
     const int nchunks = (int)bnd.size() - 1;
+    static const bool late_small = !(getenv("B2D_HOST_SMALL_COPIES") && atoi(getenv("B2D_HOST_SMALL_COPIES")) == 1);
     const bool host_copy = v->host_clamp || copy_in;
     if (host_copy) { // all chunks of the action copy go to the pool at once; chunk j is awaited right before its H2D
         size_t fb[CopyPool::MAX_CHUNKS + 1];
@@ -709,8 +710,17 @@ static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st
         CUDA_TRY(cudaStreamWaitEvent(cs, v->ev_step, 0));
         CUDA_TRY(cudaMemcpyAsync(v->host.observations + r0 * v->obs_dim, v->dev.observations + r0 * v->obs_dim,
                                  nr * v->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, cs));
-        CUDA_TRY(cudaMemcpyAsync(v->host.rewards + r0, v->dev.rewards + r0, nr * sizeof(float), cudaMemcpyDeviceToHost, cs));
-        CUDA_TRY(cudaMemcpyAsync(v->host.terminals + r0, v->dev.terminals + r0, nr, cudaMemcpyDeviceToHost, cs));
+        // rewards and terminals (5 B per env) come down as two copies of the whole vector after the last chunk's
+        // kernel instead of two small copies per chunk: every DMA operation costs ~10 us of link time whatever its size
+        if (!late_small) {
+            CUDA_TRY(cudaMemcpyAsync(v->host.rewards + r0, v->dev.rewards + r0, nr * sizeof(float), cudaMemcpyDeviceToHost, cs));
+            CUDA_TRY(cudaMemcpyAsync(v->host.terminals + r0, v->dev.terminals + r0, nr, cudaMemcpyDeviceToHost, cs));
+        } else if (j == nchunks - 1) {
+            cudaStream_t os = v->copy_streams[(j + 1) & 1];
+            CUDA_TRY(cudaStreamWaitEvent(os, v->ev_step, 0));
+            CUDA_TRY(cudaMemcpyAsync(v->host.rewards, v->dev.rewards, rows * sizeof(float), cudaMemcpyDeviceToHost, os));
+            CUDA_TRY(cudaMemcpyAsync(v->host.terminals, v->dev.terminals, rows, cudaMemcpyDeviceToHost, os));
+        }
         if (v->write_clamped)
             CUDA_TRY(cudaMemcpyAsync(v->host.actions + r0 * 4, v->dev.actions + r0 * 4, nr * 4 * sizeof(float), cudaMemcpyDeviceToHost, cs));
     }
