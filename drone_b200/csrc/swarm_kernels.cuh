@@ -333,6 +333,7 @@ __device__ __noinline__ uint2 sw_scan_odd(const float *w, int A, int a, float sx
 // two candidates per iteration on packed FP32x2, the minimum of the squared distances as one 3-input
 // integer min per pair (non-negative floats order like their bit patterns).  Exact minimum of the
 // squared distances as computed; the collision decision `distance < 1` is guarded by the caller.
+template <int UNROLL>
 __device__ __forceinline__ float sw_nearest_dist_fast(const float *w, int A, int a, const float self[3]) {
     unsigned int best = 0x7f800000u;
     if ((A & 1) == 0) {
@@ -344,7 +345,7 @@ __device__ __forceinline__ float sw_nearest_dist_fast(const float *w, int A, int
         }
         const float2 nx = make_float2(-self[0], -self[0]), ny = make_float2(-self[1], -self[1]), nz = make_float2(-self[2], -self[2]);
         const float *src = w + a2;
-#pragma unroll 4
+#pragma unroll UNROLL
         for (int c = 2; c < A; c += 2) {
             const float2 ox = *reinterpret_cast<const float2 *>(src + c);
             const float2 oy = *reinterpret_cast<const float2 *>(src + c + SW_WIN);
@@ -364,6 +365,7 @@ __device__ __forceinline__ float sw_nearest_dist_fast(const float *w, int A, int
 // AND the second smallest key.  When the two lie within two key buckets (3e-5 relative) the order of the
 // candidates is not safe against rounding -- `ambiguous` -- and the caller re-takes the decision with
 // sw_nearest_strict_call; otherwise the winner is the reference's.
+template <int UNROLL>
 __device__ __forceinline__ void sw_nearest_fast(const float *w, int A, int a, const float self[3], float other[3], bool &ambiguous) {
     constexpr unsigned int KEY_NONE = 0x7f800000u, CODE_MASK = 127u;
     other[0] = other[1] = other[2] = 0.0f;
@@ -379,7 +381,7 @@ __device__ __forceinline__ void sw_nearest_fast(const float *w, int A, int a, co
         }
         const float2 nx = make_float2(-self[0], -self[0]), ny = make_float2(-self[1], -self[1]), nz = make_float2(-self[2], -self[2]);
         const float *src = w + a2;
-#pragma unroll 4
+#pragma unroll UNROLL
         for (int c = 2; c < A; c += 2) { // window offsets c, c + 1 from a's pair
             const float2 ox = *reinterpret_cast<const float2 *>(src + c);
             const float2 oy = *reinterpret_cast<const float2 *>(src + c + SW_WIN);
@@ -412,13 +414,13 @@ constexpr float SW_GUARD_PLANE = 1e-4f;  // ring plane crossing
 constexpr float SW_GUARD_DIST = 1e-4f;   // collision: | nearest distance - 1 |
 
 // nearest-neighbour DISTANCE for compute_reward (R/drone_swarm.h:347-352)
-template <bool STRICT>
+template <bool STRICT, int UNROLL = 2>
 __device__ __forceinline__ float sw_reward_distance(const float *w, int A, int a, const float self[3], int &guard_hits) {
     if constexpr (STRICT) {
         float other[3];
         return sw_nearest_strict(w, A, a, self, other);
     } else {
-        float nd = sw_nearest_dist_fast(w, A, a, self);
+        float nd = sw_nearest_dist_fast<UNROLL>(w, A, a, self);
         if (fabsf(nd - 1.0f) < SW_GUARD_DIST) {
             float other[3];
             nd = sw_nearest_strict_call(w, A, a, self[0], self[1], self[2], other);
@@ -439,13 +441,13 @@ __device__ __noinline__ float sw_reward_distance_cold(const float *w, int A, int
 }
 
 // nearest neighbour's POSITION for compute_observations (R/drone_swarm.h:187-196)
-template <bool STRICT>
+template <bool STRICT, int UNROLL>
 __device__ __forceinline__ void sw_obs_neighbour(const float *w, int A, int a, const float self[3], float near[3], int &guard_hits) {
     if constexpr (STRICT) {
         sw_nearest_strict(w, A, a, self, near);
     } else {
         bool ambiguous;
-        sw_nearest_fast(w, A, a, self, near, ambiguous);
+        sw_nearest_fast<UNROLL>(w, A, a, self, near, ambiguous);
         if (ambiguous) {
             float other[3];
             sw_nearest_strict_call(w, A, a, self[0], self[1], self[2], other);
@@ -783,7 +785,10 @@ __device__ __noinline__ void sw_reset_phase(const SwarmDev &d, SwResetCtx *c, Sw
 // resident CTAs per SM, CTA c takes tiles c, c + grid, ...): while a tile computes (~2-3 k
 // instructions per agent) the 14 input words of the CTA's next tile stream into shared memory
 // with cp.async, so no warp ever waits on a global load at the top of a tile.
-template <bool STRICT, bool ONLY_RESET>
+// SCAN_UNROLL: unroll factor of the fast neighbour sweeps.  Two builds of the fast step: for A <= 32 the compact
+// sweep (2) wins -- the step's hot code is what costs there (32 KB instruction cache level): A = 16 113 vs 119 us, A = 32
+// 244 vs 250 us -- for longer sweeps the unrolled one (4): A = 64 544 vs 553 us (profiles/r02_ab/r02x_ab.txt, r02y_ab.txt).
+template <bool STRICT, bool ONLY_RESET, int SCAN_UNROLL = 4>
 __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_constant__ SwarmDev d) {
     // per env (3A floats apart): [old | fin | rst] = before this tick's move | after the move, or the respawn
     // position of an agent that left the arena | first position drawn by an env-wide reset
@@ -1030,7 +1035,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
         if (active) {
             const float self[3] = {g.s[0], g.s[1], g.s[2]};
             float nd = 0.0f;
-            if (A > 1) nd = sw_reward_distance<STRICT>(&s_trail.x[w0], A, a, self, guard_hits);
+            if (A > 1) nd = sw_reward_distance<STRICT, SCAN_UNROLL>(&s_trail.x[w0], A, a, self, guard_hits);
             if (task == SWARM_TASK_RACE) {
                 reward = sw_reward<STRICT>(g, self, true, A, nd);
                 if (passed > 0.0f) {
@@ -1171,7 +1176,7 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
         }
         const float self[3] = {g.s[0], g.s[1], g.s[2]};
         float near[3] = {0.0f, 0.0f, 0.0f};
-        if (A > 1) sw_obs_neighbour<STRICT>(&s_now.x[w0], A, a, self, near, guard_hits);
+        if (A > 1) sw_obs_neighbour<STRICT, SCAN_UNROLL>(&s_now.x[w0], A, a, self, near, guard_hits);
         float ring[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
         if (task == SWARM_TASK_RACE) load_ring(e, g.ring_idx, ring);
         sw_observe<STRICT>(g, A, near, task == SWARM_TASK_RACE, ring, s_obs + t * SWARM_OBS, 1);
@@ -1357,17 +1362,24 @@ static inline void swarm_vec_reset(SwarmDev &d, uint64_t seed, cudaStream_t st, 
 // dynamic shared memory opt-in is per device, and so are the SM count and the occupancy.
 static inline int swarm_step_smem(const SwarmDev &d) { return SW_DYN_SMEM + sw_ring_stage_bytes(d.epc, d.R); }
 
+constexpr int SW_COMPACT_SCAN_MAX_A = 32; // see swarm_kernel: SCAN_UNROLL
+typedef void (*swarm_step_fn)(SwarmDev);
+static inline swarm_step_fn swarm_step_kernel_for(const SwarmDev &d, int math) {
+    if (math == 1) return swarm_kernel<true, false>;
+    return d.A <= SW_COMPACT_SCAN_MAX_A ? swarm_kernel<false, false, 2> : swarm_kernel<false, false, 4>;
+}
+
 static inline int swarm_step_setup(const SwarmDev &d, int device, int grid_out[2]) {
     int sms = 0, per_sm[2] = {0, 0};
     const int smem = swarm_step_smem(d);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(swarm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM + SW_RING_STAGE_MAX) != cudaSuccess ||
-        cudaFuncSetAttribute(swarm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM + SW_RING_STAGE_MAX) != cudaSuccess ||
-        cudaFuncSetAttribute(swarm_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
-        cudaFuncSetAttribute(swarm_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], swarm_kernel<false, false>, SWARM_BLOCK, smem) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], swarm_kernel<true, false>, SWARM_BLOCK, smem) != cudaSuccess)
-        return -1;
+    for (int m = 0; m < 2; m++) {
+        const swarm_step_fn fn = swarm_step_kernel_for(d, m);
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_DYN_SMEM + SW_RING_STAGE_MAX) != cudaSuccess ||
+            cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[m], fn, SWARM_BLOCK, smem) != cudaSuccess)
+            return -1;
+    }
     const int tiles = swarm_grid(d);
     for (int m = 0; m < 2; m++) {
         if (per_sm[m] < 1) return -1;
@@ -1396,7 +1408,7 @@ static inline cudaError_t swarm_vec_step(SwarmDev &dev, const float *actions, in
     cfg.attrs = attr;
     cfg.numAttrs = overlap ? 1 : 0;
     *launches += 1;
-    return math == 1 ? cudaLaunchKernelEx(&cfg, swarm_kernel<true, false>, d) : cudaLaunchKernelEx(&cfg, swarm_kernel<false, false>, d);
+    return cudaLaunchKernelEx(&cfg, swarm_step_kernel_for(d, math), d);
 }
 
 static inline void swarm_observe_launch(SwarmDev &d, cudaStream_t st) {
