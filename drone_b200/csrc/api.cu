@@ -1123,9 +1123,11 @@ extern "C" int b2d_puff_advantage(const float *values, const float *rewards, con
 template <class K> static int policy_launch(K kernel, int slot, int threads, int warps, size_t smem, const PolicyArgs &a, cudaStream_t st) {
     static int grid_for[4][64] = {{0}};
     static size_t smem_for[4][64] = {{0}};
+    static std::mutex cache_mu; // per-device launch geometry, shared by every caller thread of the process
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return fail(B2D_EINVAL, "device ordinal out of range");
+    std::unique_lock<std::mutex> lk(cache_mu);
     if (grid_for[slot][dev] == 0 || smem_for[slot][dev] != smem) {
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, sms = 0;
@@ -1135,9 +1137,11 @@ template <class K> static int policy_launch(K kernel, int slot, int threads, int
         grid_for[slot][dev] = per_sm * sms;
         smem_for[slot][dev] = smem;
     }
+    const int slots = grid_for[slot][dev];
+    lk.unlock();
     const int tiles = (a.rows + POL_TILE - 1) / POL_TILE;
     int grid = (tiles + warps - 1) / warps;
-    if (grid > grid_for[slot][dev]) grid = grid_for[slot][dev];
+    if (grid > slots) grid = slots;
     kernel<<<grid, threads, smem, st>>>(a);
     return launch_check("policy_act_kernel");
 }
@@ -1215,8 +1219,10 @@ extern "C" int b2d_race_rollout(b2d_vec *v, const b2d_policy_weights *w, const b
     if (v->race.reset_mode != B2D_RESET_PHILOX) return fail(B2D_ESTATE, "b2d_race_rollout: not available in inject mode");
     DEVICE_SCOPE(v);
     static int grid_for[2][64] = {{0}};
+    static std::mutex cache_mu;
     const int dev = v->device, m = v->math == B2D_MATH_STRICT ? 1 : 0;
     if (dev < 0 || dev >= 64) return fail(B2D_EINVAL, "device ordinal out of range");
+    std::unique_lock<std::mutex> lk(cache_mu);
     if (grid_for[m][dev] == 0) {
         int per_sm = 0, sms = 0;
         if (m) {
@@ -1238,6 +1244,8 @@ extern "C" int b2d_race_rollout(b2d_vec *v, const b2d_policy_weights *w, const b
         if (getenv("B2D_RO_CTAS")) per_sm = atoi(getenv("B2D_RO_CTAS")); // measurement aid
         grid_for[m][dev] = per_sm * sms;
     }
+    const int ro_slots = grid_for[m][dev];
+    lk.unlock();
     // the episode bank: allocated on first use (not inside a stream capture), topped up before every launch
     cudaStream_t st = (cudaStream_t)stream;
     if (!v->race.bank) {
@@ -1264,7 +1272,7 @@ extern "C" int b2d_race_rollout(b2d_vec *v, const b2d_policy_weights *w, const b
     a.counter = device_counter;
     a.deterministic = deterministic ? 1 : 0;
     const int chunks = (v->race.n + RO_THREADS - 1) / RO_THREADS;
-    const int grid = chunks < grid_for[m][dev] ? chunks : grid_for[m][dev];
+    const int grid = chunks < ro_slots ? chunks : ro_slots;
     if (m) race_rollout_kernel<true><<<grid, RO_THREADS, RO_SMEM_BYTES, st>>>(a);
     else race_rollout_kernel<false><<<grid, RO_THREADS, RO_SMEM_BYTES, st>>>(a);
     v->launches += 1;

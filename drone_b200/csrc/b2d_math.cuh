@@ -78,8 +78,12 @@ __device__ __forceinline__ V3<T> qrot(const Q4<T> &q, const V3<T> &v) {
 }
 
 // ---- Philox4x32-10 (Salmon, Moraes, Dror, Shaw; SC'11) ---------------------------
+#ifndef B2D_PHILOX_UNROLL
+#define B2D_PHILOX_UNROLL 10
+#endif
+constexpr int PHILOX_UNROLL = B2D_PHILOX_UNROLL;
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
-#pragma unroll
+#pragma unroll PHILOX_UNROLL
     for (int r = 0; r < 10; r++) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c.x;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c.z;
