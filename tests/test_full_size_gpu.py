@@ -148,3 +148,36 @@ def test_swarm_full_size_slices_equal_the_oracle(oracle):
     log = vec.log()
     assert log["n"] == float(nterm.item()) and log["n"] > 0
     vec.close()
+
+
+@pytest.mark.parametrize("A", [16, 64])
+def test_swarm_overlapped_launches_equal_serialised_launches(A):
+    """Step launches that follow each other on one stream overlap at their edges (PDL + per-CTA completion
+    flags, swarm_kernel); launches that alternate between two streams with a full synchronisation in
+    between are plain.  Same vector, same actions: every output word, the state and the log must agree, in
+    the fast build the bench runs, at BASELINE.json's configs[2] size."""
+    from drone_b200.vec import SwarmVec
+    n, R, seed, T = SWARM_ENVS, 10, 5, 40
+    g = torch.Generator(device="cpu").manual_seed(17)
+    dtape = (torch.rand((4, n * A, 4), generator=g) * 2.0 - 1.0).cuda()
+    a = SwarmVec(n, A, R, math="fast", seed=seed)
+    b = SwarmVec(n, A, R, math="fast", seed=seed)
+    a.reset(seed)
+    b.reset(seed)
+    torch.cuda.synchronize()
+    for t in range(T):          # back to back on the current stream: launches 2..T overlap their predecessor
+        a.step(dtape[t % 4])
+    s = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for t in range(T):          # a different stream every launch, drained each time: never overlapped
+        b.step(dtape[t % 4], stream=s[t & 1])
+        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    for name in ("observations", "rewards", "terminals"):
+        x, y = getattr(a, name), getattr(b, name)
+        assert torch.equal(x.view(torch.uint8), y.view(torch.uint8)), name
+    probe = list(range(0, 64)) + list(range(n - 64, n))
+    assert np.array_equal(_bits(a.get_state(probe)), _bits(b.get_state(probe)))
+    assert a.log() == b.log()
+    assert a.step_count == b.step_count == T
+    a.close()
+    b.close()
