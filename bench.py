@@ -441,11 +441,15 @@ def bench_rollout(replays, dev, envs=1 << 20, horizon=128, impl="auto", cpu=True
                                    f"{envs:,} envs, K={horizon} steps per collect() (BASELINE.json configs[3])",
                        "l2": f"experience written per step {envs * 148 / 1e6:.0f} MB > 126 MB L2"},
             "episode_stats": vec.log(), "clocks": sampler.summary(),
-            "roofline": roofline_hbm(algo * envs, us, ro.kernel_name)}
+            "roofline": roofline_hbm(algo * envs, us, ro.kernel_name,
+                                     ncu_traffic("race_rollout_kernel_bytes_per_step") if (fused and envs == ENVS_PER_GPU) else None,
+                                     "profiles/roofline_traffic.json (per step of a K = 128 launch; not measured in this run)"
+                                     if (fused and envs == ENVS_PER_GPU) else None)}
     line["roofline"]["note"] = ("bytes that must move per env-step: " +
                                 ("the experience row only (state stays on chip for the K steps)" if fused else
                                  "env step 373 B + policy step 285 B (two kernels per step)") +
-                                "; the kernel is FP32-issue bound (exact GELU x 128 per env-step), see DESIGN.md")
+                                "; the kernel is FP32-issue bound (GELU x 128 + the env step per env-step: 2,180 warp-instructions per "
+                                "warp-step, ncu issue-active 57 % at 3 CTAs per SM = the TMEM limit), see DESIGN.md")
     vec.close()
     del ro
     torch.cuda.empty_cache()
