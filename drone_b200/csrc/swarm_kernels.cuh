@@ -49,17 +49,10 @@ namespace b2d {
 #ifndef B2D_SW_RS_POOL
 #define B2D_SW_RS_POOL 8 // per warp: prepared respawn parameters fetched by cp.async a phase ahead (0: plain loads)
 #endif
-#ifndef B2D_SW_OBS_UNROLL
-#define B2D_SW_OBS_UNROLL 0 // measured: 8 % slower (145 -> 157 us at A = 16)
-#endif
-#ifndef B2D_SW_OBS_LOOP_UNROLL
-#define B2D_SW_OBS_LOOP_UNROLL 1
-#endif
 #ifndef B2D_SW_RK4_LOOP
 #define B2D_SW_RK4_LOOP 1 // RK4 stages as a loop: the hot path shrinks by ~4.5 KB of code
 #endif
 constexpr int SWARM_BLOCK = 128;
-constexpr int SW_OBS_LOOP_UNROLL = B2D_SW_OBS_LOOP_UNROLL;
 constexpr int SWARM_OBS = 41;
 constexpr int SWARM_AGENT_BLOB = 47;
 constexpr int SWARM_AGENT_PAYLOAD = 41; // oracle/drone_oracle.c "swarm env": respawn [0:16], env reset [16:41]
@@ -1068,14 +1061,9 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
                     ilen = g.ep_len;
                     f[0] = __float2ll_rn(g.score * 1048576.0f);
                     f[1] = __float2ll_rn(g.ep_ret * 1048576.0f);
-#if B2D_SWARM_EXPERIMENT_NO_DIV
-                    f[2] = __float2ll_rn((g.collisions * len) * 1048576.0f);
-                    f[3] = __float2ll_rn((g.score * len) * 1048576.0f);
-#else
                     // (a zero numerator sends the IEEE division down its slow path: most episodes have no collision)
                     f[2] = g.collisions == 0.0f ? 0ll : __float2ll_rn((g.collisions / len) * 1048576.0f);
                     f[3] = g.score == 0.0f ? 0ll : __float2ll_rn((g.score / len) * 1048576.0f);
-#endif
                 }
                 long long sum[4] = {0ll, 0ll, 0ll, 0ll};
                 int slen = 0;
@@ -1193,26 +1181,9 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
             const float4 *src = reinterpret_cast<const float4 *>(sobs);
             float4 *dst = reinterpret_cast<float4 *>(gobs);
             const int n4 = rows_mine * SWARM_OBS / 4; // <= 10.25 * grp_size
-#if B2D_SW_OBS_UNROLL
-            // loads first, stores after: the loop form exposed the shared-memory latency once per iteration
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                float4 v[6];
-#pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    const int m = tg + (h * 6 + i) * grp_size;
-                    if (m < n4) v[i] = src[m];
-                }
-#pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    const int m = tg + (h * 6 + i) * grp_size;
-                    if (m < n4) __stcs(&dst[m], v[i]);
-                }
-            }
-#else
-#pragma unroll SW_OBS_LOOP_UNROLL
+            // (hoisting the loads of several iterations, or unrolling: measured slower, profiles/README.md)
+#pragma unroll 1
             for (int m = tg; m < n4; m += grp_size) __stcs(&dst[m], src[m]);
-#endif
         } else {
             for (int m = tg; m < rows_mine * SWARM_OBS; m += grp_size) __stcs(&gobs[m], sobs[m]);
         }
@@ -1247,9 +1218,8 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
           long long sum = 0ll;
 #pragma unroll
           for (int w = 0; w < SWARM_BLOCK / 32; w++) sum += s_wacc[w][t];
-#if !B2D_SWARM_EXPERIMENT_NO_FLUSH
           if (sum != 0ll) atomicAdd(&d.ctl->facc[t], (double)sum * (1.0 / 1048576.0));
-#endif
+
       }
       if (t == 0 && s_guard != 0) atomicAdd(&d.ctl->guard_replays, (unsigned long long)s_guard);
 #if B2D_SW_OVERLAP
