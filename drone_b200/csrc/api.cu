@@ -164,7 +164,7 @@ struct b2d_vec {
     CopyPool *pool;  // host buffers: threads that share the action copy
     // caller action arrays seen by b2d_vec_step_host_from: an array that comes back is page-locked in place
     // (cudaHostRegister) so that its H2D needs no staging copy; see step_host_impl
-    struct ActionSource { const float *ptr; size_t bytes; int seen; int state; /* 0 new, 1 registered, -1 failed */ };
+    struct ActionSource { const float *ptr; size_t bytes; int seen; int state; /* 0 new, 1 registered here, 2 pinned by the caller, -1 failed */ };
     ActionSource act_src[8];
     int act_src_clock;
     int step_ctas;   // race: CTAs of an overlapped (tape) launch = the largest grid; swarm: unused
@@ -207,6 +207,16 @@ template <class T> static int dev_alloc(b2d_vec *v, T **p, size_t count) {
     v->allocs.push_back(q);
     *p = (T *)q;
     return B2D_OK;
+}
+
+// page-locked already (cudaHostAlloc / cudaHostRegister by the caller)?  Plain host memory reports cudaMemoryTypeUnregistered.
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
 }
 
 static int check_ext(const b2d_buffers *ext) {
@@ -252,6 +262,7 @@ static int setup_buffers(b2d_vec *v, const b2d_buffers *ext) {
         for (int k = 0; k < 5; k++) {
             v->registered[k] = false;
             if (!ptrs[k]) continue;
+            if (host_is_pinned(ptrs[k])) continue; // the caller's own pinned allocation (the Python wrappers do that)
             if (cudaHostRegister(ptrs[k], bytes[k], cudaHostRegisterDefault) == cudaSuccess) v->registered[k] = true;
             else cudaGetLastError();
         }
@@ -630,13 +641,14 @@ static int step_impl(b2d_vec *v, const float *actions, cudaStream_t st, bool all
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cap);
         const bool capturing = cap != cudaStreamCaptureStatusNone; // sequence numbers would be frozen into the graph
-        const bool overlap = B2D_SW_OVERLAP && allow_overlap && !capturing && v->last_full_seq != 0 && v->last_full_seq == v->seq &&
+        const bool full = tile_begin == 0 && tile_end < 0;
+        const bool overlap = B2D_SW_OVERLAP && allow_overlap && full && !capturing && v->last_full_seq != 0 && v->last_full_seq == v->seq &&
                              v->last_stream == st;
         const unsigned int seq = ++v->seq;
         cudaError_t e = swarm_vec_step(v->swarm, actions, v->math, v->swarm_grid[v->math == B2D_MATH_STRICT ? 1 : 0], st, &v->launches,
-                                       seq, overlap);
+                                       seq, overlap, tile_begin, tile_end);
         if (e != cudaSuccess) return fail(B2D_ECUDA, "swarm_kernel launch: %s", cudaGetErrorString(e));
-        v->last_full_seq = capturing ? 0 : seq;
+        v->last_full_seq = (capturing || !full) ? 0 : seq;
         v->last_stream = st;
     }
     return launch_check("swarm_step_kernel");
@@ -685,10 +697,11 @@ static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st
     const size_t rows = (size_t)v->num_agents;
     const bool copy_in = host_actions && host_actions != v->host.actions;
     int chunks = 1;
-    if (v->kind == KIND_RACE && rows >= (1u << 17)) chunks = rows >= (1u << 19) ? 8 : 4;
-    // chunk boundaries in tiles; the first chunk is split 1:3 so that the first results start coming
-    // down after 1/32 of the vector instead of 1/8 (the pipeline's lead-in is pure latency)
-    const size_t tiles = (rows + 31) / 32, per_tiles = (tiles + chunks - 1) / chunks;
+    if (rows >= (1u << 17)) chunks = rows >= (1u << 19) ? 8 : 4;
+    // chunk boundaries in tiles (race: 32 envs; swarm: the envs one CTA steps together); the first chunk is split 1:3 so
+    // that the first results start coming down after 1/32 of the vector instead of 1/8 (the pipeline's lead-in is pure latency)
+    const size_t tile_rows = v->kind == KIND_RACE ? 32 : (size_t)v->swarm.epc * v->swarm.A;
+    const size_t tiles = (rows + tile_rows - 1) / tile_rows, per_tiles = (tiles + chunks - 1) / chunks;
     std::vector<size_t> bnd;
     bnd.push_back(0);
     if (chunks > 1 && per_tiles >= 4) bnd.push_back(per_tiles / 4);
@@ -718,22 +731,26 @@ static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st
             *victim = {host_actions, bytes, 0, 0};
             hit = victim;
         } else if (hit->state == 0) {
-            const cudaError_t e = cudaHostRegister(const_cast<float *>(host_actions), bytes, cudaHostRegisterDefault);
-            hit->state = e == cudaSuccess ? 1 : -1;
-            if (e != cudaSuccess) (void)cudaGetLastError();
+            if (host_is_pinned(host_actions)) {
+                hit->state = 2; // the caller's own pinned memory: uploaded in place, nothing to release
+            } else {
+                const cudaError_t e = cudaHostRegister(const_cast<float *>(host_actions), bytes, cudaHostRegisterDefault);
+                hit->state = e == cudaSuccess ? 1 : -1;
+                if (e != cudaSuccess) (void)cudaGetLastError();
+            }
         }
         hit->seen = ++v->act_src_clock;
-        if (hit->state == 1) { h2d_src = host_actions; deferred_copy = true; }
+        if (hit->state >= 1) { h2d_src = host_actions; deferred_copy = true; }
     }
     const bool host_copy = (v->host_clamp || copy_in) && !deferred_copy;
     if (host_copy) { // all chunks of the action copy go to the pool at once; chunk j is awaited right before its H2D
         size_t fb[CopyPool::MAX_CHUNKS + 1];
-        for (int j = 0; j <= nchunks; j++) fb[j] = (bnd[j] * 32 < rows ? bnd[j] * 32 : rows) * 4;
+        for (int j = 0; j <= nchunks; j++) fb[j] = (bnd[j] * tile_rows < rows ? bnd[j] * tile_rows : rows) * 4;
         v->pool->begin(v->host.actions, copy_in ? host_actions : v->host.actions, fb, nchunks, v->host_clamp);
     }
     for (int j = 0; j < nchunks; j++) {
-        const size_t r0 = bnd[j] * 32;
-        const size_t r1 = bnd[j + 1] * 32 < rows ? bnd[j + 1] * 32 : rows;
+        const size_t r0 = bnd[j] * tile_rows;
+        const size_t r1 = bnd[j + 1] * tile_rows < rows ? bnd[j + 1] * tile_rows : rows;
         const size_t nr = r1 - r0;
         cudaStream_t cs = v->copy_streams[j & 1];
         // the copy of later chunks overlaps the transfers of the chunks already in flight

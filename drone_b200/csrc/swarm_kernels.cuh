@@ -87,6 +87,7 @@ struct SwarmDev {
     unsigned int *chain; // [grid]
     unsigned int seq;
     int chain_wait;
+    int tile_begin, tile_end; // tiles [begin, end) stepped by this launch (host-buffer steps are issued in chunks); end <= 0: all
 };
 
 struct SwarmAgent {
@@ -814,7 +815,10 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
     const int a = t - le * A;
     const int w0 = le * 3 * A; // this env's windows
     const bool inject = d.reset_mode == 1;
-    const int ntiles = (d.n + d.epc - 1) / d.epc;
+    const int ntiles_all = (d.n + d.epc - 1) / d.epc;
+    const int ntiles = d.tile_end > 0 && d.tile_end < ntiles_all ? d.tile_end : ntiles_all;
+    // CTA c owns the tiles congruent to c modulo the grid, whatever range a launch covers
+    const int first_tile = d.tile_begin + (int)((blockIdx.x + gridDim.x - (unsigned)d.tile_begin % gridDim.x) % gridDim.x);
     const size_t pay_stride = (size_t)A * SWARM_AGENT_PAYLOAD + 2 + 6 * d.R;
 
     // Everything the phases exchange through shared memory stays inside one env, so the barriers
@@ -873,15 +877,15 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
     __syncthreads();
 
     if constexpr (!ONLY_RESET) {
-        const int e0 = blockIdx.x * d.epc + le;
-        if ((int)blockIdx.x < ntiles && le < d.epc && e0 < d.n) {
+        const int e0 = first_tile * d.epc + le;
+        if (first_tile < ntiles && le < d.epc && e0 < d.n) {
             sw_prefetch(d, stage, t, e0, e0 * A + a);
             if (ring_staged) sw_prefetch_rings(d, rstage, 0, le, a, e0);
         }
         cp_async_commit();
     }
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = first_tile; tile < ntiles; tile += gridDim.x) {
     const int e = tile * d.epc + le;
     const bool active = le < d.epc && e < d.n;
     const int k = e * A + a;
@@ -1361,11 +1365,13 @@ static inline int swarm_step_setup(const SwarmDev &d, int device, int grid_out[2
 
 // overlap: this launch directly follows step launch seq - 1 of the same handle on the same stream (api.cu step_impl)
 static inline cudaError_t swarm_vec_step(SwarmDev &dev, const float *actions, int math, int grid, cudaStream_t st, long long *launches,
-                                         unsigned int seq, bool overlap) {
+                                         unsigned int seq, bool overlap, int tile_begin = 0, int tile_end = -1) {
     SwarmDev d = dev;
     if (actions) d.act_in = actions;
     d.seq = seq;
     d.chain_wait = overlap ? 1 : 0;
+    d.tile_begin = tile_begin;
+    d.tile_end = tile_end;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);

@@ -172,6 +172,33 @@ def test_host_buffer_pipeline_equals_device_path():
     vec.close()
 
 
+@pytest.mark.parametrize("A", [16, 64, 5])
+def test_swarm_host_buffer_pipeline_equals_device_path(A):
+    """NumPy-buffer steps of large swarm vectors are issued as the same chunked H2D / kernel / D2H pipeline as the
+    race env's (tile sub-range launches of swarm_kernel); results, buffers and vec_log must equal the one-launch path."""
+    from drone_b200.drone_swarm import DroneSwarm, binding
+    from drone_b200.vec import SwarmVec
+    E, R, seed, T = (131_200 + A - 1) // A + 3, 6, 9, 10
+    env = DroneSwarm(num_envs=E, num_drones=A, max_rings=R, seed=seed, math="strict", report_interval=1 << 30)
+    vec = SwarmVec(E, A, R, seed=seed, math="strict")
+    env.reset(seed)
+    vec.reset(seed)
+    tape = action_tape(E * A, scale=1.0)
+    dtape = torch.from_numpy(tape).cuda()
+    for t in range(T):
+        obs, rew, term, trunc, info = env.step(tape[t % 16])
+        vec.step(dtape[t % 16])
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(obs), bits(vec.observations.cpu().numpy()))
+    assert np.array_equal(bits(rew), bits(vec.rewards.cpu().numpy()))
+    assert np.array_equal(term.astype(np.uint8), vec.terminals.cpu().numpy())
+    assert np.array_equal(bits(env.actions), bits(tape[(T - 1) % 16]))
+    assert binding.vec_log(env.c_envs) == {k: v for k, v in vec.log().items()}
+    assert vec.step_count == T
+    env.close()
+    vec.close()
+
+
 def test_host_step_from_a_recurring_caller_array_uploads_in_place_and_leaves_clamped_actions():
     """An action array that comes back is page-locked where it is and uploaded without the staging copy
     (api.cu step_host_impl); the env's own action buffer must still hold clamp(actions, -1, 1) at return, like
