@@ -45,6 +45,7 @@ MAX_RINGS, MAX_MOVES = 10, 1000
 TAPE_LEN, TAPE_SEED = 16, 1234
 ALGO_BYTES_PER_ENV_STEP = 373    # reads 172 + writes 201, SURVEY.md 8(d)
 ALGO_BYTES_PER_DRONE_STEP = 521  # swarm, SURVEY.md 8(d)
+SWARM_OBS_DIM = 41
 ALGO_FLOPS_PER_ENV_STEP = 1330   # as-written FP32 operations of the reference step, SURVEY.md 8(d)
 # rollout (fused policy + env kernel): per env-step only the experience row leaves the SM:
 # obs 116 + action 16 + logprob, value, reward, terminal 4 x 4 = 148 B (DESIGN.md "rollout")
@@ -358,7 +359,7 @@ def race_line(res, n, math, launch, steps, warmup, world, ms_max, which="configs
         "gpu_launches": res["launches"], "roofline": roof}
 
 
-def bench_swarm(drones, steps, warmup, dev, math="fast", envs=1 << 16, cpu=True):
+def bench_swarm(drones, steps, warmup, dev, math="fast", envs=1 << 16, cpu=True, e2e=True):
     import torch
     from drone_b200.vec import SwarmVec
     rows = envs * drones
@@ -400,6 +401,31 @@ def bench_swarm(drones, steps, warmup, dev, math="fast", envs=1 << 16, cpu=True)
     vec.close()
     del tape
     torch.cuda.empty_cache()
+    if e2e:  # the reference's NumPy-buffer contract: host actions in, host observations / rewards / terminals out, every step
+        import numpy as np
+        from drone_b200.drone_swarm import DroneSwarm
+        env = DroneSwarm(num_envs=envs, num_drones=drones, max_rings=10, seed=0, report_interval=1 << 30, buffers="host",
+                         device=dev.index, math=math)
+        env.reset(0)
+        rng = np.random.default_rng(TAPE_SEED)
+        htape = rng.uniform(-1, 1, size=(2, rows, 4)).astype(np.float32)
+        e2e_steps = max(3, min(steps, 4_000_000 * 12 // rows))
+        for k in range(3):
+            env.step(htape[k % 2])
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            obs, rew, term, trunc, info = env.step(htape[k % 2])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        checksum = float(np.abs(obs[:1 << 16]).sum(dtype=np.float64))
+        env.close()
+        del htape
+        floor = pcie_floor_ms(rows, dev, down_bytes=SWARM_OBS_DIM * 4 + 5)
+        line["e2e"] = {"value": rows * e2e_steps / dt, "unit": "drone-steps/s", "h2d_bytes_per_step": rows * 16,
+                       "d2h_bytes_per_step": rows * (SWARM_OBS_DIM * 4 + 5), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
+                       "pcie_floor_ms": floor, "ms_per_step_over_pcie_floor": dt / e2e_steps * 1e3 / floor,
+                       "api": "drone_b200.drone_swarm.DroneSwarm(buffers='host').step(np.ndarray) -> binding.vec_step_actions -> "
+                              "b2d_vec_step_host_from (chunked H2D / kernel / D2H pipeline)", "checksum": checksum}
     if cpu:
         line["cpu_baseline"] = safe_cpu_baseline("drone-steps/s", f" x {drones} drones", budget_s=8.0, drones=drones)
     return line
@@ -458,14 +484,14 @@ def bench_rollout(replays, dev, envs=1 << 20, horizon=128, impl="auto", cpu=True
     return line
 
 
-def pcie_floor_ms(n, dev, iters=5):
+def pcie_floor_ms(n, dev, iters=5, down_bytes=121):
     """The bytes of one host-buffer step (16 B/env up, 121 B/env down) as bare pinned-memory copies on two
     streams, nothing else: the floor the e2e figure sits on."""
     import torch
     up_h = torch.zeros(n * 16, dtype=torch.uint8, pin_memory=True)
-    dn_h = torch.zeros(n * 121, dtype=torch.uint8, pin_memory=True)
+    dn_h = torch.zeros(n * down_bytes, dtype=torch.uint8, pin_memory=True)
     up_d = torch.zeros(n * 16, dtype=torch.uint8, device=dev)
-    dn_d = torch.zeros(n * 121, dtype=torch.uint8, device=dev)
+    dn_d = torch.zeros(n * down_bytes, dtype=torch.uint8, device=dev)
     s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     best = None
     for _ in range(iters + 1):
@@ -528,7 +554,7 @@ def main():
                 line["cpu_baseline"] = safe_cpu_baseline(UNIT, budget_s=8.0, envs=4096)
         elif args.workload.startswith("swarm"):
             line = bench_swarm(int(args.workload[5:]), min(args.steps, 1100) if args.steps != 2000 else 1100, args.warmup, dev,
-                               math=args.math, cpu=cpu)
+                               math=args.math, cpu=cpu, e2e=not args.no_e2e)
         else:
             line = bench_rollout(max(1, min(8, args.steps // 128)) if args.steps != 2000 else 4, dev, impl=args.rollout_impl, cpu=cpu)
         print(json.dumps(line), flush=True)
