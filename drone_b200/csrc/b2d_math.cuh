@@ -21,7 +21,27 @@ struct xf {
 __device__ __forceinline__ xf operator+(xf a, xf b) { return xf(__fadd_rn(a.v, b.v)); }
 __device__ __forceinline__ xf operator-(xf a, xf b) { return xf(__fsub_rn(a.v, b.v)); }
 __device__ __forceinline__ xf operator*(xf a, xf b) { return xf(__fmul_rn(a.v, b.v)); }
+// IEEE division.  A zero numerator fails div.rn's range check (FCHK) and sends the warp down a ~100-instruction slow
+// path with one lane active -- and a freshly reset drone is all zeros (velocity, rates, rotor speeds), so half of all
+// warps took that path at dozens of divisions per strict step (swarm strict, A = 16: 357 -> 282 us).  0 / b for a finite
+// non-zero b is a signed zero, exactly: those lanes divide 1 / b instead and get their zero back.
+__device__ __forceinline__ float xdiv_rn(float a, float b) {
+    const bool zero = a == 0.0f && b != 0.0f && fabsf(b) <= 3.402823466e38f;
+    const float q = __fdiv_rn(zero ? 1.0f : a, b);
+    return zero ? (b > 0.0f ? a : -a) : q;
+}
+// (operator/ stays the plain sequence: episode generation, whose numerators are never zero, is on the fast kernels' hot
+// path; the strict step's own arithmetic and observations use sdiv<>)
 __device__ __forceinline__ xf operator/(xf a, xf b) { return xf(__fdiv_rn(a.v, b.v)); }
+// The same division as ONE out-of-line copy, for the race env's STRICT step (rigid-body rates, quaternion
+// normalisation): it inlined ~45 division sequences and was instruction-cache bound (`no_instruction` 3.7 stall cycles
+// per issue); calling one copy takes it from 182 to 149 us per 1 M envs.  (The swarm's strict step is slower with the
+// call, 315 vs 282 us, and keeps the inline form: sdiv<false>.)
+__device__ __noinline__ float xdiv_out(float a, float b) { return xdiv_rn(a, b); }
+template <bool OUT> __device__ __forceinline__ xf sdiv(xf a, xf b) {
+    if constexpr (OUT) return xf(xdiv_out(a.v, b.v));
+    else return xf(xdiv_rn(a.v, b.v));
+}
 __device__ __forceinline__ xf operator-(xf a) { return xf(-a.v); }
 __device__ __forceinline__ xf xsqrt(xf a) { return xf(__fsqrt_rn(a.v)); }
 // clamp with the reference's branch order (NaN falls through), DR/dronelib.h:73-79

@@ -35,6 +35,7 @@ template <class T> struct Rate { // d(pos)/dt is the probed body's own velocity
 #define B2D_MAX_OMEGA 50.0f
 
 // ------------------------------------------------------------------ strict path
+template <bool OUT = true>
 __device__ __forceinline__ void rates_strict(const Body<xf> &b, const DroneParams &p, const xf want[4],
                                              xf inv_kmot, Rate<xf> &k) {
     xf thrust[4];
@@ -47,9 +48,9 @@ __device__ __forceinline__ void rates_strict(const Body<xf> &b, const DroneParam
     lift_body.z = thrust[0] + thrust[1] + thrust[2] + thrust[3];
     V3<xf> lift = qrot(b.q, lift_body);
     xf nbd = xf(-p.bd);
-    k.dvel.x = (lift.x + nbd * b.vel.x) / xf(p.mass);
-    k.dvel.y = (lift.y + nbd * b.vel.y) / xf(p.mass);
-    k.dvel.z = ((lift.z + nbd * b.vel.z) / xf(p.mass)) - xf(p.g);
+    k.dvel.x = sdiv<OUT>(lift.x + nbd * b.vel.x, xf(p.mass));
+    k.dvel.y = sdiv<OUT>(lift.y + nbd * b.vel.y, xf(p.mass));
+    k.dvel.z = sdiv<OUT>(lift.z + nbd * b.vel.z, xf(p.mass)) - xf(p.g);
     Q4<xf> wq;
     wq.w = xf(0.0f); wq.x = b.w.x; wq.y = b.w.y; wq.z = b.w.z;
     Q4<xf> dq = qmul(b.q, wq);
@@ -62,11 +63,12 @@ __device__ __forceinline__ void rates_strict(const Body<xf> &b, const DroneParam
     xf tix = (xf(p.iyy) - xf(p.izz)) * b.w.y * b.w.z;
     xf tiy = (xf(p.izz) - xf(p.ixx)) * b.w.z * b.w.x;
     xf tiz = (xf(p.ixx) - xf(p.iyy)) * b.w.x * b.w.y;
-    k.dw.x = (tpx + nkad * b.w.x + tix) / xf(p.ixx);
-    k.dw.y = (tpy + nkad * b.w.y + tiy) / xf(p.iyy);
-    k.dw.z = (tpz + nkad * b.w.z + tiz + tmz) / xf(p.izz);
+    k.dw.x = sdiv<OUT>(tpx + nkad * b.w.x + tix, xf(p.ixx));
+    k.dw.y = sdiv<OUT>(tpy + nkad * b.w.y + tiy, xf(p.iyy));
+    k.dw.z = sdiv<OUT>(tpz + nkad * b.w.z + tiz + tmz, xf(p.izz));
 }
 
+template <bool OUT = true>
 __device__ __forceinline__ void probe_strict(const Body<xf> &b, const V3<xf> &dpos, const Rate<xf> &k, xf h,
                                              Body<xf> &o) {
     o.pos.x = b.pos.x + dpos.x * h; o.pos.y = b.pos.y + dpos.y * h; o.pos.z = b.pos.z + dpos.z * h;
@@ -78,11 +80,12 @@ __device__ __forceinline__ void probe_strict(const Body<xf> &b, const V3<xf> &dp
     for (int m = 0; m < 4; m++) o.rpm[m] = b.rpm[m] + k.drpm[m] * h;
     xf n = xsqrt(o.q.w * o.q.w + o.q.x * o.q.x + o.q.y * o.q.y + o.q.z * o.q.z);
     if (n.v > 0.0f) {
-        o.q.w = o.q.w / n; o.q.x = o.q.x / n; o.q.y = o.q.y / n; o.q.z = o.q.z / n;
+        o.q.w = sdiv<OUT>(o.q.w, n); o.q.x = sdiv<OUT>(o.q.x, n); o.q.y = sdiv<OUT>(o.q.y, n); o.q.z = sdiv<OUT>(o.q.z, n);
     }
 }
 
 // state layout: s[0:3] pos, [3:6] vel, [6:10] quat wxyz, [10:13] omega, [13:17] rpm
+template <bool OUT = true>
 __device__ __forceinline__ void advance_body_strict(float s[17], const DroneParams &p, const float act[4]) {
     Body<xf> b, tmp;
     b.pos.x = s[0]; b.pos.y = s[1]; b.pos.z = s[2];
@@ -102,12 +105,12 @@ __device__ __forceinline__ void advance_body_strict(float s[17], const DronePara
     Rate<xf> k, acc;
     V3<xf> accp;
     // k1
-    rates_strict(b, p, want, inv_kmot, k);
+    rates_strict<OUT>(b, p, want, inv_kmot, k);
     acc = k;
     accp = b.vel;
-    probe_strict(b, b.vel, k, hh, tmp);
+    probe_strict<OUT>(b, b.vel, k, hh, tmp);
     // k2
-    rates_strict(tmp, p, want, inv_kmot, k);
+    rates_strict<OUT>(tmp, p, want, inv_kmot, k);
     {
         V3<xf> v2 = tmp.vel;
 #define B2D_ACC2(f) acc.f = acc.f + two * k.f
@@ -116,10 +119,10 @@ __device__ __forceinline__ void advance_body_strict(float s[17], const DronePara
         B2D_ACC2(dq.w); B2D_ACC2(dq.x); B2D_ACC2(dq.y); B2D_ACC2(dq.z);
         B2D_ACC2(dw.x); B2D_ACC2(dw.y); B2D_ACC2(dw.z);
         B2D_ACC2(drpm[0]); B2D_ACC2(drpm[1]); B2D_ACC2(drpm[2]); B2D_ACC2(drpm[3]);
-        probe_strict(b, v2, k, hh, tmp);
+        probe_strict<OUT>(b, v2, k, hh, tmp);
     }
     // k3
-    rates_strict(tmp, p, want, inv_kmot, k);
+    rates_strict<OUT>(tmp, p, want, inv_kmot, k);
     {
         V3<xf> v3 = tmp.vel;
         accp.x = accp.x + two * v3.x; accp.y = accp.y + two * v3.y; accp.z = accp.z + two * v3.z;
@@ -128,10 +131,10 @@ __device__ __forceinline__ void advance_body_strict(float s[17], const DronePara
         B2D_ACC2(dw.x); B2D_ACC2(dw.y); B2D_ACC2(dw.z);
         B2D_ACC2(drpm[0]); B2D_ACC2(drpm[1]); B2D_ACC2(drpm[2]); B2D_ACC2(drpm[3]);
 #undef B2D_ACC2
-        probe_strict(b, v3, k, h, tmp);
+        probe_strict<OUT>(b, v3, k, h, tmp);
     }
     // k4
-    rates_strict(tmp, p, want, inv_kmot, k);
+    rates_strict<OUT>(tmp, p, want, inv_kmot, k);
     const xf h6 = h / xf(6.0f);
 #define B2D_FIN(dst, a, kk) dst = dst + ((a) + (kk)) * h6
     B2D_FIN(b.pos.x, accp.x, tmp.vel.x); B2D_FIN(b.pos.y, accp.y, tmp.vel.y); B2D_FIN(b.pos.z, accp.z, tmp.vel.z);
@@ -144,7 +147,7 @@ __device__ __forceinline__ void advance_body_strict(float s[17], const DronePara
 #undef B2D_FIN
     xf n = xsqrt(b.q.w * b.q.w + b.q.x * b.q.x + b.q.y * b.q.y + b.q.z * b.q.z);
     if (n.v > 0.0f) {
-        b.q.w = b.q.w / n; b.q.x = b.q.x / n; b.q.y = b.q.y / n; b.q.z = b.q.z / n;
+        b.q.w = sdiv<OUT>(b.q.w, n); b.q.x = sdiv<OUT>(b.q.x, n); b.q.y = sdiv<OUT>(b.q.y, n); b.q.z = sdiv<OUT>(b.q.z, n);
     }
     s[0] = b.pos.x.v; s[1] = b.pos.y.v; s[2] = b.pos.z.v;
     s[3] = xclamp(b.vel.x, -B2D_MAX_VEL, B2D_MAX_VEL).v;
