@@ -122,6 +122,7 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop_evt = threading.Event()
+        self._go = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -133,9 +134,16 @@ class ClockSampler(threading.Thread):
         except Exception:  # noqa: BLE001
             self.ok = False
 
+    def arm(self):
+        """Begin sampling.  Called by the timing code right AFTER it has queued the timed launches: the GPU is then
+        busy with them for the rest of the region, and the NVML calls (which contend with the CUDA launch path for
+        driver locks) do not sit in front of the launches -- that cost 2-3 us per step in a 20-step region."""
+        self._go.set()
+
     def run(self):
         if not self.ok:
             return
+        self._go.wait()
         while not self._stop_evt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
@@ -149,6 +157,7 @@ class ClockSampler(threading.Thread):
 
     def stop(self):
         self._stop_evt.set()
+        self._go.set()
         if self.ok:
             self.join(timeout=2)
 
@@ -311,11 +320,13 @@ def time_race(n, math, launch, steps, warmup, dev, rank=0, world=1, dist=None):
             for j in range(k):
                 vec.step(tape[(t0 + j) % TAPE_LEN])
 
+    # (NVML is initialised BEFORE the warm-up: its first initialisation takes ~0.1 s, and a GPU left idle that long between
+    # the warm-up and a 20-step timed region starts the region below its boost clock)
+    sampler = ClockSampler(physical_gpu_index(dev.index))
     t = 0
     run_steps(t, INTERNAL_WARMUP + warmup)  # episodes last ~40 steps: the reset rate is steady after 64
     t += INTERNAL_WARMUP + warmup
     barrier()
-    sampler = ClockSampler(physical_gpu_index(dev.index))
     sampler.start()
     launches0 = vec.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -323,6 +334,7 @@ def time_race(n, math, launch, steps, warmup, dev, rank=0, world=1, dist=None):
     run_steps(t, steps)
     t += steps
     ev1.record(stream)
+    sampler.arm()
     barrier()
     sampler.stop()
     launches = vec.kernel_launches - launches0
@@ -367,10 +379,10 @@ def bench_swarm(drones, steps, warmup, dev, math="fast", envs=1 << 16, cpu=True,
     g = torch.Generator(device="cpu").manual_seed(TAPE_SEED)
     tape = (torch.rand((4, rows, 4), generator=g) * 2.0 - 1.0).to(dev)
     vec.reset(0)
+    sampler = ClockSampler(physical_gpu_index(dev.index))
     for t in range(max(warmup, 20)):
         vec.step(tape[t % 4])
     torch.cuda.synchronize()
-    sampler = ClockSampler(physical_gpu_index(dev.index))
     sampler.start()
     l0 = vec.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -378,6 +390,7 @@ def bench_swarm(drones, steps, warmup, dev, math="fast", envs=1 << 16, cpu=True,
     for t in range(steps):
         vec.step(tape[t % 4])
     ev1.record()
+    sampler.arm()
     torch.cuda.synchronize()
     sampler.stop()
     ms = ev0.elapsed_time(ev1)
@@ -410,7 +423,7 @@ def bench_swarm(drones, steps, warmup, dev, math="fast", envs=1 << 16, cpu=True,
         rng = np.random.default_rng(TAPE_SEED)
         htape = rng.uniform(-1, 1, size=(2, rows, 4)).astype(np.float32)
         e2e_steps = max(3, min(steps, 4_000_000 * 12 // rows))
-        for k in range(3):
+        for k in range(4):  # (both tape arrays twice: a recurring action array is page-locked on its second use)
             env.step(htape[k % 2])
         t0 = time.perf_counter()
         for k in range(e2e_steps):
@@ -441,9 +454,9 @@ def bench_rollout(replays, dev, envs=1 << 20, horizon=128, impl="auto", cpu=True
     vec.reset(0)
     policy = DronePolicy().to(dev)
     ro = DeviceRollout(vec, policy, horizon=horizon, policy_impl=impl)
+    sampler = ClockSampler(physical_gpu_index(dev.index))
     ro.collect()
     torch.cuda.synchronize()
-    sampler = ClockSampler(physical_gpu_index(dev.index))
     sampler.start()
     l0 = ro.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -451,6 +464,7 @@ def bench_rollout(replays, dev, envs=1 << 20, horizon=128, impl="auto", cpu=True
     for _ in range(replays):
         ro.collect()
     ev1.record()
+    sampler.arm()
     torch.cuda.synchronize()
     sampler.stop()
     ms = ev0.elapsed_time(ev1)
@@ -591,7 +605,7 @@ def main():
         rng = np.random.default_rng(TAPE_SEED + rank)
         htape = rng.uniform(-1, 1, size=(4, n, 4)).astype(np.float32)
         e2e_steps = max(3, min(args.steps, 200))
-        for k in range(3):
+        for k in range(max(args.warmup, 8)):  # (every tape array at least twice: a recurring action array is page-locked on its second use)
             env.step(htape[k % 4])
         barrier()
         t0 = time.perf_counter()
