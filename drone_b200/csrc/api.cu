@@ -162,11 +162,6 @@ struct b2d_vec {
     int math, write_clamped;
     bool host_clamp; // host buffers: leave clamp(action, -1, 1) in the caller's action array like DR/dronelib.h:437
     CopyPool *pool;  // host buffers: threads that share the action copy
-    // caller action arrays seen by b2d_vec_step_host_from: an array that comes back is page-locked in place
-    // (cudaHostRegister) so that its H2D needs no staging copy; see step_host_impl
-    struct ActionSource { const float *ptr; size_t bytes; int seen; int state; /* 0 new, 1 registered here, 2 pinned by the caller, -1 failed */ };
-    ActionSource act_src[8];
-    int act_src_clock;
     int step_ctas;   // race: CTAs of an overlapped (tape) launch = the largest grid; swarm: unused
     int single_ctas; // race: CTAs of a launch that runs alone
     RaceDev race;
@@ -540,8 +535,7 @@ extern "C" int b2d_vec_close(b2d_vec *v) {
     }
     delete v->pool;
     v->pool = nullptr;
-    for (auto &e : v->act_src)
-        if (e.state == 1) cudaHostUnregister(const_cast<float *>(e.ptr));
+
     for (void *p : v->allocs) cudaFree(p);
     if (v->d_payload) cudaFree(v->d_payload);
     if (v->d_blob_tmp) cudaFree(v->d_blob_tmp);
@@ -709,38 +703,22 @@ static int step_host_impl(b2d_vec *v, const float *host_actions, cudaStream_t st
     bnd.push_back(tiles);
     const int nchunks = (int)bnd.size() - 1;
     static const bool late_small = !(getenv("B2D_HOST_SMALL_COPIES") && atoi(getenv("B2D_HOST_SMALL_COPIES")) == 1);
-    // Actions straight from the caller's array.  The reference's wrapper copies the caller's actions into the env's
-    // action buffer and the step leaves them clamped there (`self.actions[:] = actions`, DR/dronelib.h:437).  That
-    // 16 B/env CPU copy used to sit in front of every chunk's upload -- one core at memcpy speed needs 1.5-2.5 ms for
-    // 1 M envs, which is the whole PCIe budget on a slow or shared host.  A caller array that comes back a second time
-    // is page-locked in place, its chunks go up by DMA from where they are (the kernel clamps what it reads), and the
-    // clamped copy into the env's buffer is made by this thread AFTER the last chunk is issued, while the results
-    // drain -- same buffer contents at return, nothing in front of the transfers.
+    // Actions straight from the caller's array when it is PAGE-LOCKED memory (cudaHostAlloc / cudaHostRegister by the
+    // caller: `DroneRace.pinned_actions()` hands out such an array).  The reference's wrapper copies the caller's actions
+    // into the env's action buffer and the step leaves them clamped there (`self.actions[:] = actions`, DR/dronelib.h:437).
+    // That 16 B/env CPU copy otherwise sits in front of every chunk's upload -- one core at memcpy speed needs 1.5-2.5 ms
+    // for 1 M envs, which is the whole PCIe budget on a slow or shared host.  From pinned memory the chunks go up by DMA
+    // from where they are (the kernel clamps what it reads) and the clamped copy into the env's buffer is made by this
+    // thread AFTER the last chunk is issued, while the results drain -- same buffer contents at return, nothing in front of
+    // the transfers.  The library never page-locks caller memory itself: a registration would outlive a freed array whose
+    // address the allocator hands out again, and DMA would then read the old pages.  (Checked per call: one driver query.)
     const float *h2d_src = v->host.actions;
     bool deferred_copy = false;
-    static const bool reg_ok = !(getenv("B2D_HOST_REGISTER_ACTIONS") && atoi(getenv("B2D_HOST_REGISTER_ACTIONS")) == 0);
-    if (copy_in && reg_ok && !v->write_clamped) {
-        const size_t bytes = rows * 4 * sizeof(float);
-        b2d_vec::ActionSource *hit = nullptr, *victim = &v->act_src[0];
-        for (auto &e : v->act_src) {
-            if (e.ptr == host_actions && e.bytes == bytes) { hit = &e; break; }
-            if (e.seen < victim->seen) victim = &e; // (seen doubles as the last-use clock)
-        }
-        if (!hit) {
-            if (victim->state == 1) cudaHostUnregister(const_cast<float *>(victim->ptr));
-            *victim = {host_actions, bytes, 0, 0};
-            hit = victim;
-        } else if (hit->state == 0) {
-            if (host_is_pinned(host_actions)) {
-                hit->state = 2; // the caller's own pinned memory: uploaded in place, nothing to release
-            } else {
-                const cudaError_t e = cudaHostRegister(const_cast<float *>(host_actions), bytes, cudaHostRegisterDefault);
-                hit->state = e == cudaSuccess ? 1 : -1;
-                if (e != cudaSuccess) (void)cudaGetLastError();
-            }
-        }
-        hit->seen = ++v->act_src_clock;
-        if (hit->state >= 1) { h2d_src = host_actions; deferred_copy = true; }
+    static const bool inplace_ok = !(getenv("B2D_HOST_INPLACE_ACTIONS") && atoi(getenv("B2D_HOST_INPLACE_ACTIONS")) == 0);
+    if (copy_in && inplace_ok && !v->write_clamped && host_is_pinned(host_actions) &&
+        host_is_pinned(reinterpret_cast<const char *>(host_actions) + rows * 4 * sizeof(float) - 1)) {
+        h2d_src = host_actions;
+        deferred_copy = true;
     }
     const bool host_copy = (v->host_clamp || copy_in) && !deferred_copy;
     if (host_copy) { // all chunks of the action copy go to the pool at once; chunk j is awaited right before its H2D

@@ -97,6 +97,12 @@ class DroneSwarm(PufferEnv):
 
         return (self.observations, self.rewards, self.terminals, self.truncations, info)
 
+    def pinned_actions(self):
+        """A page-locked float32 action array of this env's shape.  `step()` uploads such an array by DMA from where
+        it is (no staging copy on the CPU); any other NumPy array works too and is copied into `self.actions` first,
+        like the reference's wrapper does."""
+        return _pinned(tuple(self.actions.shape), np.float32)
+
     def render(self):
         binding.vec_render(self.c_envs, 0)
 

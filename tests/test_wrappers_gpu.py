@@ -199,10 +199,11 @@ def test_swarm_host_buffer_pipeline_equals_device_path(A):
     vec.close()
 
 
-def test_host_step_from_a_recurring_caller_array_uploads_in_place_and_leaves_clamped_actions():
-    """An action array that comes back is page-locked where it is and uploaded without the staging copy
-    (api.cu step_host_impl); the env's own action buffer must still hold clamp(actions, -1, 1) at return, like
-    the reference's (dronelib.h:437), and the results must equal those of fresh (copied) arrays."""
+def test_host_step_from_a_pinned_caller_array_uploads_in_place_and_leaves_clamped_actions():
+    """A page-locked action array (env.pinned_actions()) is uploaded from where it is, without the staging copy
+    (api.cu step_host_impl); the env's own action buffer must still hold clamp(actions, -1, 1) at return, like the
+    reference's (dronelib.h:437), and the results must equal those of ordinary (copied) arrays.  The library never
+    page-locks caller memory itself: arrays that are freed and re-allocated at the same address stay correct."""
     from drone_b200.drone_race import DroneRace
     n, seed = 140_003, 5
     a = DroneRace(num_envs=n, seed=seed, math="strict", report_interval=1 << 30)
@@ -210,18 +211,19 @@ def test_host_step_from_a_recurring_caller_array_uploads_in_place_and_leaves_cla
     a.reset(seed)
     b.reset(seed)
     rng = np.random.default_rng(3)
-    recurring = np.empty((n, 4), np.float32)
+    pinned = a.pinned_actions()
+    assert pinned.shape == (n, 4) and pinned.dtype == np.float32
     for t in range(5):
         fresh = rng.uniform(-1.6, 1.6, size=(n, 4)).astype(np.float32)
         fresh[7, 2] = np.nan
-        recurring[:] = fresh                    # same array object every step: registered from its second use on
-        oa, ra, ta, _, _ = a.step(recurring)
-        ob, rb, tb, _, _ = b.step(fresh.copy())  # a new array every step: always the copy path
+        pinned[:] = fresh
+        oa, ra, ta, _, _ = a.step(pinned)          # in-place upload
+        ob, rb, tb, _, _ = b.step(fresh.copy())    # a new pageable array every step (same address, most likely): copy path
         assert np.array_equal(bits(oa), bits(ob)) and np.array_equal(bits(ra), bits(rb)) and np.array_equal(ta, tb), t
         want = np.clip(fresh, -1.0, 1.0)
         assert np.array_equal(bits(a.actions), bits(want)), t
         assert np.array_equal(bits(b.actions), bits(want)), t
-        assert np.array_equal(bits(recurring), bits(fresh)), t  # the caller's array is read, never written
+        assert np.array_equal(bits(pinned), bits(fresh)), t  # the caller's array is read, never written
     a.close()
     b.close()
 
