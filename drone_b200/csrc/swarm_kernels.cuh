@@ -49,6 +49,9 @@ namespace b2d {
 #ifndef B2D_SW_RS_POOL
 #define B2D_SW_RS_POOL 8 // per warp: prepared respawn parameters fetched by cp.async a phase ahead (0: plain loads)
 #endif
+#ifndef B2D_SW_OBS_BULK
+#define B2D_SW_OBS_BULK 1 // observation rows leave shared memory as one asynchronous bulk copy per group (cp.async.bulk)
+#endif
 #ifndef B2D_SW_RK4_LOOP
 #define B2D_SW_RK4_LOOP 1 // RK4 stages as a loop: the hot path shrinks by ~4.5 KB of code
 #endif
@@ -1156,6 +1159,9 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
         s_now.put(w0 + a, g.s[0], g.s[1], g.s[2]);
         s_now.put(w0 + A + a, g.s[0], g.s[1], g.s[2]);
     }
+#if B2D_SW_OBS_BULK
+    if (t == grp_first) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the previous tile's rows have left the staging area
+#endif
     env_sync();
 
     // ---- phase 4: state out, observations (R/drone_swarm.h:131-217) staged through shared memory
@@ -1173,6 +1179,9 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
         if (task == SWARM_TASK_RACE) load_ring(e, g.ring_idx, ring);
         sw_observe<STRICT>(g, A, near, task == SWARM_TASK_RACE, ring, s_obs + t * SWARM_OBS, 1);
     }
+#if B2D_SW_OBS_BULK
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // this thread's row becomes visible to the bulk-copy engine
+#endif
     env_sync();
     {   // each group stores its own rows of the tile (contiguous in shared and in global memory)
         const int rows_here = min(d.epc, d.n - tile * d.epc) * A;
@@ -1181,6 +1190,21 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
         float *gobs = d.obs + row0 * SWARM_OBS;
         const float *sobs = s_obs + (size_t)grp_first * SWARM_OBS;
         const int tg = t - grp_first;
+#if B2D_SW_OBS_BULK
+        // One asynchronous bulk copy, shared -> global, issued by the group's first thread: the copy engine moves the
+        // 164 B x rows while the threads go on (the per-lane LDS.128 -> STG loop it replaces was 4 % of the step's
+        // instructions and 9 % of its stall samples at A = 16: every iteration waited for its shared-memory load).  The
+        // staging area is next written in the next tile's phase 4; the issuing thread waits for the engine to have READ
+        // it before the env's barrier that precedes those writes.
+        if (rows_mine > 0 && (rows_mine & 3) == 0 && (row0 & 3) == 0 && (grp_first & 3) == 0 && (reinterpret_cast<uintptr_t>(gobs) & 15) == 0) {
+            if (tg == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gobs),
+                             "r"((uint32_t)__cvta_generic_to_shared(sobs)), "r"((uint32_t)(rows_mine * SWARM_OBS * 4))
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else
+#endif
         if ((rows_mine & 3) == 0 && (row0 & 3) == 0 && (grp_first & 3) == 0) { // 16-byte aligned: float4 stores
             const float4 *src = reinterpret_cast<const float4 *>(sobs);
             float4 *dst = reinterpret_cast<float4 *>(gobs);
@@ -1212,6 +1236,9 @@ __global__ void __launch_bounds__(SWARM_BLOCK, 3) swarm_kernel(const __grid_cons
     // shared arrays from their next writers, except the old / fin arrays, which are last read before this
     // tile's final barriers
   }
+#if B2D_SW_OBS_BULK
+  if (t == grp_first) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // the last tile's rows are in global memory
+#endif
   if constexpr (!ONLY_RESET) {
       cp_async_wait<0>();
       __syncwarp();
