@@ -130,8 +130,11 @@ int b2d_vec_step_tape(b2d_vec *vec, const float *device_tape, int tape_len, int 
  * the b2d_buffers given at create time (location == B2D_MEM_HOST); pinned
  * memory is fastest.  Not capturable. */
 int b2d_vec_step_host(b2d_vec *vec, void *cuda_stream);
-/* same, taking this step's actions from another host array of the same shape: they are first
- * copied into the caller-visible action buffer (DR/drone_race.py:59 `self.actions[:] = actions`) */
+/* same, taking this step's actions from another host array of the same shape: they end up in the
+ * caller-visible action buffer (DR/drone_race.py:59 `self.actions[:] = actions`), clamped like the
+ * reference leaves them (DR/dronelib.h:437).  A PAGE-LOCKED `host_actions` (cudaHostAlloc /
+ * cudaHostRegister by the caller) is uploaded by DMA from where it is and that copy is made while the
+ * results come down; pageable memory is copied first, chunk by chunk.  `host_actions` is only read. */
 int b2d_vec_step_host_from(b2d_vec *vec, const float *host_actions, void *cuda_stream);
 /* host-buffer form of vec_reset: reset + observations D2H + sync */
 int b2d_vec_reset_host(b2d_vec *vec, uint64_t seed, void *cuda_stream);
